@@ -1,0 +1,18 @@
+"""avsl_b200 — B200-native (sm_100a) audio-visual speech front-end.
+
+A drop-in for the data front-end of hhoangphuoc/AVSL: Whisper log-mel spectrograms
+(``audio``), landmark-driven lip-ROI extraction, crop and normalisation (``lips``) and
+AV-HuBERT modality fusion (``fusion``), as hand-written CUDA kernels behind a C ABI
+(``include/avfe.h`` -> ``avsl_b200/lib/libavfe.so``).  There is no CPU fallback: every
+function raises if the library has not been built or no CUDA device is present.
+"""
+from . import _lib  # noqa: F401
+from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram,
+                    mel_filters, pad_or_trim, peak_normalize)
+from .frontend import AVFrontEnd, PackedBatch, algorithmic_bytes, pack_utterances, shard
+from .fusion import ModalityFusion, fuse_modalities, modality_dropout_flags, modality_dropout_mask
+from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,
+                   landmarks_interpolate, lip_roi_batch, load_video_feats, mean_face_landmarks,
+                   trim_video_to_audio, warp_img)
+
+__version__ = "0.1.0"

@@ -1,0 +1,169 @@
+"""Audio front-end: host-side mirror of the reference's Whisper audio call sites.
+
+Same names and argument meaning as the functions the reference calls
+(``avsl/whisper_flamingo_ft_ami.py:209-213``: ``whisper.pad_or_trim`` and
+``whisper.log_mel_spectrogram(audio, n_mels, padding)``; ``preprocess/audio_process.py:301-319``
+for the waveform normalisation).  All arithmetic runs in libavfe.so on the GPU; numpy / CPU
+inputs are staged through pinned memory and results come back in the container type the
+reference would have returned.
+"""
+from __future__ import annotations
+
+import ctypes
+import functools
+import math
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SAMPLE_RATE = 16000
+N_FFT = 400
+HOP_LENGTH = 160
+N_FREQ = 201
+CHUNK_LENGTH = 30
+N_SAMPLES = CHUNK_LENGTH * SAMPLE_RATE   # 480000
+N_FRAMES = N_SAMPLES // HOP_LENGTH       # 3000
+
+
+@functools.lru_cache(maxsize=None)
+def _mel_filters_np(n_mels: int) -> np.ndarray:
+    """Slaney-scale, slaney-normalised triangular filterbank [n_mels, 201] float32 — the matrix
+    openai-whisper ships as assets/mel_filters.npz (librosa.filters.mel(sr=16000, n_fft=400))."""
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, f / f_sp)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+    fft_freqs = np.linspace(0.0, SAMPLE_RATE / 2.0, N_FREQ)
+    mel_pts = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(SAMPLE_RATE / 2.0), n_mels + 2))
+    fdiff = np.diff(mel_pts)
+    ramps = mel_pts[:, None] - fft_freqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    fb = np.maximum(0.0, np.minimum(lower, upper))
+    fb *= (2.0 / (mel_pts[2:] - mel_pts[:-2]))[:, None]
+    return np.ascontiguousarray(fb.astype(np.float32))
+
+
+_FILTER_CACHE: dict = {}
+
+
+def mel_filters(device, n_mels: int = 80) -> torch.Tensor:
+    """``whisper.audio.mel_filters(device, n_mels)``: [n_mels, 201] float32 on ``device``."""
+    if n_mels <= 0 or n_mels > 128:
+        raise ValueError(f"Unsupported n_mels: {n_mels}")
+    key = (str(torch.device(device)), n_mels)
+    if key not in _FILTER_CACHE:
+        _FILTER_CACHE[key] = torch.from_numpy(_mel_filters_np(n_mels)).to(device)
+    return _FILTER_CACHE[key]
+
+
+def _to_cuda_f32(x, device=None) -> tuple:
+    """-> (contiguous float32 CUDA tensor, kind) with kind in {'numpy','cpu','cuda'}."""
+    _lib.require_cuda()
+    if isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        kind = "numpy"
+    elif torch.is_tensor(x):
+        t = x
+        kind = "cuda" if x.is_cuda else "cpu"
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.float32))
+        kind = "numpy"
+    if not t.is_cuda:
+        t = t.to(torch.float32).contiguous()
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = t.pin_memory().to(dev, non_blocking=True)
+    else:
+        t = t.to(torch.float32).contiguous()
+    return t, kind
+
+
+def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
+    """``whisper.pad_or_trim``: zero-pad or cut ``axis`` to ``length``; numpy in -> numpy out,
+    tensor in -> tensor out (same device)."""
+    if axis not in (-1, (array.ndim - 1)):
+        raise NotImplementedError("pad_or_trim is implemented for the last axis only")
+    t, kind = _to_cuda_f32(array)
+    lead = t.shape[:-1]
+    L_in = t.shape[-1]
+    B = int(np.prod(lead)) if lead else 1
+    out = torch.empty((*lead, length), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.call("avfe_pad_or_trim_f32", _lib.ptr(t), B, L_in, length, _lib.ptr(out), _lib.stream_ptr())
+    if kind == "numpy":
+        return out.cpu().numpy()
+    return out.cpu() if kind == "cpu" else out
+
+
+def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80,
+                        padding: int = 0, device: Optional[Union[str, torch.device]] = None,
+                        filters: Optional[torch.Tensor] = None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for ``whisper.log_mel_spectrogram(audio, n_mels, padding, device)``.
+
+    audio: [..., L] float waveform at 16 kHz (numpy array, CPU tensor or CUDA tensor).
+    Returns float32 ``[..., n_mels, (L + padding) // 160]``.  CUDA input (or an explicit
+    ``device``) keeps the result on the GPU; numpy / CPU input gets a CPU tensor back, as the
+    reference does.  The max-8 dB floor is applied per clip (the reference calls this once per
+    sample).  ``out`` (CUDA, contiguous) lets a caller write straight into a batch buffer.
+    """
+    if n_mels <= 0 or n_mels > 128:
+        raise ValueError(f"Unsupported n_mels: {n_mels}")
+    t, kind = _to_cuda_f32(audio, device)
+    if t.dim() == 0:
+        raise ValueError("audio must have at least one dimension")
+    lead = tuple(t.shape[:-1])
+    L = int(t.shape[-1])
+    B = int(np.prod(lead)) if lead else 1
+    n_frames = (L + padding) // HOP_LENGTH
+    if B > 0 and n_frames > 0 and L + padding <= N_FFT // 2:
+        # torch.stft: "Padding size should be less than the corresponding input dimension"
+        raise RuntimeError("log_mel_spectrogram: reflect padding (200) needs more than 200 samples")
+    fb = filters if filters is not None else mel_filters(t.device, n_mels)
+    if not (fb.is_cuda and fb.dtype == torch.float32 and fb.is_contiguous() and tuple(fb.shape) == (n_mels, N_FREQ)):
+        fb = fb.to(t.device, torch.float32).contiguous()
+        if tuple(fb.shape) != (n_mels, N_FREQ):
+            raise ValueError("filters must be [n_mels, 201]")
+    shape = (*lead, n_mels, n_frames)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=t.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == shape):
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    with torch.cuda.device(t.device):
+        lib = _lib.load()
+        ws_bytes = int(lib.avfe_logmel_workspace_bytes(B, L, padding, n_mels))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=t.device)
+        _lib.call("avfe_logmel_f32", _lib.ptr(t), B, L, padding, n_mels, _lib.ptr(fb), _lib.ptr(out),
+                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    if kind in ("numpy", "cpu") and device is None:
+        return out.cpu()
+    return out
+
+
+def peak_normalize(audio: Union[np.ndarray, torch.Tensor]):
+    """The waveform conditioning of ``preprocess_audio_for_whisper`` /
+    ``process_audio_dual_encoder['waveform']`` (preprocess/audio_process.py:291-293,312-317)
+    without the file load: float32 cast; clips with a sample outside [-1, 1] are divided by
+    max(|max|, |min|).  [..., L] -> same shape, same container type."""
+    t, kind = _to_cuda_f32(audio)
+    lead = tuple(t.shape[:-1])
+    L = int(t.shape[-1])
+    B = int(np.prod(lead)) if lead else 1
+    out = torch.empty_like(t)
+    scratch = torch.empty(max(2 * B, 2), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.call("avfe_peak_normalize_f32", _lib.ptr(t), B, L, _lib.ptr(out), _lib.ptr(scratch),
+                  _lib.stream_ptr())
+    if kind == "numpy":
+        return out.cpu().numpy()
+    return out.cpu() if kind == "cpu" else out

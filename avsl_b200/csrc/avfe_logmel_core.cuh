@@ -1,0 +1,164 @@
+// Log-mel building blocks, compiled for the device (avfe_logmel.cu) and for the host
+// (tests/hostcheck: TEST-ONLY harness that steps these codelets thread by thread on the CPU
+// to check the index algebra against the oracle; not a product path).
+//
+// STFT of one tile = 32 consecutive frames of one clip = 16 complex 400-point FFTs
+// (frames 2g and 2g+1 ride in the real and imaginary parts of FFT g).  400 = 20 x 20
+// Cooley-Tukey; each 20-point DFT is a register-resident 4 x 5 prime-factor (Good-Thomas)
+// codelet with no internal twiddles.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AVFE_HD __host__ __device__ __forceinline__
+#else
+#define AVFE_HD inline
+#endif
+
+namespace avfe {
+namespace lm {
+
+constexpr int kNfft = 400;
+constexpr int kHop = 160;
+constexpr int kBins = 201;
+constexpr int kTileFrames = 32;
+constexpr int kPairs = kTileFrames / 2;                          // 16 complex FFTs per tile
+constexpr int kThreads = kPairs * 20;                            // 320: one thread per (FFT, column)
+constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5360
+constexpr int kZRow = 21;            // float2 row stride of the 20x20 exchange (20 + 1 pad)
+constexpr int kZPair = 20 * kZRow;   // 420 float2 per FFT (840 words = 8 mod 32 banks)
+constexpr int kPStride = 201;        // odd stride: lane = frame reads are conflict-free
+
+AVFE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+AVFE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+AVFE_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// forward 4-point DFT (W = -i)
+AVFE_HD void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+  const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+  x0 = cadd(t0, t2);
+  x2 = csub(t0, t2);
+  x1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
+  x3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
+}
+
+// forward 5-point DFT
+AVFE_HD void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+  const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+  const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+  const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  x1 = make_float2(m1.x + n1.y, m1.y - n1.x);   // m1 - i*n1
+  x4 = make_float2(m1.x - n1.y, m1.y + n1.x);   // m1 + i*n1
+  x2 = make_float2(m2.x + n2.y, m2.y - n2.x);
+  x3 = make_float2(m2.x - n2.y, m2.y + n2.x);
+}
+
+// In-place forward 20-point DFT, natural order in and out.
+// Good-Thomas: n = (5*n1 + 4*n2) mod 20, k = (5*k1 + 16*k2) mod 20.
+AVFE_HD void dft20(float2 (&x)[20]) {
+  float2 a[4][5];
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1)
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) a[n1][n2] = x[(5 * n1 + 4 * n2) % 20];
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2) dft4(a[0][n2], a[1][n2], a[2][n2], a[3][n2]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft5(a[k1][0], a[k1][1], a[k1][2], a[k1][3], a[k1][4]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) x[(5 * k1 + 16 * k2) % 20] = a[k1][k2];
+}
+
+// Source sample for padded-signal position p (p = 0 is 200 samples before the clip start):
+// torch.stft(center=True, pad_mode="reflect") over the clip zero-extended to Lp = L + padding.
+AVFE_HD float padded_sample(const float* clip, int64_t L, int64_t Lp, int64_t p) {
+  int64_t j = p - kNfft / 2;
+  if (j < 0) j = -j;
+  if (j >= Lp) j = 2 * (Lp - 1) - j;
+  if (j < 0 || j >= L) return 0.0f;   // zero padding (or beyond the last computed frame)
+  return clip[j];
+}
+
+// Stage 1, thread (g, j): column j of FFT g.  z[m] = hann[j+20m] * (xa + i*xb)[j+20m];
+// 20-point DFT over m; times W400^(j*k1); stored at Z[g][k1][j].
+// tw[k1*20 + j] = exp(-2*pi*i*j*k1/400).
+AVFE_HD void stage1(int g, int j, const float* tile, const float* hann, const float2* tw,
+                    float2* Z) {
+  float2 x[20];
+  const float* fa = tile + (2 * g) * kHop + j;
+  const float* fb = fa + kHop;
+#pragma unroll
+  for (int m = 0; m < 20; ++m) {
+    const float w = hann[j + 20 * m];
+    x[m] = make_float2(w * fa[20 * m], w * fb[20 * m]);
+  }
+  dft20(x);
+  float2* z = Z + g * kZPair + j;
+  z[0] = x[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 20; ++k1) z[k1 * kZRow] = cmul(x[k1], tw[k1 * 20 + j]);
+}
+
+// Stage 2, thread (g, k1): 20-point DFT over j of row k1, in place:
+// slot [g][k1][k2] then holds bin k = k1 + 20*k2.
+AVFE_HD void stage2(int g, int k1, float2* Z) {
+  float2 x[20];
+  float2* z = Z + g * kZPair + k1 * kZRow;
+#pragma unroll
+  for (int j = 0; j < 20; ++j) x[j] = z[j];
+  dft20(x);
+#pragma unroll
+  for (int k2 = 0; k2 < 20; ++k2) z[k2] = x[k2];
+}
+
+AVFE_HD int zslot(int k) { return (k % 20) * kZRow + k / 20; }
+
+// Untangle the two real frames packed in FFT g at bin k (0..200) and store both powers.
+// Xa = (Z[k] + conj(Z[400-k]))/2, Xb = (Z[k] - conj(Z[400-k]))/(2i).
+AVFE_HD void split_power(int g, int k, const float2* Z, float* P) {
+  const float2* z = Z + g * kZPair;
+  const float2 u = z[zslot(k)];
+  const float2 v = z[zslot(k == 0 ? 0 : kNfft - k)];
+  const float ar = u.x + v.x, ai = u.y - v.y;
+  const float br = u.y + v.y, bi = v.x - u.x;
+  P[(2 * g) * kPStride + k] = 0.25f * (ar * ar + ai * ai);
+  P[(2 * g + 1) * kPStride + k] = 0.25f * (br * br + bi * bi);
+}
+
+// log10(max(mel, 1e-10)) for one (frame, filter): dot product over the filter's support.
+AVFE_HD float mel_log10(const float* Prow, const float* fbrow, int k0, int k1) {
+  float acc = 0.0f;
+  for (int k = k0; k < k1; ++k) acc = fmaf(fbrow[k], Prow[k], acc);
+  acc = fmaxf(acc, 1e-10f);
+#if defined(__CUDA_ARCH__)
+  return __log2f(acc) * 0.30102999566398120f;   // MUFU.LG2: abs error ~1e-6 in log10 units
+#else
+  return log2f(acc) * 0.30102999566398120f;
+#endif
+}
+
+// order-preserving float <-> int key for atomicMax
+AVFE_HD int float_key(float f) {
+  union { float f; int i; } u;
+  u.f = f;
+  return u.i >= 0 ? u.i : (u.i ^ 0x7fffffff);
+}
+AVFE_HD float key_float(int k) {
+  union { float f; int i; } u;
+  u.i = k >= 0 ? k : (k ^ 0x7fffffff);
+  return u.f;
+}
+
+}  // namespace lm
+}  // namespace avfe

@@ -1,0 +1,180 @@
+"""Batched AV front-end: what ``AmiVideoHFDataset.__getitem__`` computes per sample
+(``avsl/whisper_flamingo_ft_ami.py:187-313``: pad_or_trim -> log-mel; lip frames -> crop 88 ->
+normalise -> trim) and what ``extract_lip_frames`` computes per video, for a whole batch of
+utterances in a handful of kernel launches on one GPU.
+
+Utterances are independent, so multi-GPU operation is one process per GPU, each taking the
+utterances ``i % world_size == rank`` (``shard``); there is no collective on the hot path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .audio import HOP_LENGTH, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, mel_filters
+from .lips import IMAGE_CROP_SIZE, IMAGE_MEAN, IMAGE_STD, LipBatch, lip_roi_batch
+
+FPS = 25
+
+
+@dataclass
+class PackedBatch:
+    """A batch of utterances stored back to back (host-pinned or device tensors).
+
+    audio          float32 [sum L_i]     waveforms, 16 kHz
+    audio_offsets  int64   [U+1]
+    frames         uint8   [N,H,W,3]     BGR frames of all clips, N = sum T_i
+    clip_offsets   int64   [U+1]
+    landmarks      float64 [N,68,2]
+    lm_valid       uint8   [N]           0 = detection failed (reference: None)
+    """
+    audio: torch.Tensor
+    audio_offsets: torch.Tensor
+    frames: torch.Tensor
+    clip_offsets: torch.Tensor
+    landmarks: torch.Tensor
+    lm_valid: Optional[torch.Tensor]
+
+    FIELDS = ("audio", "audio_offsets", "frames", "clip_offsets", "landmarks", "lm_valid")
+
+    @property
+    def n_utts(self) -> int:
+        return int(self.audio_offsets.numel()) - 1
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size()
+                   for f in self.FIELDS if getattr(self, f) is not None)
+
+    def pin(self) -> "PackedBatch":
+        return PackedBatch(*[None if getattr(self, f) is None else getattr(self, f).cpu().contiguous().pin_memory()
+                             for f in self.FIELDS])
+
+    def to(self, device, non_blocking: bool = True) -> "PackedBatch":
+        return PackedBatch(*[None if getattr(self, f) is None else getattr(self, f).to(device, non_blocking=non_blocking)
+                             for f in self.FIELDS])
+
+
+def pack_utterances(audios: Sequence[np.ndarray], videos: Sequence[np.ndarray],
+                    landmarks: Sequence[np.ndarray], valids: Optional[Sequence[np.ndarray]] = None,
+                    audio_max_length: Optional[int] = N_SAMPLES) -> PackedBatch:
+    """Host-side packing of per-utterance arrays.  Audio is cut to ``audio_max_length``
+    (pad_or_trim's trim half; the pad half happens on the GPU) and video to the frame count the
+    reference keeps, round(audio_max_length / 16000 * 25) (whisper_flamingo_ft_ami.py:299-302)."""
+    assert len(audios) == len(videos) == len(landmarks)
+    max_frames = None if audio_max_length is None else round(audio_max_length / SAMPLE_RATE * FPS)
+    a_list, v_list, l_list, m_list = [], [], [], []
+    for i in range(len(audios)):
+        a = np.asarray(audios[i], dtype=np.float32).reshape(-1)
+        if audio_max_length is not None:
+            a = a[:audio_max_length]
+        v = np.asarray(videos[i], dtype=np.uint8)
+        lm = np.asarray(landmarks[i], dtype=np.float64)
+        ok = np.ones(len(v), dtype=np.uint8) if valids is None else np.asarray(valids[i], dtype=np.uint8)
+        if max_frames is not None:
+            v, lm, ok = v[:max_frames], lm[:max_frames], ok[:max_frames]
+        a_list.append(a); v_list.append(v); l_list.append(lm); m_list.append(ok)
+    a_off = np.concatenate([[0], np.cumsum([len(a) for a in a_list])]).astype(np.int64)
+    c_off = np.concatenate([[0], np.cumsum([len(v) for v in v_list])]).astype(np.int64)
+    return PackedBatch(torch.from_numpy(np.concatenate(a_list)), torch.from_numpy(a_off),
+                       torch.from_numpy(np.concatenate(v_list)), torch.from_numpy(c_off),
+                       torch.from_numpy(np.concatenate(l_list)), torch.from_numpy(np.concatenate(m_list)))
+
+
+class AVFrontEnd:
+    """Log-mel + lip-ROI features for a packed batch of utterances on one GPU."""
+
+    def __init__(self, n_mels: int = 80, audio_max_length: int = N_SAMPLES, device=None,
+                 want_gray: bool = True, want_lip_u8: bool = False,
+                 image_crop_size: int = IMAGE_CROP_SIZE, image_mean: float = IMAGE_MEAN,
+                 image_std: float = IMAGE_STD):
+        _lib.require_cuda()
+        _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_mels = n_mels
+        self.audio_max_length = audio_max_length
+        self.want_gray = want_gray
+        self.want_lip_u8 = want_lip_u8
+        self.crop = image_crop_size
+        self.mean, self.std = image_mean, image_std
+        self.filters = mel_filters(self.device, n_mels)
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    @staticmethod
+    def model_n_mels(model_name: str) -> int:
+        """avsl/whisper_flamingo_ft_ami.py:212."""
+        return 80 if "large-v3" not in model_name else 128
+
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    # ---------------------------------------------------------------- device-resident path
+    def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] skips
+        the pad_or_trim launch when the caller already holds the padded matrix.
+        Returns device tensors: mel [U,n_mels,F], lip [N,88,88,1], gray [N,H,W] (optional),
+        lip_u8 [N,96,96] (optional)."""
+        U, L = batch.n_utts, self.audio_max_length
+        with torch.cuda.device(self.device):
+            if padded_audio is None:
+                padded_audio = self._buf("audio", (U, L), torch.float32)
+                _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(batch.audio), _lib.ptr(batch.audio_offsets),
+                          U, L, _lib.ptr(padded_audio), _lib.stream_ptr())
+            mel = self._buf("mel", (U, self.n_mels, L // HOP_LENGTH), torch.float32)
+            log_mel_spectrogram(padded_audio, self.n_mels, filters=self.filters, out=mel)
+            N, H, W = (int(s) for s in batch.frames.shape[:3])
+            reuse = LipBatch(self._buf("gray", (N, H, W), torch.uint8) if self.want_gray else None,
+                             self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
+                             self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
+                             batch.clip_offsets)
+            lip_roi_batch(batch.frames, batch.clip_offsets, batch.landmarks, batch.lm_valid,
+                          want_gray=self.want_gray, want_u8=self.want_lip_u8, crop=self.crop,
+                          image_mean=self.mean, image_std=self.std, out=reuse)
+        out = {"mel": mel, "lip": reuse.lip_f32.unsqueeze(-1)}
+        if reuse.gray is not None:
+            out["gray"] = reuse.gray
+        if reuse.lip_u8 is not None:
+            out["lip_u8"] = reuse.lip_u8
+        return out
+
+    # ---------------------------------------------------------------- host-buffer path (e2e)
+    def forward_host(self, batch: PackedBatch, host_out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``batch`` lives in (pinned) host memory: H2D copy of every input, the kernels, and a
+        D2H copy of the features the reference's ``__getitem__`` returns (mel and lip)."""
+        dev = batch.to(self.device, non_blocking=True)
+        res = self.forward_device(dev)
+        if host_out is None:
+            host_out = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory() for k in ("mel", "lip")}
+        for k in ("mel", "lip"):
+            host_out[k].copy_(res[k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host_out
+
+    @staticmethod
+    def split_lip(lip: torch.Tensor, clip_offsets) -> List[torch.Tensor]:
+        """Per-utterance [T_i,88,88,1] views of the packed lip tensor."""
+        off = [int(x) for x in clip_offsets.tolist()]
+        return [lip[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def shard(n_items: int, rank: int, world_size: int) -> np.ndarray:
+    """Indices of the utterances rank ``rank`` of ``world_size`` processes owns."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank must be in [0, world_size)")
+    return np.arange(rank, n_items, world_size)
+
+
+def algorithmic_bytes(n_utts: int, n_frames: int, H: int = 224, W: int = 224, n_mels: int = 80,
+                      audio_len: int = N_SAMPLES, crop: int = IMAGE_CROP_SIZE) -> int:
+    """per utterance 4*L + 4*n_mels*(L/160); per frame H*W*3 + 68*2*8 + H*W +
+    crop*crop*4."""
+    per_utt = 4 * audio_len + 4 * n_mels * (audio_len // HOP_LENGTH)
+    per_frame = H * W * 3 + 68 * 2 * 8 + H * W + crop * crop * 4
+    return n_utts * per_utt + n_frames * per_frame

@@ -1,0 +1,183 @@
+/*
+ * avfe.h — C ABI of libavfe.so, the B200 (sm_100a) audio-visual front-end.
+ *
+ * The reference (hhoangphuoc/AVSL) has no FFI: its hot path is plain Python functions that
+ * call torch / OpenCV / scikit-image on the CPU.  Each entry point below replaces the
+ * arithmetic of one (or a fused run of) those functions; the reference symbol is cited as
+ * file:line into the reference tree.  `avsl_b200/*.py` is the host-side mirror that keeps the
+ * reference names and signatures and calls these symbols through ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (cudaMalloc'd on the current device), row-major,
+ *    caller-allocated and caller-owned; inputs are const and never written;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream); no call synchronises the host, allocates device memory or keeps state, so
+ *    calls are re-entrant and may be issued concurrently from several host threads;
+ *  - every function returns 0 on success or a negative avfe_status; nothing throws across
+ *    the ABI and nothing falls back to the CPU.
+ */
+#ifndef AVFE_H_
+#define AVFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AVFE_API __declspec(dllexport)
+#else
+#define AVFE_API __attribute__((visibility("default")))
+#endif
+
+typedef void* avfe_stream_t; /* cudaStream_t */
+
+enum avfe_status {
+  AVFE_OK = 0,
+  AVFE_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, unsupported shape */
+  AVFE_ERR_UNSUPPORTED = -2,   /* parameter combination not implemented (e.g. n_mels > 128) */
+  AVFE_ERR_WORKSPACE = -3,     /* workspace NULL / too small / misaligned */
+  AVFE_ERR_CUDA = -4,          /* a CUDA runtime call or launch failed (see cudaGetLastError) */
+  AVFE_ERR_ALIGNMENT = -5      /* a pointer does not meet the documented alignment */
+};
+
+enum avfe_fuse_mode { AVFE_FUSE_CONCAT = 0, AVFE_FUSE_SUM = 1, AVFE_FUSE_WSUM = 2 };
+enum avfe_dtype { AVFE_F32 = 0, AVFE_F16 = 1, AVFE_BF16 = 2 };
+
+/* library version: major*10000 + minor*100 + patch */
+AVFE_API int avfe_version(void);
+/* static string for an avfe_status (never NULL) */
+AVFE_API const char* avfe_strerror(int status);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+AVFE_API uint64_t avfe_launch_count(void);
+
+/* ------------------------------------------------------------------ audio (A1..A3) */
+
+/* whisper.pad_or_trim(array, length) on the last axis — call site
+ * avsl/whisper_flamingo_ft_ami.py:209-210.  in [B, L_in] -> out [B, L_out], zero padded. */
+AVFE_API int avfe_pad_or_trim_f32(const float* in, int64_t B, int64_t L_in, int64_t L_out,
+                                  float* out, avfe_stream_t stream);
+
+/* Same, for a ragged batch stored back to back: clip b = in[offsets[b] : offsets[b+1]]
+ * (offsets int64 [B+1], device) -> out [B, L_out]. */
+AVFE_API int avfe_pad_or_trim_ragged_f32(const float* in, const int64_t* offsets, int64_t B,
+                                         int64_t L_out, float* out, avfe_stream_t stream);
+
+/* preprocess_audio_for_whisper's peak normalisation, preprocess/audio_process.py:312-317
+ * (same code at :291-293): per clip, if max > 1 or min < -1 divide by max(|max|,|min|).
+ * audio [B, L] -> out [B, L] (out may alias audio).  scratch: >= 2*B floats. */
+AVFE_API int avfe_peak_normalize_f32(const float* audio, int64_t B, int64_t L, float* out,
+                                     float* scratch, avfe_stream_t stream);
+
+/* whisper.log_mel_spectrogram(audio, n_mels, padding) — call site
+ * avsl/whisper_flamingo_ft_ami.py:212-213 (HF twin avsl/whisper_ft.py:347-350):
+ * zero-pad `padding` samples, reflect-centre, Hann(400) STFT hop 160, drop the last frame,
+ * |.|^2, mel_filters @, clamp 1e-10, log10, per-CLIP max-8 floor, (x+4)/4.
+ *   audio       [B, L] float32
+ *   mel_filters [n_mels, 201] float32 (n_mels <= 128)
+ *   out         [B, n_mels, (L+padding)/160] float32
+ *   workspace   avfe_logmel_workspace_bytes(...) bytes, 16-byte aligned
+ * Requires L + padding >= 201 (reflect padding), like torch.stft. */
+AVFE_API size_t avfe_logmel_workspace_bytes(int64_t B, int64_t L, int64_t padding, int n_mels);
+AVFE_API int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
+                             int n_mels, const float* mel_filters, float* out,
+                             void* workspace, size_t workspace_bytes, avfe_stream_t stream);
+
+/* ------------------------------------------------------------------ video (V1..V8) */
+
+/* cv2.cvtColor(frame, COLOR_BGR2GRAY) — preprocess/video_process.py:201-214:
+ * Y = (3735*B + 19235*G + 9798*R + 16384) >> 15.  bgr [N,H,W,3] u8 -> gray [N,H,W] u8. */
+AVFE_API int avfe_bgr2gray_u8(const uint8_t* bgr, int64_t N, int H, int W, uint8_t* gray,
+                              avfe_stream_t stream);
+
+/* skimage.transform.warp(img, inverse_map=tform.inverse, output_shape) followed by
+ * (*255).astype(uint8) — utils/lips_cropping.py:104-107 (warp_img) and :122-124
+ * (apply_transform) — for a GIVEN transform.  gray [H,W] u8; inv_matrix = 3x3 row-major
+ * float64 of tform.inverse.params; out [out_h,out_w] u8.  Bit-exact float64 evaluation. */
+AVFE_API int avfe_warp_affine_u8(const uint8_t* gray, int H, int W, const double* inv_matrix,
+                                 int out_h, int out_w, uint8_t* out, avfe_stream_t stream);
+
+/* The fused lip-ROI path for a batch of clips: gray conversion (V1), landmark
+ * interpolation (V2, utils/lips_cropping.py:41-89), 12-frame forward window smoothing and
+ * tail reuse (V3, preprocess/video_process.py:369-370,417-475), similarity fit on the 5
+ * stable points to the mean face (V4, utils/lips_cropping.py:104), warp to std_size (V4/V5),
+ * landmark transform (V6), cut_patch (V7, utils/lips_cropping.py:127-163), centre crop +
+ * normalise (V8, utils/hf_video_utils.py:113-138).
+ *
+ *   frames       [N, H, W, channels] u8, channels = 3 (BGR) or 1 (already gray); N = total
+ *                frames of all clips, clips stored back to back
+ *   clip_offsets [n_clips+1] int64 (device): clip k owns frames [off[k], off[k+1])
+ *   landmarks    [N, 68, 2] float64 (x, y) in frame pixels
+ *   lm_valid     [N] u8 or NULL (= all valid); 0 marks a failed detection (reference: None)
+ *   mean_face    [68, 2] float64 (resources/20words_mean_face.npy)
+ *   tforms_in    [N, 18] float64 or NULL: per frame the forward 3x3 (tform.params) followed by
+ *                the inverse 3x3 (tform.inverse.params), both affine.  When given, the transform
+ *                is taken from here instead of being fitted (apply_transform semantics) and the
+ *                warp is bit-exact for those matrices.
+ *   std_size 300, roi 96 (even), crop 88 (<= roi, same parity), window 12
+ *   mean/std     normalisation constants (0.421 / 0.165)
+ * outputs (each nullable):
+ *   gray_out [N,H,W] u8          bit-exact cv2 gray frames (channels==3 only)
+ *   lip_u8   [N,roi,roi] u8      what extract_lip_frames returns
+ *   lip_f32  [N,crop,crop] f32   what load_video_feats returns ([T,88,88,1])
+ *   crop_rc  [N,2] int32         row/col of the ROI's top-left corner in the std frame
+ *   tforms   [N,18] float64      forward 3x3 then inverse 3x3 used for each frame
+ * A clip without any valid landmark yields zero ROIs and crop_rc = -1 (the host shim maps
+ * that to the reference's empty-array return).
+ *   workspace avfe_lip_workspace_bytes(N) bytes, 16-byte aligned. */
+AVFE_API size_t avfe_lip_workspace_bytes(int64_t N);
+AVFE_API int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N, int H, int W,
+                                const int64_t* clip_offsets, int64_t n_clips,
+                                const double* landmarks, const uint8_t* lm_valid,
+                                const double* mean_face, const double* tforms_in,
+                                int std_size, int roi, int crop, int window,
+                                float mean, float std,
+                                uint8_t* gray_out, uint8_t* lip_u8, float* lip_f32,
+                                int32_t* crop_rc, double* tforms,
+                                void* workspace, size_t workspace_bytes, avfe_stream_t stream);
+
+/* landmarks_interpolate — utils/lips_cropping.py:41-89 — alone: fills frames whose lm_valid is
+ * 0 by linear interpolation between the neighbouring detections of the same clip
+ * (start + idx/float(n) * delta) and by replication at the clip ends; a clip with no
+ * detection at all is filled with NaN (reference: returns None).  out [N,68,2] float64. */
+AVFE_API int avfe_landmarks_interpolate(const double* landmarks, const uint8_t* lm_valid,
+                                        const int64_t* clip_offsets, int64_t n_clips, int64_t N,
+                                        double* out, avfe_stream_t stream);
+
+/* skimage.transform.estimate_transform('similarity', src, dst) — utils/lips_cropping.py:104 —
+ * for n 2-D points (closed form of skimage's _umeyama).  out18 = forward 3x3 then inverse 3x3,
+ * float64 row-major. */
+AVFE_API int avfe_similarity_fit(const double* src, const double* dst, int n, double* out18,
+                                 avfe_stream_t stream);
+
+/* cut_patch(img, landmarks, height, width) — utils/lips_cropping.py:127-163 — on a 2-D uint8
+ * image: centre = mean of the n landmarks (x, y), clamped so the patch fits, Python round().
+ * out [2*half_h, 2*half_w] u8; rc (nullable) receives the chosen top-left (row, col). */
+AVFE_API int avfe_cut_patch_u8(const uint8_t* img, int H, int W, const double* landmarks, int n,
+                               int half_h, int half_w, uint8_t* out, int32_t* rc,
+                               avfe_stream_t stream);
+
+/* load_video_feats arithmetic on an existing ROI stack — utils/hf_video_utils.py:113-138,
+ * utils/data_loading.py:46-66,101-118: /255, centre crop, (x-mean)/std in float32.
+ * roi_u8 [N, Hin, Win] u8 -> out [N, crop, crop] f32 (crop <= min(Hin,Win)). */
+AVFE_API int avfe_video_feats_u8(const uint8_t* roi_u8, int64_t N, int Hin, int Win, int crop,
+                                 float mean, float std, float* out, avfe_stream_t stream);
+
+/* ------------------------------------------------------------------ fusion (F1..F3) */
+
+/* AVHuBERTEncoderWrapper.forward's fusion block — avsl/modules/av_hubert_encoder.py:315-326,
+ * with the modality-dropout decision (:292-298) supplied as a per-sample mask.
+ *   fa, fv [B, C, T] of `dtype`; mask [B,2] u8 (col 0 audio present, col 1 video present) or
+ *   NULL (= all present); a missing modality is zero-filled and NOT read.
+ *   mode CONCAT -> out [B, 2C, T]; SUM -> fa+fv [B, C, T]; WSUM -> w_a*fa + w_v*fv [B, C, T]. */
+AVFE_API int avfe_fuse(const void* fa, const void* fv, const uint8_t* mask, int mode,
+                       float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
+                       void* out, avfe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVFE_H_ */

@@ -1,0 +1,87 @@
+// TEST-ONLY host harness.  Steps the __host__ __device__ codelets of libavfe
+// (avfe_logmel_core.cuh, avfe_lip_math.cuh) thread by thread on the CPU so the index algebra
+// (Good-Thomas maps, 20x20 exchange layout, two-frames-per-FFT untangling, reflect padding,
+// similarity fit, bilinear blend order) can be checked against the oracle in the no-GPU test
+// tier.  It is never loaded by avsl_b200 and is not a CPU fallback: the product path only
+// calls libavfe.so kernels.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "avfe_lip_math.cuh"
+#include "avfe_logmel_core.cuh"
+
+using namespace avfe;
+
+extern "C" {
+
+// raw log10-mel of one tile (32 frames starting at t0) -> out[n_mels][32]
+void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_mels,
+                    const float* fb, float* out) {
+  using namespace lm;
+  std::vector<float> hann(kNfft);
+  std::vector<float2> tw(kNfft);
+  for (int i = 0; i < kNfft; ++i) hann[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kNfft));
+  for (int k1 = 0; k1 < 20; ++k1)
+    for (int j = 0; j < 20; ++j) {
+      const double a = -2.0 * M_PI * ((j * k1) % kNfft) / kNfft;
+      tw[k1 * 20 + j] = make_float2((float)cos(a), (float)sin(a));
+    }
+  std::vector<float> buf(kTileFrames * kPStride + 16);
+  std::vector<float2> Z(kPairs * kZPair);
+  for (int i = 0; i < kTileSamples; ++i) buf[i] = padded_sample(clip, L, Lp, t0 * kHop + i);
+  for (int tid = 0; tid < kThreads; ++tid) stage1(tid / 20, tid % 20, buf.data(), hann.data(), tw.data(), Z.data());
+  for (int tid = 0; tid < kThreads; ++tid) stage2(tid / 20, tid % 20, Z.data());
+  for (int i = 0; i < kPairs * kBins; ++i) split_power(i / kBins, i % kBins, Z.data(), buf.data());
+  for (int m = 0; m < n_mels; ++m) {
+    int lo = kBins, hi = 0;
+    for (int k = 0; k < kBins; ++k)
+      if (fb[m * kBins + k] != 0.0f) { lo = lo < k ? lo : k; hi = k + 1; }
+    if (lo >= hi) { lo = 0; hi = 0; }
+    for (int f = 0; f < kTileFrames; ++f)
+      out[m * kTileFrames + f] = mel_log10(buf.data() + f * kPStride, fb + m * kBins, lo, hi);
+  }
+}
+
+void hc_dft20(const float* in_ri, float* out_ri) {
+  float2 x[20];
+  for (int i = 0; i < 20; ++i) x[i] = make_float2(in_ri[2 * i], in_ri[2 * i + 1]);
+  lm::dft20(x);
+  for (int i = 0; i < 20; ++i) { out_ri[2 * i] = x[i].x; out_ri[2 * i + 1] = x[i].y; }
+}
+
+int hc_float_key(float f) { return lm::float_key(f); }
+float hc_key_float(int k) { return lm::key_float(k); }
+
+void hc_similarity_fit(const double* src, const double* dst, int n, double* fwd6, double* inv6) {
+  similarity_fit(reinterpret_cast<const double(*)[2]>(src), reinterpret_cast<const double(*)[2]>(dst), n, fwd6);
+  affine_inverse(fwd6, inv6);
+}
+
+void hc_crop_origin(double cx, double cy, int half, int std_size, int* rc) {
+  crop_origin(cx, cy, half, half, std_size, std_size, &rc[0], &rc[1]);
+}
+
+// warp window [r0, r0+h) x [c0, c0+w) of the std frame with inverse matrix rows inv6
+void hc_warp_window(const uint8_t* gray, int H, int W, const double* inv6, int r0, int c0, int h,
+                    int w, uint8_t* out) {
+  double lut[256];
+  for (int k = 0; k < 256; ++k) lut[k] = f64div((double)k, 255.0);
+  auto tap = [&](int r, int c) -> uint32_t { return gray[(size_t)r * W + c]; };
+  for (int pr = 0; pr < h; ++pr)
+    for (int pc = 0; pc < w; ++pc) {
+      const double tfr = (double)(r0 + pr), tfc = (double)(c0 + pc);
+      const double sc = f64add(f64add(f64mul(inv6[0], tfc), f64mul(inv6[1], tfr)), inv6[2]);
+      const double sr = f64add(f64add(f64mul(inv6[3], tfc), f64mul(inv6[4], tfr)), inv6[5]);
+      out[pr * w + pc] = bilinear_u8(sr, sc, H, W, lut, tap);
+    }
+}
+
+void hc_gray(const uint8_t* bgr, int64_t n, uint8_t* gray) {
+  for (int64_t i = 0; i < n; ++i)
+    gray[i] = (uint8_t)gray_from_bgr(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+}
+
+}  // extern "C"
