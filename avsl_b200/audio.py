@@ -126,7 +126,7 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
     L = int(t.shape[-1])
     B = int(np.prod(lead)) if lead else 1
     n_frames = (L + padding) // HOP_LENGTH
-    if B > 0 and n_frames > 0 and L + padding <= N_FFT // 2:
+    if L + padding <= N_FFT // 2:
         # torch.stft: "Padding size should be less than the corresponding input dimension"
         raise RuntimeError("log_mel_spectrogram: reflect padding (200) needs more than 200 samples")
     fb = filters if filters is not None else mel_filters(t.device, n_mels)

@@ -116,30 +116,44 @@ class AVFrontEnd:
         return t
 
     # ---------------------------------------------------------------- device-resident path
-    def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None,
+                       mark=None) -> Dict[str, torch.Tensor]:
         """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] skips
-        the pad_or_trim launch when the caller already holds the padded matrix.
+        the pad_or_trim launch when the caller already holds the padded matrix.  ``mark(name)``
+        (optional) is called after each stage is enqueued (bench.py records CUDA events there).
         Returns device tensors: mel [U,n_mels,F], lip [N,88,88,1], gray [N,H,W] (optional),
         lip_u8 [N,96,96] (optional)."""
         U, L = batch.n_utts, self.audio_max_length
+        mark = mark or (lambda name: None)
         with torch.cuda.device(self.device):
+            mark("start")
             if padded_audio is None:
                 padded_audio = self._buf("audio", (U, L), torch.float32)
                 _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(batch.audio), _lib.ptr(batch.audio_offsets),
                           U, L, _lib.ptr(padded_audio), _lib.stream_ptr())
+                mark("pad")
             mel = self._buf("mel", (U, self.n_mels, L // HOP_LENGTH), torch.float32)
             log_mel_spectrogram(padded_audio, self.n_mels, filters=self.filters, out=mel)
+            mark("logmel")
             N, H, W = (int(s) for s in batch.frames.shape[:3])
-            reuse = LipBatch(self._buf("gray", (N, H, W), torch.uint8) if self.want_gray else None,
-                             self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
+            src = batch.frames
+            gray = None
+            if self.want_gray and batch.frames.dim() == 4:
+                # gray frames are a deliverable: convert once, then warp from the gray frames
+                gray = self._buf("gray", (N, H, W), torch.uint8)
+                _lib.call("avfe_bgr2gray_u8", _lib.ptr(batch.frames), N, H, W, _lib.ptr(gray), _lib.stream_ptr())
+                src = gray
+                mark("gray")
+            reuse = LipBatch(None, self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
                              self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
                              batch.clip_offsets)
-            lip_roi_batch(batch.frames, batch.clip_offsets, batch.landmarks, batch.lm_valid,
-                          want_gray=self.want_gray, want_u8=self.want_lip_u8, crop=self.crop,
-                          image_mean=self.mean, image_std=self.std, out=reuse)
+            lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid, want_gray=False,
+                          want_u8=self.want_lip_u8, crop=self.crop, image_mean=self.mean,
+                          image_std=self.std, out=reuse)
+            mark("lip")
         out = {"mel": mel, "lip": reuse.lip_f32.unsqueeze(-1)}
-        if reuse.gray is not None:
-            out["gray"] = reuse.gray
+        if gray is not None:
+            out["gray"] = gray
         if reuse.lip_u8 is not None:
             out["lip_u8"] = reuse.lip_u8
         return out

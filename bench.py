@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — AV front-end throughput (audio-seconds per second) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--utts U] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], "full AMI-shaped AV front-end sweep"): the 10,000 seeded
+synthetic utterances (durations clip(lognormal(ln 3, 0.9), 0.3, 30) s, 16 kHz audio zero-padded
+to 30 s as the reference's pad_or_trim does, 25 fps 224x224 BGR closeups with 68-point landmarks,
+5% failed detections) are sharded i % world == rank; ONE STEP = one batch of U consecutive
+utterances of the rank's shard through log-mel (n_mels 80) + gray + lip-ROI warp/crop/normalise.
+The 10k sweep itself does not fit one GPU (169 GB of BGR frames), so a step is the largest unit
+that is kept resident; per-GPU work is fixed as N grows (weak scaling), no collective on the path.
+
+`value`  : device-resident (inputs in HBM before the timed region), CUDA events, max over ranks.
+`e2e`    : same batch through AVFrontEnd.forward_host: pinned host buffers -> H2D -> kernels ->
+           D2H of the features the reference's __getitem__ returns (mel + lip), every step.
+`roofline`: the dominant kernel's algorithmic bytes / its own CUDA-event time inside the timed steps.
+`cpu_baseline` (N=1, rank 0): the oracle restatement of the reference CPU path on a bounded sample.
+`--impl reference`: that CPU path alone, on rank 0, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MELS = 80
+AUDIO_LEN = 480000
+H = W = 224
+N_SWEEP = 10000
+SEED = 3407
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--utts", type=int, default=128, help="utterances per GPU per step")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = auto (bounded to ~10-30 s)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def rank_utterances(rank: int, world: int, utts: int):
+    """(indices into the 10k sweep, durations [s]) of this rank's step batch."""
+    from avsl_b200 import synth
+    durs = synth.ami_durations(N_SWEEP, SEED)
+    idx = synth.shard_indices(N_SWEEP, rank, world)[:utts]
+    return idx, durs[idx]
+
+
+def host_sample(idx, durs, n):
+    """numpy inputs of the first n utterances of a step batch (CPU baseline / reference arm).
+    Same generators and seeds as the GPU workload's landmarks; frames from the numpy generator."""
+    from avsl_b200 import synth
+    audios, vids, lms, vals = [], [], [], []
+    for k in range(n):
+        d, i = float(durs[k]), int(idx[k])
+        T = max(1, int(round(d * 25)))
+        audios.append(synth.audio_clip(int(round(d * 16000)), SEED + i))
+        f, _, _ = synth.video_clip(T, H, W, seed=SEED + i, invalid_frac=0.0)
+        lm, v = synth.landmarks_for_clip(T, H, W, seed=SEED + i, invalid_frac=0.05)
+        vids.append(f); lms.append(lm); vals.append(v)
+    return audios, vids, lms, vals
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port), all host cores."""
+    if rank != 0:
+        return
+    from avsl_b200.lips import mean_face_landmarks
+    from oracle import baseline
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    idx, durs = rank_utterances(0, world, args.utts)
+    n = args.cpu_sample_utts or 8
+    audios, vids, lms, vals = host_sample(idx, durs, n)
+    audio_s = float(sum(durs[:n]))
+    cf = baseline.CpuFrontend(audios, vids, lms, vals, mean_face_landmarks(), N_MELS, AUDIO_LEN)
+    for _ in range(args.warmup):
+        cf.run()
+    t = 0.0
+    for _ in range(args.steps):
+        t += cf.run()
+    cf.close()
+    value = audio_s * args.steps / t
+    sample = f"{n} utterances ({audio_s:.2f} audio-s, {sum(len(v) for v in vids)} frames) of the step batch per step"
+    line = {
+        "impl": "reference", "metric": "av_frontend_audio_seconds_per_second", "value": value,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (log-mel) / u8+f64 (lip ROI)", "data": "synthetic",
+        "config": workload_config(args, world, int(sum(len(v) for v in vids)), n),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "workers": cf.workers, "torch_threads": torch.get_num_threads(),
+                         "note": "oracle restatement (torch.stft on all threads; numpy float64 warp restricted to the cut_patch window, fork Pool(cores-1) over 48-frame chunks); scikit-image/dlib are not installable here"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, n_frames, n_utts):
+    return {"workload": "configs[4] AMI-shaped AV front-end sweep (10k seeded utterances, i%world==rank shards); "
+                        "one step = one batch of consecutive utterances of the shard",
+            "utterances_per_gpu_per_step": n_utts, "frames_per_gpu_per_step": n_frames,
+            "n_mels": N_MELS, "audio_pad_samples": AUDIO_LEN, "video": f"{H}x{W} BGR 25 fps",
+            "outputs": "mel f32 [U,80,3000] + gray u8 [N,224,224] + lip f32 [N,88,88]",
+            "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"utterance-sharded x{world}, no collective"}
+
+
+# ------------------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    rank, local, world = dist_env()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                   "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # The CPU-baseline sample and its worker pool are created BEFORE CUDA is initialised in this
+    # process (fork after CUDA init is unsafe); the workers only ever run numpy code.
+    cf = None
+    want_cpu = (world == 1 and rank == 0 and not args.no_cpu_baseline)
+    if want_cpu:
+        from avsl_b200.lips import mean_face_landmarks
+        from oracle import baseline
+        idx0, durs0 = rank_utterances(0, 1, args.utts)
+        n_cpu = args.cpu_sample_utts or 8
+        cf = baseline.CpuFrontend(*host_sample(idx0, durs0, n_cpu), mean_face_landmarks(), N_MELS, AUDIO_LEN)
+        cpu_audio_s = float(sum(durs0[:n_cpu]))
+
+    import torch
+    import torch.distributed as dist
+    import avsl_b200 as A
+    from avsl_b200 import _lib, synth
+    from avsl_b200.frontend import AVFrontEnd, PackedBatch, algorithmic_bytes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---------------- build the rank's step batch, resident in HBM ----------------
+    idx, durs = rank_utterances(rank, world, args.utts)
+    U = len(idx)
+    T = np.maximum(1, np.round(durs * 25).astype(np.int64))
+    clip_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+    N = int(clip_off[-1])
+    a_len = np.round(durs * 16000).astype(np.int64)
+    a_off = np.concatenate([[0], np.cumsum(a_len)]).astype(np.int64)
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    audio = (torch.randn(int(a_off[-1]), generator=g, device=dev) * 0.1).clamp_(-1, 1)
+    frames = synth.video_frames_cuda(N, H, W, seed=SEED + rank, device=dev)
+    lms, vals = [], []
+    for k in range(U):
+        lm, v = synth.landmarks_for_clip(int(T[k]), H, W, seed=SEED + int(idx[k]), invalid_frac=0.05)
+        lms.append(lm); vals.append(v)
+    batch_dev = PackedBatch(audio, torch.from_numpy(a_off).to(dev), frames, torch.from_numpy(clip_off).to(dev),
+                            torch.from_numpy(np.concatenate(lms)).to(dev),
+                            torch.from_numpy(np.concatenate(vals)).to(dev))
+    fe = AVFrontEnd(n_mels=N_MELS, audio_max_length=AUDIO_LEN, device=dev, want_gray=True)
+    padded = torch.empty((U, AUDIO_LEN), dtype=torch.float32, device=dev)
+    _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(audio), _lib.ptr(batch_dev.audio_offsets), U, AUDIO_LEN,
+              _lib.ptr(padded), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    audio_s = float(durs.sum())
+    alg_bytes = algorithmic_bytes(U, N, H, W, N_MELS, AUDIO_LEN)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timed region ----------------
+    stage_names = ["logmel", "gray", "lip"]
+    events = []
+
+    def make_mark(store):
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            store.append((name, e))
+        return mark
+
+    for _ in range(max(3, args.warmup)):
+        fe.forward_device(batch_dev, padded_audio=padded)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        fe.forward_device(batch_dev, padded_audio=padded, mark=make_mark(events))
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    stage_ms = {n: 0.0 for n in stage_names}
+    prev = None
+    for name, e in events:
+        if name != "start" and prev is not None and name in stage_ms:
+            stage_ms[name] += prev.elapsed_time(e)
+        prev = e
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+
+    t_max = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([audio_s, float(alg_bytes), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)      # off the timed path: reporting only
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t_max.item())
+    audio_s_all, alg_bytes_all, launches_all = (float(x) for x in tot.tolist())
+    value = audio_s_all * args.steps / (elapsed_ms * 1e-3)
+
+    # ---------------- end-to-end through host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = batch_dev.pin()
+        host_out = None
+        e2e_steps = args.steps
+        for _ in range(2):
+            host_out = fe.forward_host(host, host_out)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(e2e_steps):
+            host_out = fe.forward_host(host, host_out)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("mel", "lip"))
+        e2e = {"value": audio_s_all * e2e_steps / (float(ms.item()) * 1e-3), "unit": "audio-s/s",
+               "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(ms.item()) / e2e_steps, "steps": e2e_steps}
+        del host, host_out
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    kernel_bytes = {
+        "logmel": U * (4 * AUDIO_LEN + 4 * N_MELS * (AUDIO_LEN // 160)),
+        "gray": N * (H * W * 3 + H * W),
+        "lip": N * (68 * 2 * 8 + 88 * 88 * 4),
+    }
+    kernel_names = {"logmel": "logmel_tile_kernel (+prep, finalize)", "gray": "gray_vec_kernel",
+                    "lip": "tform_kernel + warp_kernel (+lm_fill)"}
+    dominant = max(stage_ms, key=lambda k: stage_ms[k])
+    stages = {}
+    for k in stage_names:
+        ach = kernel_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0
+        stages[k] = {"kernel": kernel_names[k], "ms": stage_ms[k], "algorithmic_bytes": kernel_bytes[k],
+                     "achieved_gbs": ach, "frac": ach / peak}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dominant)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": stages[dominant]["achieved_gbs"],
+                "peak": peak, "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes[dominant],
+                "stages": stages,
+                "path": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 if world == 1 else alg_bytes_all * args.steps / (elapsed_ms * 1e-3) / 1e9,
+                         "frac_of_peak_per_gpu": (alg_bytes_all / world) * args.steps / (elapsed_ms * 1e-3) / 1e9 / peak}}
+
+    # ---------------- CPU baseline on a bounded sample (N=1, rank 0) ----------------
+    cpu_baseline = None
+    if want_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cf.run()
+        reps, t = 0, 0.0
+        while t < 10.0 and reps < 40:
+            t += cf.run()
+            reps += 1
+        cf.close()
+        cpu_baseline = {"value": cpu_audio_s * reps / t, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"first {n_cpu} utterances of the step batch ({cpu_audio_s:.2f} audio-s, {cf.n_frames} frames) x {reps} passes = {t:.1f} s CPU wall",
+                        "workers": cf.workers, "torch_threads": torch.get_num_threads()}
+
+    if rank == 0:
+        line = {
+            "metric": "av_frontend_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (log-mel) / u8+f64 (lip ROI)", "data": "synthetic",
+            "config": workload_config(args, world, N, U), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "audio_seconds_per_step": audio_s_all,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

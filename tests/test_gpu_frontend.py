@@ -1,0 +1,60 @@
+"""GPU: the batched AV front-end (host-buffer path and device path) vs per-utterance oracle."""
+import numpy as np
+import pytest
+import torch
+
+import avsl_b200 as A
+from avsl_b200 import synth
+from oracle import lips as OL
+from oracle import logmel as OM
+
+pytestmark = pytest.mark.gpu
+
+
+def _utts(n, seed=0):
+    rng = np.random.default_rng(seed)
+    durs = [0.36, 1.0, 2.52][:n] if n <= 3 else list(rng.uniform(0.3, 2.0, n).round(2))
+    audios, vids, lms, vals = [], [], [], []
+    for i, d in enumerate(durs):
+        T = max(1, int(round(d * 25)))
+        audios.append(synth.audio_clip(int(d * 16000), seed + i))
+        f, lm, v = synth.video_clip(T, 96, 128, seed=seed + 10 + i, invalid_frac=0.1)
+        vids.append(f); lms.append(lm); vals.append(v)
+    return audios, vids, lms, vals
+
+
+def test_forward_host_matches_per_utterance_oracle():
+    audios, vids, lms, vals = _utts(3)
+    L = 48000
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=L, want_lip_u8=True)
+    batch = A.pack_utterances(audios, vids, lms, vals, audio_max_length=L).pin()
+    out = fe.forward_host(batch)
+    assert out["mel"].shape == (3, 80, 300)
+    lips = fe.split_lip(out["lip"], batch.clip_offsets)
+    mf = A.mean_face_landmarks()
+    for i in range(3):
+        ref_mel = OM.log_mel_spectrogram(OM.pad_or_trim(audios[i], L), 80)
+        assert (out["mel"][i] - ref_mel).abs().max().item() <= 1e-4
+        lst = [lms[i][k] if vals[i][k] else None for k in range(len(lms[i]))]
+        roi, _, _ = OL.extract_lip_frames_from_arrays(OL.bgr2gray(vids[i]), lst, mf)
+        ref_feats = OL.video_feats_from_u8(roi)
+        assert lips[i].shape == ref_feats.shape and lips[i].dtype == torch.float32
+        assert np.abs(lips[i].numpy() - ref_feats).max() <= (1 / 255) / 0.165 + 1e-6
+
+
+def test_device_path_equals_host_path_and_is_repeatable():
+    audios, vids, lms, vals = _utts(5, seed=3)
+    fe = A.AVFrontEnd(n_mels=128, audio_max_length=32000)
+    batch = A.pack_utterances(audios, vids, lms, vals, audio_max_length=32000)
+    host = fe.forward_host(batch.pin())
+    dev = fe.forward_device(batch.to("cuda"))
+    assert torch.equal(dev["mel"].cpu(), host["mel"]) and torch.equal(dev["lip"].cpu(), host["lip"])
+    np.testing.assert_array_equal(dev["gray"].cpu().numpy(), OL.bgr2gray(np.concatenate(vids)))
+    assert A.AVFrontEnd.model_n_mels("large-v3") == 128 and A.AVFrontEnd.model_n_mels("large-v2") == 80
+
+
+def test_launch_counter_counts_kernels():
+    from avsl_b200 import _lib
+    before = _lib.launch_count()
+    A.bgr2gray(np.zeros((2, 32, 32, 3), np.uint8))
+    assert _lib.launch_count() > before

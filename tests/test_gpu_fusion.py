@@ -1,0 +1,84 @@
+"""GPU parity: modality fusion through the C ABI vs the oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+import avsl_b200 as A
+from avsl_b200 import synth
+from oracle import fusion as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(t):
+    return t.contiguous().view(torch.int32 if t.element_size() == 4 else torch.int16)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fuse_bit_exact_small(dtype, mode, masked):
+    fa, fv, mask = synth.fusion_inputs(6, 40, 50, seed=3, dtype=dtype)
+    fa[0, 0, 0] = -0.0                                  # signed zeros survive exactly as in torch
+    m = mask if masked else None
+    out = A.fuse_modalities(fa.cuda(), fv.cuda(), m, mode, weights=(0.3, 0.7)).cpu()
+    ref = O.fuse(fa, fv, m, mode, 0.3, 0.7)
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    assert torch.equal(_bits(out), _bits(ref))
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 13), (1, 1, 1), (2, 5, 3)])
+def test_fuse_unaligned_shapes(shape):
+    B, C, T = shape
+    fa, fv, mask = synth.fusion_inputs(B, C, T, seed=5)
+    for mode in ("concat", "add", "weighted_sum"):
+        out = A.fuse_modalities(fa.cuda(), fv.cuda(), mask, mode).cpu()
+        assert torch.equal(_bits(out), _bits(O.fuse(fa, fv, mask, mode)))
+    # misaligned base pointers (views offset by one element) take the element-wise kernel
+    big = torch.randn(B * C * T + 1).cuda()
+    fa_m = big[1:].view(B, C, T)
+    out = A.fuse_modalities(fa_m, fv.cuda(), None, "add").cpu()
+    assert torch.equal(_bits(out), _bits(O.fuse(fa_m.cpu(), fv, None, "add")))
+
+
+def test_config4_full_size_concat_and_sum():
+    fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
+    cat = A.fuse_modalities(fa, fv, mask, "concat")
+    assert cat.shape == (64, 2048, 750)
+    m = torch.from_numpy(mask).cuda().bool()
+    exp_a = torch.where(m[:, 0].view(-1, 1, 1), fa, torch.zeros((), device="cuda"))
+    exp_v = torch.where(m[:, 1].view(-1, 1, 1), fv, torch.zeros((), device="cuda"))
+    assert torch.equal(cat[:, :1024], exp_a) and torch.equal(cat[:, 1024:], exp_v)
+    s = A.fuse_modalities(fa, fv, mask, "add")
+    assert torch.equal(s, exp_a + exp_v)
+    # size-independent property: sum == first half + second half of concat
+    assert torch.equal(s, cat[:, :1024] + cat[:, 1024:])
+    h = A.fuse_modalities(fa.half(), fv.half(), mask, "add")
+    assert torch.equal(h, (exp_a.half().float() + exp_v.half().float()).half())
+
+
+def test_errors_follow_reference():
+    fa, fv, _ = synth.fusion_inputs(2, 4, 4, device="cuda")
+    with pytest.raises(ValueError, match="Unsupported fusion type"):
+        A.fuse_modalities(fa, fv, None, "gated")
+    with pytest.raises(ValueError, match="At least one input modality"):
+        A.fuse_modalities(fa, fv, np.array([[0, 0], [1, 1]]), "add")
+    with pytest.raises(ValueError):
+        A.fuse_modalities(fa, fv[:, :2], None, "add")
+
+
+def test_modality_fusion_module_matches_reference_block():
+    fa, fv, _ = synth.fusion_inputs(4, 8, 16, device="cuda")
+    fuse = A.ModalityFusion("concat", modality_dropout=0.5, audio_dropout=0.5).train()
+    np.random.seed(3407)
+    outs = [fuse(fa, fv) for _ in range(8)]
+    np.random.seed(3407)
+    for o in outs:
+        ua, uv = O.modality_dropout_flags(True, 0.5, 0.5)
+        mask = np.tile(np.array([[ua, uv]], dtype=np.uint8), (4, 1))
+        assert torch.equal(o.cpu(), O.fuse(fa.cpu(), fv.cpu(), mask, "concat"))
+    fuse.eval()
+    assert torch.equal(fuse(fa, fv).cpu(), torch.cat([fa, fv], dim=1).cpu())
+    assert torch.equal(fuse(fa, fv, modality_override="visual")[:, :8].cpu(), torch.zeros(4, 8, 16))
+    with pytest.raises(ValueError, match="At least one input modality"):
+        A.ModalityFusion(use_audio=False)(fa, None)
