@@ -3,131 +3,167 @@
 // Reference: preprocess/video_process.py:201-214,369-475; utils/lips_cropping.py:41-163;
 // utils/hf_video_utils.py:113-138.
 //
-// Kernels (all HBM-bound integer/byte work except the float64 blend):
-//   lm_fill_kernel   one CTA per frame; fills failed detections (V2)
-//   tform_kernel     one thread per frame; window mean, similarity fit, inverse, crop origin
-//   gray_vec_kernel  streaming BGR->gray, 16 px per thread, coalesced 128-bit loads staged
-//                    through warp-private shared memory so each thread owns 48 contiguous bytes
-//   warp_kernel      one CTA per frame; float64 bilinear taps + u8 ROI + normalised f32 crop
+// Kernels
+//   tform_kernel      one WARP per frame: failed detections are interpolated on the fly (V2),
+//                     12-frame window mean of the 5 stable points (V3), closed-form similarity
+//                     fit + inverse (V4), mouth-centre transform (V6) and cut_patch origin (V7)
+//   lip_queue_kernel  persistent CTAs pulling items from one atomic work queue.  Two item kinds
+//                     are interleaved frame by frame so that they overlap on every SM:
+//                       gray item  8192 px of streaming BGR->gray (HBM-bound, integer dp4a)
+//                       warp item  one frame's ROI: source footprint staged in shared memory,
+//                                  float64 bilinear blend in skimage's operation order,
+//                                  u8 ROI + normalised f32 centre crop (FP64-pipe-bound)
+//   gray_vec_kernel   the gray conversion alone (avfe_bgr2gray_u8)
+//   small single-purpose kernels for the per-function entry points (warp_full, cut_patch, ...)
 #include "avfe_common.cuh"
 #include "avfe_lip_math.cuh"
 
 namespace avfe {
 
-// ------------------------------------------------------------------ V2: landmark fill
+// ------------------------------------------------------------------ landmarks with on-the-fly fill
+struct LmView {
+  const double* lm;       // [N,68,2]
+  const uint8_t* valid;   // [N] or nullptr
+  int64_t beg, end;       // the clip's frame range
+};
+
+// previous / next valid frame of the clip (p < beg or q >= end when there is none)
+__device__ __forceinline__ void lm_neighbours(const LmView& v, int64_t f, int64_t& p, int64_t& q) {
+  p = f; q = f;
+  if (v.valid == nullptr) return;
+  while (p >= v.beg && !v.valid[p]) --p;
+  while (q < v.end && !v.valid[q]) ++q;
+}
+
+// element e (0..135) of frame f after landmarks_interpolate (utils/lips_cropping.py:41-89)
+__device__ __forceinline__ double lm_value(const LmView& v, int64_t f, int64_t p, int64_t q, int e) {
+  if (p == f) return v.lm[f * 136 + e];
+  const bool has_p = p >= v.beg, has_q = q < v.end;
+  if (!has_p && !has_q) return nan("");          // no detection in the whole clip
+  if (!has_p) return v.lm[q * 136 + e];          // leading frames replicate the first detection
+  if (!has_q) return v.lm[p * 136 + e];          // trailing frames replicate the last detection
+  // start + idx/float(stop-start) * delta   (utils/lips_cropping.py:54-57)
+  const double s = v.lm[p * 136 + e], t = v.lm[q * 136 + e];
+  const double w = f64div((double)(f - p), (double)(q - p));
+  return f64add(s, f64mul(w, f64sub(t, s)));
+}
+
+__device__ __forceinline__ int64_t find_clip(const int64_t* __restrict__ clip_offsets, int64_t n_clips,
+                                             int64_t f) {
+  int64_t lo = 0, hi = n_clips;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (clip_offsets[mid] <= f) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// V2 alone (avfe_landmarks_interpolate): one CTA per frame
 __global__ void __launch_bounds__(160)
 lm_fill_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
                const int64_t* __restrict__ clip_offsets, int64_t n_clips, int64_t N,
                double* __restrict__ out) {
   const int64_t f = blockIdx.x;
   if (f >= N) return;
-  // locate the clip: binary search over the (small) offsets array
-  int64_t lo = 0, hi = n_clips;
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (clip_offsets[mid] <= f) lo = mid; else hi = mid;
-  }
-  const int64_t beg = clip_offsets[lo], end = clip_offsets[lo + 1];
-  int64_t p = f, q = f;                       // previous / next valid frame of the clip
-  while (p >= beg && !valid[p]) --p;
-  while (q < end && !valid[q]) ++q;
+  const int64_t c = find_clip(clip_offsets, n_clips, f);
+  LmView v{lm, valid, clip_offsets[c], clip_offsets[c + 1]};
+  int64_t p, q;
+  lm_neighbours(v, f, p, q);
   const int t = threadIdx.x;
-  if (t >= kNumLandmarks * 2) return;
-  double v;
-  if (p == f) {
-    v = lm[f * 136 + t];
-  } else if (p < beg && q >= end) {
-    v = nan("");                              // no detection in the whole clip
-  } else if (p < beg) {
-    v = lm[q * 136 + t];                      // leading frames replicate the first detection
-  } else if (q >= end) {
-    v = lm[p * 136 + t];                      // trailing frames replicate the last detection
-  } else {
-    // start + idx/float(stop-start) * delta   (utils/lips_cropping.py:54-57)
-    const double s = lm[p * 136 + t], e = lm[q * 136 + t];
-    const double w = f64div((double)(f - p), (double)(q - p));
-    v = f64add(s, f64mul(w, f64sub(e, s)));
-  }
-  out[f * 136 + t] = v;
+  if (t < kNumLandmarks * 2) out[f * 136 + t] = lm_value(v, f, p, q, t);
 }
 
 // ------------------------------------------------------------------ V3+V4(fit)+V6+V7
-// per-frame record written to the workspace and consumed by warp_kernel
+// per-frame record written to the workspace and consumed by the warp items
 struct FrameXform {
   double inv[6];   // rows 0,1 of tform.inverse.params
   int32_t r0, c0;  // cut_patch origin in the std frame (or -1,-1)
   int32_t pad[2];
 };
 
-__global__ void __launch_bounds__(128)
-tform_kernel(const double* __restrict__ lm, const int64_t* __restrict__ clip_offsets,
-             int64_t n_clips, int64_t N, const double* __restrict__ mean_face,
-             const double* __restrict__ tforms_in, int std_size, int roi, int window,
-             FrameXform* __restrict__ xf, int32_t* __restrict__ crop_rc,
-             double* __restrict__ tforms_out) {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= N) return;
-  int64_t lo = 0, hi = n_clips;
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (clip_offsets[mid] <= f) lo = mid; else hi = mid;
-  }
-  const int64_t beg = clip_offsets[lo];
-  const int64_t T = clip_offsets[lo + 1] - beg;
-  const int stable[kNumStable] = {33, 36, 39, 42, 45};
+constexpr int kTformWarps = 4;
+
+__global__ void __launch_bounds__(kTformWarps * 32)
+tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
+             const int64_t* __restrict__ clip_offsets, int64_t n_clips, int64_t N,
+             const double* __restrict__ mean_face, const double* __restrict__ tforms_in,
+             int std_size, int roi, int window, FrameXform* __restrict__ xf,
+             int32_t* __restrict__ crop_rc, double* __restrict__ tforms_out,
+             unsigned* __restrict__ queue_counter) {
+  if (queue_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0u;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * kTformWarps + (threadIdx.x >> 5);
+  if (f >= N) return;                                  // warp-uniform
+  const int64_t c = find_clip(clip_offsets, n_clips, f);
+  LmView v{lm, valid, clip_offsets[c], clip_offsets[c + 1]};
+  const int64_t T = v.end - v.beg;
+  // margin = min(T, 12); frame i <= T-margin is fitted on mean(lm[i:i+margin]); later frames
+  // reuse the transform of frame T-margin (preprocess/video_process.py:369-370,417-427,455-464)
+  const int margin = (int)(T < window ? T : window);   // window <= 31 is enforced by the caller
+  int64_t i0 = f - v.beg;
+  if (i0 > T - margin) i0 = T - margin;
+  const int64_t w0 = v.beg + i0;
+  // lanes 0..margin-1 look up the neighbours of window frame `lane`, lane 31 those of frame f
+  const int64_t mine = (lane < margin) ? (w0 + lane) : f;
+  int64_t p, q;
+  lm_neighbours(v, mine, p, q);
 
   double fwd[6], inv[6];
   if (tforms_in != nullptr) {
     const double* ti = tforms_in + f * 18;
-    fwd[0] = ti[0]; fwd[1] = ti[1]; fwd[2] = ti[2]; fwd[3] = ti[3]; fwd[4] = ti[4]; fwd[5] = ti[5];
-    inv[0] = ti[9]; inv[1] = ti[10]; inv[2] = ti[11]; inv[3] = ti[12]; inv[4] = ti[13]; inv[5] = ti[14];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { fwd[k] = ti[k]; inv[k] = ti[9 + k]; }
   } else {
-    // margin = min(T, 12); frame i <= T-margin is fitted on mean(lm[i:i+margin]); later
-    // frames reuse the transform of frame T-margin (preprocess/video_process.py:369-370,
-    // 417-427,455-464).
-    const int64_t margin = T < window ? T : window;
-    int64_t i = f - beg;
-    if (i > T - margin) i = T - margin;
-    const double* base = lm + (beg + i) * 136;
+    // lanes 0..9 own one coordinate of one stable point (33,36,39,42,45); np.mean(axis=0) adds
+    // the window rows in order
+    const int slot = lane % 10;
+    const int e = (33 + 3 * (slot >> 1)) * 2 + (slot & 1);
+    double acc = 0.0;
+    for (int j = 0; j < margin; ++j) {
+      const int64_t pj = __shfl_sync(full, p, j), qj = __shfl_sync(full, q, j);
+      acc = f64add(acc, lm_value(v, w0 + j, pj, qj, e));
+    }
+    const double mean = f64div(acc, (double)margin);
     double src[kNumStable][2], dst[kNumStable][2];
 #pragma unroll
     for (int k = 0; k < kNumStable; ++k) {
-      double ax = 0.0, ay = 0.0;
-      for (int64_t j = 0; j < margin; ++j) {       // np.mean(axis=0): sequential row adds
-        ax = f64add(ax, base[j * 136 + stable[k] * 2 + 0]);
-        ay = f64add(ay, base[j * 136 + stable[k] * 2 + 1]);
-      }
-      src[k][0] = f64div(ax, (double)margin);
-      src[k][1] = f64div(ay, (double)margin);
-      dst[k][0] = mean_face[stable[k] * 2 + 0];
-      dst[k][1] = mean_face[stable[k] * 2 + 1];
+      src[k][0] = __shfl_sync(full, mean, 2 * k);
+      src[k][1] = __shfl_sync(full, mean, 2 * k + 1);
+      dst[k][0] = mean_face[(33 + 3 * k) * 2 + 0];
+      dst[k][1] = mean_face[(33 + 3 * k) * 2 + 1];
     }
-    similarity_fit(src, dst, kNumStable, fwd);
+    similarity_fit(src, dst, kNumStable, fwd);          // every lane computes the same fit
     affine_inverse(fwd, inv);
   }
-  // trans(cur_landmarks)[48:68] -> mean -> cut_patch origin
-  const double* cur = lm + f * 136;
+  // trans(cur_landmarks)[48:68] -> mean -> cut_patch origin; lane k < 20 transforms point 48+k
+  const int64_t pf = __shfl_sync(full, p, 31), qf = __shfl_sync(full, q, 31);
+  const int k = 48 + (lane % 20);
+  const double x = lm_value(v, f, pf, qf, 2 * k), y = lm_value(v, f, pf, qf, 2 * k + 1);
+  const double tx = f64add(f64add(f64mul(x, fwd[0]), f64mul(y, fwd[1])), fwd[2]);
+  const double ty = f64add(f64add(f64mul(x, fwd[3]), f64mul(y, fwd[4])), fwd[5]);
   double cx = 0.0, cy = 0.0;
-  for (int k = 48; k < 68; ++k) {
-    const double x = cur[2 * k], y = cur[2 * k + 1];
-    cx = f64add(cx, f64add(f64add(f64mul(x, fwd[0]), f64mul(y, fwd[1])), fwd[2]));
-    cy = f64add(cy, f64add(f64add(f64mul(x, fwd[3]), f64mul(y, fwd[4])), fwd[5]));
+#pragma unroll
+  for (int j = 0; j < 20; ++j) {
+    cx = f64add(cx, __shfl_sync(full, tx, j));
+    cy = f64add(cy, __shfl_sync(full, ty, j));
   }
   cx = f64div(cx, 20.0);
   cy = f64div(cy, 20.0);
+  if (lane != 0) return;
   int r0, c0;
   crop_origin(cx, cy, roi / 2, roi / 2, std_size, std_size, &r0, &c0);
   FrameXform o;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) o.inv[k] = inv[k];
+  for (int j = 0; j < 6; ++j) o.inv[j] = inv[j];
   o.r0 = r0; o.c0 = c0; o.pad[0] = 0; o.pad[1] = 0;
   xf[f] = o;
   if (crop_rc != nullptr) { crop_rc[2 * f] = r0; crop_rc[2 * f + 1] = c0; }
   if (tforms_out != nullptr) {
     double* to = tforms_out + f * 18;
-    to[0] = fwd[0]; to[1] = fwd[1]; to[2] = fwd[2]; to[3] = fwd[3]; to[4] = fwd[4]; to[5] = fwd[5];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { to[j] = fwd[j]; to[9 + j] = inv[j]; }
     to[6] = 0.0; to[7] = 0.0; to[8] = 1.0;
-    to[9] = inv[0]; to[10] = inv[1]; to[11] = inv[2]; to[12] = inv[3]; to[13] = inv[4]; to[14] = inv[5];
     to[15] = 0.0; to[16] = 0.0; to[17] = 1.0;
   }
 }
@@ -162,9 +198,27 @@ __device__ __forceinline__ uint4 gray16(const uint32_t (&w)[12]) {
 constexpr int kGrayThreads = 256;
 constexpr int kGrayWarps = kGrayThreads / 32;
 
-// Each warp iteration converts 512 px: 96 coalesced 16-byte loads (3 per lane) into the
+// One warp converts one group of 512 px: 96 coalesced 16-byte loads (3 per lane) into the
 // warp's 1536-byte shared slab, then every lane reads back its own 48 contiguous bytes
 // (stride 48 B = 12 banks: conflict-free for 128-bit accesses) and stores 16 gray bytes.
+__device__ __forceinline__ void gray_group(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                           uint4* slab, int lane) {
+  const uint4 a = ldg_stream(src + lane);
+  const uint4 b = ldg_stream(src + lane + 32);
+  const uint4 c = ldg_stream(src + lane + 64);
+  slab[lane] = a;
+  slab[lane + 32] = b;
+  slab[lane + 64] = c;
+  __syncwarp();
+  uint32_t w[12];
+  const uint4 q0 = slab[3 * lane], q1 = slab[3 * lane + 1], q2 = slab[3 * lane + 2];
+  __syncwarp();
+  w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+  w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+  w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+  stg_stream(dst + lane, gray16(w));
+}
+
 __global__ void __launch_bounds__(kGrayThreads)
 gray_vec_kernel(const uint4* __restrict__ bgr, int64_t ngroups /* of 512 px */,
                 uint4* __restrict__ gray) {
@@ -172,23 +226,8 @@ gray_vec_kernel(const uint4* __restrict__ bgr, int64_t ngroups /* of 512 px */,
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp_global = (int64_t)blockIdx.x * kGrayWarps + wid;
   const int64_t nwarps = (int64_t)gridDim.x * kGrayWarps;
-  for (int64_t g = warp_global; g < ngroups; g += nwarps) {
-    const uint4* src = bgr + g * 96;
-    const uint4 a = ldg_stream(src + lane);
-    const uint4 b = ldg_stream(src + lane + 32);
-    const uint4 c = ldg_stream(src + lane + 64);
-    slab[wid][lane] = a;
-    slab[wid][lane + 32] = b;
-    slab[wid][lane + 64] = c;
-    __syncwarp();
-    uint32_t w[12];
-    const uint4 q0 = slab[wid][3 * lane], q1 = slab[wid][3 * lane + 1], q2 = slab[wid][3 * lane + 2];
-    __syncwarp();
-    w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
-    w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
-    w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
-    stg_stream(gray + g * 32 + lane, gray16(w));
-  }
+  for (int64_t g = warp_global; g < ngroups; g += nwarps)
+    gray_group(bgr + g * 96, gray + g * 32, slab[wid], lane);
 }
 
 // tail / unaligned path: one pixel per thread
@@ -224,58 +263,199 @@ static int launch_gray(const uint8_t* bgr, int64_t npx, uint8_t* gray, cudaStrea
   return check_launch();
 }
 
-// ------------------------------------------------------------------ V4/V5 warp + V7 + V8
-constexpr int kWarpThreads = 256;
+// ------------------------------------------------------------------ work-queue kernel
+constexpr int kQThreads = 256;
+constexpr int kQWarps = kQThreads / 32;
+constexpr int kGroupsPerItem = 16;          // gray item = 16 groups = 8192 px (24 KB in, 8 KB out)
+constexpr int kTileBytes = 36864;           // staged source footprint of one ROI (e.g. 192 x 192)
+constexpr int kMaxRoi = 128;
 
-__device__ __forceinline__ void fill_luts(double* lut255, float* lutn, float mean, float stdv) {
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-    lut255[k] = f64div((double)k, 255.0);                                   // img_as_float
-    if (lutn) lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), mean), stdv);
+struct LipJob {
+  const uint8_t* frames;   // [N,H,W,channels]
+  int channels, H, W;
+  int64_t N;
+  const FrameXform* xf;
+  int roi, crop;
+  float mean, stdv;
+  uint8_t* gray_out;       // nullable: no gray items
+  uint8_t* lip_u8;         // nullable
+  float* lip_f32;          // nullable
+  unsigned* counter;
+  int gray_items;          // gray items per frame (0 = none)
+  int groups;              // full 512-px groups per frame
+  int has_warp;            // 1 if ROI outputs are wanted
+};
+
+struct QSmem {
+  double lut255[256];                 // k / 255.0 (img_as_float)
+  double colx[kMaxRoi], coly[kMaxRoi], rowx[kMaxRoi], rowy[kMaxRoi];
+  float lutn[256];                    // ((k/255) - mean) / std in float32
+  int bbox[4];                        // rmin, cmin, rows, pitch of the staged footprint
+  unsigned item[2];
+  union {
+    uint4 slab[kQWarps][96];
+    uint8_t tile[kTileBytes];
+  } u;
+};
+
+__device__ __forceinline__ void gray_item(const LipJob& j, int64_t f, int sub, QSmem& sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t npx = (int64_t)j.H * j.W;
+  const uint4* src = reinterpret_cast<const uint4*>(j.frames + f * npx * 3);
+  uint4* dst = reinterpret_cast<uint4*>(j.gray_out + f * npx);
+  const int g0 = sub * kGroupsPerItem;
+  const int g1 = min(g0 + kGroupsPerItem, j.groups);
+  for (int g = g0 + wid; g < g1; g += kQWarps)
+    gray_group(src + (int64_t)g * 96, dst + (int64_t)g * 32, sm.u.slab[wid], lane);
+  if (sub == j.gray_items - 1) {                       // pixels past the last full group
+    const uint8_t* b = j.frames + f * npx * 3;
+    uint8_t* o = j.gray_out + f * npx;
+    for (int64_t i = (int64_t)j.groups * 512 + threadIdx.x; i < npx; i += kQThreads)
+      o[i] = (uint8_t)gray_from_bgr(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
   }
 }
 
-// One CTA per frame.  SRC_BGR: taps are converted from the BGR frame on the fly (used when
-// the caller does not want the gray frames materialised); otherwise taps come from the gray
-// frame (just written by gray_vec_kernel, typically still in L2).
-template <bool SRC_BGR>
-__global__ void __launch_bounds__(kWarpThreads)
-warp_kernel(const uint8_t* __restrict__ src, int H, int W, const FrameXform* __restrict__ xf,
-            int roi, int crop, float mean, float stdv, uint8_t* __restrict__ lip_u8,
-            float* __restrict__ lip_f32) {
-  __shared__ double lut255[256];
-  __shared__ float lutn[256];
-  fill_luts(lut255, lutn, mean, stdv);
-  const int64_t f = blockIdx.x;
-  const FrameXform x = xf[f];
-  __syncthreads();
-  const int off = (roi - crop) / 2;
-  // evaluate the whole ROI only when the u8 ROI is wanted, else just the centre crop
-  const int lo = lip_u8 ? 0 : off, span = lip_u8 ? roi : crop;
-  const uint8_t* img = src + (size_t)f * H * W * (SRC_BGR ? 3 : 1);
-  auto tap = [&](int r, int c) -> uint32_t {
-    if (SRC_BGR) {
-      const uint8_t* p = img + ((size_t)r * W + c) * 3;
-      return gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2));
-    }
-    return __ldg(img + (size_t)r * W + c);
-  };
-  for (int idx = threadIdx.x; idx < span * span; idx += kWarpThreads) {
-    const int pr = lo + idx / span, pc = lo + idx % span;   // position inside the ROI
-    uint8_t v = 0;
-    if (x.r0 >= 0) {
-      const double tfr = (double)(x.r0 + pr), tfc = (double)(x.c0 + pc);
-      // _transform_affine: x_ = M0*x + M1*y + M2 ; y_ = M3*x + M4*y + M5
-      const double sc = f64add(f64add(f64mul(x.inv[0], tfc), f64mul(x.inv[1], tfr)), x.inv[2]);
-      const double sr = f64add(f64add(f64mul(x.inv[3], tfc), f64mul(x.inv[4], tfr)), x.inv[5]);
-      v = bilinear_u8(sr, sc, H, W, lut255, tap);
-    }
-    if (lip_u8) lip_u8[(size_t)f * roi * roi + (size_t)pr * roi + pc] = v;
-    if (lip_f32) {
+// SPAN = side of the evaluated window (96 when the u8 ROI is wanted, 88 for the centre crop
+// only, 0 = run-time value).
+template <int SPAN>
+__device__ __forceinline__ void warp_item(const LipJob& j, int64_t f, QSmem& sm) {
+  const int tid = threadIdx.x;
+  const FrameXform x = j.xf[f];
+  const int off = (j.roi - j.crop) / 2;
+  const int lo = j.lip_u8 ? 0 : off;
+  const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
+  const int H = j.H, W = j.W;
+  uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
+  float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
+  if (x.r0 < 0) {                                      // clip without any detection: zero ROI
+    for (int idx = tid; idx < span * span; idx += kQThreads) {
+      const int pr = lo + idx / span, pc = lo + idx % span;
+      if (out_u8) out_u8[pr * j.roi + pc] = 0;
       const int cr = pr - off, cc = pc - off;
-      if (cr >= 0 && cr < crop && cc >= 0 && cc < crop)
-        lip_f32[(size_t)f * crop * crop + (size_t)cr * crop + cc] = lutn[v];
+      if (out_f32 && cr >= 0 && cr < j.crop && cc >= 0 && cc < j.crop) out_f32[cr * j.crop + cc] = sm.lutn[0];
+    }
+    return;
+  }
+  // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with the
+  // same two roundings per product as skimage's _transform_affine
+  if (tid < span) {
+    const double t = (double)(x.c0 + lo + tid);
+    sm.colx[tid] = f64mul(x.inv[0], t);
+    sm.coly[tid] = f64mul(x.inv[3], t);
+  } else if (tid >= 128 && tid < 128 + span) {
+    const double t = (double)(x.r0 + lo + tid - 128);
+    sm.rowx[tid - 128] = f64mul(x.inv[1], t);
+    sm.rowy[tid - 128] = f64mul(x.inv[4], t);
+  }
+  if (tid == 0) {
+    // source footprint: an affine map takes its extrema at the window corners
+    double rmin = 1e300, rmax = -1e300, cmin = 1e300, cmax = -1e300;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double tr = (double)(x.r0 + lo + ((k & 1) ? span - 1 : 0));
+      const double tc = (double)(x.c0 + lo + ((k & 2) ? span - 1 : 0));
+      const double sc = x.inv[0] * tc + x.inv[1] * tr + x.inv[2];
+      const double sr = x.inv[3] * tc + x.inv[4] * tr + x.inv[5];
+      rmin = fmin(rmin, sr); rmax = fmax(rmax, sr);
+      cmin = fmin(cmin, sc); cmax = fmax(cmax, sc);
+    }
+    // one pixel of slack each side; taps outside the staged box fall back to global memory
+    int r0 = (int)fmax(floor(rmin) - 1.0, 0.0), r1 = (int)fmin(ceil(rmax) + 1.0, (double)(H - 1));
+    int c0 = (int)fmax(floor(cmin) - 1.0, 0.0), c1 = (int)fmin(ceil(cmax) + 1.0, (double)(W - 1));
+    int rows = r1 - r0 + 1, cols = c1 - c0 + 1;
+    if (!(rmin == rmin) || rows <= 0 || cols <= 0) { rows = 0; cols = 0; r0 = 0; c0 = 0; }
+    const int pitch = (cols + 3) & ~3;
+    if ((int64_t)rows * pitch > kTileBytes) { rows = 0; }   // too large: use global taps only
+    sm.bbox[0] = r0; sm.bbox[1] = c0; sm.bbox[2] = rows; sm.bbox[3] = pitch;
+  }
+  __syncthreads();
+  const int br0 = sm.bbox[0], bc0 = sm.bbox[1], brows = sm.bbox[2], pitch = sm.bbox[3];
+  const bool bgr = (j.channels == 3);
+  const uint8_t* img = j.frames + f * (int64_t)H * W * (bgr ? 3 : 1);
+  // stage the footprint (converted to gray on the way in when the source is BGR)
+  {
+    const int bcols = min(pitch, W - bc0);
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int r = wid; r < brows; r += kQWarps) {          // one warp per footprint row
+      const uint8_t* row = img + ((int64_t)(br0 + r) * W + bc0) * (bgr ? 3 : 1);
+      for (int c = lane; c < pitch; c += 32) {
+        uint32_t v = 0;
+        if (c < bcols) {
+          if (bgr) {
+            const uint8_t* p = row + 3 * c;
+            v = gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+          } else {
+            v = __ldg(row + c);
+          }
+        }
+        sm.u.tile[r * pitch + c] = (uint8_t)v;
+      }
     }
   }
+  __syncthreads();
+  auto tap = [&](int r, int c) -> uint32_t {
+    const int rr = r - br0, cc = c - bc0;
+    if ((unsigned)rr < (unsigned)brows && (unsigned)cc < (unsigned)pitch) return sm.u.tile[rr * pitch + cc];
+    const int64_t px = (int64_t)r * W + c;               // outside the staged box (rare)
+    if (bgr) {
+      const uint8_t* p = img + px * 3;
+      return gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+    }
+    return __ldg(img + px);
+  };
+  const double m2 = x.inv[2], m5 = x.inv[5];
+  for (int idx = tid; idx < span * span; idx += kQThreads) {
+    const int r = idx / span, c = idx - r * span;        // constant divisor when SPAN != 0
+    const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
+    const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
+    const uint32_t v = bilinear_u8(sr, sc, H, W, sm.lut255, tap);
+    const int pr = lo + r, pc = lo + c;
+    if (out_u8) out_u8[pr * j.roi + pc] = (uint8_t)v;
+    if (out_f32) {
+      const int cr = pr - off, cc = pc - off;
+      if ((unsigned)cr < (unsigned)j.crop && (unsigned)cc < (unsigned)j.crop)
+        out_f32[cr * j.crop + cc] = sm.lutn[v];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kQThreads, 4)
+lip_queue_kernel(const LipJob j) {
+  __shared__ QSmem sm;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 256; k += kQThreads) {
+    sm.lut255[k] = f64div((double)k, 255.0);
+    sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
+  }
+  const unsigned per_frame = (unsigned)(j.gray_items + j.has_warp);
+  const unsigned total = (unsigned)j.N * per_frame;
+  if (tid == 0) sm.item[0] = atomicAdd(j.counter, 1u);
+  __syncthreads();
+  unsigned t = sm.item[0];
+  int buf = 0;
+  while (t < total) {
+    // fetch the next item while this one is processed (only thread 0's warp waits on the atomic)
+    if (tid == 0) sm.item[buf ^ 1] = atomicAdd(j.counter, 1u);
+    const int64_t f = t / per_frame;
+    const int sub = (int)(t - (unsigned)f * per_frame);
+    if (sub < j.gray_items) {
+      gray_item(j, f, sub, sm);
+    } else if (j.lip_u8 != nullptr && j.roi == 96) {
+      warp_item<96>(j, f, sm);
+    } else if (j.lip_u8 == nullptr && j.crop == 88) {
+      warp_item<88>(j, f, sm);
+    } else {
+      warp_item<0>(j, f, sm);
+    }
+    __syncthreads();               // item done: shared staging is free, next index is visible
+    buf ^= 1;
+    t = sm.item[buf];
+  }
+}
+
+// ------------------------------------------------------------------ single-purpose kernels
+__device__ __forceinline__ void fill_lut255(double* lut255) {
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) lut255[k] = f64div((double)k, 255.0);
 }
 
 // Full-frame warp with a caller-supplied inverse matrix (affine or projective).
@@ -283,7 +463,7 @@ __global__ void __launch_bounds__(256)
 warp_full_kernel(const uint8_t* __restrict__ gray, int H, int W, const double* __restrict__ M,
                  int out_h, int out_w, uint8_t* __restrict__ out) {
   __shared__ double lut255[256];
-  fill_luts(lut255, nullptr, 0.f, 1.f);
+  fill_lut255(lut255);
   __syncthreads();
   const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
   const double m6 = M[6], m7 = M[7], m8 = M[8];
@@ -388,8 +568,8 @@ extern "C" int avfe_warp_affine_u8(const uint8_t* gray, int H, int W, const doub
 
 extern "C" size_t avfe_lip_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  // filled landmarks [N,68,2] f64 + one FrameXform per frame
-  return (size_t)N * 136 * sizeof(double) + (size_t)N * sizeof(FrameXform) + 64;
+  // one FrameXform per frame + the work-queue counter
+  return (size_t)N * sizeof(FrameXform) + 256;
 }
 
 extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N, int H, int W,
@@ -405,40 +585,47 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
   if (roi <= 0 || (roi & 1) || crop <= 0 || crop > roi || ((roi - crop) & 1) || window <= 0 ||
       std_size < roi)
     return AVFE_ERR_INVALID_ARG;
+  if (roi > kMaxRoi || window > 31) return AVFE_ERR_UNSUPPORTED;
   if (N == 0 || n_clips == 0) return AVFE_OK;
   if (!frames || !clip_offsets || !landmarks || !mean_face) return AVFE_ERR_INVALID_ARG;
   if (gray_out && channels != 3) return AVFE_ERR_INVALID_ARG;
-  if (N > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  if (N > 0x0fffffffLL) return AVFE_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < avfe_lip_workspace_bytes(N) || !aligned16(workspace))
     return AVFE_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  double* lm_filled = static_cast<double*>(workspace);
-  FrameXform* xf = reinterpret_cast<FrameXform*>(lm_filled + (size_t)N * 136);
-  const double* lm = landmarks;
-  if (lm_valid != nullptr) {
-    lm_fill_kernel<<<(unsigned)N, 160, 0, s>>>(landmarks, lm_valid, clip_offsets, n_clips, N,
-                                               lm_filled);
-    count_launch();
-    lm = lm_filled;
-  }
-  tform_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(lm, clip_offsets, n_clips, N, mean_face,
-                                                          tforms_in, std_size, roi, window, xf,
-                                                          crop_rc, tforms);
+  unsigned* counter = static_cast<unsigned*>(workspace);
+  FrameXform* xf = reinterpret_cast<FrameXform*>(static_cast<char*>(workspace) + 256);
+  tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(
+      landmarks, lm_valid, clip_offsets, n_clips, N, mean_face, tforms_in, std_size, roi, window,
+      xf, crop_rc, tforms, counter);
   count_launch();
+
+  const int64_t npx = (int64_t)H * W;
+  const bool want_roi = (lip_u8 != nullptr) || (lip_f32 != nullptr);
+  // gray items ride in the queue when every frame starts 16-byte aligned; otherwise the flat
+  // streaming kernel converts the whole batch first
+  bool gray_in_queue = false;
   if (gray_out != nullptr) {
-    int rc = launch_gray(frames, N * (int64_t)H * W, gray_out, s);
-    if (rc != AVFE_OK) return rc;
-  }
-  if (lip_u8 != nullptr || lip_f32 != nullptr) {
-    if (channels == 3 && gray_out == nullptr) {
-      warp_kernel<true><<<(unsigned)N, kWarpThreads, 0, s>>>(frames, H, W, xf, roi, crop, mean, std,
-                                                            lip_u8, lip_f32);
-    } else {
-      const uint8_t* g = (channels == 3) ? gray_out : frames;
-      warp_kernel<false><<<(unsigned)N, kWarpThreads, 0, s>>>(g, H, W, xf, roi, crop, mean, std,
-                                                             lip_u8, lip_f32);
+    gray_in_queue = want_roi && (npx % 16 == 0) && npx >= 512 && aligned16(frames) && aligned16(gray_out);
+    if (!gray_in_queue) {
+      int rc = launch_gray(frames, N * npx, gray_out, s);
+      if (rc != AVFE_OK) return rc;
     }
+  }
+  if (want_roi) {
+    LipJob j;
+    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = xf;
+    j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
+    j.gray_out = gray_in_queue ? gray_out : nullptr;
+    j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
+    j.groups = (int)(npx / 512);
+    j.gray_items = gray_in_queue ? (j.groups + kGroupsPerItem - 1) / kGroupsPerItem : 0;
+    j.has_warp = 1;
+    const int64_t total = N * (int64_t)(j.gray_items + 1);
+    if (total > 0xfffffff0LL) return AVFE_ERR_UNSUPPORTED;
+    int64_t ctas = total < 4 * kNumSMs ? total : 4 * kNumSMs;      // 4 resident CTAs per SM
+    lip_queue_kernel<<<(unsigned)ctas, kQThreads, 0, s>>>(j);
     count_launch();
   }
   return check_launch();

@@ -23,72 +23,170 @@ namespace lm {
 // avsl_b200/build.py and rounded to float32.
 #include "avfe_logmel_tables.inc"
 
+constexpr int kMaxPacked = 1024;   // packed filter weights kept in shared memory (slaney: ~400-470)
+constexpr int kMaxMels = 128;
+
+// Filterbank in sparse form, built by logmel_prep_kernel in the workspace.
+struct MelPack {
+  int2 bounds[kMaxMels];   // first bin, support length
+  int woff[kMaxMels];      // offset of the filter's weights in wts
+  int total;               // sum of support lengths; > kMaxPacked => weights stay in global fb
+  int pad[3];
+  float wts[kMaxPacked];
+};
+
 struct Smem {
-  float2 Z[kPairs * kZPair];                 // 53,760 B  20x20 exchange / spectra
-  float buf[kTileFrames * kPStride + 16];    // 25,792 B  audio tile (5360), then powers
-  float2 tw[kNfft];                          //  3,200 B
-  float hann[kNfft];                         //  1,600 B
+  float2 Z[kPairs * kZPair];            // 55,424 B  20x20 exchange / spectra, then power rows
+  float audio[2][kTileSamples];         // 42,880 B  double-buffered reflect-padded audio span
+  float2 tw[kNfft];                     //  3,200 B
+  float hann[kNfft];                    //  1,600 B
+  float wts[kMaxPacked];                //  4,096 B
+  int2 bounds[kMaxMels];                //  1,024 B
+  int woff[kMaxMels];                   //    512 B
   int red[16];
 };
 
-__global__ void logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B,
-                                   int* __restrict__ clip_max, int2* __restrict__ bounds) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) clip_max[i] = INT_MIN;
-  if (blockIdx.x == 0 && threadIdx.x < n_mels) {
-    const float* row = fb + (size_t)threadIdx.x * kBins;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// block 0: sparse form of the filterbank; blocks 1..: per-clip max keys <- -inf
+__global__ void __launch_bounds__(1024)
+logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __restrict__ clip_max,
+                   MelPack* __restrict__ pack) {
+  if (blockIdx.x > 0) {
+    const int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    if (i < B) clip_max[i] = INT_MIN;
+    return;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int m = wid; m < n_mels; m += 32) {                 // one warp per filter
+    const float* row = fb + (size_t)m * kBins;
     int lo = kBins, hi = 0;
-    for (int k = 0; k < kBins; ++k)
-      if (row[k] != 0.0f) { lo = min(lo, k); hi = k + 1; }
-    if (lo >= hi) { lo = 0; hi = 0; }
-    bounds[threadIdx.x] = make_int2(lo, hi);
+    for (int k = lane; k < kBins; k += 32)
+      if (row[k] != 0.0f) { lo = min(lo, k); hi = max(hi, k + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) pack->bounds[m] = (lo < hi) ? make_int2(lo, hi - lo) : make_int2(0, 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int m = 0; m < n_mels; ++m) { pack->woff[m] = acc; acc += pack->bounds[m].y; }
+    pack->total = acc;
+  }
+  __syncthreads();
+  if (pack->total <= kMaxPacked) {
+    for (int m = wid; m < n_mels; m += 32) {
+      const int2 bd = pack->bounds[m];
+      const int off = pack->woff[m];
+      for (int k = lane; k < bd.y; k += 32) pack->wts[off + k] = fb[(size_t)m * kBins + bd.x + k];
+    }
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_t Lp,
                    int64_t n_frames, int n_mels, const float* __restrict__ fb,
-                   const int2* __restrict__ bounds, float* __restrict__ out,
+                   const MelPack* __restrict__ pack, float* __restrict__ out,
                    int* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool packed = pack->total <= kMaxPacked;
   for (int i = tid; i < kNfft; i += kThreads) {
     sm.tw[i] = make_float2(kTwRe[i], kTwIm[i]);
     sm.hann[i] = kHann[i];
   }
+  for (int i = tid; i < n_mels; i += kThreads) { sm.bounds[i] = pack->bounds[i]; sm.woff[i] = pack->woff[i]; }
+  if (packed)
+    for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
   const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
   const int64_t n_tiles = B * tiles_per_clip;
   const int g = tid / 20, j = tid % 20;
+  const bool base_ok = ((reinterpret_cast<uintptr_t>(audio) & 15u) == 0) && (L % 4 == 0);
+  const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // Interior tiles (no reflection, no zero padding) are fetched with 16-byte cp.async one tile
+  // ahead; clip-edge tiles are assembled sample by sample when their turn comes.
+  auto is_fast = [&](int64_t tile) -> bool {
+    const int64_t p0 = (tile % tiles_per_clip) * kTileFrames * kHop;
+    return base_ok && p0 >= kNfft / 2 && p0 - kNfft / 2 + kTileSamples <= L;
+  };
+  auto prefetch = [&](int64_t tile, int buf) {
+    if (tile < n_tiles && is_fast(tile)) {
+      const int64_t b = tile / tiles_per_clip;
+      const int64_t p0 = (tile % tiles_per_clip) * kTileFrames * kHop;
+      const float* src = audio + b * L + (p0 - kNfft / 2);
+      for (int i = tid; i < kTileSamples / 4; i += kThreads) cp_async16(&sm.audio[buf][4 * i], src + 4 * i);
+    }
+    cp_async_commit();
+  };
+
+  int cur = 0;
+  prefetch(blockIdx.x, 0);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
     const int64_t b = tile / tiles_per_clip;
     const int64_t t0 = (tile % tiles_per_clip) * kTileFrames;
-    const float* clip = audio + b * L;
-    __syncthreads();                       // previous tile's mel phase is done with sm.buf
-    // ---- stage the reflect-padded audio span of the 32 frames (coalesced) ----
-    const int64_t p0 = t0 * kHop;
-    for (int i = tid; i < kTileSamples; i += kThreads)
-      sm.buf[i] = padded_sample(clip, L, Lp, p0 + i);
-    __syncthreads();
-    // ---- 16 complex FFT-400: columns, twiddle, rows ----
-    stage1(g, j, sm.buf, sm.hann, sm.tw, sm.Z);
-    __syncthreads();
-    stage2(g, j, sm.Z);
-    __syncthreads();
-    // ---- untangle the two real frames of each FFT, power spectrum into sm.buf ----
-    for (int i = tid; i < kPairs * kBins; i += kThreads) split_power(i / kBins, i % kBins, sm.Z, sm.buf);
-    __syncthreads();
-    // ---- sparse mel projection + log10: warp = filter, lane = frame ----
+    prefetch(tile + gridDim.x, cur ^ 1);
+    cp_async_wait<1>();                                  // this tile's group has landed
+    float* au = sm.audio[cur];
+    bool nz = false;
+    if (is_fast(tile)) {
+      for (int i = tid; i < kTileSamples / 4; i += kThreads) {   // the chunks this thread fetched
+        const float4 q = reinterpret_cast<const float4*>(au)[i];
+        nz |= (q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f) | (q.w != 0.0f);
+      }
+    } else {
+      const float* clip = audio + b * L;
+      const int64_t p0 = t0 * kHop;
+      for (int i = tid; i < kTileSamples; i += kThreads) {
+        const float q = padded_sample(clip, L, Lp, p0 + i);
+        au[i] = q;
+        nz |= (q != 0.0f);
+      }
+    }
+    // barrier: tile visible to all, previous tile's power rows no longer needed
+    const int any = __syncthreads_or(nz ? 1 : 0);
     const int64_t t = t0 + lane;
     const bool live = t < n_frames;
     float vmax = -INFINITY;
-    for (int m = wid; m < n_mels; m += kThreads / 32) {
-      const int2 bd = bounds[m];
-      const float v = mel_log10(sm.buf + lane * kPStride, fb + (size_t)m * kBins, bd.x, bd.y);
+    if (!any) {
+      // all 32 frames are digital silence: |X|^2 = 0 -> mel = 0 -> log10(1e-10); skip the FFTs
       if (live) {
-        out[(b * n_mels + m) * n_frames + t] = v;
-        vmax = fmaxf(vmax, v);
+        for (int m = wid; m < n_mels; m += kThreads / 32) out[(b * n_mels + m) * n_frames + t] = floor_v;
+        vmax = floor_v;
+      }
+    } else {
+      // ---- 16 complex FFT-400: columns, twiddle, rows ----
+      stage1(g, j, au, sm.hann, sm.tw, sm.Z);
+      __syncthreads();
+      stage2(g, j, sm.Z);
+      __syncthreads();
+      // ---- untangle the two real frames of each FFT; power rows overwrite the Z slab ----
+      float pa[kBinsPerThread], pb[kBinsPerThread];
+      split_load(g, j, sm.Z, pa, pb);
+      __syncthreads();
+      float* P = reinterpret_cast<float*>(sm.Z);
+      split_store(g, j, P, pa, pb);
+      __syncthreads();
+      // ---- sparse mel projection + log10: warp = filter, lane = frame ----
+      const float* prow = P + prow_offset(lane);
+      for (int m = wid; m < n_mels; m += kThreads / 32) {
+        const int2 bd = sm.bounds[m];
+        const float* w = packed ? (sm.wts + sm.woff[m]) : (fb + (size_t)m * kBins + bd.x);
+        const float v = mel_log10(prow + bd.x, w, bd.y);
+        if (live) {
+          out[(b * n_mels + m) * n_frames + t] = v;
+          vmax = fmaxf(vmax, v);
+        }
       }
     }
 #pragma unroll
@@ -101,11 +199,27 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       atomicMax(clip_max + b, k);
     }
   }
+  cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(256)
 logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
                        int64_t per_clip, int64_t total) {
+  if ((per_clip & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const int64_t n4 = total >> 2, per4 = per_clip >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const float floor_v = __fsub_rn(key_float(clip_max[i / per4]), 8.0f);
+      float4 x = o4[i];
+      x.x = __fmul_rn(__fadd_rn(fmaxf(x.x, floor_v), 4.0f), 0.25f);
+      x.y = __fmul_rn(__fadd_rn(fmaxf(x.y, floor_v), 4.0f), 0.25f);
+      x.z = __fmul_rn(__fadd_rn(fmaxf(x.z, floor_v), 4.0f), 0.25f);
+      x.w = __fmul_rn(__fadd_rn(fmaxf(x.w, floor_v), 4.0f), 0.25f);
+      o4[i] = x;
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float floor_v = __fsub_rn(key_float(clip_max[i / per_clip]), 8.0f);
@@ -184,7 +298,8 @@ using namespace avfe;
 extern "C" size_t avfe_logmel_workspace_bytes(int64_t B, int64_t L, int64_t padding, int n_mels) {
   (void)L; (void)padding;
   if (B < 0 || n_mels < 0) return 0;
-  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + (size_t)n_mels * sizeof(int2) + 64;
+  (void)n_mels;
+  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + 64;
 }
 
 extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
@@ -202,13 +317,11 @@ extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t
     return AVFE_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int* clip_max = static_cast<int*>(workspace);
-  int2* bounds = reinterpret_cast<int2*>(static_cast<char*>(workspace) +
-                                         (((size_t)B * sizeof(int) + 15) & ~(size_t)15));
+  lm::MelPack* pack = reinterpret_cast<lm::MelPack*>(static_cast<char*>(workspace) +
+                                                     (((size_t)B * sizeof(int) + 15) & ~(size_t)15));
 
-  const int prep_threads = 128;
-  const int64_t prep_ctas = (B + prep_threads - 1) / prep_threads;
-  lm::logmel_prep_kernel<<<(unsigned)(prep_ctas > 0 ? prep_ctas : 1), prep_threads, 0, s>>>(
-      mel_filters, n_mels, B, clip_max, bounds);
+  lm::logmel_prep_kernel<<<(unsigned)(1 + (B + 1023) / 1024), 1024, 0, s>>>(mel_filters, n_mels, B,
+                                                                           clip_max, pack);
   count_launch();
 
   // per-device attribute: set on every call (cheap) so multi-device processes stay correct
@@ -220,11 +333,11 @@ extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t
   const int64_t n_tiles = B * ((n_frames + lm::kTileFrames - 1) / lm::kTileFrames);
   int64_t ctas = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;   // 2 resident CTAs per SM
   lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
-      audio, B, L, Lp, n_frames, n_mels, mel_filters, bounds, out, clip_max);
+      audio, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max);
   count_launch();
 
   const int64_t per_clip = (int64_t)n_mels * n_frames, total = B * per_clip;
-  int64_t fin = (total + 255) / 256;
+  int64_t fin = (total / 4 + 255) / 256 + 1;
   if (fin > (int64_t)kNumSMs * 16) fin = (int64_t)kNumSMs * 16;
   lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, per_clip, total);
   count_launch();

@@ -28,8 +28,11 @@ constexpr int kPairs = kTileFrames / 2;                          // 16 complex F
 constexpr int kThreads = kPairs * 20;                            // 320: one thread per (FFT, column)
 constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5360
 constexpr int kZRow = 21;            // float2 row stride of the 20x20 exchange (20 + 1 pad)
-constexpr int kZPair = 20 * kZRow;   // 420 float2 per FFT (840 words = 8 mod 32 banks)
-constexpr int kPStride = 201;        // odd stride: lane = frame reads are conflict-free
+// float2 per FFT: >= 20*21 - 1, and 2*433 = 866 = 2 (mod 32) so that the two power rows that
+// later overwrite each FFT's slab (frame 2g at +0, frame 2g+1 at +433 floats) start at bank
+// 2g and 2g+17: the 32 frames of a tile sit in 32 different banks (lane = frame reads).
+constexpr int kZPair = 433;
+constexpr int kBinsPerThread = 11;   // thread (g, j) untangles bins k = j + 20*m, m = 0..10
 
 AVFE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 AVFE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -122,30 +125,64 @@ AVFE_HD void stage2(int g, int k1, float2* Z) {
   for (int k2 = 0; k2 < 20; ++k2) z[k2] = x[k2];
 }
 
-AVFE_HD int zslot(int k) { return (k % 20) * kZRow + k / 20; }
+// Float offset of the power row of tile frame f (0..31) inside the Z storage.
+AVFE_HD int prow_offset(int f) { return (f >> 1) * (2 * kZPair) + (f & 1) * kZPair; }
 
-// Untangle the two real frames packed in FFT g at bin k (0..200) and store both powers.
-// Xa = (Z[k] + conj(Z[400-k]))/2, Xb = (Z[k] - conj(Z[400-k]))/(2i).
-AVFE_HD void split_power(int g, int k, const float2* Z, float* P) {
+// Untangle the two real frames packed in FFT g.  Thread (g, j) owns bins k = j + 20*m
+// (m = 0..10; m = 10 exists only for j = 0, k = 200).  Bin k sits in slot j*21 + m; its mirror
+// 400-k in slot (20-j)*21 + (19-m) for j > 0 and slot 20-m for j = 0 (slot 0 for k = 0).
+// Xa = (Z[k] + conj(Z[400-k]))/2, Xb = (Z[k] - conj(Z[400-k]))/(2i); powers kept in registers
+// (phase A) so that phase B can overwrite the Z slab with the two power rows after a barrier.
+AVFE_HD void split_load(int g, int j, const float2* Z, float (&pa)[kBinsPerThread],
+                        float (&pb)[kBinsPerThread]) {
   const float2* z = Z + g * kZPair;
-  const float2 u = z[zslot(k)];
-  const float2 v = z[zslot(k == 0 ? 0 : kNfft - k)];
-  const float ar = u.x + v.x, ai = u.y - v.y;
-  const float br = u.y + v.y, bi = v.x - u.x;
-  P[(2 * g) * kPStride + k] = 0.25f * (ar * ar + ai * ai);
-  P[(2 * g + 1) * kPStride + k] = 0.25f * (br * br + bi * bi);
+#pragma unroll
+  for (int m = 0; m < kBinsPerThread; ++m) {
+    if (m == 10 && j != 0) { pa[m] = 0.0f; pb[m] = 0.0f; continue; }
+    const int ms = (j == 0) ? ((m == 0) ? 0 : 20 - m) : (20 - j) * kZRow + (19 - m);
+    const float2 u = z[j * kZRow + m];
+    const float2 v = z[ms];
+    const float ar = u.x + v.x, ai = u.y - v.y;
+    const float br = u.y + v.y, bi = v.x - u.x;
+    pa[m] = 0.25f * (ar * ar + ai * ai);
+    pb[m] = 0.25f * (br * br + bi * bi);
+  }
 }
 
-// log10(max(mel, 1e-10)) for one (frame, filter): dot product over the filter's support.
-AVFE_HD float mel_log10(const float* Prow, const float* fbrow, int k0, int k1) {
-  float acc = 0.0f;
-  for (int k = k0; k < k1; ++k) acc = fmaf(fbrow[k], Prow[k], acc);
+AVFE_HD void split_store(int g, int j, float* P, const float (&pa)[kBinsPerThread],
+                         const float (&pb)[kBinsPerThread]) {
+  float* ra = P + prow_offset(2 * g) + j;
+  float* rb = P + prow_offset(2 * g + 1) + j;
+#pragma unroll
+  for (int m = 0; m < kBinsPerThread; ++m) {
+    if (m == 10 && j != 0) continue;
+    ra[20 * m] = pa[m];
+    rb[20 * m] = pb[m];
+  }
+}
+
+AVFE_HD float log10_floor(float acc) {
   acc = fmaxf(acc, 1e-10f);
 #if defined(__CUDA_ARCH__)
   return __log2f(acc) * 0.30102999566398120f;   // MUFU.LG2: abs error ~1e-6 in log10 units
 #else
   return log2f(acc) * 0.30102999566398120f;
 #endif
+}
+
+// log10(max(mel, 1e-10)) for one (frame, filter): dot product over the filter's support.
+// Prow points at the first bin of the support, w at the filter's n packed weights.
+AVFE_HD float mel_log10(const float* Prow, const float* w, int n) {
+  float a0 = 0.0f, a1 = 0.0f;
+  int k = 0;
+  for (; k + 4 <= n; k += 4) {
+    a0 = fmaf(w[k], Prow[k], a0);
+    a1 = fmaf(w[k + 1], Prow[k + 1], a1);
+    a0 = fmaf(w[k + 2], Prow[k + 2], a0);
+    a1 = fmaf(w[k + 3], Prow[k + 3], a1);
+  }
+  for (; k < n; ++k) a0 = fmaf(w[k], Prow[k], a0);
+  return log10_floor(a0 + a1);
 }
 
 // order-preserving float <-> int key for atomicMax

@@ -88,7 +88,7 @@ class AVFrontEnd:
     """Log-mel + lip-ROI features for a packed batch of utterances on one GPU."""
 
     def __init__(self, n_mels: int = 80, audio_max_length: int = N_SAMPLES, device=None,
-                 want_gray: bool = True, want_lip_u8: bool = False,
+                 want_gray: bool = True, want_lip_u8: bool = False, fused: bool = True,
                  image_crop_size: int = IMAGE_CROP_SIZE, image_mean: float = IMAGE_MEAN,
                  image_std: float = IMAGE_STD):
         _lib.require_cuda()
@@ -98,6 +98,7 @@ class AVFrontEnd:
         self.audio_max_length = audio_max_length
         self.want_gray = want_gray
         self.want_lip_u8 = want_lip_u8
+        self.fused = fused
         self.crop = image_crop_size
         self.mean, self.std = image_mean, image_std
         self.filters = mel_filters(self.device, n_mels)
@@ -138,18 +139,22 @@ class AVFrontEnd:
             N, H, W = (int(s) for s in batch.frames.shape[:3])
             src = batch.frames
             gray = None
-            if self.want_gray and batch.frames.dim() == 4:
-                # gray frames are a deliverable: convert once, then warp from the gray frames
-                gray = self._buf("gray", (N, H, W), torch.uint8)
-                _lib.call("avfe_bgr2gray_u8", _lib.ptr(batch.frames), N, H, W, _lib.ptr(gray), _lib.stream_ptr())
-                src = gray
-                mark("gray")
-            reuse = LipBatch(None, self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
+            bgr = batch.frames.dim() == 4
+            if self.want_gray and bgr:
+                gray = self._buf("gray", (N, H, W), torch.uint8)       # gray frames are a deliverable
+                if not self.fused:
+                    # two passes: stream-convert everything, then warp from the gray frames
+                    _lib.call("avfe_bgr2gray_u8", _lib.ptr(batch.frames), N, H, W, _lib.ptr(gray), _lib.stream_ptr())
+                    src = gray
+                    mark("gray")
+            reuse = LipBatch(gray if (self.fused and bgr) else None,
+                             self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
                              self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
                              batch.clip_offsets)
-            lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid, want_gray=False,
-                          want_u8=self.want_lip_u8, crop=self.crop, image_mean=self.mean,
-                          image_std=self.std, out=reuse)
+            # fused: one work-queue launch interleaves the streaming gray items with the FP64 warp items
+            lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid,
+                          want_gray=self.fused and gray is not None, want_u8=self.want_lip_u8,
+                          crop=self.crop, image_mean=self.mean, image_std=self.std, out=reuse)
             mark("lip")
         out = {"mel": mel, "lip": reuse.lip_f32.unsqueeze(-1)}
         if gray is not None:

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = auto (bounded to ~10-30 s)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="gray and warp as two passes instead of one work queue")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -247,7 +248,7 @@ def main():
     batch_dev = PackedBatch(audio, torch.from_numpy(a_off).to(dev), frames, torch.from_numpy(clip_off).to(dev),
                             torch.from_numpy(np.concatenate(lms)).to(dev),
                             torch.from_numpy(np.concatenate(vals)).to(dev))
-    fe = AVFrontEnd(n_mels=N_MELS, audio_max_length=AUDIO_LEN, device=dev, want_gray=True)
+    fe = AVFrontEnd(n_mels=N_MELS, audio_max_length=AUDIO_LEN, device=dev, want_gray=True, fused=not args.unfused)
     padded = torch.empty((U, AUDIO_LEN), dtype=torch.float32, device=dev)
     _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(audio), _lib.ptr(batch_dev.audio_offsets), U, AUDIO_LEN,
               _lib.ptr(padded), _lib.stream_ptr())
@@ -304,6 +305,50 @@ def main():
     audio_s_all, alg_bytes_all, launches_all = (float(x) for x in tot.tolist())
     value = audio_s_all * args.steps / (elapsed_ms * 1e-3)
 
+    # ---------------- side measurements: the other BASELINE configs, same timing hygiene -------
+    # configs[2] dense log-mel (64 x 30 s of noise: no silent tiles) and configs[3] fusion
+    # (B=64, C=1024, T=750, masked); inputs > L2 or L2 flushed by the 2.2 GB video pass between.
+    def time_op(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    side = {}
+    if rank == 0:
+        dense = synth.audio_batch(64, AUDIO_LEN, SEED, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+        for n_mels in (80, 128):
+            mel_out = torch.empty((64, n_mels, AUDIO_LEN // 160), device=dev)
+
+            def run_dense():
+                flush.zero_()
+                A.log_mel_spectrogram(dense, n_mels, out=mel_out)
+            ms_flush = time_op(lambda: flush.zero_(), 10)
+            ms = time_op(run_dense, 10) - ms_flush
+            nbytes = 64 * (4 * AUDIO_LEN + 4 * n_mels * (AUDIO_LEN // 160))
+            side[f"logmel_dense_{n_mels}"] = {"kernel": "logmel_prep+tile+finalize, 64 x 30 s dense noise (configs[2])",
+                                              "ms": ms, "algorithmic_bytes": nbytes,
+                                              "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                                              "audio_s_per_s": 64 * 30.0 / (ms * 1e-3)}
+        del dense, flush
+        fa, fv, fmask = synth.fusion_inputs(64, 1024, 750, seed=SEED, device=dev)
+        present = int(fmask.sum())
+        E1 = 1024 * 750 * 4
+        for mode in ("concat", "add", "weighted_sum"):
+            fout = torch.empty((64, 2048 if mode == "concat" else 1024, 750), device=dev)
+            ms = time_op(lambda: A.fuse_modalities(fa, fv, fmask, mode, out=fout), 20)
+            nbytes = present * E1 + fout.numel() * 4
+            side[f"fuse_{mode}"] = {"kernel": "fuse_vec_kernel (configs[3], masked: absent modalities not read)",
+                                    "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+        del fa, fv
+
     # ---------------- end-to-end through host buffers ----------------
     e2e = None
     if not args.no_e2e:
@@ -334,19 +379,28 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    fused = not args.unfused
     kernel_bytes = {
         "logmel": U * (4 * AUDIO_LEN + 4 * N_MELS * (AUDIO_LEN // 160)),
         "gray": N * (H * W * 3 + H * W),
-        "lip": N * (68 * 2 * 8 + 88 * 88 * 4),
+        "lip": N * (68 * 2 * 8 + 88 * 88 * 4) + (N * (H * W * 3 + H * W) if fused else 0),
     }
-    kernel_names = {"logmel": "logmel_tile_kernel (+prep, finalize)", "gray": "gray_vec_kernel",
-                    "lip": "tform_kernel + warp_kernel (+lm_fill)"}
+    if fused:
+        stage_names = ["logmel", "lip"]
+        stage_ms.pop("gray", None)
+    kernel_names = {"logmel": "logmel_prep + logmel_tile_kernel + logmel_finalize (AMI batch: silent tiles take the exact zero-tile shortcut)",
+                    "gray": "gray_vec_kernel",
+                    "lip": ("tform_kernel + lip_queue_kernel (gray items + warp items in one work queue)" if fused
+                            else "tform_kernel + lip_queue_kernel (warp items, taps from the gray frames)")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k])
     stages = {}
     for k in stage_names:
         ach = kernel_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0
         stages[k] = {"kernel": kernel_names[k], "ms": stage_ms[k], "algorithmic_bytes": kernel_bytes[k],
                      "achieved_gbs": ach, "frac": ach / peak}
+    for k, v in side.items():
+        v["frac"] = v["achieved_gbs"] / peak
+        stages[k] = v
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):

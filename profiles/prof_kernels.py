@@ -1,0 +1,63 @@
+"""Small driver for ncu captures: runs one hot-path kernel group a few times on BASELINE-sized
+synthetic input.  Usage (on the GPU box):
+
+    python profiles/prof_kernels.py logmel|lip|fuse|all [--iters 3]
+
+Numbers printed by a run under ncu are never bench values; bench.py is the only source of those.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import avsl_b200 as A  # noqa: E402
+from avsl_b200 import lips as L  # noqa: E402
+from avsl_b200 import synth  # noqa: E402
+
+
+def run_logmel(iters, n_mels=80, batch=64):
+    a = synth.audio_batch(batch, 480000, 3407, device="cuda")
+    out = torch.empty((batch, n_mels, 3000), device="cuda")
+    for _ in range(iters):
+        A.log_mel_spectrogram(a, n_mels, out=out)
+    torch.cuda.synchronize()
+
+
+def run_lip(iters, clips=32, T=250):
+    N = clips * T
+    frames = synth.video_frames_cuda(N, 224, 224, device="cuda")
+    lms, vals = zip(*[synth.landmarks_for_clip(T, seed=3407 + i) for i in range(clips)])
+    lm = torch.from_numpy(np.concatenate(lms)).cuda()
+    valid = torch.from_numpy(np.concatenate(vals)).cuda()
+    off = torch.arange(0, N + 1, T, dtype=torch.int64, device="cuda")
+    res = None
+    for _ in range(iters):
+        res = L.lip_roi_batch(frames, off, lm, valid, want_gray=True, want_f32=True, out=res)
+    torch.cuda.synchronize()
+
+
+def run_fuse(iters):
+    fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
+    for mode in ("concat", "add"):
+        out = None
+        for _ in range(iters):
+            out = A.fuse_modalities(fa, fv, mask, mode, out=out)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["logmel", "lip", "fuse", "all"])
+    ap.add_argument("--iters", type=int, default=3)
+    a = ap.parse_args()
+    if a.which in ("logmel", "all"):
+        run_logmel(a.iters)
+    if a.which in ("lip", "all"):
+        run_lip(a.iters)
+    if a.which in ("fuse", "all"):
+        run_fuse(a.iters)
+    print("done", a.which)

@@ -29,19 +29,27 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
       const double a = -2.0 * M_PI * ((j * k1) % kNfft) / kNfft;
       tw[k1 * 20 + j] = make_float2((float)cos(a), (float)sin(a));
     }
-  std::vector<float> buf(kTileFrames * kPStride + 16);
+  std::vector<float> buf(kTileSamples);
   std::vector<float2> Z(kPairs * kZPair);
+  std::vector<float> pa(kThreads * kBinsPerThread), pb(kThreads * kBinsPerThread);
   for (int i = 0; i < kTileSamples; ++i) buf[i] = padded_sample(clip, L, Lp, t0 * kHop + i);
   for (int tid = 0; tid < kThreads; ++tid) stage1(tid / 20, tid % 20, buf.data(), hann.data(), tw.data(), Z.data());
   for (int tid = 0; tid < kThreads; ++tid) stage2(tid / 20, tid % 20, Z.data());
-  for (int i = 0; i < kPairs * kBins; ++i) split_power(i / kBins, i % kBins, Z.data(), buf.data());
+  // phase A (all threads), barrier, phase B (all threads): power rows overwrite the Z slab
+  for (int tid = 0; tid < kThreads; ++tid)
+    split_load(tid / 20, tid % 20, Z.data(), *reinterpret_cast<float(*)[kBinsPerThread]>(&pa[tid * kBinsPerThread]),
+               *reinterpret_cast<float(*)[kBinsPerThread]>(&pb[tid * kBinsPerThread]));
+  float* P = reinterpret_cast<float*>(Z.data());
+  for (int tid = 0; tid < kThreads; ++tid)
+    split_store(tid / 20, tid % 20, P, *reinterpret_cast<float(*)[kBinsPerThread]>(&pa[tid * kBinsPerThread]),
+                *reinterpret_cast<float(*)[kBinsPerThread]>(&pb[tid * kBinsPerThread]));
   for (int m = 0; m < n_mels; ++m) {
     int lo = kBins, hi = 0;
     for (int k = 0; k < kBins; ++k)
       if (fb[m * kBins + k] != 0.0f) { lo = lo < k ? lo : k; hi = k + 1; }
     if (lo >= hi) { lo = 0; hi = 0; }
     for (int f = 0; f < kTileFrames; ++f)
-      out[m * kTileFrames + f] = mel_log10(buf.data() + f * kPStride, fb + m * kBins, lo, hi);
+      out[m * kTileFrames + f] = mel_log10(P + prow_offset(f) + lo, fb + m * kBins + lo, hi - lo);
   }
 }
 
