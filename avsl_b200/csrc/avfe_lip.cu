@@ -7,14 +7,14 @@
 //   tform_kernel      one WARP per frame: failed detections are interpolated on the fly (V2),
 //                     12-frame window mean of the 5 stable points (V3), closed-form similarity
 //                     fit + inverse (V4), mouth-centre transform (V6) and cut_patch origin (V7)
-//   lip_queue_kernel  persistent CTAs pulling items from one atomic work queue.  Two item kinds
-//                     are interleaved frame by frame so that they overlap on every SM:
-//                       gray item  8192 px of streaming BGR->gray (HBM-bound, integer dp4a)
-//                       warp item  one frame's ROI: source footprint staged in shared memory,
-//                                  float64 bilinear blend in skimage's operation order,
-//                                  u8 ROI + normalised f32 centre crop (FP64-pipe-bound)
+//   lip_fused_kernel  (avfe_lip_queue.cuh) persistent, warp-specialised: stream warps convert
+//                     BGR->gray at HBM speed while compute warps pull one frame's ROI at a time
+//                     from a work queue (footprint staged in shared memory, float64 bilinear
+//                     blend in skimage's operation order, u8 ROI + normalised f32 centre crop)
 //   gray_vec_kernel   the gray conversion alone (avfe_bgr2gray_u8)
 //   small single-purpose kernels for the per-function entry points (warp_full, cut_patch, ...)
+#include <stddef.h>
+
 #include "avfe_common.cuh"
 #include "avfe_lip_math.cuh"
 
@@ -263,195 +263,11 @@ static int launch_gray(const uint8_t* bgr, int64_t npx, uint8_t* gray, cudaStrea
   return check_launch();
 }
 
-// ------------------------------------------------------------------ work-queue kernel
-constexpr int kQThreads = 256;
-constexpr int kQWarps = kQThreads / 32;
-constexpr int kGroupsPerItem = 16;          // gray item = 16 groups = 8192 px (24 KB in, 8 KB out)
-constexpr int kTileBytes = 36864;           // staged source footprint of one ROI (e.g. 192 x 192)
-constexpr int kMaxRoi = 128;
+}  // namespace avfe
 
-struct LipJob {
-  const uint8_t* frames;   // [N,H,W,channels]
-  int channels, H, W;
-  int64_t N;
-  const FrameXform* xf;
-  int roi, crop;
-  float mean, stdv;
-  uint8_t* gray_out;       // nullable: no gray items
-  uint8_t* lip_u8;         // nullable
-  float* lip_f32;          // nullable
-  unsigned* counter;
-  int gray_items;          // gray items per frame (0 = none)
-  int groups;              // full 512-px groups per frame
-  int has_warp;            // 1 if ROI outputs are wanted
-};
+#include "avfe_lip_queue.cuh"   // lip_fused_kernel: stream warps + compute warps
 
-struct QSmem {
-  double lut255[256];                 // k / 255.0 (img_as_float)
-  double colx[kMaxRoi], coly[kMaxRoi], rowx[kMaxRoi], rowy[kMaxRoi];
-  float lutn[256];                    // ((k/255) - mean) / std in float32
-  int bbox[4];                        // rmin, cmin, rows, pitch of the staged footprint
-  unsigned item[2];
-  union {
-    uint4 slab[kQWarps][96];
-    uint8_t tile[kTileBytes];
-  } u;
-};
-
-__device__ __forceinline__ void gray_item(const LipJob& j, int64_t f, int sub, QSmem& sm) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t npx = (int64_t)j.H * j.W;
-  const uint4* src = reinterpret_cast<const uint4*>(j.frames + f * npx * 3);
-  uint4* dst = reinterpret_cast<uint4*>(j.gray_out + f * npx);
-  const int g0 = sub * kGroupsPerItem;
-  const int g1 = min(g0 + kGroupsPerItem, j.groups);
-  for (int g = g0 + wid; g < g1; g += kQWarps)
-    gray_group(src + (int64_t)g * 96, dst + (int64_t)g * 32, sm.u.slab[wid], lane);
-  if (sub == j.gray_items - 1) {                       // pixels past the last full group
-    const uint8_t* b = j.frames + f * npx * 3;
-    uint8_t* o = j.gray_out + f * npx;
-    for (int64_t i = (int64_t)j.groups * 512 + threadIdx.x; i < npx; i += kQThreads)
-      o[i] = (uint8_t)gray_from_bgr(b[3 * i], b[3 * i + 1], b[3 * i + 2]);
-  }
-}
-
-// SPAN = side of the evaluated window (96 when the u8 ROI is wanted, 88 for the centre crop
-// only, 0 = run-time value).
-template <int SPAN>
-__device__ __forceinline__ void warp_item(const LipJob& j, int64_t f, QSmem& sm) {
-  const int tid = threadIdx.x;
-  const FrameXform x = j.xf[f];
-  const int off = (j.roi - j.crop) / 2;
-  const int lo = j.lip_u8 ? 0 : off;
-  const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
-  const int H = j.H, W = j.W;
-  uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
-  float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
-  if (x.r0 < 0) {                                      // clip without any detection: zero ROI
-    for (int idx = tid; idx < span * span; idx += kQThreads) {
-      const int pr = lo + idx / span, pc = lo + idx % span;
-      if (out_u8) out_u8[pr * j.roi + pc] = 0;
-      const int cr = pr - off, cc = pc - off;
-      if (out_f32 && cr >= 0 && cr < j.crop && cc >= 0 && cc < j.crop) out_f32[cr * j.crop + cc] = sm.lutn[0];
-    }
-    return;
-  }
-  // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with the
-  // same two roundings per product as skimage's _transform_affine
-  if (tid < span) {
-    const double t = (double)(x.c0 + lo + tid);
-    sm.colx[tid] = f64mul(x.inv[0], t);
-    sm.coly[tid] = f64mul(x.inv[3], t);
-  } else if (tid >= 128 && tid < 128 + span) {
-    const double t = (double)(x.r0 + lo + tid - 128);
-    sm.rowx[tid - 128] = f64mul(x.inv[1], t);
-    sm.rowy[tid - 128] = f64mul(x.inv[4], t);
-  }
-  if (tid == 0) {
-    // source footprint: an affine map takes its extrema at the window corners
-    double rmin = 1e300, rmax = -1e300, cmin = 1e300, cmax = -1e300;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double tr = (double)(x.r0 + lo + ((k & 1) ? span - 1 : 0));
-      const double tc = (double)(x.c0 + lo + ((k & 2) ? span - 1 : 0));
-      const double sc = x.inv[0] * tc + x.inv[1] * tr + x.inv[2];
-      const double sr = x.inv[3] * tc + x.inv[4] * tr + x.inv[5];
-      rmin = fmin(rmin, sr); rmax = fmax(rmax, sr);
-      cmin = fmin(cmin, sc); cmax = fmax(cmax, sc);
-    }
-    // one pixel of slack each side; taps outside the staged box fall back to global memory
-    int r0 = (int)fmax(floor(rmin) - 1.0, 0.0), r1 = (int)fmin(ceil(rmax) + 1.0, (double)(H - 1));
-    int c0 = (int)fmax(floor(cmin) - 1.0, 0.0), c1 = (int)fmin(ceil(cmax) + 1.0, (double)(W - 1));
-    int rows = r1 - r0 + 1, cols = c1 - c0 + 1;
-    if (!(rmin == rmin) || rows <= 0 || cols <= 0) { rows = 0; cols = 0; r0 = 0; c0 = 0; }
-    const int pitch = (cols + 3) & ~3;
-    if ((int64_t)rows * pitch > kTileBytes) { rows = 0; }   // too large: use global taps only
-    sm.bbox[0] = r0; sm.bbox[1] = c0; sm.bbox[2] = rows; sm.bbox[3] = pitch;
-  }
-  __syncthreads();
-  const int br0 = sm.bbox[0], bc0 = sm.bbox[1], brows = sm.bbox[2], pitch = sm.bbox[3];
-  const bool bgr = (j.channels == 3);
-  const uint8_t* img = j.frames + f * (int64_t)H * W * (bgr ? 3 : 1);
-  // stage the footprint (converted to gray on the way in when the source is BGR)
-  {
-    const int bcols = min(pitch, W - bc0);
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int r = wid; r < brows; r += kQWarps) {          // one warp per footprint row
-      const uint8_t* row = img + ((int64_t)(br0 + r) * W + bc0) * (bgr ? 3 : 1);
-      for (int c = lane; c < pitch; c += 32) {
-        uint32_t v = 0;
-        if (c < bcols) {
-          if (bgr) {
-            const uint8_t* p = row + 3 * c;
-            v = gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2));
-          } else {
-            v = __ldg(row + c);
-          }
-        }
-        sm.u.tile[r * pitch + c] = (uint8_t)v;
-      }
-    }
-  }
-  __syncthreads();
-  auto tap = [&](int r, int c) -> uint32_t {
-    const int rr = r - br0, cc = c - bc0;
-    if ((unsigned)rr < (unsigned)brows && (unsigned)cc < (unsigned)pitch) return sm.u.tile[rr * pitch + cc];
-    const int64_t px = (int64_t)r * W + c;               // outside the staged box (rare)
-    if (bgr) {
-      const uint8_t* p = img + px * 3;
-      return gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2));
-    }
-    return __ldg(img + px);
-  };
-  const double m2 = x.inv[2], m5 = x.inv[5];
-  for (int idx = tid; idx < span * span; idx += kQThreads) {
-    const int r = idx / span, c = idx - r * span;        // constant divisor when SPAN != 0
-    const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
-    const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
-    const uint32_t v = bilinear_u8(sr, sc, H, W, sm.lut255, tap);
-    const int pr = lo + r, pc = lo + c;
-    if (out_u8) out_u8[pr * j.roi + pc] = (uint8_t)v;
-    if (out_f32) {
-      const int cr = pr - off, cc = pc - off;
-      if ((unsigned)cr < (unsigned)j.crop && (unsigned)cc < (unsigned)j.crop)
-        out_f32[cr * j.crop + cc] = sm.lutn[v];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kQThreads, 4)
-lip_queue_kernel(const LipJob j) {
-  __shared__ QSmem sm;
-  const int tid = threadIdx.x;
-  for (int k = tid; k < 256; k += kQThreads) {
-    sm.lut255[k] = f64div((double)k, 255.0);
-    sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
-  }
-  const unsigned per_frame = (unsigned)(j.gray_items + j.has_warp);
-  const unsigned total = (unsigned)j.N * per_frame;
-  if (tid == 0) sm.item[0] = atomicAdd(j.counter, 1u);
-  __syncthreads();
-  unsigned t = sm.item[0];
-  int buf = 0;
-  while (t < total) {
-    // fetch the next item while this one is processed (only thread 0's warp waits on the atomic)
-    if (tid == 0) sm.item[buf ^ 1] = atomicAdd(j.counter, 1u);
-    const int64_t f = t / per_frame;
-    const int sub = (int)(t - (unsigned)f * per_frame);
-    if (sub < j.gray_items) {
-      gray_item(j, f, sub, sm);
-    } else if (j.lip_u8 != nullptr && j.roi == 96) {
-      warp_item<96>(j, f, sm);
-    } else if (j.lip_u8 == nullptr && j.crop == 88) {
-      warp_item<88>(j, f, sm);
-    } else {
-      warp_item<0>(j, f, sm);
-    }
-    __syncthreads();               // item done: shared staging is free, next index is visible
-    buf ^= 1;
-    t = sm.item[buf];
-  }
-}
+namespace avfe {
 
 // ------------------------------------------------------------------ single-purpose kernels
 __device__ __forceinline__ void fill_lut255(double* lut255) {
@@ -468,7 +284,7 @@ warp_full_kernel(const uint8_t* __restrict__ gray, int H, int W, const double* _
   const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
   const double m6 = M[6], m7 = M[7], m8 = M[8];
   const bool affine = (m6 == 0.0) && (m7 == 0.0) && (m8 == 1.0);
-  auto tap = [&](int r, int c) -> uint32_t { return __ldg(gray + (size_t)r * W + c); };
+  auto tap = [&](int r, int c) -> double { return lut255[__ldg(gray + (size_t)r * W + c)]; };
   const int64_t total = (int64_t)out_h * out_w;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -480,7 +296,7 @@ warp_full_kernel(const uint8_t* __restrict__ gray, int H, int W, const double* _
       sc = f64div(sc, z);
       sr = f64div(sr, z);
     }
-    out[idx] = bilinear_u8(sr, sc, H, W, lut255, tap);
+    out[idx] = bilinear_u8(sr, sc, H, W, tap);
   }
 }
 
@@ -603,29 +419,37 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
 
   const int64_t npx = (int64_t)H * W;
   const bool want_roi = (lip_u8 != nullptr) || (lip_f32 != nullptr);
-  // gray items ride in the queue when every frame starts 16-byte aligned; otherwise the flat
-  // streaming kernel converts the whole batch first
-  bool gray_in_queue = false;
-  if (gray_out != nullptr) {
-    gray_in_queue = want_roi && (npx % 16 == 0) && npx >= 512 && aligned16(frames) && aligned16(gray_out);
-    if (!gray_in_queue) {
-      int rc = launch_gray(frames, N * npx, gray_out, s);
-      if (rc != AVFE_OK) return rc;
-    }
+  // the gray conversion rides along in the fused launch when the pixel stream is 16-byte
+  // aligned; otherwise (or when no ROI is wanted) the flat streaming kernel does it
+  const bool fuse_gray = want_roi && gray_out != nullptr && aligned16(frames) && aligned16(gray_out) &&
+                         N * npx >= 512;
+  if (gray_out != nullptr && !fuse_gray) {
+    int rc = launch_gray(frames, N * npx, gray_out, s);
+    if (rc != AVFE_OK) return rc;
   }
   if (want_roi) {
     LipJob j;
     j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = xf;
     j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
-    j.gray_out = gray_in_queue ? gray_out : nullptr;
+    j.gray_out = fuse_gray ? gray_out : nullptr;
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
-    j.groups = (int)(npx / 512);
-    j.gray_items = gray_in_queue ? (j.groups + kGroupsPerItem - 1) / kGroupsPerItem : 0;
-    j.has_warp = 1;
-    const int64_t total = N * (int64_t)(j.gray_items + 1);
-    if (total > 0xfffffff0LL) return AVFE_ERR_UNSUPPORTED;
-    int64_t ctas = total < 4 * kNumSMs ? total : 4 * kNumSMs;      // 4 resident CTAs per SM
-    lip_queue_kernel<<<(unsigned)ctas, kQThreads, 0, s>>>(j);
+    j.ngroups = (N * npx) / 512;
+    if (fuse_gray) {
+      const int smem = (int)sizeof(FusedSmem);
+      if (cudaFuncSetAttribute(lip_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return AVFE_ERR_CUDA;
+      }
+      lip_fused_kernel<true><<<2 * kNumSMs, 2 * kGroupThreads, smem, s>>>(j);   // 2 resident CTAs per SM
+    } else {
+      const int smem = (int)offsetof(FusedSmem, slab);
+      if (cudaFuncSetAttribute(lip_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return AVFE_ERR_CUDA;
+      }
+      const int64_t ctas = N < 2 * kNumSMs ? N : 2 * kNumSMs;   // 2 resident CTAs per SM
+      lip_fused_kernel<false><<<(unsigned)ctas, kGroupThreads, smem, s>>>(j);
+    }
     count_launch();
   }
   return check_launch();

@@ -94,10 +94,10 @@ AVFE_HD void crop_origin(double cx, double cy, int half_h, int half_w, int img_h
 }
 
 // One output pixel of skimage _warp_fast (order 1, mode 'constant', cval 0) on an
-// img_as_float'ed uint8 image, then (*255).astype(uint8).  `lut[k]` must hold k/255.0.
-// `tap(r, c)` returns the uint8 source pixel (only called in range).
+// img_as_float'ed uint8 image, then (*255).astype(uint8).
+// `tap(r, c)` returns the source pixel as float64 k/255.0 (only called for in-frame taps).
 template <typename TapFn>
-AVFE_HD uint8_t bilinear_u8(double r, double c, int H, int W, const double* lut, TapFn tap) {
+AVFE_HD uint8_t bilinear_u8(double r, double c, int H, int W, TapFn tap) {
   const double fr = floor(r), fc = floor(c);
   // far outside the image every tap is cval; also keeps the int conversions in range
   if (!(fr >= -2.0 && fr <= (double)H + 1.0 && fc >= -2.0 && fc <= (double)W + 1.0)) return 0;
@@ -106,10 +106,10 @@ AVFE_HD uint8_t bilinear_u8(double r, double c, int H, int W, const double* lut,
   const double dr = f64sub(r, fr), dc = f64sub(c, fc);
   const bool r0ok = (minr >= 0) && (minr < H), r1ok = (maxr >= 0) && (maxr < H);
   const bool c0ok = (minc >= 0) && (minc < W), c1ok = (maxc >= 0) && (maxc < W);
-  const double tl = (r0ok && c0ok) ? lut[tap(minr, minc)] : 0.0;
-  const double tr = (r0ok && c1ok) ? lut[tap(minr, maxc)] : 0.0;
-  const double bl = (r1ok && c0ok) ? lut[tap(maxr, minc)] : 0.0;
-  const double br = (r1ok && c1ok) ? lut[tap(maxr, maxc)] : 0.0;
+  const double tl = (r0ok && c0ok) ? tap(minr, minc) : 0.0;
+  const double tr = (r0ok && c1ok) ? tap(minr, maxc) : 0.0;
+  const double bl = (r1ok && c0ok) ? tap(maxr, minc) : 0.0;
+  const double br = (r1ok && c1ok) ? tap(maxr, maxc) : 0.0;
   const double omc = f64sub(1.0, dc), omr = f64sub(1.0, dr);
   const double top = f64add(f64mul(omc, tl), f64mul(dc, tr));
   const double bot = f64add(f64mul(omc, bl), f64mul(dc, br));

@@ -40,7 +40,7 @@ struct Smem {
   float audio[2][kTileSamples];         // 42,880 B  double-buffered reflect-padded audio span
   float2 tw[kNfft];                     //  3,200 B
   float hann[kNfft];                    //  1,600 B
-  float wts[kMaxPacked];                //  4,096 B
+  __align__(16) float wts[kMaxPacked];  //  4,096 B  zero-padded to quads
   int2 bounds[kMaxMels];                //  1,024 B
   int woff[kMaxMels];                   //    512 B
   int red[16];
@@ -79,7 +79,7 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int m = 0; m < n_mels; ++m) { pack->woff[m] = acc; acc += pack->bounds[m].y; }
+    for (int m = 0; m < n_mels; ++m) { pack->woff[m] = acc; acc += (pack->bounds[m].y + 3) & ~3; }   // quads
     pack->total = acc;
   }
   __syncthreads();
@@ -87,7 +87,9 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
     for (int m = wid; m < n_mels; m += 32) {
       const int2 bd = pack->bounds[m];
       const int off = pack->woff[m];
-      for (int k = lane; k < bd.y; k += 32) pack->wts[off + k] = fb[(size_t)m * kBins + bd.x + k];
+      const int padded = (bd.y + 3) & ~3;
+      for (int k = lane; k < padded; k += 32)
+        pack->wts[off + k] = (k < bd.y) ? fb[(size_t)m * kBins + bd.x + k] : 0.0f;
     }
   }
 }
@@ -181,8 +183,9 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       const float* prow = P + prow_offset(lane);
       for (int m = wid; m < n_mels; m += kThreads / 32) {
         const int2 bd = sm.bounds[m];
-        const float* w = packed ? (sm.wts + sm.woff[m]) : (fb + (size_t)m * kBins + bd.x);
-        const float v = mel_log10(prow + bd.x, w, bd.y);
+        const float v = packed
+            ? mel_log10_quads(prow + bd.x, reinterpret_cast<const float4*>(sm.wts + sm.woff[m]), (bd.y + 3) >> 2)
+            : mel_log10(prow + bd.x, fb + (size_t)m * kBins + bd.x, bd.y);
         if (live) {
           out[(b * n_mels + m) * n_frames + t] = v;
           vmax = fmaxf(vmax, v);

@@ -171,18 +171,26 @@ AVFE_HD float log10_floor(float acc) {
 }
 
 // log10(max(mel, 1e-10)) for one (frame, filter): dot product over the filter's support.
-// Prow points at the first bin of the support, w at the filter's n packed weights.
-AVFE_HD float mel_log10(const float* Prow, const float* w, int n) {
+// Prow points at the first bin of the support; w holds the filter's weights zero-padded to a
+// multiple of four and 16-byte aligned (n4 = number of quads), so there is no tail loop.  The
+// power rows are long enough (433 floats) for the padded reads.
+AVFE_HD float mel_log10_quads(const float* Prow, const float4* w, int n4) {
   float a0 = 0.0f, a1 = 0.0f;
-  int k = 0;
-  for (; k + 4 <= n; k += 4) {
-    a0 = fmaf(w[k], Prow[k], a0);
-    a1 = fmaf(w[k + 1], Prow[k + 1], a1);
-    a0 = fmaf(w[k + 2], Prow[k + 2], a0);
-    a1 = fmaf(w[k + 3], Prow[k + 3], a1);
+  for (int q = 0; q < n4; ++q) {
+    const float4 c = w[q];
+    a0 = fmaf(c.x, Prow[4 * q], a0);
+    a1 = fmaf(c.y, Prow[4 * q + 1], a1);
+    a0 = fmaf(c.z, Prow[4 * q + 2], a0);
+    a1 = fmaf(c.w, Prow[4 * q + 3], a1);
   }
-  for (; k < n; ++k) a0 = fmaf(w[k], Prow[k], a0);
   return log10_floor(a0 + a1);
+}
+
+// generic form (weights anywhere, any length) for filterbanks too dense to be packed
+AVFE_HD float mel_log10(const float* Prow, const float* w, int n) {
+  float acc = 0.0f;
+  for (int k = 0; k < n; ++k) acc = fmaf(w[k], Prow[k], acc);
+  return log10_floor(acc);
 }
 
 // order-preserving float <-> int key for atomicMax

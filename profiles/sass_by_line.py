@@ -33,26 +33,40 @@ def ncu_rows(report, kernel_sub, index=0):
     return sel[index]
 
 
-def sass_lines(lib, kernel_sub):
+def sass_lines(lib, kernel_sub, want_len=None):
+    """Per-instruction (file, line) of the kernel; with several matching .text sections (template
+    instantiations) the one whose length equals the ncu row count is used."""
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
+    sections = []
+    for cubin in sorted(glob.glob(os.path.join(tmp, "*.cubin"))):
         txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
         if kernel_sub not in txt:
             continue
-        res, cur_line, active = [], None, False
+        cur_line, cur = None, None
         for ln in txt.splitlines():
-            if ln.startswith("\t.text.") or ln.startswith(".text."):
-                active = kernel_sub in ln
+            m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+            if m:
+                cur = [] if kernel_sub in m.group(1) else None
+                if cur is not None:
+                    sections.append(cur)
+                continue
+            if cur is None:
+                continue
             m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
             if m:
                 cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
                 continue
-            if active and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
-                res.append((cur_line, ln.split("*/", 1)[1].strip().rstrip(";")))
-        if res:
-            return res
-    raise SystemExit("kernel not found in " + lib)
+            if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
+                cur.append((cur_line, ln.split("*/", 1)[1].strip().rstrip(";")))
+    sections = [s for s in sections if s]
+    if not sections:
+        raise SystemExit("kernel not found in " + lib)
+    if want_len is not None:
+        for s in sections:
+            if len(s) == want_len:
+                return s
+    return sections[0]
 
 
 def main():
@@ -60,8 +74,8 @@ def main():
     index = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     blk = ncu_rows(report, ksub, index)
     ix = {h: i for i, h in enumerate(blk["hdr"])}
-    sass = sass_lines(lib, ksub)
     rows = blk["rows"]
+    sass = sass_lines(lib, ksub, len(rows))
     print(f"# {blk['name'][:100]}\n# ncu rows {len(rows)}  nvdisasm instrs {len(sass)}")
     n = min(len(rows), len(sass))
     per = collections.defaultdict(lambda: [0, 0, collections.Counter()])

@@ -48,8 +48,14 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
     for (int k = 0; k < kBins; ++k)
       if (fb[m * kBins + k] != 0.0f) { lo = lo < k ? lo : k; hi = k + 1; }
     if (lo >= hi) { lo = 0; hi = 0; }
-    for (int f = 0; f < kTileFrames; ++f)
-      out[m * kTileFrames + f] = mel_log10(P + prow_offset(f) + lo, fb + m * kBins + lo, hi - lo);
+    {
+      // same packed form the kernel uses: weights zero-padded to quads
+      const int n4 = (hi - lo + 3) >> 2;
+      alignas(16) float wq[208] = {0};
+      for (int k = lo; k < hi; ++k) wq[k - lo] = fb[m * kBins + k];
+      for (int f = 0; f < kTileFrames; ++f)
+        out[m * kTileFrames + f] = mel_log10_quads(P + prow_offset(f) + lo, reinterpret_cast<const float4*>(wq), n4);
+    }
   }
 }
 
@@ -77,13 +83,13 @@ void hc_warp_window(const uint8_t* gray, int H, int W, const double* inv6, int r
                     int w, uint8_t* out) {
   double lut[256];
   for (int k = 0; k < 256; ++k) lut[k] = f64div((double)k, 255.0);
-  auto tap = [&](int r, int c) -> uint32_t { return gray[(size_t)r * W + c]; };
+  auto tap = [&](int r, int c) -> double { return lut[gray[(size_t)r * W + c]]; };
   for (int pr = 0; pr < h; ++pr)
     for (int pc = 0; pc < w; ++pc) {
       const double tfr = (double)(r0 + pr), tfc = (double)(c0 + pc);
       const double sc = f64add(f64add(f64mul(inv6[0], tfc), f64mul(inv6[1], tfr)), inv6[2]);
       const double sr = f64add(f64add(f64mul(inv6[3], tfc), f64mul(inv6[4], tfr)), inv6[5]);
-      out[pr * w + pc] = bilinear_u8(sr, sc, H, W, lut, tap);
+      out[pr * w + pc] = bilinear_u8(sr, sc, H, W, tap);
     }
 }
 
