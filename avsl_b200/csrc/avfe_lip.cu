@@ -74,12 +74,65 @@ lm_fill_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
 }
 
 // ------------------------------------------------------------------ V3+V4(fit)+V6+V7
-// per-frame record written to the workspace and consumed by the warp items
+// per-frame record written to the workspace by tform_kernel and consumed by the compute warps
 struct FrameXform {
-  double inv[6];   // rows 0,1 of tform.inverse.params
-  int32_t r0, c0;  // cut_patch origin in the std frame (or -1,-1)
-  int32_t pad[2];
+  double inv[6];     // rows 0,1 of tform.inverse.params
+  int32_t r0, c0;    // cut_patch origin in the std frame (or -1,-1)
+  uint32_t box_lo;   // source footprint: r0 | c0 << 13 | interior << 26 | staged << 27
+  uint32_t box_hi;   //                   rows | pitch << 13
 };
+
+constexpr int kTilePx = 9216;   // staged footprint capacity (e.g. 96 x 96 source pixels)
+constexpr int kMaxRoi = 128;
+
+// Source footprint of one ROI window, frame-clipped and aligned for cp.async staging.
+struct Footprint {
+  int r0, c0, rows, pitch;   // staged box; rows == 0: nothing staged
+  bool interior;             // every tap of every output pixel lies inside the frame and the box
+  bool staged;               // the box goes through shared memory (else taps come from global)
+};
+
+__device__ __forceinline__ Footprint unpack_footprint(const FrameXform& x) {
+  Footprint fp;
+  fp.r0 = (int)(x.box_lo & 0x1fffu);
+  fp.c0 = (int)((x.box_lo >> 13) & 0x1fffu);
+  fp.interior = ((x.box_lo >> 26) & 1u) != 0;
+  fp.staged = ((x.box_lo >> 27) & 1u) != 0;
+  fp.rows = (int)(x.box_hi & 0x1fffu);
+  fp.pitch = (int)((x.box_hi >> 13) & 0x1fffu);
+  return fp;
+}
+
+// align = pixel alignment of the box's first column and pitch (16 or 4; 0 = do not stage)
+__device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, int H, int W, int align) {
+  x.box_lo = 0u; x.box_hi = 0u;
+  if (x.r0 < 0 || align == 0 || H > 8191 || W > 8191) return;
+  // an affine map takes its extrema at the window corners
+  double rmin = 1e300, rmax = -1e300, cmin = 1e300, cmax = -1e300;
+  for (int k = 0; k < 4; ++k) {
+    const double tr = (double)(x.r0 + lo + ((k & 1) ? span - 1 : 0));
+    const double tc = (double)(x.c0 + lo + ((k & 2) ? span - 1 : 0));
+    const double sc = x.inv[0] * tc + x.inv[1] * tr + x.inv[2];
+    const double sr = x.inv[3] * tc + x.inv[4] * tr + x.inv[5];
+    rmin = fmin(rmin, sr); rmax = fmax(rmax, sr);
+    cmin = fmin(cmin, sc); cmax = fmax(cmax, sc);
+  }
+  const bool finite = (rmin == rmin) && (cmin == cmin) && fabs(rmin) < 1e9 && fabs(rmax) < 1e9 &&
+                      fabs(cmin) < 1e9 && fabs(cmax) < 1e9;
+  if (!finite) return;
+  // one pixel of slack each side (covers the rounding of the hoisted evaluation)
+  const double fr0 = floor(rmin) - 1.0, fr1 = ceil(rmax) + 1.0;
+  const double fc0 = floor(cmin) - 1.0, fc1 = ceil(cmax) + 1.0;
+  const bool interior = fr0 >= 0.0 && fc0 >= 0.0 && fr1 <= (double)(H - 1) && fc1 <= (double)(W - 1);
+  const int r0 = (int)fmax(fr0, 0.0), c0 = ((int)fmax(fc0, 0.0)) & ~(align - 1);
+  const int rows = (int)fmin(fr1, (double)(H - 1)) - r0 + 1;
+  const int cols = (int)fmin(fc1, (double)(W - 1)) - c0 + 1;
+  if (rows <= 0 || cols <= 0) return;                       // window entirely off-frame
+  const int pitch = min((cols + align - 1) & ~(align - 1), W - c0);   // W % align == 0
+  if (rows * pitch > kTilePx) return;                       // too large: taps from global memory
+  x.box_lo = (uint32_t)r0 | ((uint32_t)c0 << 13) | (interior ? (1u << 26) : 0u) | (1u << 27);
+  x.box_hi = (uint32_t)rows | ((uint32_t)pitch << 13);
+}
 
 constexpr int kTformWarps = 4;
 
@@ -87,9 +140,9 @@ __global__ void __launch_bounds__(kTformWarps * 32)
 tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
              const int64_t* __restrict__ clip_offsets, int64_t n_clips, int64_t N,
              const double* __restrict__ mean_face, const double* __restrict__ tforms_in,
-             int std_size, int roi, int window, FrameXform* __restrict__ xf,
-             int32_t* __restrict__ crop_rc, double* __restrict__ tforms_out,
-             unsigned* __restrict__ queue_counter) {
+             int std_size, int roi, int window, int fp_lo, int fp_span, int H, int W, int fp_align,
+             FrameXform* __restrict__ xf, int32_t* __restrict__ crop_rc,
+             double* __restrict__ tforms_out, unsigned* __restrict__ queue_counter) {
   if (queue_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0u;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -156,7 +209,8 @@ tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
   FrameXform o;
 #pragma unroll
   for (int j = 0; j < 6; ++j) o.inv[j] = inv[j];
-  o.r0 = r0; o.c0 = c0; o.pad[0] = 0; o.pad[1] = 0;
+  o.r0 = r0; o.c0 = c0;
+  pack_footprint(o, fp_lo, fp_span, H, W, fp_align);
   xf[f] = o;
   if (crop_rc != nullptr) { crop_rc[2 * f] = r0; crop_rc[2 * f + 1] = c0; }
   if (tforms_out != nullptr) {
@@ -412,9 +466,17 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
 
   unsigned* counter = static_cast<unsigned*>(workspace);
   FrameXform* xf = reinterpret_cast<FrameXform*>(static_cast<char*>(workspace) + 256);
+  // footprint staging: 16-byte cp.async when frame rows keep that alignment, else 4-byte, else none
+  const int C = channels;
+  const uintptr_t fbase = reinterpret_cast<uintptr_t>(frames);
+  int fp_align = 0;
+  if (W % 16 == 0 && (fbase & 15u) == 0) fp_align = 16;
+  else if (W % 4 == 0 && (fbase & 3u) == 0) fp_align = 4;
+  (void)C;
+  const int fp_lo = lip_u8 ? 0 : (roi - crop) / 2, fp_span = lip_u8 ? roi : crop;
   tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(
       landmarks, lm_valid, clip_offsets, n_clips, N, mean_face, tforms_in, std_size, roi, window,
-      xf, crop_rc, tforms, counter);
+      fp_lo, fp_span, H, W, fp_align, xf, crop_rc, tforms, counter);
   count_launch();
 
   const int64_t npx = (int64_t)H * W;
@@ -422,7 +484,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
   // the gray conversion rides along in the fused launch when the pixel stream is 16-byte
   // aligned; otherwise (or when no ROI is wanted) the flat streaming kernel does it
   const bool fuse_gray = want_roi && gray_out != nullptr && aligned16(frames) && aligned16(gray_out) &&
-                         N * npx >= 512;
+                         N * npx >= 1024;
   if (gray_out != nullptr && !fuse_gray) {
     int rc = launch_gray(frames, N * npx, gray_out, s);
     if (rc != AVFE_OK) return rc;
@@ -434,21 +496,22 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
     j.gray_out = fuse_gray ? gray_out : nullptr;
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
     j.ngroups = (N * npx) / 512;
+    j.stage_align = fp_align;
     if (fuse_gray) {
       const int smem = (int)sizeof(FusedSmem);
       if (cudaFuncSetAttribute(lip_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
         cudaGetLastError();
         return AVFE_ERR_CUDA;
       }
-      lip_fused_kernel<true><<<2 * kNumSMs, 2 * kGroupThreads, smem, s>>>(j);   // 2 resident CTAs per SM
+      lip_fused_kernel<true><<<kNumSMs, kComputeThreads + kStreamThreads, smem, s>>>(j);   // one CTA per SM
     } else {
-      const int smem = (int)offsetof(FusedSmem, slab);
+      const int smem = (int)offsetof(FusedSmem, ring);
       if (cudaFuncSetAttribute(lip_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
         cudaGetLastError();
         return AVFE_ERR_CUDA;
       }
       const int64_t ctas = N < 2 * kNumSMs ? N : 2 * kNumSMs;   // 2 resident CTAs per SM
-      lip_fused_kernel<false><<<(unsigned)ctas, kGroupThreads, smem, s>>>(j);
+      lip_fused_kernel<false><<<(unsigned)ctas, kComputeThreads, smem, s>>>(j);
     }
     count_launch();
   }

@@ -1,10 +1,13 @@
 // lip_fused_kernel: the gray conversion and the ROI warp of a batch in ONE persistent launch,
-// warp-specialised so that both kinds of work are resident on every SM all the time:
+// one 1024-thread CTA per SM, warp-specialised so that both kinds of work are resident on
+// every SM all the time:
 //
-//   stream warps   (8 per CTA) BGR->gray over the flat pixel stream, statically strided, six
-//                  128-bit loads in flight per lane; HBM-bound, integer dp2a
-//   compute warps  (8 per CTA) one frame's ROI per work-queue item: the source footprint of the
-//                  NEXT item is fetched with cp.async while the current one is blended (gray
+//   stream warps   (16) BGR->gray over the flat pixel stream in 1024-px chunks, statically
+//                  strided; each warp owns a 3-stage cp.async ring (3 KB per stage), so 6 KB per
+//                  warp (96 KB per SM) are in flight WHILE a chunk is being converted;
+//                  HBM-bound, integer dp2a
+//   compute warps  (16) one frame's ROI per work-queue item: the source footprint of the NEXT
+//                  item is fetched with 16-byte cp.async while the current one is blended (gray
 //                  computed from the BGR footprint, so there is no dependency on the stream
 //                  warps), float64 bilinear blend in skimage's operation order, u8 ROI +
 //                  normalised f32 centre crop; FP64-pipe / issue-bound
@@ -15,10 +18,12 @@
 
 namespace avfe {
 
-constexpr int kGroupThreads = 256;
-constexpr int kGroupWarps = kGroupThreads / 32;
-constexpr int kTilePx = 9216;               // staged footprint capacity (e.g. 96 x 96 source px)
-constexpr int kMaxRoi = 128;
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kStreamWarps = 16;
+constexpr int kStreamThreads = kStreamWarps * 32;
+constexpr int kRingStages = 3;
+constexpr int kChunkVec = 192;              // one stream chunk = 2 groups = 1024 px = 192 uint4 in
 
 struct LipJob {
   const uint8_t* frames;   // [N,H,W,channels]
@@ -32,6 +37,7 @@ struct LipJob {
   float* lip_f32;          // nullable
   unsigned* counter;       // work queue of the compute group (zeroed by tform_kernel)
   int64_t ngroups;         // full 512-px groups in the flat pixel stream
+  int stage_align;         // cp.async width for footprints (16 or 4); 0 = footprints not staged
 };
 
 struct FusedSmem {
@@ -40,25 +46,30 @@ struct FusedSmem {
   float lutn[256];                    // ((k/255) - mean) / std in float32
   unsigned item[2];
   unsigned pad[2];
-  uint32_t raw[2][kTilePx * 3 / 4];   // cp.async landing zone: footprint bytes as fetched
+  uint4 raw[2][kTilePx * 3 / 16];     // cp.async landing zone: footprint bytes as in the frame
   uint16_t tile[kTilePx];             // gray footprint, stored as 8*k (byte offset into lut255)
-  uint4 slab[kGroupWarps][2][96];     // stream group: two 512-px groups per warp
+  uint4 ring[kStreamWarps][kRingStages][kChunkVec];   // stream group (absent when not streaming)
 };
 
-__device__ __forceinline__ void group_barrier(int id) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kGroupThreads) : "memory");
+__device__ __forceinline__ void compute_barrier() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kComputeThreads) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- gray, dp2a form
 // 2*Y = 2*(3735 B + 19235 G + 9798 R) + 32768, so that Y = byte 2 of the accumulator: two dp2a
 // per pixel (16-bit coefficients against the byte pair where the pixel's bytes sit) and no
-// byte extraction.  K(a, b) packs the doubled coefficients of (lower byte, upper byte).
+// byte extraction.  K2(a, b) packs the doubled coefficients of (lower byte, upper byte).
 #define AVFE_K2(a, b) ((uint32_t)(2 * (a)) | ((uint32_t)(2 * (b)) << 16))
 __device__ __forceinline__ uint32_t gray_acc(uint32_t w, uint32_t wn, int o) {
   switch (o) {                       // o = byte offset of the pixel inside w (compile-time)
@@ -93,108 +104,75 @@ __device__ __forceinline__ void stream_group_run(const LipJob& j, FusedSmem& sm,
   const int lane = tid & 31, wid = tid >> 5;
   const uint4* src = reinterpret_cast<const uint4*>(j.frames);
   uint4* dst = reinterpret_cast<uint4*>(j.gray_out);
-  uint4* s0 = sm.slab[wid][0];
-  uint4* s1 = sm.slab[wid][1];
-  const int64_t stride = (int64_t)gridDim.x * kGroupWarps;
-  int64_t g = (int64_t)blockIdx.x * kGroupWarps + wid;
-  // two groups (1024 px, 3 KB) per iteration: six independent 128-bit loads per lane, staged
-  // through the warp's slab so that every lane then owns 48 contiguous bytes (16 px)
-  for (; g + stride < j.ngroups; g += 2 * stride) {
-    const uint4* a = src + g * 96;
-    const uint4* b = src + (g + stride) * 96;
-    const uint4 a0 = ldg_stream(a + lane), a1 = ldg_stream(a + lane + 32), a2 = ldg_stream(a + lane + 64);
-    const uint4 b0 = ldg_stream(b + lane), b1 = ldg_stream(b + lane + 32), b2 = ldg_stream(b + lane + 64);
-    s0[lane] = a0; s0[lane + 32] = a1; s0[lane + 64] = a2;
-    s1[lane] = b0; s1[lane + 32] = b1; s1[lane + 64] = b2;
+  uint4(*ring)[kChunkVec] = sm.ring[wid];
+  const int64_t nchunks = j.ngroups / 2;                       // 2 groups (1024 px) per chunk
+  const int64_t stride = (int64_t)gridDim.x * kStreamWarps;
+  const int64_t first = (int64_t)blockIdx.x * kStreamWarps + wid;
+  auto issue = [&](int64_t c, int stage) {
+    if (c < nchunks) {
+      const uint4* p = src + c * kChunkVec;
+#pragma unroll
+      for (int i = 0; i < kChunkVec / 32; ++i) cp_async16(&ring[stage][lane + 32 * i], p + lane + 32 * i);
+    }
+    cp_async_commit_group();
+  };
+  issue(first, 0);
+  issue(first + stride, 1);
+  int stage = 0;
+  for (int64_t c = first; c < nchunks; c += stride) {
+    int nxt = stage + 2; if (nxt >= kRingStages) nxt -= kRingStages;
+    issue(c + 2 * stride, nxt);                                // keeps two chunks in flight
+    cp_async_wait_group<2>();                                  // chunk c has landed (this lane's part)
     __syncwarp();
-    const uint4 p0 = s0[3 * lane], p1 = s0[3 * lane + 1], p2 = s0[3 * lane + 2];
-    const uint4 q0 = s1[3 * lane], q1 = s1[3 * lane + 1], q2 = s1[3 * lane + 2];
-    __syncwarp();
-    stg_stream(dst + g * 32 + lane, gray16_dp2a(p0, p1, p2));
-    stg_stream(dst + (g + stride) * 32 + lane, gray16_dp2a(q0, q1, q2));
+    const uint4* s = ring[stage];
+    // lane owns 48 contiguous bytes (16 px) of each of the chunk's two groups
+    const uint4 p0 = s[3 * lane], p1 = s[3 * lane + 1], p2 = s[3 * lane + 2];
+    const uint4 q0 = s[96 + 3 * lane], q1 = s[96 + 3 * lane + 1], q2 = s[96 + 3 * lane + 2];
+    __syncwarp();                                              // slot may be refilled from now on
+    stg_stream(dst + c * 64 + lane, gray16_dp2a(p0, p1, p2));
+    stg_stream(dst + c * 64 + 32 + lane, gray16_dp2a(q0, q1, q2));
+    if (++stage == kRingStages) stage = 0;
   }
-  if (g < j.ngroups) {
-    const uint4* a = src + g * 96;
-    const uint4 a0 = ldg_stream(a + lane), a1 = ldg_stream(a + lane + 32), a2 = ldg_stream(a + lane + 64);
-    s0[lane] = a0; s0[lane + 32] = a1; s0[lane + 64] = a2;
-    __syncwarp();
-    const uint4 p0 = s0[3 * lane], p1 = s0[3 * lane + 1], p2 = s0[3 * lane + 2];
-    stg_stream(dst + g * 32 + lane, gray16_dp2a(p0, p1, p2));
-  }
-  // pixels past the last full group (whole batch, not per frame)
+  cp_async_wait_group<0>();
+  // pixels past the last full chunk (whole batch, not per frame)
   const int64_t npx = j.N * (int64_t)j.H * j.W;
-  for (int64_t i = j.ngroups * 512 + (int64_t)blockIdx.x * kGroupThreads + tid; i < npx;
-       i += (int64_t)gridDim.x * kGroupThreads)
+  for (int64_t i = nchunks * 1024 + (int64_t)blockIdx.x * kStreamThreads + tid; i < npx;
+       i += (int64_t)gridDim.x * kStreamThreads)
     j.gray_out[i] = (uint8_t)gray_from_bgr(j.frames[3 * i], j.frames[3 * i + 1], j.frames[3 * i + 2]);
 }
 
 // ---------------------------------------------------------------- compute group
-// Source footprint of one ROI window, frame-clipped and 4-pixel aligned.
-struct Footprint {
-  int r0, c0, rows, pitch;   // staged box (pitch % 4 == 0); rows == 0: nothing staged
-  bool interior;             // every tap of every output pixel lies inside the frame
-  bool staged;               // the box is in shared memory (else taps come from global memory)
-};
-
-__device__ __forceinline__ Footprint footprint_of(const FrameXform& x, int lo, int span, int H, int W,
-                                                  bool can_stage) {
-  Footprint fp{0, 0, 0, 0, false, false};
-  if (x.r0 < 0) return fp;
-  // an affine map takes its extrema at the window corners
-  double rmin = 1e300, rmax = -1e300, cmin = 1e300, cmax = -1e300;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double tr = (double)(x.r0 + lo + ((k & 1) ? span - 1 : 0));
-    const double tc = (double)(x.c0 + lo + ((k & 2) ? span - 1 : 0));
-    const double sc = x.inv[0] * tc + x.inv[1] * tr + x.inv[2];
-    const double sr = x.inv[3] * tc + x.inv[4] * tr + x.inv[5];
-    rmin = fmin(rmin, sr); rmax = fmax(rmax, sr);
-    cmin = fmin(cmin, sc); cmax = fmax(cmax, sc);
-  }
-  const bool finite = (rmin == rmin) && (cmin == cmin) && fabs(rmin) < 1e9 && fabs(rmax) < 1e9 &&
-                      fabs(cmin) < 1e9 && fabs(cmax) < 1e9;
-  if (!finite) return fp;
-  // one pixel of slack each side (covers the rounding of the hoisted evaluation)
-  const double fr0 = floor(rmin) - 1.0, fr1 = ceil(rmax) + 1.0;
-  const double fc0 = floor(cmin) - 1.0, fc1 = ceil(cmax) + 1.0;
-  fp.interior = fr0 >= 0.0 && fc0 >= 0.0 && fr1 <= (double)(H - 1) && fc1 <= (double)(W - 1);
-  const int r0 = (int)fmax(fr0, 0.0), c0 = ((int)fmax(fc0, 0.0)) & ~3;
-  const int rows = (int)fmin(fr1, (double)(H - 1)) - r0 + 1;
-  const int cols = (int)fmin(fc1, (double)(W - 1)) - c0 + 1;
-  if (rows <= 0 || cols <= 0) { fp.interior = false; return fp; }   // window entirely off-frame
-  const int pitch = min((cols + 3) & ~3, W - c0);                    // W % 4 == 0 when can_stage
-  fp.r0 = r0; fp.c0 = c0; fp.rows = rows; fp.pitch = pitch;
-  fp.staged = can_stage && (rows * pitch <= kTilePx);
-  if (!fp.staged) fp.interior = false;
-  return fp;
-}
-
-// issue the cp.async copies of one footprint into raw[buf] (bytes exactly as in the frame)
+// issue the cp.async copies of one footprint into raw (bytes exactly as in the frame)
 __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, const Footprint& fp,
-                                                   uint32_t* raw, int tid) {
+                                                   uint4* raw, int tid) {
   if (fp.staged) {
     const int C = j.channels;
-    const int wpr = fp.pitch * C / 4;                    // words per footprint row
-    const int total = fp.rows * wpr;
-    const unsigned magic = (0xFFFFFFFFu / (unsigned)wpr) + 1u;   // exact idx / wpr (idx < 2^16)
-    const uint8_t* base = j.frames + (f * (int64_t)j.H * j.W + (int64_t)fp.r0 * j.W + fp.c0) * C;
     const int64_t row_bytes = (int64_t)j.W * C;
-    for (int idx = tid; idx < total; idx += kGroupThreads) {
-      const int r = (int)__umulhi((unsigned)idx, magic), w = idx - r * wpr;
-      cp_async4(raw + idx, base + r * row_bytes + 4 * w);
+    const uint8_t* base = j.frames + (f * (int64_t)j.H * j.W + (int64_t)fp.r0 * j.W + fp.c0) * C;
+    const int lane = tid & 31, wid = tid >> 5;
+    if (j.stage_align == 16) {
+      const int vpr = fp.pitch * C / 16;                 // 16-byte chunks per footprint row
+      for (int r = wid; r < fp.rows; r += kComputeWarps)
+        for (int v = lane; v < vpr; v += 32) cp_async16(raw + r * vpr + v, base + r * row_bytes + 16 * v);
+    } else {
+      const int wpr = fp.pitch * C / 4;
+      uint32_t* raw32 = reinterpret_cast<uint32_t*>(raw);
+      for (int r = wid; r < fp.rows; r += kComputeWarps)
+        for (int w = lane; w < wpr; w += 32) cp_async4(raw32 + r * wpr + w, base + r * row_bytes + 4 * w);
     }
   }
   cp_async_commit_group();
 }
 
 // raw footprint bytes -> tile (8 * gray), four pixels per step
-__device__ __forceinline__ void convert_footprint(const LipJob& j, const Footprint& fp, const uint32_t* raw,
+__device__ __forceinline__ void convert_footprint(const LipJob& j, const Footprint& fp, const uint4* raw4,
                                                   uint16_t* tile, int tid) {
   if (!fp.staged) return;
+  const uint32_t* raw = reinterpret_cast<const uint32_t*>(raw4);
   const int quads = fp.rows * fp.pitch / 4;
   uint2* t2 = reinterpret_cast<uint2*>(tile);
   if (j.channels == 3) {
-    for (int q = tid; q < quads; q += kGroupThreads) {
+    for (int q = tid; q < quads; q += kComputeThreads) {
       uint32_t a[4];
       gray_acc4(raw[3 * q], raw[3 * q + 1], raw[3 * q + 2], a);
       // Y = byte 2 of a[k]; store 8*Y as u16: (a >> 13) & 0x7f8
@@ -202,7 +180,7 @@ __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footpri
                          ((a[2] >> 13) & 0x7f8u) | (((a[3] >> 13) & 0x7f8u) << 16));
     }
   } else {
-    for (int q = tid; q < quads; q += kGroupThreads) {
+    for (int q = tid; q < quads; q += kComputeThreads) {
       const uint32_t w = raw[q];
       t2[q] = make_uint2(((w & 0xffu) << 3) | (((w >> 8) & 0xffu) << 19),
                          (((w >> 16) & 0xffu) << 3) | (((w >> 24) & 0xffu) << 19));
@@ -245,7 +223,7 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
   float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
   const int npix = span * span;
   if (x.r0 < 0) {                                      // clip without any detection: zero ROI
-    for (int idx = tid; idx < npix; idx += kGroupThreads) {
+    for (int idx = tid; idx < npix; idx += kComputeThreads) {
       const int pr = lo + idx / span, pc = lo + idx % span;
       if (out_u8) out_u8[pr * j.roi + pc] = 0;
       const int cr = pr - off, cc = pc - off;
@@ -265,7 +243,7 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
   };
   const double m2 = x.inv[2], m5 = x.inv[5];
 #pragma unroll 2
-  for (int idx = tid; idx < npix; idx += kGroupThreads) {
+  for (int idx = tid; idx < npix; idx += kComputeThreads) {
     const int r = idx / span, c = idx - r * span;        // constant divisor when SPAN != 0
     const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
     const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
@@ -286,24 +264,21 @@ __device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm
   const int off = (j.roi - j.crop) / 2;
   const int lo = j.lip_u8 ? 0 : off;
   const int span = j.lip_u8 ? j.roi : j.crop;
-  // 4-byte cp.async staging needs 4-aligned footprint rows
-  const bool can_stage = (j.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(j.frames) & 3u) == 0);
   if (tid == 0) { sm.item[0] = atomicAdd(j.counter, 1u); sm.item[1] = atomicAdd(j.counter, 1u); }
-  group_barrier(2);
+  compute_barrier();
   unsigned t = sm.item[0], tn = sm.item[1];
-  group_barrier(2);
-  FrameXform x;
-  Footprint fp{0, 0, 0, 0, false, false};
+  compute_barrier();
   int cur = 0;
   if (t < total) {
-    x = j.xf[t];
-    fp = footprint_of(x, lo, span, j.H, j.W, can_stage);     // every thread computes the same box
-    prefetch_footprint(j, (int64_t)t, fp, sm.raw[0], tid);
+    const FrameXform x0 = j.xf[t];
+    prefetch_footprint(j, (int64_t)t, unpack_footprint(x0), sm.raw[0], tid);
   }
   while (t < total) {
     if (tid == 0) sm.item[cur] = atomicAdd(j.counter, 1u);   // item after next, read at the loop end
-    cp_async_wait_all();
-    group_barrier(2);                                        // raw[cur] complete for all threads
+    const FrameXform x = j.xf[t];                            // 64 B, same for every thread
+    const Footprint fp = unpack_footprint(x);
+    cp_async_wait_group<0>();
+    compute_barrier();                                       // raw[cur] complete for all threads
     convert_footprint(j, fp, sm.raw[cur], sm.tile, tid);
     if (x.r0 >= 0) {
       // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
@@ -318,42 +293,37 @@ __device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm
         sm.rowy[tid - 128] = f64mul(x.inv[4], tr);
       }
     }
-    group_barrier(2);                                        // tile + tables ready
+    compute_barrier();                                       // tile + tables ready
     if (tn < total) {                                        // next footprint streams in meanwhile
       const FrameXform xn = j.xf[tn];
-      const Footprint fpn = footprint_of(xn, lo, span, j.H, j.W, can_stage);
-      prefetch_footprint(j, (int64_t)tn, fpn, sm.raw[cur ^ 1], tid);
+      prefetch_footprint(j, (int64_t)tn, unpack_footprint(xn), sm.raw[cur ^ 1], tid);
     }
     if (j.lip_u8 != nullptr && j.roi == 96) blend_item<96>(j, (int64_t)t, x, fp, sm, tid);
     else if (j.lip_u8 == nullptr && j.crop == 88) blend_item<88>(j, (int64_t)t, x, fp, sm, tid);
     else blend_item<0>(j, (int64_t)t, x, fp, sm, tid);
-    group_barrier(2);              // item done: tile and tables are free, sm.item[cur] is visible
+    compute_barrier();             // item done: tile and tables are free, sm.item[cur] is visible
     const unsigned tnn = sm.item[cur];
     t = tn; tn = tnn;
     cur ^= 1;
-    if (t < total) {               // recomputed rather than kept live across the blend (registers)
-      x = j.xf[t];
-      fp = footprint_of(x, lo, span, j.H, j.W, can_stage);
-    }
   }
-  cp_async_wait_all();
+  cp_async_wait_group<0>();
 }
 
-// STREAM: CTA = 8 compute warps + 8 stream warps; otherwise 8 compute warps only.
+// STREAM: CTA = 16 compute warps + 16 stream warps, one CTA per SM; otherwise 16 compute warps.
 template <bool STREAM>
-__global__ void __launch_bounds__(STREAM ? 2 * kGroupThreads : kGroupThreads, 2)
+__global__ void __launch_bounds__(STREAM ? kComputeThreads + kStreamThreads : kComputeThreads, STREAM ? 1 : 2)
 lip_fused_kernel(const LipJob j) {
   extern __shared__ __align__(16) unsigned char fused_smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
   const int tid = threadIdx.x;
-  if (tid < kGroupThreads) {
-    for (int k = tid; k < 256; k += kGroupThreads) {
+  if (tid < kComputeThreads) {
+    for (int k = tid; k < 256; k += kComputeThreads) {
       sm.lut255[k] = f64div((double)k, 255.0);
       sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
     }
     compute_group_run(j, sm, tid);     // starts with a group barrier: LUTs are visible
   } else if (STREAM) {
-    stream_group_run(j, sm, tid - kGroupThreads);
+    stream_group_run(j, sm, tid - kComputeThreads);
   }
 }
 
