@@ -510,7 +510,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
         cudaGetLastError();
         return AVFE_ERR_CUDA;
       }
-      const int64_t ctas = N < 2 * kNumSMs ? N : 2 * kNumSMs;   // 2 resident CTAs per SM
+      const int64_t ctas = N < kNumSMs ? N : kNumSMs;           // one 768-thread CTA per SM
       lip_fused_kernel<false><<<(unsigned)ctas, kComputeThreads, smem, s>>>(j);
     }
     count_launch();

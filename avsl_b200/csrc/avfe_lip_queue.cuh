@@ -18,11 +18,11 @@
 
 namespace avfe {
 
-constexpr int kComputeWarps = 16;
+constexpr int kComputeWarps = 24;           // the blend is issue-bound: it gets most of the warps
 constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kStreamWarps = 16;
+constexpr int kStreamWarps = 8;
 constexpr int kStreamThreads = kStreamWarps * 32;
-constexpr int kRingStages = 3;
+constexpr int kRingStages = 4;              // 3 chunks (9 KB) per stream warp in flight
 constexpr int kChunkVec = 192;              // one stream chunk = 2 groups = 1024 px = 192 uint4 in
 
 struct LipJob {
@@ -46,6 +46,7 @@ struct FusedSmem {
   float lutn[256];                    // ((k/255) - mean) / std in float32
   unsigned item[2];
   unsigned pad[2];
+  FrameXform xf[2];                   // descriptors of the current / next item (one fetch per item)
   uint4 raw[2][kTilePx * 3 / 16];     // cp.async landing zone: footprint bytes as in the frame
   uint16_t tile[kTilePx];             // gray footprint, stored as 8*k (byte offset into lut255)
   uint4 ring[kStreamWarps][kRingStages][kChunkVec];   // stream group (absent when not streaming)
@@ -118,11 +119,12 @@ __device__ __forceinline__ void stream_group_run(const LipJob& j, FusedSmem& sm,
   };
   issue(first, 0);
   issue(first + stride, 1);
+  issue(first + 2 * stride, 2);
   int stage = 0;
   for (int64_t c = first; c < nchunks; c += stride) {
-    int nxt = stage + 2; if (nxt >= kRingStages) nxt -= kRingStages;
-    issue(c + 2 * stride, nxt);                                // keeps two chunks in flight
-    cp_async_wait_group<2>();                                  // chunk c has landed (this lane's part)
+    int nxt = stage + 3; if (nxt >= kRingStages) nxt -= kRingStages;
+    issue(c + 3 * stride, nxt);                                // keeps three chunks in flight
+    cp_async_wait_group<3>();                                  // chunk c has landed (this lane's part)
     __syncwarp();
     const uint4* s = ring[stage];
     // lane owns 48 contiguous bytes (16 px) of each of the chunk's two groups
@@ -242,19 +244,44 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
     return sm.lut255[bgr ? gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2)) : (uint32_t)__ldg(p)];
   };
   const double m2 = x.inv[2], m5 = x.inv[5];
-#pragma unroll 2
-  for (int idx = tid; idx < npix; idx += kComputeThreads) {
-    const int r = idx / span, c = idx - r * span;        // constant divisor when SPAN != 0
-    const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
-    const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
-    const uint32_t v = fp.interior ? bilinear_interior(sr, sc, sm.tile, pitch, br0, bc0, sm.lut255)
-                                   : (uint32_t)bilinear_u8(sr, sc, H, W, tap);
+  auto emit = [&](int r, int c, uint32_t v) {
     const int pr = lo + r, pc = lo + c;
     if (out_u8) out_u8[pr * j.roi + pc] = (uint8_t)v;
     if (out_f32) {
       const int cr = pr - off, cc = pc - off;
       if ((unsigned)cr < (unsigned)j.crop && (unsigned)cc < (unsigned)j.crop)
         out_f32[cr * j.crop + cc] = sm.lutn[v];
+    }
+  };
+  if (fp.interior && SPAN != 0) {
+    // common case.  Thread = (column c, row phase): the column products stay in registers, the
+    // row products are warp-wide broadcasts, rows advance by 8 with no index arithmetic, and
+    // the fully unrolled rows give the scheduler independent chains to interleave.
+    constexpr int S = SPAN ? SPAN : 8;                  // (SPAN == 0 never reaches this branch)
+    if (tid < 8 * S) {
+      const int rr = tid / S, c = tid - rr * S;
+      const double cx = sm.colx[c], cy = sm.coly[c];
+#pragma unroll
+      for (int i = 0; i < S / 8; ++i) {
+        const int r = rr + 8 * i;
+        const double sc = f64add(f64add(cx, sm.rowx[r]), m2);
+        const double sr = f64add(f64add(cy, sm.rowy[r]), m5);
+        emit(r, c, bilinear_interior(sr, sc, sm.tile, pitch, br0, bc0, sm.lut255));
+      }
+    }
+  } else if (fp.interior) {
+    for (int idx = tid; idx < npix; idx += kComputeThreads) {
+      const int r = idx / span, c = idx - r * span;
+      const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
+      const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
+      emit(r, c, bilinear_interior(sr, sc, sm.tile, pitch, br0, bc0, sm.lut255));
+    }
+  } else {
+    for (int idx = tid; idx < npix; idx += kComputeThreads) {
+      const int r = idx / span, c = idx - r * span;
+      const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
+      const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
+      emit(r, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
     }
   }
 }
@@ -267,15 +294,19 @@ __device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm
   if (tid == 0) { sm.item[0] = atomicAdd(j.counter, 1u); sm.item[1] = atomicAdd(j.counter, 1u); }
   compute_barrier();
   unsigned t = sm.item[0], tn = sm.item[1];
+  // the 64-byte descriptor of an item is fetched once, by 4 lanes, one item ahead
+  auto fetch_xf = [&](unsigned item, int slot) {
+    if (tid < 4 && item < total)
+      reinterpret_cast<uint4*>(&sm.xf[slot])[tid] = reinterpret_cast<const uint4*>(j.xf + item)[tid];
+  };
+  fetch_xf(t, 0);
+  fetch_xf(tn, 1);
   compute_barrier();
   int cur = 0;
-  if (t < total) {
-    const FrameXform x0 = j.xf[t];
-    prefetch_footprint(j, (int64_t)t, unpack_footprint(x0), sm.raw[0], tid);
-  }
+  if (t < total) prefetch_footprint(j, (int64_t)t, unpack_footprint(sm.xf[0]), sm.raw[0], tid);
   while (t < total) {
     if (tid == 0) sm.item[cur] = atomicAdd(j.counter, 1u);   // item after next, read at the loop end
-    const FrameXform x = j.xf[t];                            // 64 B, same for every thread
+    const FrameXform x = sm.xf[cur];
     const Footprint fp = unpack_footprint(x);
     cp_async_wait_group<0>();
     compute_barrier();                                       // raw[cur] complete for all threads
@@ -294,15 +325,14 @@ __device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm
       }
     }
     compute_barrier();                                       // tile + tables ready
-    if (tn < total) {                                        // next footprint streams in meanwhile
-      const FrameXform xn = j.xf[tn];
-      prefetch_footprint(j, (int64_t)tn, unpack_footprint(xn), sm.raw[cur ^ 1], tid);
-    }
+    if (tn < total)                                          // next footprint streams in meanwhile
+      prefetch_footprint(j, (int64_t)tn, unpack_footprint(sm.xf[cur ^ 1]), sm.raw[cur ^ 1], tid);
     if (j.lip_u8 != nullptr && j.roi == 96) blend_item<96>(j, (int64_t)t, x, fp, sm, tid);
     else if (j.lip_u8 == nullptr && j.crop == 88) blend_item<88>(j, (int64_t)t, x, fp, sm, tid);
     else blend_item<0>(j, (int64_t)t, x, fp, sm, tid);
-    compute_barrier();             // item done: tile and tables are free, sm.item[cur] is visible
+    compute_barrier();             // item done: tile, tables and sm.xf[cur] are free, sm.item[cur] visible
     const unsigned tnn = sm.item[cur];
+    fetch_xf(tnn, cur);            // descriptor of the item after next (read two barriers from now)
     t = tn; tn = tnn;
     cur ^= 1;
   }
@@ -311,7 +341,7 @@ __device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm
 
 // STREAM: CTA = 16 compute warps + 16 stream warps, one CTA per SM; otherwise 16 compute warps.
 template <bool STREAM>
-__global__ void __launch_bounds__(STREAM ? kComputeThreads + kStreamThreads : kComputeThreads, STREAM ? 1 : 2)
+__global__ void __launch_bounds__(STREAM ? kComputeThreads + kStreamThreads : kComputeThreads, 1)
 lip_fused_kernel(const LipJob j) {
   extern __shared__ __align__(16) unsigned char fused_smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);

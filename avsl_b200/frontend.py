@@ -190,6 +190,21 @@ def shard(n_items: int, rank: int, world_size: int) -> np.ndarray:
     return np.arange(rank, n_items, world_size)
 
 
+def aggregate_rank_stats(elapsed_ms: float, audio_seconds: float, alg_bytes: float, launches: float = 0.0,
+                         device="cpu"):
+    """Job-level numbers from per-rank ones: time = MAX over ranks, work = SUM over ranks.
+    This reporting reduction is the only collective in the package and is off the hot path.
+    Returns (elapsed_ms_max, audio_seconds_total, alg_bytes_total, launches_total)."""
+    import torch.distributed as dist
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    w = torch.tensor([audio_seconds, alg_bytes, launches], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    a, b, c = (float(v) for v in w.tolist())
+    return float(t.item()), a, b, c
+
+
 def algorithmic_bytes(n_utts: int, n_frames: int, H: int = 224, W: int = 224, n_mels: int = 80,
                       audio_len: int = N_SAMPLES, crop: int = IMAGE_CROP_SIZE) -> int:
     """per utterance 4*L + 4*n_mels*(L/160); per frame H*W*3 + 68*2*8 + H*W +
