@@ -413,6 +413,20 @@ cut_patch_kernel(const uint8_t* __restrict__ img, int H, int W, const double* __
 // ====================================================================== C ABI
 using namespace avfe;
 
+template <bool STREAM, int SPAN>
+static int launch_fused(const LipJob& j, cudaStream_t s) {
+  const int smem = STREAM ? (int)sizeof(FusedSmem) : (int)offsetof(FusedSmem, ring);
+  if (cudaFuncSetAttribute(lip_fused_kernel<STREAM, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           smem) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  const int threads = STREAM ? 1024 : Roles<SPAN>::kHandoverThreads;
+  const int64_t ctas = j.N < kNumSMs ? j.N : kNumSMs;                  // one persistent CTA per SM
+  lip_fused_kernel<STREAM, SPAN><<<(unsigned)(STREAM ? kNumSMs : ctas), threads, smem, s>>>(j);
+  return AVFE_OK;
+}
+
 extern "C" int avfe_bgr2gray_u8(const uint8_t* bgr, int64_t N, int H, int W, uint8_t* gray,
                                 avfe_stream_t stream) {
   if (N < 0 || H < 0 || W < 0) return AVFE_ERR_INVALID_ARG;
@@ -497,22 +511,20 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
     j.ngroups = (N * npx) / 512;
     j.stage_align = fp_align;
+    // window side known at compile time for the two standard configurations
+    const int span_sel = (lip_u8 != nullptr && roi == 96) ? 96
+                       : (lip_u8 == nullptr && lip_f32 != nullptr && crop == 88) ? 88 : 0;
+    int rc = AVFE_OK;
     if (fuse_gray) {
-      const int smem = (int)sizeof(FusedSmem);
-      if (cudaFuncSetAttribute(lip_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-        cudaGetLastError();
-        return AVFE_ERR_CUDA;
-      }
-      lip_fused_kernel<true><<<kNumSMs, kComputeThreads + kStreamThreads, smem, s>>>(j);   // one CTA per SM
+      if (span_sel == 96) rc = launch_fused<true, 96>(j, s);
+      else if (span_sel == 88) rc = launch_fused<true, 88>(j, s);
+      else rc = launch_fused<true, 0>(j, s);
     } else {
-      const int smem = (int)offsetof(FusedSmem, ring);
-      if (cudaFuncSetAttribute(lip_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-        cudaGetLastError();
-        return AVFE_ERR_CUDA;
-      }
-      const int64_t ctas = N < kNumSMs ? N : kNumSMs;           // one 768-thread CTA per SM
-      lip_fused_kernel<false><<<(unsigned)ctas, kComputeThreads, smem, s>>>(j);
+      if (span_sel == 96) rc = launch_fused<false, 96>(j, s);
+      else if (span_sel == 88) rc = launch_fused<false, 88>(j, s);
+      else rc = launch_fused<false, 0>(j, s);
     }
+    if (rc != AVFE_OK) return rc;
     count_launch();
   }
   return check_launch();

@@ -1,29 +1,40 @@
 // lip_fused_kernel: the gray conversion and the ROI warp of a batch in ONE persistent launch,
-// one 1024-thread CTA per SM, warp-specialised so that both kinds of work are resident on
-// every SM all the time:
+// one CTA per SM, three warp roles that never wait on a CTA-wide barrier:
 //
-//   stream warps   (16) BGR->gray over the flat pixel stream in 1024-px chunks, statically
-//                  strided; each warp owns a 3-stage cp.async ring (3 KB per stage), so 6 KB per
-//                  warp (96 KB per SM) are in flight WHILE a chunk is being converted;
-//                  HBM-bound, integer dp2a
-//   compute warps  (16) one frame's ROI per work-queue item: the source footprint of the NEXT
-//                  item is fetched with 16-byte cp.async while the current one is blended (gray
-//                  computed from the BGR footprint, so there is no dependency on the stream
-//                  warps), float64 bilinear blend in skimage's operation order, u8 ROI +
-//                  normalised f32 centre crop; FP64-pipe / issue-bound
+//   blend warps    (22 for an 88-px window, 24 for 96) float64 bilinear blend of one frame's ROI
+//                  in skimage's operation order, u8 ROI + normalised f32 centre crop; thread =
+//                  (column, row phase), rows fully unrolled; issue / FP64-pipe bound
+//   producer warps (2) pull frames from an atomic work queue and prepare them one item ahead in
+//                  a double-buffered slot: source footprint fetched with 16-byte cp.async (next
+//                  item's copy in flight while this one is converted), BGR->gray in shared memory
+//                  (so there is no dependency on the stream warps), coordinate tables, descriptor
+//   stream warps   (the remaining 8 / 6) BGR->gray over the flat pixel stream in 1024-px chunks,
+//                  statically strided, each warp with its own 4-stage cp.async ring (9 KB in
+//                  flight per warp while a chunk is converted); HBM-bound, integer dp2a
 //
-// The two groups never synchronise with each other (compute warps use named barrier 2); the
-// FP64 work hides under the memory time of the stream warps.  Included by avfe_lip.cu only.
+// Producer and blend warps hand slots over with named barriers (FULL/EMPTY per slot); the stream
+// warps synchronise with nobody.  The FP64 work hides under the stream's memory time.
+// Included by avfe_lip.cu only.
 #pragma once
 
 namespace avfe {
 
-constexpr int kComputeWarps = 24;           // the blend is issue-bound: it gets most of the warps
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kStreamWarps = 8;
-constexpr int kStreamThreads = kStreamWarps * 32;
+constexpr int kProducerWarps = 2;
+constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kRingStages = 4;              // 3 chunks (9 KB) per stream warp in flight
 constexpr int kChunkVec = 192;              // one stream chunk = 2 groups = 1024 px = 192 uint4 in
+constexpr int kMaxStreamWarps = 8;
+constexpr unsigned kItemDone = 0xffffffffu;
+
+// warp roles for a compile-time window side (0 = run-time side, laid out like 88)
+template <int SPAN>
+struct Roles {
+  static constexpr int kSide = SPAN ? SPAN : 88;
+  static constexpr int kBlendWarps = 8 * kSide / 32;                  // 22 or 24
+  static constexpr int kBlendThreads = kBlendWarps * 32;
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kProducerWarps;   // 8 or 6
+  static constexpr int kHandoverThreads = kBlendThreads + kProducerThreads;
+};
 
 struct LipJob {
   const uint8_t* frames;   // [N,H,W,channels]
@@ -35,25 +46,35 @@ struct LipJob {
   uint8_t* gray_out;       // stream group output (nullptr: no stream group)
   uint8_t* lip_u8;         // nullable
   float* lip_f32;          // nullable
-  unsigned* counter;       // work queue of the compute group (zeroed by tform_kernel)
+  unsigned* counter;       // work queue of the producers (zeroed by tform_kernel)
   int64_t ngroups;         // full 512-px groups in the flat pixel stream
   int stage_align;         // cp.async width for footprints (16 or 4); 0 = footprints not staged
 };
 
-struct FusedSmem {
-  double lut255[256];                 // k / 255.0 (img_as_float)
-  double colx[kMaxRoi], coly[kMaxRoi], rowx[kMaxRoi], rowy[kMaxRoi];
-  float lutn[256];                    // ((k/255) - mean) / std in float32
-  unsigned item[2];
-  unsigned pad[2];
-  FrameXform xf[2];                   // descriptors of the current / next item (one fetch per item)
-  uint4 raw[2][kTilePx * 3 / 16];     // cp.async landing zone: footprint bytes as in the frame
+struct ItemSlot {
+  FrameXform x;                       // descriptor of the frame (matrix rows, crop origin, footprint)
+  unsigned item;                      // frame index, or kItemDone
+  unsigned pad[3];
+  double colx[kMaxRoi], coly[kMaxRoi], rowx[kMaxRoi], rowy[kMaxRoi];   // hoisted M0*c, M3*c, M1*r, M4*r
   uint16_t tile[kTilePx];             // gray footprint, stored as 8*k (byte offset into lut255)
-  uint4 ring[kStreamWarps][kRingStages][kChunkVec];   // stream group (absent when not streaming)
 };
 
-__device__ __forceinline__ void compute_barrier() {
-  asm volatile("bar.sync 2, %0;" ::"n"(kComputeThreads) : "memory");
+struct FusedSmem {
+  double lut255[256];                 // k / 255.0 (img_as_float)
+  float lutn[256];                    // ((k/255) - mean) / std in float32
+  unsigned next_item[2];              // producer-internal hand-off of queue indices
+  unsigned pad[2];
+  ItemSlot slot[2];
+  uint4 raw[2][kTilePx * 3 / 16];     // cp.async landing zone: footprint bytes as in the frame
+  uint4 ring[kMaxStreamWarps][kRingStages][kChunkVec];   // stream warps (absent when not streaming)
+};
+
+// named barriers: 1 = producers only, 2/3 = FULL[slot], 4/5 = EMPTY[slot]
+__device__ __forceinline__ void bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -100,15 +121,15 @@ __device__ __forceinline__ uint4 gray16_dp2a(const uint4& q0, const uint4& q1, c
   return r;
 }
 
-// ---------------------------------------------------------------- stream group
-__device__ __forceinline__ void stream_group_run(const LipJob& j, FusedSmem& sm, int tid) {
+// ---------------------------------------------------------------- stream warps
+__device__ __forceinline__ void stream_run(const LipJob& j, FusedSmem& sm, int tid, int n_warps) {
   const int lane = tid & 31, wid = tid >> 5;
   const uint4* src = reinterpret_cast<const uint4*>(j.frames);
   uint4* dst = reinterpret_cast<uint4*>(j.gray_out);
   uint4(*ring)[kChunkVec] = sm.ring[wid];
   const int64_t nchunks = j.ngroups / 2;                       // 2 groups (1024 px) per chunk
-  const int64_t stride = (int64_t)gridDim.x * kStreamWarps;
-  const int64_t first = (int64_t)blockIdx.x * kStreamWarps + wid;
+  const int64_t stride = (int64_t)gridDim.x * n_warps;
+  const int64_t first = (int64_t)blockIdx.x * n_warps + wid;
   auto issue = [&](int64_t c, int stage) {
     if (c < nchunks) {
       const uint4* p = src + c * kChunkVec;
@@ -138,12 +159,13 @@ __device__ __forceinline__ void stream_group_run(const LipJob& j, FusedSmem& sm,
   cp_async_wait_group<0>();
   // pixels past the last full chunk (whole batch, not per frame)
   const int64_t npx = j.N * (int64_t)j.H * j.W;
-  for (int64_t i = nchunks * 1024 + (int64_t)blockIdx.x * kStreamThreads + tid; i < npx;
-       i += (int64_t)gridDim.x * kStreamThreads)
+  const int nthreads = n_warps * 32;
+  for (int64_t i = nchunks * 1024 + (int64_t)blockIdx.x * nthreads + tid; i < npx;
+       i += (int64_t)gridDim.x * nthreads)
     j.gray_out[i] = (uint8_t)gray_from_bgr(j.frames[3 * i], j.frames[3 * i + 1], j.frames[3 * i + 2]);
 }
 
-// ---------------------------------------------------------------- compute group
+// ---------------------------------------------------------------- producer warps
 // issue the cp.async copies of one footprint into raw (bytes exactly as in the frame)
 __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, const Footprint& fp,
                                                    uint4* raw, int tid) {
@@ -154,12 +176,12 @@ __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, c
     const int lane = tid & 31, wid = tid >> 5;
     if (j.stage_align == 16) {
       const int vpr = fp.pitch * C / 16;                 // 16-byte chunks per footprint row
-      for (int r = wid; r < fp.rows; r += kComputeWarps)
+      for (int r = wid; r < fp.rows; r += kProducerWarps)
         for (int v = lane; v < vpr; v += 32) cp_async16(raw + r * vpr + v, base + r * row_bytes + 16 * v);
     } else {
       const int wpr = fp.pitch * C / 4;
       uint32_t* raw32 = reinterpret_cast<uint32_t*>(raw);
-      for (int r = wid; r < fp.rows; r += kComputeWarps)
+      for (int r = wid; r < fp.rows; r += kProducerWarps)
         for (int w = lane; w < wpr; w += 32) cp_async4(raw32 + r * wpr + w, base + r * row_bytes + 4 * w);
     }
   }
@@ -174,7 +196,8 @@ __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footpri
   const int quads = fp.rows * fp.pitch / 4;
   uint2* t2 = reinterpret_cast<uint2*>(tile);
   if (j.channels == 3) {
-    for (int q = tid; q < quads; q += kComputeThreads) {
+#pragma unroll 4
+    for (int q = tid; q < quads; q += kProducerThreads) {
       uint32_t a[4];
       gray_acc4(raw[3 * q], raw[3 * q + 1], raw[3 * q + 2], a);
       // Y = byte 2 of a[k]; store 8*Y as u16: (a >> 13) & 0x7f8
@@ -182,7 +205,8 @@ __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footpri
                          ((a[2] >> 13) & 0x7f8u) | (((a[3] >> 13) & 0x7f8u) << 16));
     }
   } else {
-    for (int q = tid; q < quads; q += kComputeThreads) {
+#pragma unroll 4
+    for (int q = tid; q < quads; q += kProducerThreads) {
       const uint32_t w = raw[q];
       t2[q] = make_uint2(((w & 0xffu) << 3) | (((w >> 8) & 0xffu) << 19),
                          (((w >> 16) & 0xffu) << 3) | (((w >> 24) & 0xffu) << 19));
@@ -190,6 +214,68 @@ __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footpri
   }
 }
 
+template <int SPAN>
+__device__ __forceinline__ void producer_run(const LipJob& j, FusedSmem& sm, int tid) {
+  using R = Roles<SPAN>;
+  const unsigned total = (unsigned)j.N;
+  const int off = (j.roi - j.crop) / 2;
+  const int lo = j.lip_u8 ? 0 : off;
+  const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
+  // queue indices are drawn by thread 0 and handed to the other 63 producer threads through
+  // sm.next_item + the producers-only barrier
+  if (tid == 0) { sm.next_item[0] = atomicAdd(j.counter, 1u); sm.next_item[1] = atomicAdd(j.counter, 1u); }
+  bar_sync(1, kProducerThreads);
+  unsigned t = sm.next_item[0], tn = sm.next_item[1];
+  bar_sync(1, kProducerThreads);
+  FrameXform x, xn;
+  if (t < total) {
+    x = j.xf[t];
+    prefetch_footprint(j, (int64_t)t, unpack_footprint(x), sm.raw[0], tid);
+  } else {
+    cp_async_commit_group();
+  }
+  for (unsigned k = 0;; ++k) {
+    const int s = (int)(k & 1u);
+    ItemSlot& slot = sm.slot[s];
+    if (t >= total) {                                   // queue drained: tell the blend warps
+      if (k >= 2) bar_sync(4 + s, R::kHandoverThreads);
+      if (tid == 0) slot.item = kItemDone;
+      bar_arrive(2 + s, R::kHandoverThreads);
+      break;
+    }
+    // next item's footprint goes in flight before this one is converted
+    if (tn < total) {
+      xn = j.xf[tn];
+      prefetch_footprint(j, (int64_t)tn, unpack_footprint(xn), sm.raw[s ^ 1], tid);
+    } else {
+      cp_async_commit_group();
+    }
+    if (tid == 0) sm.next_item[s] = atomicAdd(j.counter, 1u);   // item after next
+    cp_async_wait_group<1>();                           // this item's copies have landed (own part)
+    bar_sync(1, kProducerThreads);                      // ... for both producer warps; next_item visible
+    const unsigned tnn = sm.next_item[s];
+    if (k >= 2) bar_sync(4 + s, R::kHandoverThreads);   // blend warps released this slot (item k-2)
+    const Footprint fp = unpack_footprint(x);
+    convert_footprint(j, fp, sm.raw[s], slot.tile, tid);
+    if (x.r0 >= 0) {
+      // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
+      // the same two roundings per product as skimage's _transform_affine
+      for (int i = tid; i < span; i += kProducerThreads) {
+        const double tc = (double)(x.c0 + lo + i), tr = (double)(x.r0 + lo + i);
+        slot.colx[i] = f64mul(x.inv[0], tc);
+        slot.coly[i] = f64mul(x.inv[3], tc);
+        slot.rowx[i] = f64mul(x.inv[1], tr);
+        slot.rowy[i] = f64mul(x.inv[4], tr);
+      }
+    }
+    if (tid == 0) { slot.x = x; slot.item = t; }
+    bar_arrive(2 + s, R::kHandoverThreads);             // slot FULL
+    t = tn; tn = tnn; x = xn;
+  }
+  cp_async_wait_group<0>();
+}
+
+// ---------------------------------------------------------------- blend warps
 __device__ __forceinline__ double lut_at(const double* lut, uint32_t off8) {
   return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(lut) + off8);
 }
@@ -212,11 +298,12 @@ __device__ __forceinline__ uint32_t bilinear_interior(double r, double c, const 
   return (uint32_t)(int)f64mul(v, 255.0);
 }
 
-// SPAN = side of the evaluated window (96 when the u8 ROI is wanted, 88 for the centre crop
-// only, 0 = run-time value).  The footprint has already been converted into sm.tile.
 template <int SPAN>
-__device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const FrameXform& x,
-                                           const Footprint& fp, FusedSmem& sm, int tid) {
+__device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const ItemSlot& slot,
+                                           const FusedSmem& sm, int tid) {
+  using R = Roles<SPAN>;
+  const FrameXform& x = slot.x;
+  const Footprint fp = unpack_footprint(x);
   const int off = (j.roi - j.crop) / 2;
   const int lo = j.lip_u8 ? 0 : off;
   const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
@@ -224,27 +311,11 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
   uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
   float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
   const int npix = span * span;
-  if (x.r0 < 0) {                                      // clip without any detection: zero ROI
-    for (int idx = tid; idx < npix; idx += kComputeThreads) {
-      const int pr = lo + idx / span, pc = lo + idx % span;
-      if (out_u8) out_u8[pr * j.roi + pc] = 0;
-      const int cr = pr - off, cc = pc - off;
-      if (out_f32 && cr >= 0 && cr < j.crop && cc >= 0 && cc < j.crop) out_f32[cr * j.crop + cc] = sm.lutn[0];
-    }
-    return;
-  }
-  const bool bgr = (j.channels == 3);
-  const uint8_t* img = j.frames + f * (int64_t)H * W * (bgr ? 3 : 1);
-  const int br0 = fp.r0, bc0 = fp.c0, brows = fp.staged ? fp.rows : 0, pitch = fp.pitch;
-  auto tap = [&](int r, int c) -> double {
-    const int rr = r - br0, cc = c - bc0;
-    if ((unsigned)rr < (unsigned)brows && (unsigned)cc < (unsigned)pitch)
-      return lut_at(sm.lut255, sm.tile[rr * pitch + cc]);
-    const uint8_t* p = img + ((int64_t)r * W + c) * (bgr ? 3 : 1);       // not staged: global tap
-    return sm.lut255[bgr ? gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2)) : (uint32_t)__ldg(p)];
-  };
-  const double m2 = x.inv[2], m5 = x.inv[5];
   auto emit = [&](int r, int c, uint32_t v) {
+    if (SPAN == 88) {                                   // centre crop only: window == f32 output
+      out_f32[r * 88 + c] = sm.lutn[v];
+      return;
+    }
     const int pr = lo + r, pc = lo + c;
     if (out_u8) out_u8[pr * j.roi + pc] = (uint8_t)v;
     if (out_f32) {
@@ -253,107 +324,81 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
         out_f32[cr * j.crop + cc] = sm.lutn[v];
     }
   };
+  if (x.r0 < 0) {                                       // clip without any detection: zero ROI
+    for (int idx = tid; idx < npix; idx += R::kBlendThreads) emit(idx / span, idx % span, 0u);
+    return;
+  }
+  const double m2 = x.inv[2], m5 = x.inv[5];
+  const int br0 = fp.r0, bc0 = fp.c0, pitch = fp.pitch;
   if (fp.interior && SPAN != 0) {
     // common case.  Thread = (column c, row phase): the column products stay in registers, the
     // row products are warp-wide broadcasts, rows advance by 8 with no index arithmetic, and
     // the fully unrolled rows give the scheduler independent chains to interleave.
-    constexpr int S = SPAN ? SPAN : 8;                  // (SPAN == 0 never reaches this branch)
-    if (tid < 8 * S) {
-      const int rr = tid / S, c = tid - rr * S;
-      const double cx = sm.colx[c], cy = sm.coly[c];
+    constexpr int S = R::kSide;
+    const int rr = tid / S, c = tid - rr * S;           // every blend thread owns one column phase
+    const double cx = slot.colx[c], cy = slot.coly[c];
 #pragma unroll
-      for (int i = 0; i < S / 8; ++i) {
-        const int r = rr + 8 * i;
-        const double sc = f64add(f64add(cx, sm.rowx[r]), m2);
-        const double sr = f64add(f64add(cy, sm.rowy[r]), m5);
-        emit(r, c, bilinear_interior(sr, sc, sm.tile, pitch, br0, bc0, sm.lut255));
-      }
+    for (int i = 0; i < S / 8; ++i) {
+      const int r = rr + 8 * i;
+      const double sc = f64add(f64add(cx, slot.rowx[r]), m2);
+      const double sr = f64add(f64add(cy, slot.rowy[r]), m5);
+      emit(r, c, bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, sm.lut255));
     }
-  } else if (fp.interior) {
-    for (int idx = tid; idx < npix; idx += kComputeThreads) {
-      const int r = idx / span, c = idx - r * span;
-      const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
-      const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
-      emit(r, c, bilinear_interior(sr, sc, sm.tile, pitch, br0, bc0, sm.lut255));
-    }
-  } else {
-    for (int idx = tid; idx < npix; idx += kComputeThreads) {
-      const int r = idx / span, c = idx - r * span;
-      const double sc = f64add(f64add(sm.colx[c], sm.rowx[r]), m2);
-      const double sr = f64add(f64add(sm.coly[c], sm.rowy[r]), m5);
-      emit(r, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
-    }
+    return;
   }
-}
-
-__device__ __forceinline__ void compute_group_run(const LipJob& j, FusedSmem& sm, int tid) {
-  const unsigned total = (unsigned)j.N;
-  const int off = (j.roi - j.crop) / 2;
-  const int lo = j.lip_u8 ? 0 : off;
-  const int span = j.lip_u8 ? j.roi : j.crop;
-  if (tid == 0) { sm.item[0] = atomicAdd(j.counter, 1u); sm.item[1] = atomicAdd(j.counter, 1u); }
-  compute_barrier();
-  unsigned t = sm.item[0], tn = sm.item[1];
-  // the 64-byte descriptor of an item is fetched once, by 4 lanes, one item ahead
-  auto fetch_xf = [&](unsigned item, int slot) {
-    if (tid < 4 && item < total)
-      reinterpret_cast<uint4*>(&sm.xf[slot])[tid] = reinterpret_cast<const uint4*>(j.xf + item)[tid];
+  const bool bgr = (j.channels == 3);
+  const uint8_t* img = j.frames + f * (int64_t)H * W * (bgr ? 3 : 1);
+  const int brows = fp.staged ? fp.rows : 0;
+  auto tap = [&](int r, int c) -> double {
+    const int rr = r - br0, cc = c - bc0;
+    if ((unsigned)rr < (unsigned)brows && (unsigned)cc < (unsigned)pitch)
+      return lut_at(sm.lut255, slot.tile[rr * pitch + cc]);
+    const uint8_t* p = img + ((int64_t)r * W + c) * (bgr ? 3 : 1);       // not staged: global tap
+    return sm.lut255[bgr ? gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2)) : (uint32_t)__ldg(p)];
   };
-  fetch_xf(t, 0);
-  fetch_xf(tn, 1);
-  compute_barrier();
-  int cur = 0;
-  if (t < total) prefetch_footprint(j, (int64_t)t, unpack_footprint(sm.xf[0]), sm.raw[0], tid);
-  while (t < total) {
-    if (tid == 0) sm.item[cur] = atomicAdd(j.counter, 1u);   // item after next, read at the loop end
-    const FrameXform x = sm.xf[cur];
-    const Footprint fp = unpack_footprint(x);
-    cp_async_wait_group<0>();
-    compute_barrier();                                       // raw[cur] complete for all threads
-    convert_footprint(j, fp, sm.raw[cur], sm.tile, tid);
-    if (x.r0 >= 0) {
-      // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
-      // the same two roundings per product as skimage's _transform_affine
-      if (tid < span) {
-        const double tc = (double)(x.c0 + lo + tid);
-        sm.colx[tid] = f64mul(x.inv[0], tc);
-        sm.coly[tid] = f64mul(x.inv[3], tc);
-      } else if (tid >= 128 && tid < 128 + span) {
-        const double tr = (double)(x.r0 + lo + tid - 128);
-        sm.rowx[tid - 128] = f64mul(x.inv[1], tr);
-        sm.rowy[tid - 128] = f64mul(x.inv[4], tr);
-      }
-    }
-    compute_barrier();                                       // tile + tables ready
-    if (tn < total)                                          // next footprint streams in meanwhile
-      prefetch_footprint(j, (int64_t)tn, unpack_footprint(sm.xf[cur ^ 1]), sm.raw[cur ^ 1], tid);
-    if (j.lip_u8 != nullptr && j.roi == 96) blend_item<96>(j, (int64_t)t, x, fp, sm, tid);
-    else if (j.lip_u8 == nullptr && j.crop == 88) blend_item<88>(j, (int64_t)t, x, fp, sm, tid);
-    else blend_item<0>(j, (int64_t)t, x, fp, sm, tid);
-    compute_barrier();             // item done: tile, tables and sm.xf[cur] are free, sm.item[cur] visible
-    const unsigned tnn = sm.item[cur];
-    fetch_xf(tnn, cur);            // descriptor of the item after next (read two barriers from now)
-    t = tn; tn = tnn;
-    cur ^= 1;
+  for (int idx = tid; idx < npix; idx += R::kBlendThreads) {
+    const int r = idx / span, c = idx - r * span;
+    const double sc = f64add(f64add(slot.colx[c], slot.rowx[r]), m2);
+    const double sr = f64add(f64add(slot.coly[c], slot.rowy[r]), m5);
+    const uint32_t v = fp.interior ? bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, sm.lut255)
+                                   : (uint32_t)bilinear_u8(sr, sc, H, W, tap);
+    emit(r, c, v);
   }
-  cp_async_wait_group<0>();
 }
 
-// STREAM: CTA = 16 compute warps + 16 stream warps, one CTA per SM; otherwise 16 compute warps.
-template <bool STREAM>
-__global__ void __launch_bounds__(STREAM ? kComputeThreads + kStreamThreads : kComputeThreads, 1)
+template <int SPAN>
+__device__ __forceinline__ void blend_run(const LipJob& j, FusedSmem& sm, int tid) {
+  using R = Roles<SPAN>;
+  for (int k = tid; k < 256; k += R::kBlendThreads) {
+    sm.lut255[k] = f64div((double)k, 255.0);
+    sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
+  }
+  // the first FULL barrier also publishes the LUTs among the blend warps
+  for (unsigned k = 0;; ++k) {
+    const int s = (int)(k & 1u);
+    bar_sync(2 + s, R::kHandoverThreads);               // wait for slot FULL
+    const ItemSlot& slot = sm.slot[s];
+    const unsigned item = slot.item;
+    if (item == kItemDone) break;
+    blend_item<SPAN>(j, (int64_t)item, slot, sm, tid);
+    bar_arrive(4 + s, R::kHandoverThreads);             // slot EMPTY
+  }
+}
+
+// STREAM: blend + producer + stream warps (1024 threads); otherwise blend + producer warps only.
+template <bool STREAM, int SPAN>
+__global__ void __launch_bounds__(STREAM ? 1024 : Roles<SPAN>::kHandoverThreads, 1)
 lip_fused_kernel(const LipJob j) {
+  using R = Roles<SPAN>;
   extern __shared__ __align__(16) unsigned char fused_smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
   const int tid = threadIdx.x;
-  if (tid < kComputeThreads) {
-    for (int k = tid; k < 256; k += kComputeThreads) {
-      sm.lut255[k] = f64div((double)k, 255.0);
-      sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
-    }
-    compute_group_run(j, sm, tid);     // starts with a group barrier: LUTs are visible
+  if (tid < R::kBlendThreads) {
+    blend_run<SPAN>(j, sm, tid);
+  } else if (tid < R::kHandoverThreads) {
+    producer_run<SPAN>(j, sm, tid - R::kBlendThreads);
   } else if (STREAM) {
-    stream_group_run(j, sm, tid - kComputeThreads);
+    stream_run(j, sm, tid - R::kHandoverThreads, R::kStreamWarps);
   }
 }
 
