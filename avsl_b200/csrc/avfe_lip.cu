@@ -82,7 +82,7 @@ struct FrameXform {
   uint32_t box_hi;   //                   rows | pitch << 13
 };
 
-constexpr int kTilePx = 9216;   // staged footprint capacity (e.g. 96 x 96 source pixels)
+constexpr int kTilePx = 8192;   // staged footprint capacity (e.g. 80 x 96 source pixels + alignment)
 constexpr int kMaxRoi = 128;
 
 // Source footprint of one ROI window, frame-clipped and aligned for cp.async staging.

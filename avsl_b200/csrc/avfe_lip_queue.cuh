@@ -4,10 +4,11 @@
 //   blend warps    (22 for an 88-px window, 24 for 96) float64 bilinear blend of one frame's ROI
 //                  in skimage's operation order, u8 ROI + normalised f32 centre crop; thread =
 //                  (column, row phase), rows fully unrolled; issue / FP64-pipe bound
-//   producer warps (2) pull frames from an atomic work queue and prepare them one item ahead in
-//                  a double-buffered slot: source footprint fetched with 16-byte cp.async (next
-//                  item's copy in flight while this one is converted), BGR->gray in shared memory
-//                  (so there is no dependency on the stream warps), coordinate tables, descriptor
+//   producer warps (2) pull frames from an atomic work queue and stage them one to two items
+//                  ahead in double-buffered slots: frame descriptor + source footprint fetched
+//                  with 16-byte cp.async.  The blend warps turn the raw BGR footprint into gray
+//                  in shared memory themselves (704 threads, two quads each - so there is no
+//                  dependency on the stream warps) and release the slot right after that
 //   stream warps   (the remaining 8 / 6) BGR->gray over the flat pixel stream in 1024-px chunks,
 //                  statically strided, each warp with its own 4-stage cp.async ring (9 KB in
 //                  flight per warp while a chunk is converted); HBM-bound, integer dp2a
@@ -33,7 +34,8 @@ struct Roles {
   static constexpr int kBlendWarps = 8 * kSide / 32;                  // 22 or 24
   static constexpr int kBlendThreads = kBlendWarps * 32;
   static constexpr int kStreamWarps = 32 - kBlendWarps - kProducerWarps;   // 8 or 6
-  static constexpr int kHandoverThreads = kBlendThreads + kProducerThreads;
+  static constexpr int kHandoverThreads = kBlendThreads + kProducerThreads;   // blend + producer threads
+  static constexpr int kSlotThreads = kBlendThreads + 32;   // a slot's barriers: blend warps + its producer warp
 };
 
 struct LipJob {
@@ -51,25 +53,32 @@ struct LipJob {
   int stage_align;         // cp.async width for footprints (16 or 4); 0 = footprints not staged
 };
 
-struct ItemSlot {
-  FrameXform x;                       // descriptor of the frame (matrix rows, crop origin, footprint)
+struct ItemDesc {
+  FrameXform x;                       // matrix rows, crop origin, packed footprint
   unsigned item;                      // frame index, or kItemDone
   unsigned pad[3];
+};
+
+struct BlendBuf {                     // private to the blend warps, double-buffered per item
   double colx[kMaxRoi], coly[kMaxRoi], rowx[kMaxRoi], rowy[kMaxRoi];   // hoisted M0*c, M3*c, M1*r, M4*r
-  uint16_t tile[kTilePx];             // gray footprint, stored as 8*k (byte offset into lut255)
+  uint16_t tile[kTilePx];             // gray footprint, stored as 128*k (byte offset of lut255 row k)
 };
 
 struct FusedSmem {
-  double lut255[256];                 // k / 255.0 (img_as_float)
+  // k / 255.0 (img_as_float), 16 interleaved copies: entry (k, c) at [k*16 + c].  A lane reads
+  // copy (lane & 15), so the 16 lanes of a 64-bit shared-load phase always hit 16 different bank
+  // pairs whatever their k: the tap lookups are bank-conflict free.
+  double lut255[256 * 16];
   float lutn[256];                    // ((k/255) - mean) / std in float32
   unsigned next_item[2];              // producer-internal hand-off of queue indices
   unsigned pad[2];
-  ItemSlot slot[2];
-  uint4 raw[2][kTilePx * 3 / 16];     // cp.async landing zone: footprint bytes as in the frame
+  ItemDesc desc[2];                   // slot s: written by the producers, read by the blend warps
+  BlendBuf buf[2];
+  uint4 raw[2][kTilePx * 3 / 16];     // slot s: cp.async landing zone, footprint bytes as in the frame
   uint4 ring[kMaxStreamWarps][kRingStages][kChunkVec];   // stream warps (absent when not streaming)
 };
 
-// named barriers: 1 = producers only, 2/3 = FULL[slot], 4/5 = EMPTY[slot]
+// named barriers: 1 = producers only, 2/3 = FULL[slot], 4/5 = EMPTY[slot], 6 = blend warps only
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -173,16 +182,24 @@ __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, c
     const int C = j.channels;
     const int64_t row_bytes = (int64_t)j.W * C;
     const uint8_t* base = j.frames + (f * (int64_t)j.H * j.W + (int64_t)fp.r0 * j.W + fp.c0) * C;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int lane = tid & 31;                           // one producer warp copies one footprint
     if (j.stage_align == 16) {
       const int vpr = fp.pitch * C / 16;                 // 16-byte chunks per footprint row
-      for (int r = wid; r < fp.rows; r += kProducerWarps)
-        for (int v = lane; v < vpr; v += 32) cp_async16(raw + r * vpr + v, base + r * row_bytes + 16 * v);
+      const int total = fp.rows * vpr;
+      const unsigned magic = (0xFFFFFFFFu / (unsigned)vpr) + 1u;       // exact idx / vpr (idx < 2^16)
+      for (int idx = lane; idx < total; idx += 32) {
+        const int r = (int)__umulhi((unsigned)idx, magic), v = idx - r * vpr;
+        cp_async16(raw + idx, base + r * row_bytes + 16 * v);
+      }
     } else {
       const int wpr = fp.pitch * C / 4;
+      const int total = fp.rows * wpr;
+      const unsigned magic = (0xFFFFFFFFu / (unsigned)wpr) + 1u;
       uint32_t* raw32 = reinterpret_cast<uint32_t*>(raw);
-      for (int r = wid; r < fp.rows; r += kProducerWarps)
-        for (int w = lane; w < wpr; w += 32) cp_async4(raw32 + r * wpr + w, base + r * row_bytes + 4 * w);
+      for (int idx = lane; idx < total; idx += 32) {
+        const int r = (int)__umulhi((unsigned)idx, magic), w = idx - r * wpr;
+        cp_async4(raw32 + idx, base + r * row_bytes + 4 * w);
+      }
     }
   }
   cp_async_commit_group();
@@ -190,93 +207,60 @@ __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, c
 
 // raw footprint bytes -> tile (8 * gray), four pixels per step
 __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footprint& fp, const uint4* raw4,
-                                                  uint16_t* tile, int tid) {
+                                                  uint16_t* tile, int tid, int nthreads) {
   if (!fp.staged) return;
   const uint32_t* raw = reinterpret_cast<const uint32_t*>(raw4);
   const int quads = fp.rows * fp.pitch / 4;
   uint2* t2 = reinterpret_cast<uint2*>(tile);
   if (j.channels == 3) {
-#pragma unroll 4
-    for (int q = tid; q < quads; q += kProducerThreads) {
+    for (int q = tid; q < quads; q += nthreads) {
       uint32_t a[4];
       gray_acc4(raw[3 * q], raw[3 * q + 1], raw[3 * q + 2], a);
-      // Y = byte 2 of a[k]; store 8*Y as u16: (a >> 13) & 0x7f8
-      t2[q] = make_uint2(((a[0] >> 13) & 0x7f8u) | (((a[1] >> 13) & 0x7f8u) << 16),
-                         ((a[2] >> 13) & 0x7f8u) | (((a[3] >> 13) & 0x7f8u) << 16));
+      // Y = byte 2 of a[k]; store 128*Y as u16: (a >> 9) & 0x7f80
+      t2[q] = make_uint2(((a[0] >> 9) & 0x7f80u) | (((a[1] >> 9) & 0x7f80u) << 16),
+                         ((a[2] >> 9) & 0x7f80u) | (((a[3] >> 9) & 0x7f80u) << 16));
     }
   } else {
-#pragma unroll 4
-    for (int q = tid; q < quads; q += kProducerThreads) {
+    for (int q = tid; q < quads; q += nthreads) {
       const uint32_t w = raw[q];
-      t2[q] = make_uint2(((w & 0xffu) << 3) | (((w >> 8) & 0xffu) << 19),
-                         (((w >> 16) & 0xffu) << 3) | (((w >> 24) & 0xffu) << 19));
+      t2[q] = make_uint2(((w & 0xffu) << 7) | (((w >> 8) & 0xffu) << 23),
+                         (((w >> 16) & 0xffu) << 7) | (((w >> 24) & 0xffu) << 23));
     }
   }
 }
 
+// Each of the two producer warps owns one slot and runs its own chain, independently of the
+// other: draw a frame from the queue, fetch its descriptor, wait until the blend warps have
+// released the slot, copy the footprint, publish.  While the blend warps work on one slot the
+// other warp's copy is in flight.
 template <int SPAN>
 __device__ __forceinline__ void producer_run(const LipJob& j, FusedSmem& sm, int tid) {
   using R = Roles<SPAN>;
   const unsigned total = (unsigned)j.N;
-  const int off = (j.roi - j.crop) / 2;
-  const int lo = j.lip_u8 ? 0 : off;
-  const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
-  // queue indices are drawn by thread 0 and handed to the other 63 producer threads through
-  // sm.next_item + the producers-only barrier
-  if (tid == 0) { sm.next_item[0] = atomicAdd(j.counter, 1u); sm.next_item[1] = atomicAdd(j.counter, 1u); }
-  bar_sync(1, kProducerThreads);
-  unsigned t = sm.next_item[0], tn = sm.next_item[1];
-  bar_sync(1, kProducerThreads);
-  FrameXform x, xn;
-  if (t < total) {
-    x = j.xf[t];
-    prefetch_footprint(j, (int64_t)t, unpack_footprint(x), sm.raw[0], tid);
-  } else {
-    cp_async_commit_group();
-  }
-  for (unsigned k = 0;; ++k) {
-    const int s = (int)(k & 1u);
-    ItemSlot& slot = sm.slot[s];
-    if (t >= total) {                                   // queue drained: tell the blend warps
-      if (k >= 2) bar_sync(4 + s, R::kHandoverThreads);
-      if (tid == 0) slot.item = kItemDone;
-      bar_arrive(2 + s, R::kHandoverThreads);
+  const int lane = tid & 31, s = tid >> 5;              // slot == producer warp index
+  for (unsigned n = 0;; ++n) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(j.counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    FrameXform x;
+    if (t < total) x = j.xf[t];
+    if (n >= 1) bar_sync(4 + s, R::kSlotThreads);       // blend warps are done with this slot's previous item
+    if (t >= total) {
+      if (lane == 0) sm.desc[s].item = kItemDone;
+      __syncwarp();
+      bar_arrive(2 + s, R::kSlotThreads);
       break;
     }
-    // next item's footprint goes in flight before this one is converted
-    if (tn < total) {
-      xn = j.xf[tn];
-      prefetch_footprint(j, (int64_t)tn, unpack_footprint(xn), sm.raw[s ^ 1], tid);
-    } else {
-      cp_async_commit_group();
-    }
-    if (tid == 0) sm.next_item[s] = atomicAdd(j.counter, 1u);   // item after next
-    cp_async_wait_group<1>();                           // this item's copies have landed (own part)
-    bar_sync(1, kProducerThreads);                      // ... for both producer warps; next_item visible
-    const unsigned tnn = sm.next_item[s];
-    if (k >= 2) bar_sync(4 + s, R::kHandoverThreads);   // blend warps released this slot (item k-2)
-    const Footprint fp = unpack_footprint(x);
-    convert_footprint(j, fp, sm.raw[s], slot.tile, tid);
-    if (x.r0 >= 0) {
-      // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
-      // the same two roundings per product as skimage's _transform_affine
-      for (int i = tid; i < span; i += kProducerThreads) {
-        const double tc = (double)(x.c0 + lo + i), tr = (double)(x.r0 + lo + i);
-        slot.colx[i] = f64mul(x.inv[0], tc);
-        slot.coly[i] = f64mul(x.inv[3], tc);
-        slot.rowx[i] = f64mul(x.inv[1], tr);
-        slot.rowy[i] = f64mul(x.inv[4], tr);
-      }
-    }
-    if (tid == 0) { slot.x = x; slot.item = t; }
-    bar_arrive(2 + s, R::kHandoverThreads);             // slot FULL
-    t = tn; tn = tnn; x = xn;
+    prefetch_footprint(j, (int64_t)t, unpack_footprint(x), sm.raw[s], lane);
+    if (lane == 0) { sm.desc[s].x = x; sm.desc[s].item = t; }
+    cp_async_wait_group<0>();
+    __syncwarp();
+    bar_arrive(2 + s, R::kSlotThreads);                 // slot FULL
   }
-  cp_async_wait_group<0>();
 }
 
 // ---------------------------------------------------------------- blend warps
-__device__ __forceinline__ double lut_at(const double* lut, uint32_t off8) {
+__device__ __forceinline__ double lut_at(const double* lut, uint32_t off8) {   // off8 = 128 * k
   return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(lut) + off8);
 }
 
@@ -299,11 +283,11 @@ __device__ __forceinline__ uint32_t bilinear_interior(double r, double c, const 
 }
 
 template <int SPAN>
-__device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const ItemSlot& slot,
+__device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const FrameXform& x,
+                                           const Footprint& fp, const BlendBuf& slot,
                                            const FusedSmem& sm, int tid) {
   using R = Roles<SPAN>;
-  const FrameXform& x = slot.x;
-  const Footprint fp = unpack_footprint(x);
+  const double* lut = sm.lut255 + (tid & 15);           // this lane's copy of the k/255 table
   const int off = (j.roi - j.crop) / 2;
   const int lo = j.lip_u8 ? 0 : off;
   const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
@@ -342,7 +326,7 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Ite
       const int r = rr + 8 * i;
       const double sc = f64add(f64add(cx, slot.rowx[r]), m2);
       const double sr = f64add(f64add(cy, slot.rowy[r]), m5);
-      emit(r, c, bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, sm.lut255));
+      emit(r, c, bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, lut));
     }
     return;
   }
@@ -352,15 +336,15 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Ite
   auto tap = [&](int r, int c) -> double {
     const int rr = r - br0, cc = c - bc0;
     if ((unsigned)rr < (unsigned)brows && (unsigned)cc < (unsigned)pitch)
-      return lut_at(sm.lut255, slot.tile[rr * pitch + cc]);
+      return lut_at(lut, slot.tile[rr * pitch + cc]);
     const uint8_t* p = img + ((int64_t)r * W + c) * (bgr ? 3 : 1);       // not staged: global tap
-    return sm.lut255[bgr ? gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2)) : (uint32_t)__ldg(p)];
+    return lut[16 * (bgr ? gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2)) : (uint32_t)__ldg(p))];
   };
   for (int idx = tid; idx < npix; idx += R::kBlendThreads) {
     const int r = idx / span, c = idx - r * span;
     const double sc = f64add(f64add(slot.colx[c], slot.rowx[r]), m2);
     const double sr = f64add(f64add(slot.coly[c], slot.rowy[r]), m5);
-    const uint32_t v = fp.interior ? bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, sm.lut255)
+    const uint32_t v = fp.interior ? bilinear_interior(sr, sc, slot.tile, pitch, br0, bc0, lut)
                                    : (uint32_t)bilinear_u8(sr, sc, H, W, tap);
     emit(r, c, v);
   }
@@ -370,18 +354,44 @@ template <int SPAN>
 __device__ __forceinline__ void blend_run(const LipJob& j, FusedSmem& sm, int tid) {
   using R = Roles<SPAN>;
   for (int k = tid; k < 256; k += R::kBlendThreads) {
-    sm.lut255[k] = f64div((double)k, 255.0);
+    const double q = f64div((double)k, 255.0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) sm.lut255[k * 16 + c] = q;
     sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.mean), j.stdv);
   }
-  // the first FULL barrier also publishes the LUTs among the blend warps
-  for (unsigned k = 0;; ++k) {
+  const int off = (j.roi - j.crop) / 2;
+  const int lo = j.lip_u8 ? 0 : off;
+  const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
+  bool alive0 = true, alive1 = true;                    // a slot's producer publishes kItemDone once
+  for (unsigned k = 0; alive0 || alive1; ++k) {
     const int s = (int)(k & 1u);
-    bar_sync(2 + s, R::kHandoverThreads);               // wait for slot FULL
-    const ItemSlot& slot = sm.slot[s];
-    const unsigned item = slot.item;
-    if (item == kItemDone) break;
-    blend_item<SPAN>(j, (int64_t)item, slot, sm, tid);
-    bar_arrive(4 + s, R::kHandoverThreads);             // slot EMPTY
+    if (!(s ? alive1 : alive0)) continue;
+    bar_sync(2 + s, R::kSlotThreads);                   // slot FULL: descriptor + raw footprint landed
+    const unsigned item = sm.desc[s].item;
+    if (item == kItemDone) {
+      if (s) alive1 = false; else alive0 = false;
+      continue;
+    }
+    const FrameXform x = sm.desc[s].x;
+    const Footprint fp = unpack_footprint(x);
+    BlendBuf& buf = sm.buf[s];
+    convert_footprint(j, fp, sm.raw[s], buf.tile, tid, R::kBlendThreads);
+    if (x.r0 >= 0) {
+      // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
+      // the same two roundings per product as skimage's _transform_affine
+      if (tid < span) {
+        const double tc = (double)(x.c0 + lo + tid);
+        buf.colx[tid] = f64mul(x.inv[0], tc);
+        buf.coly[tid] = f64mul(x.inv[3], tc);
+      } else if (tid >= 128 && tid < 128 + span) {
+        const double tr = (double)(x.r0 + lo + tid - 128);
+        buf.rowx[tid - 128] = f64mul(x.inv[1], tr);
+        buf.rowy[tid - 128] = f64mul(x.inv[4], tr);
+      }
+    }
+    bar_sync(6, R::kBlendThreads);                      // tile + tables ready; raw/desc no longer read
+    bar_arrive(4 + s, R::kSlotThreads);                 // slot EMPTY: its producer may refill it
+    blend_item<SPAN>(j, (int64_t)item, x, fp, buf, sm, tid);
   }
 }
 
