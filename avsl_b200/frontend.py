@@ -183,6 +183,51 @@ class AVFrontEnd:
         return [lip[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
+class HostPipeline:
+    """Steady-state host-buffer path: ``depth`` front-ends, each with its own stream and device
+    buffers, so that the H2D copy of batch i+1, the kernels of batch i and the D2H copy of batch
+    i-1 overlap (PCIe is full duplex and the copy engines run beside the SMs).  Every batch still
+    pays its full H2D of inputs and D2H of mel + lip; only the waiting is overlapped."""
+
+    def __init__(self, depth: int = 2, **frontend_kwargs):
+        self.fes = [AVFrontEnd(**frontend_kwargs) for _ in range(depth)]
+        dev = self.fes[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.events = [None] * depth
+        self.outs: List[Optional[Dict[str, torch.Tensor]]] = [None] * depth
+        self.device = dev
+
+    def submit(self, i: int, batch: PackedBatch) -> None:
+        """Enqueue batch ``i`` (pinned host tensors) on slot ``i % depth``; returns immediately."""
+        k = i % len(self.fes)
+        if self.events[k] is not None:
+            self.events[k].synchronize()              # slot's previous batch fully drained
+        fe, st = self.fes[k], self.streams[k]
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            dev = batch.to(self.device, non_blocking=True)
+            res = fe.forward_device(dev)
+            if self.outs[k] is None or any(tuple(self.outs[k][n].shape) != tuple(res[n].shape) for n in ("mel", "lip")):
+                self.outs[k] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in ("mel", "lip")}
+            for n in ("mel", "lip"):
+                self.outs[k][n].copy_(res[n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.events[k] = ev
+
+    def result(self, i: int) -> Dict[str, torch.Tensor]:
+        """Host features of batch ``i`` (blocks until its D2H copy has landed); valid until the
+        slot is submitted to again."""
+        k = i % len(self.fes)
+        self.events[k].synchronize()
+        return self.outs[k]
+
+    def drain(self) -> None:
+        for ev in self.events:
+            if ev is not None:
+                ev.synchronize()
+
+
 def shard(n_items: int, rank: int, world_size: int) -> np.ndarray:
     """Indices of the utterances rank ``rank`` of ``world_size`` processes owns."""
     if not (0 <= rank < world_size):

@@ -88,56 +88,74 @@ def host_sample(idx, durs, n):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled DURING the timed region: a thread polls NVML
+    every ~2 ms (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.samples = []          # (sm_mhz, power_w, reasons_mask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, pw, mask))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        if self.h is None:
+            return
+        self._stop.clear()
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def pause(self):
+        """Stop sampling (between timed regions); start() resumes and keeps earlier samples."""
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            self.thread = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 7:
-                continue
-            try:
-                sm.append(float(p[0])); smax.append(float(p[1])); power.append(float(p[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        self.pause()
+        if self.h is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml unavailable"], "samples": 0}
+        sm = [x[0] for x in self.samples]
+        mask = 0
+        for x in self.samples:
+            mask |= x[2]
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "power_w_max": max(x[1] for x in self.samples), "samples": len(sm),
+                "how": "NVML polled every ~2 ms during the timed regions (device-resident steps and e2e steps)"}
 
 
 # ------------------------------------------------------------------------------- reference arm
@@ -285,7 +303,7 @@ def main():
         fe.forward_device(batch_dev, padded_audio=padded, mark=make_mark(events))
     t_end.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.pause()
     launches = _lib.launch_count() - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     stage_ms = {n: 0.0 for n in stage_names}
@@ -353,25 +371,54 @@ def main():
     e2e = None
     if not args.no_e2e:
         host = batch_dev.pin()
-        host_out = None
         e2e_steps = args.steps
+        # (a) strictly serial: H2D -> kernels -> D2H -> host sync, every step
+        host_out = None
         for _ in range(2):
             host_out = fe.forward_host(host, host_out)
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
         t0.record()
         for _ in range(e2e_steps):
             host_out = fe.forward_host(host, host_out)
         t1.record()
         barrier()
-        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        ms_serial = t0.elapsed_time(t1)
+        # (b) steady state: two slots, so batch i+1's H2D overlaps batch i's kernels and D2H.
+        #     Same bytes per step in both directions; results of every step land in pinned memory.
+        pipe = A.HostPipeline(depth=2, n_mels=N_MELS, audio_max_length=AUDIO_LEN, device=dev,
+                              want_gray=True, fused=not args.unfused)
+        for i in range(2):
+            pipe.submit(i, host)
+        pipe.drain()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(e2e_steps):
+            pipe.submit(i, host)
+        pipe.drain()
+        t1.record()
+        barrier()
+        sampler.pause()
+        ms_pipe = t0.elapsed_time(t1)
+        assert torch.equal(pipe.result(e2e_steps - 1)["mel"], host_out["mel"])
+        assert torch.equal(pipe.result(e2e_steps - 1)["lip"], host_out["lip"])
+        ms = torch.tensor([ms_pipe, ms_serial], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_pipe, ms_serial = (float(v) for v in ms.tolist())
         d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("mel", "lip"))
-        e2e = {"value": audio_s_all * e2e_steps / (float(ms.item()) * 1e-3), "unit": "audio-s/s",
+        e2e = {"value": audio_s_all * e2e_steps / (ms_pipe * 1e-3), "unit": "audio-s/s",
                "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(ms.item()) / e2e_steps, "steps": e2e_steps}
+               "ms_per_step": ms_pipe / e2e_steps, "steps": e2e_steps,
+               "api": "avsl_b200.HostPipeline(depth=2).submit(i, pinned PackedBatch) -> result(i): H2D of every input and D2H of mel+lip for every step, two slots in flight",
+               "serial": {"value": audio_s_all * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
+                          "api": "AVFrontEnd.forward_host (H2D -> kernels -> D2H -> sync, one step at a time)"}}
+        del pipe
         del host, host_out
+
+    clocks = sampler.stop()
 
     # ---------------- roofline of the dominant kernel ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -390,8 +437,8 @@ def main():
         stage_ms.pop("gray", None)
     kernel_names = {"logmel": "logmel_prep + logmel_tile_kernel + logmel_finalize (AMI batch: silent tiles take the exact zero-tile shortcut)",
                     "gray": "gray_vec_kernel",
-                    "lip": ("tform_kernel + lip_queue_kernel (gray items + warp items in one work queue)" if fused
-                            else "tform_kernel + lip_queue_kernel (warp items, taps from the gray frames)")}
+                    "lip": ("tform_kernel + lip_fused_kernel<stream,88> (stream warps: BGR->gray; blend warps: ROI warp/crop/normalise)" if fused
+                            else "tform_kernel + lip_fused_kernel<nostream,88> (ROI warp only, taps from the gray frames)")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k])
     stages = {}
     for k in stage_names:
@@ -405,7 +452,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dominant)
+            tj = json.load(open(tpath)).get(dominant)      # {"bytes_per_unit": ..., "unit": "frame"|"clip"}
+            units = {"frame": N, "clip": U}[tj["unit"]]
+            traffic = int(tj["bytes_per_unit"] * units)    # ncu capture scaled to this launch's unit count
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": stages[dominant]["achieved_gbs"],
@@ -421,7 +470,7 @@ def main():
         torch.set_num_threads(os.cpu_count() or 1)
         cf.run()
         reps, t = 0, 0.0
-        while t < 10.0 and reps < 40:
+        while t < 10.0 and reps < 400:
             t += cf.run()
             reps += 1
         cf.close()

@@ -58,3 +58,23 @@ def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     A.bgr2gray(np.zeros((2, 32, 32, 3), np.uint8))
     assert _lib.launch_count() > before
+
+
+def test_host_pipeline_matches_serial_path():
+    """Two slots in flight give the same bytes as the step-at-a-time path, for every step."""
+    batches = []
+    for seed in (0, 3, 7):
+        audios, vids, lms, vals = _utts(4, seed=seed)
+        batches.append(A.pack_utterances(audios, vids, lms, vals, audio_max_length=32000).pin())
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=32000)
+    ref = [{k: v.clone() for k, v in fe.forward_host(b).items()} for b in batches]
+    pipe = A.HostPipeline(depth=2, n_mels=80, audio_max_length=32000)
+    for rounds in range(2):
+        for i, b in enumerate(batches):
+            pipe.submit(i, b)
+            if i >= 1:                                     # consume with one step of lag
+                got = pipe.result(i - 1)
+                assert torch.equal(got["mel"], ref[i - 1]["mel"]) and torch.equal(got["lip"], ref[i - 1]["lip"])
+        got = pipe.result(len(batches) - 1)
+        assert torch.equal(got["mel"], ref[-1]["mel"]) and torch.equal(got["lip"], ref[-1]["lip"])
+    pipe.drain()
