@@ -28,21 +28,19 @@ constexpr int kMaxMels = 128;
 
 // Filterbank in sparse form, built by logmel_prep_kernel in the workspace.
 struct MelPack {
-  int2 bounds[kMaxMels];   // first bin, support length
-  int woff[kMaxMels];      // offset of the filter's weights in wts
-  int total;               // sum of support lengths; > kMaxPacked => weights stay in global fb
+  int4 rec[kMaxMels];      // per filter: first bin, support length, offset of its weights in wts, quads
+  int total;               // sum of quad-padded support lengths; > kMaxPacked => weights stay in global fb
   int pad[3];
   float wts[kMaxPacked];
 };
 
 struct Smem {
-  float2 Z[kPairs * kZPair];            // 55,424 B  20x20 exchange / spectra, then power rows
-  float audio[2][kTileSamples];         // 42,880 B  double-buffered reflect-padded audio span
+  float2 Z[kPairs * kZPair];            // 53,760 B  20x20 exchange / spectra, then the 32 power rows
+  float audio[2][kTileFloats];          // 45,600 B  double-buffered reflect-padded audio span (skewed)
   float2 tw[kNfft];                     //  3,200 B
   float hann[kNfft];                    //  1,600 B
   __align__(16) float wts[kMaxPacked];  //  4,096 B  zero-padded to quads
-  int2 bounds[kMaxMels];                //  1,024 B
-  int woff[kMaxMels];                   //    512 B
+  int4 rec[kMaxMels];                   //  2,048 B
   int red[16];
 };
 
@@ -74,22 +72,20 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) pack->bounds[m] = (lo < hi) ? make_int2(lo, hi - lo) : make_int2(0, 0);
+    if (lane == 0) pack->rec[m] = (lo < hi) ? make_int4(lo, hi - lo, 0, (hi - lo + 3) >> 2) : make_int4(0, 0, 0, 0);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int m = 0; m < n_mels; ++m) { pack->woff[m] = acc; acc += (pack->bounds[m].y + 3) & ~3; }   // quads
+    for (int m = 0; m < n_mels; ++m) { pack->rec[m].z = acc; acc += 4 * pack->rec[m].w; }   // quads
     pack->total = acc;
   }
   __syncthreads();
   if (pack->total <= kMaxPacked) {
     for (int m = wid; m < n_mels; m += 32) {
-      const int2 bd = pack->bounds[m];
-      const int off = pack->woff[m];
-      const int padded = (bd.y + 3) & ~3;
-      for (int k = lane; k < padded; k += 32)
-        pack->wts[off + k] = (k < bd.y) ? fb[(size_t)m * kBins + bd.x + k] : 0.0f;
+      const int4 rc = pack->rec[m];
+      for (int k = lane; k < 4 * rc.w; k += 32)
+        pack->wts[rc.z + k] = (k < rc.y) ? fb[(size_t)m * kBins + rc.x + k] : 0.0f;
     }
   }
 }
@@ -107,43 +103,50 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
     sm.tw[i] = make_float2(kTwRe[i], kTwIm[i]);
     sm.hann[i] = kHann[i];
   }
-  for (int i = tid; i < n_mels; i += kThreads) { sm.bounds[i] = pack->bounds[i]; sm.woff[i] = pack->woff[i]; }
+  for (int i = tid; i < n_mels; i += kThreads) sm.rec[i] = pack->rec[i];
   if (packed)
     for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
-  const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
-  const int64_t n_tiles = B * tiles_per_clip;
+  // tiles are numbered clip-major; this CTA takes tiles blockIdx.x, +gridDim.x, ...; the
+  // (clip, tile-in-clip) pair is advanced incrementally in 32-bit arithmetic
+  const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
   const int g = tid / 20, j = tid % 20;
   const bool base_ok = ((reinterpret_cast<uintptr_t>(audio) & 15u) == 0) && (L % 4 == 0);
   const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
+  const int step_b = (int)(gridDim.x / (unsigned)tiles_per_clip);
+  const int step_t = (int)(gridDim.x % (unsigned)tiles_per_clip);
 
   // Interior tiles (no reflection, no zero padding) are fetched with 16-byte cp.async one tile
   // ahead; clip-edge tiles are assembled sample by sample when their turn comes.
-  auto is_fast = [&](int64_t tile) -> bool {
-    const int64_t p0 = (tile % tiles_per_clip) * kTileFrames * kHop;
+  auto is_fast = [&](int tt) -> bool {
+    const int64_t p0 = (int64_t)tt * (kTileFrames * kHop);
     return base_ok && p0 >= kNfft / 2 && p0 - kNfft / 2 + kTileSamples <= L;
   };
-  auto prefetch = [&](int64_t tile, int buf) {
-    if (tile < n_tiles && is_fast(tile)) {
-      const int64_t b = tile / tiles_per_clip;
-      const int64_t p0 = (tile % tiles_per_clip) * kTileFrames * kHop;
-      const float* src = audio + b * L + (p0 - kNfft / 2);
-      for (int i = tid; i < kTileSamples / 4; i += kThreads) cp_async16(&sm.audio[buf][4 * i], src + 4 * i);
+  auto prefetch = [&](int64_t b, int tt, int buf) {
+    if (b < B && is_fast(tt)) {
+      const float* src = audio + b * L + ((int64_t)tt * (kTileFrames * kHop) - kNfft / 2);
+      for (int i = tid; i < kTileSamples / 4; i += kThreads)
+        cp_async16(&sm.audio[buf][tile_pos(4 * i)], src + 4 * i);     // skew is a multiple of 4 floats
     }
     cp_async_commit();
   };
 
+  int64_t b = blockIdx.x / (unsigned)tiles_per_clip;
+  int tt = (int)(blockIdx.x % (unsigned)tiles_per_clip);
   int cur = 0;
-  prefetch(blockIdx.x, 0);
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
-    const int64_t b = tile / tiles_per_clip;
-    const int64_t t0 = (tile % tiles_per_clip) * kTileFrames;
-    prefetch(tile + gridDim.x, cur ^ 1);
+  prefetch(b, tt, 0);
+  for (; b < B; cur ^= 1) {
+    // next tile of this CTA
+    int64_t bn = b + step_b;
+    int tn = tt + step_t;
+    if (tn >= tiles_per_clip) { tn -= tiles_per_clip; ++bn; }
+    prefetch(bn, tn, cur ^ 1);
     cp_async_wait<1>();                                  // this tile's group has landed
+    const int64_t t0 = (int64_t)tt * kTileFrames;
     float* au = sm.audio[cur];
     bool nz = false;
-    if (is_fast(tile)) {
+    if (is_fast(tt)) {
       for (int i = tid; i < kTileSamples / 4; i += kThreads) {   // the chunks this thread fetched
-        const float4 q = reinterpret_cast<const float4*>(au)[i];
+        const float4 q = *reinterpret_cast<const float4*>(&au[tile_pos(4 * i)]);
         nz |= (q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f) | (q.w != 0.0f);
       }
     } else {
@@ -151,7 +154,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       const int64_t p0 = t0 * kHop;
       for (int i = tid; i < kTileSamples; i += kThreads) {
         const float q = padded_sample(clip, L, Lp, p0 + i);
-        au[i] = q;
+        au[tile_pos(i)] = q;
         nz |= (q != 0.0f);
       }
     }
@@ -160,10 +163,12 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
     const int64_t t = t0 + lane;
     const bool live = t < n_frames;
     float vmax = -INFINITY;
+    float* orow = out + (b * n_mels + wid) * n_frames + t;       // filter `wid`, this lane's frame
+    const int64_t ostep = (int64_t)(kThreads / 32) * n_frames;
     if (!any) {
       // all 32 frames are digital silence: |X|^2 = 0 -> mel = 0 -> log10(1e-10); skip the FFTs
       if (live) {
-        for (int m = wid; m < n_mels; m += kThreads / 32) out[(b * n_mels + m) * n_frames + t] = floor_v;
+        for (int m = wid; m < n_mels; m += kThreads / 32, orow += ostep) *orow = floor_v;
         vmax = floor_v;
       }
     } else {
@@ -172,7 +177,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       __syncthreads();
       stage2(g, j, sm.Z);
       __syncthreads();
-      // ---- untangle the two real frames of each FFT; power rows overwrite the Z slab ----
+      // ---- untangle the two real frames of each FFT; power rows overwrite the Z storage ----
       float pa[kBinsPerThread], pb[kBinsPerThread];
       split_load(g, j, sm.Z, pa, pb);
       __syncthreads();
@@ -181,13 +186,12 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       __syncthreads();
       // ---- sparse mel projection + log10: warp = filter, lane = frame ----
       const float* prow = P + prow_offset(lane);
-      for (int m = wid; m < n_mels; m += kThreads / 32) {
-        const int2 bd = sm.bounds[m];
-        const float v = packed
-            ? mel_log10_quads(prow + bd.x, reinterpret_cast<const float4*>(sm.wts + sm.woff[m]), (bd.y + 3) >> 2)
-            : mel_log10(prow + bd.x, fb + (size_t)m * kBins + bd.x, bd.y);
+      for (int m = wid; m < n_mels; m += kThreads / 32, orow += ostep) {
+        const int4 rc = sm.rec[m];                       // first bin, length, weight offset, quads
+        const float v = packed ? mel_log10_quads(prow + rc.x, reinterpret_cast<const float4*>(sm.wts + rc.z), rc.w)
+                               : mel_log10(prow + rc.x, fb + (size_t)m * kBins + rc.x, rc.y);
         if (live) {
-          out[(b * n_mels + m) * n_frames + t] = v;
+          *orow = v;
           vmax = fmaxf(vmax, v);
         }
       }
@@ -201,6 +205,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       for (int w = 1; w < kThreads / 32; ++w) k = max(k, sm.red[w]);
       atomicMax(clip_max + b, k);
     }
+    b = bn; tt = tn;
   }
   cp_async_wait<0>();
 }

@@ -28,10 +28,17 @@ constexpr int kPairs = kTileFrames / 2;                          // 16 complex F
 constexpr int kThreads = kPairs * 20;                            // 320: one thread per (FFT, column)
 constexpr int kTileSamples = (kTileFrames - 1) * kHop + kNfft;   // 5360
 constexpr int kZRow = 21;            // float2 row stride of the 20x20 exchange (20 + 1 pad)
-// float2 per FFT: >= 20*21 - 1, and 2*433 = 866 = 2 (mod 32) so that the two power rows that
-// later overwrite each FFT's slab (frame 2g at +0, frame 2g+1 at +433 floats) start at bank
-// 2g and 2g+17: the 32 frames of a tile sit in 32 different banks (lane = frame reads).
-constexpr int kZPair = 433;
+// float2 per FFT: 840 words = 8 (mod 32), so a warp's tail lanes (next FFT, columns 0..11) land
+// on banks 8..31 while its lanes 16..19 use banks 0..7: conflict-free 64-bit exchanges
+constexpr int kZPair = 20 * kZRow;
+// After the spectra have been consumed the whole Z storage is free; the 32 power rows are
+// written there with an odd stride so that lane = frame reads hit 32 different banks.
+constexpr int kPStride = 203;        // >= 201 bins + the 3 padded reads of the quad-packed mel filters
+// The staged audio span is skewed by 20 floats per 320 samples: FFT g+1 reads exactly 320
+// samples after FFT g, i.e. the same banks; the skew moves its lanes (columns 0..11) to banks
+// 20..31, next to lanes 0..19 of FFT g.
+constexpr int kTileSkew = 20;
+constexpr int kTileFloats = kTileSamples + kTileSkew * (kTileSamples / 320 + 1);   // 5700
 constexpr int kBinsPerThread = 11;   // thread (g, j) untangles bins k = j + 20*m, m = 0..10
 
 AVFE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -96,15 +103,22 @@ AVFE_HD float padded_sample(const float* clip, int64_t L, int64_t Lp, int64_t p)
 // Stage 1, thread (g, j): column j of FFT g.  z[m] = hann[j+20m] * (xa + i*xb)[j+20m];
 // 20-point DFT over m; times W400^(j*k1); stored at Z[g][k1][j].
 // tw[k1*20 + j] = exp(-2*pi*i*j*k1/400).
+// physical position of span sample s in the skewed tile
+AVFE_HD int tile_pos(int s) { return s + kTileSkew * (s / 320); }
+
 AVFE_HD void stage1(int g, int j, const float* tile, const float* hann, const float2* tw,
                     float2* Z) {
   float2 x[20];
-  const float* fa = tile + (2 * g) * kHop + j;
-  const float* fb = fa + kHop;
+  // frame 2g starts at span sample 320g, frame 2g+1 160 later; within the thread's 20 reads the
+  // skew block index is g plus one or two carries that depend on (j + 20m) only
+  const float* base = tile + 320 * g + kTileSkew * g + j;
 #pragma unroll
   for (int m = 0; m < 20; ++m) {
     const float w = hann[j + 20 * m];
-    x[m] = make_float2(w * fa[20 * m], w * fb[20 * m]);
+    const int oa = 20 * m, ob = 160 + 20 * m;            // offsets inside the pair's 320-blocks
+    const int ca = (oa + j >= 320) ? kTileSkew : 0;      // oa + j <= 399
+    const int cb = (ob + j >= 320) ? kTileSkew : 0;      // ob + j <= 559
+    x[m] = make_float2(w * base[oa + ca], w * base[ob + cb]);
   }
   dft20(x);
   float2* z = Z + g * kZPair + j;
@@ -126,13 +140,13 @@ AVFE_HD void stage2(int g, int k1, float2* Z) {
 }
 
 // Float offset of the power row of tile frame f (0..31) inside the Z storage.
-AVFE_HD int prow_offset(int f) { return (f >> 1) * (2 * kZPair) + (f & 1) * kZPair; }
+AVFE_HD int prow_offset(int f) { return f * kPStride; }
 
 // Untangle the two real frames packed in FFT g.  Thread (g, j) owns bins k = j + 20*m
 // (m = 0..10; m = 10 exists only for j = 0, k = 200).  Bin k sits in slot j*21 + m; its mirror
 // 400-k in slot (20-j)*21 + (19-m) for j > 0 and slot 20-m for j = 0 (slot 0 for k = 0).
 // Xa = (Z[k] + conj(Z[400-k]))/2, Xb = (Z[k] - conj(Z[400-k]))/(2i); powers kept in registers
-// (phase A) so that phase B can overwrite the Z slab with the two power rows after a barrier.
+// (phase A) so that phase B can overwrite the Z storage with the power rows after a barrier.
 AVFE_HD void split_load(int g, int j, const float2* Z, float (&pa)[kBinsPerThread],
                         float (&pb)[kBinsPerThread]) {
   const float2* z = Z + g * kZPair;
@@ -159,6 +173,10 @@ AVFE_HD void split_store(int g, int j, float* P, const float (&pa)[kBinsPerThrea
     ra[20 * m] = pa[m];
     rb[20 * m] = pb[m];
   }
+  // the quad-packed mel filters may read up to 3 floats past bin 200 (with zero weights): keep
+  // those slots finite (0 * NaN would poison the dot product)
+  if (j == 1) { ra[200] = 0.0f; ra[201] = 0.0f; rb[200] = 0.0f; rb[201] = 0.0f; }   // bins 201, 202
+  if (j == 2 && g == kPairs - 1) rb[kPStride - 2] = 0.0f;                          // one past the last row
 }
 
 AVFE_HD float log10_floor(float acc) {
@@ -176,12 +194,19 @@ AVFE_HD float log10_floor(float acc) {
 // power rows are long enough (433 floats) for the padded reads.
 AVFE_HD float mel_log10_quads(const float* Prow, const float4* w, int n4) {
   float a0 = 0.0f, a1 = 0.0f;
-  for (int q = 0; q < n4; ++q) {
-    const float4 c = w[q];
-    a0 = fmaf(c.x, Prow[4 * q], a0);
-    a1 = fmaf(c.y, Prow[4 * q + 1], a1);
-    a0 = fmaf(c.z, Prow[4 * q + 2], a0);
-    a1 = fmaf(c.w, Prow[4 * q + 3], a1);
+  // slaney filters need 1..4 quads: one guarded, fully unrolled block of four per trip
+  for (int q0 = 0; q0 < n4; q0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u;
+      if (q < n4) {
+        const float4 c = w[q];
+        a0 = fmaf(c.x, Prow[4 * q], a0);
+        a1 = fmaf(c.y, Prow[4 * q + 1], a1);
+        a0 = fmaf(c.z, Prow[4 * q + 2], a0);
+        a1 = fmaf(c.w, Prow[4 * q + 3], a1);
+      }
+    }
   }
   return log10_floor(a0 + a1);
 }

@@ -29,10 +29,10 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
       const double a = -2.0 * M_PI * ((j * k1) % kNfft) / kNfft;
       tw[k1 * 20 + j] = make_float2((float)cos(a), (float)sin(a));
     }
-  std::vector<float> buf(kTileSamples);
+  std::vector<float> buf(kTileFloats);
   std::vector<float2> Z(kPairs * kZPair);
   std::vector<float> pa(kThreads * kBinsPerThread), pb(kThreads * kBinsPerThread);
-  for (int i = 0; i < kTileSamples; ++i) buf[i] = padded_sample(clip, L, Lp, t0 * kHop + i);
+  for (int i = 0; i < kTileSamples; ++i) buf[tile_pos(i)] = padded_sample(clip, L, Lp, t0 * kHop + i);
   for (int tid = 0; tid < kThreads; ++tid) stage1(tid / 20, tid % 20, buf.data(), hann.data(), tw.data(), Z.data());
   for (int tid = 0; tid < kThreads; ++tid) stage2(tid / 20, tid % 20, Z.data());
   // phase A (all threads), barrier, phase B (all threads): power rows overwrite the Z slab
