@@ -55,6 +55,23 @@ def _mel_filters_np(n_mels: int) -> np.ndarray:
 
 
 _FILTER_CACHE: dict = {}
+_PACK_CACHE: dict = {}
+
+
+def _filter_pack(fb: torch.Tensor, n_mels: int) -> torch.Tensor:
+    """Sparse form of a filterbank tensor (avfe_logmel_prepare), built once per tensor."""
+    key = (fb.data_ptr(), str(fb.device), n_mels, fb._version)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] is fb:
+        return hit[1]
+    lib = _lib.load()
+    pack = torch.empty(int(lib.avfe_logmel_pack_bytes()), dtype=torch.uint8, device=fb.device)
+    with torch.cuda.device(fb.device):
+        _lib.call("avfe_logmel_prepare", _lib.ptr(fb), n_mels, _lib.ptr(pack), _lib.stream_ptr())
+    if len(_PACK_CACHE) > 16:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (fb, pack)      # holding fb keeps data_ptr from being recycled
+    return pack
 
 
 def mel_filters(device, n_mels: int = 80) -> torch.Tensor:
@@ -143,8 +160,9 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
         lib = _lib.load()
         ws_bytes = int(lib.avfe_logmel_workspace_bytes(B, L, padding, n_mels))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=t.device)
-        _lib.call("avfe_logmel_f32", _lib.ptr(t), B, L, padding, n_mels, _lib.ptr(fb), _lib.ptr(out),
-                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        pack = _filter_pack(fb, n_mels)
+        _lib.call("avfe_logmel_prepared_f32", _lib.ptr(t), B, L, padding, n_mels, _lib.ptr(fb), _lib.ptr(pack),
+                  _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     if kind in ("numpy", "cpu") and device is None:
         return out.cpu()
     return out

@@ -30,7 +30,13 @@ constexpr int kMaxMels = 128;
 struct MelPack {
   int4 rec[kMaxMels];      // per filter: first bin, support length, offset of its weights in wts, quads
   int total;               // sum of quad-padded support lengths; > kMaxPacked => weights stay in global fb
-  int pad[3];
+  int max_quads;           // longest support in quads
+  int balanced;            // 1 if assign[] is valid (every filter <= 4 quads, n_mels <= 128)
+  int pad[1];
+  // mel work split for the tile kernel: thread i computes filter (a & 0xff) for (a >> 16) frames
+  // starting at tile frame ((a >> 8) & 0xff); threads are grouped by quad count so warps do not
+  // diverge, and every thread gets ~12-16 (quad, frame) units
+  unsigned assign[kThreads];
   float wts[kMaxPacked];
 };
 
@@ -41,6 +47,7 @@ struct Smem {
   float hann[kNfft];                    //  1,600 B
   __align__(16) float wts[kMaxPacked];  //  4,096 B  zero-padded to quads
   int4 rec[kMaxMels];                   //  2,048 B
+  unsigned assign[kThreads];            //  1,280 B
   int red[16];
 };
 
@@ -56,12 +63,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __global__ void __launch_bounds__(1024)
 logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __restrict__ clip_max,
                    MelPack* __restrict__ pack) {
-  if (blockIdx.x > 0) {
-    const int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    if (i < B) clip_max[i] = INT_MIN;
-    return;
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  (void)B; (void)clip_max;
+  if (blockIdx.x > 0) return;
+  // filter supports, weight offsets and the balanced mel work table, all in parallel over the
+  // filters (a serial thread would crawl through dependent shared-memory round trips)
+  __shared__ int s_lo[kMaxMels], s_len[kMaxMels], s_q[kMaxMels], s_woff[kMaxMels];
+  __shared__ int s_tier_total[4];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < 4) s_tier_total[tid] = 0;
   for (int m = wid; m < n_mels; m += 32) {                 // one warp per filter
     const float* row = fb + (size_t)m * kBins;
     int lo = kBins, hi = 0;
@@ -72,20 +81,64 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) pack->rec[m] = (lo < hi) ? make_int4(lo, hi - lo, 0, (hi - lo + 3) >> 2) : make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+      const int len = lo < hi ? hi - lo : 0;
+      s_lo[m] = lo < hi ? lo : 0; s_len[m] = len; s_q[m] = (len + 3) >> 2;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int m = 0; m < n_mels; ++m) { pack->rec[m].z = acc; acc += 4 * pack->rec[m].w; }   // quads
-    pack->total = acc;
+  // threads per filter under tier r: ~16 (quad, frame) units per thread first, coarser tiers if
+  // the CTA's 320 threads do not suffice
+  auto tm_of = [](int q, int tier) -> int {
+    switch (tier) {
+      case 0:  return q <= 1 ? 2 : (q == 2 ? 4 : 8);
+      case 1:  return q <= 1 ? 2 : (q == 4 ? 8 : 4);
+      case 2:  return q <= 1 ? 1 : (q == 2 ? 2 : 4);
+      default: return 1;
+    }
+  };
+  int total = 0, mq = 0;
+  if (tid < n_mels) {
+    int woff = 0;
+    for (int m = 0; m < n_mels; ++m) {                     // every thread scans all filters: n_mels <= 128
+      if (m < tid) woff += 4 * s_q[m];
+      total += 4 * s_q[m];
+      mq = max(mq, s_q[m]);
+    }
+    s_woff[tid] = woff;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) atomicAdd(&s_tier_total[r], tm_of(s_q[tid], r));
   }
   __syncthreads();
-  if (pack->total <= kMaxPacked) {
+  int tier = 3;
+  for (int r = 3; r >= 0; --r) if (s_tier_total[r] <= kThreads) tier = r;
+  const bool ok = (n_mels <= kMaxMels) && (n_mels <= kThreads);
+  if (tid < n_mels) {
+    // max quads over all filters (every thread computed it) decides whether the table is usable
+    const bool balanced = ok && mq <= 4;
+    const int q = s_q[tid], tmm = tm_of(q, tier);
+    int off = 0;                                           // threads before this filter: larger quad counts first
+    for (int m = 0; m < n_mels; ++m) {
+      const int qm = s_q[m];
+      if (qm > q || (qm == q && m < tid)) off += tm_of(qm, tier);
+    }
+    const int nf = kTileFrames / tmm;
+    if (balanced)
+      for (int i = 0; i < tmm; ++i)
+        pack->assign[off + i] = (unsigned)tid | ((unsigned)(i * nf) << 8) | ((unsigned)nf << 16);
+    pack->rec[tid] = make_int4(s_lo[tid], s_len[tid], s_woff[tid], q);
+    if (tid == 0) { pack->total = total; pack->max_quads = mq; pack->balanced = balanced ? 1 : 0; }
+  }
+  // unused tail of the table
+  for (int i = s_tier_total[tier] + tid; i < kThreads; i += blockDim.x) pack->assign[i] = 0u;
+  // packed, quad-padded weights
+  int all = 0;
+  for (int m = 0; m < n_mels; ++m) all += 4 * s_q[m];
+  if (all <= kMaxPacked) {
     for (int m = wid; m < n_mels; m += 32) {
-      const int4 rc = pack->rec[m];
-      for (int k = lane; k < 4 * rc.w; k += 32)
-        pack->wts[rc.z + k] = (k < rc.y) ? fb[(size_t)m * kBins + rc.x + k] : 0.0f;
+      const int off = s_woff[m], len = s_len[m], lo = s_lo[m];
+      for (int k = lane; k < 4 * s_q[m]; k += 32)
+        pack->wts[off + k] = (k < len) ? fb[(size_t)m * kBins + lo + k] : 0.0f;
     }
   }
 }
@@ -94,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_t Lp,
                    int64_t n_frames, int n_mels, const float* __restrict__ fb,
                    const MelPack* __restrict__ pack, float* __restrict__ out,
-                   int* __restrict__ clip_max) {
+                   int* __restrict__ clip_max, uint8_t* __restrict__ silent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -104,6 +157,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
     sm.hann[i] = kHann[i];
   }
   for (int i = tid; i < n_mels; i += kThreads) sm.rec[i] = pack->rec[i];
+  sm.assign[tid] = pack->assign[tid];
   if (packed)
     for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
   // tiles are numbered clip-major; this CTA takes tiles blockIdx.x, +gridDim.x, ...; the
@@ -112,6 +166,7 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
   const int g = tid / 20, j = tid % 20;
   const bool base_ok = ((reinterpret_cast<uintptr_t>(audio) & 15u) == 0) && (L % 4 == 0);
   const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
+  const bool mel_fast = packed && pack->balanced != 0;
   const int step_b = (int)(gridDim.x / (unsigned)tiles_per_clip);
   const int step_t = (int)(gridDim.x % (unsigned)tiles_per_clip);
 
@@ -160,17 +215,12 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
     }
     // barrier: tile visible to all, previous tile's power rows no longer needed
     const int any = __syncthreads_or(nz ? 1 : 0);
-    const int64_t t = t0 + lane;
-    const bool live = t < n_frames;
     float vmax = -INFINITY;
-    float* orow = out + (b * n_mels + wid) * n_frames + t;       // filter `wid`, this lane's frame
-    const int64_t ostep = (int64_t)(kThreads / 32) * n_frames;
+    if (tid == 0) silent[b * tiles_per_clip + tt] = any ? 0 : 1;
     if (!any) {
-      // all 32 frames are digital silence: |X|^2 = 0 -> mel = 0 -> log10(1e-10); skip the FFTs
-      if (live) {
-        for (int m = wid; m < n_mels; m += kThreads / 32, orow += ostep) *orow = floor_v;
-        vmax = floor_v;
-      }
+      // all 32 frames are digital silence: |X|^2 = 0 -> mel = 0 -> log10(1e-10).  No FFT and no
+      // store: logmel_finalize_kernel writes the final constant for silent tiles directly.
+      vmax = floor_v;
     } else {
       // ---- 16 complex FFT-400: columns, twiddle, rows ----
       stage1(g, j, au, sm.hann, sm.tw, sm.Z);
@@ -184,15 +234,67 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
       float* P = reinterpret_cast<float*>(sm.Z);
       split_store(g, j, P, pa, pb);
       __syncthreads();
-      // ---- sparse mel projection + log10: warp = filter, lane = frame ----
-      const float* prow = P + prow_offset(lane);
-      for (int m = wid; m < n_mels; m += kThreads / 32, orow += ostep) {
-        const int4 rc = sm.rec[m];                       // first bin, length, weight offset, quads
-        const float v = packed ? mel_log10_quads(prow + rc.x, reinterpret_cast<const float4*>(sm.wts + rc.z), rc.w)
-                               : mel_log10(prow + rc.x, fb + (size_t)m * kBins + rc.x, rc.y);
-        if (live) {
-          *orow = v;
-          vmax = fmaxf(vmax, v);
+      // ---- sparse mel projection + log10 ----
+      if (mel_fast) {
+        // thread = (filter m, run of nf consecutive frames) from the balanced table: the filter's
+        // <= 16 quad-padded weights sit in registers, so a (filter, frame) pair costs 4 LDS + 4
+        // FFMA per quad.  Results are staged in the (now free) audio buffer and written out row
+        // by row so that the global stores are coalesced.
+        float* stage_out = au;                           // [n_mels][32]
+        const unsigned a = sm.assign[tid];
+        const int nf = (int)(a >> 16);
+        if (nf > 0) {
+          const int m = (int)(a & 0xffu), f0 = (int)((a >> 8) & 0xffu);
+          const int4 rc = sm.rec[m];                     // first bin, length, weight offset, quads
+          const float4* wq = reinterpret_cast<const float4*>(sm.wts + rc.z);
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 w0 = rc.w > 0 ? wq[0] : z4, w1 = rc.w > 1 ? wq[1] : z4;
+          const float4 w2 = rc.w > 2 ? wq[2] : z4, w3 = rc.w > 3 ? wq[3] : z4;
+          const float* prow = P + prow_offset(f0) + rc.x;
+          float* so = stage_out + m * kTileFrames + f0;
+          for (int i = 0; i < nf; ++i, prow += kPStride) {
+            float a0 = 0.0f, a1 = 0.0f;
+            a0 = fmaf(w0.x, prow[0], a0); a1 = fmaf(w0.y, prow[1], a1);
+            a0 = fmaf(w0.z, prow[2], a0); a1 = fmaf(w0.w, prow[3], a1);
+            if (rc.w > 1) {                               // uniform within a warp (threads sorted by quads)
+              a0 = fmaf(w1.x, prow[4], a0); a1 = fmaf(w1.y, prow[5], a1);
+              a0 = fmaf(w1.z, prow[6], a0); a1 = fmaf(w1.w, prow[7], a1);
+              if (rc.w > 2) {
+                a0 = fmaf(w2.x, prow[8], a0); a1 = fmaf(w2.y, prow[9], a1);
+                a0 = fmaf(w2.z, prow[10], a0); a1 = fmaf(w2.w, prow[11], a1);
+                if (rc.w > 3) {
+                  a0 = fmaf(w3.x, prow[12], a0); a1 = fmaf(w3.y, prow[13], a1);
+                  a0 = fmaf(w3.z, prow[14], a0); a1 = fmaf(w3.w, prow[15], a1);
+                }
+              }
+            }
+            so[i] = log10_floor(a0 + a1);
+          }
+        }
+        __syncthreads();
+        const int64_t t = t0 + lane;
+        if (t < n_frames) {
+          float* orow = out + (b * n_mels + wid) * n_frames + t;
+          for (int m = wid; m < n_mels; m += kThreads / 32, orow += (int64_t)(kThreads / 32) * n_frames) {
+            const float v = stage_out[m * kTileFrames + lane];
+            *orow = v;
+            vmax = fmaxf(vmax, v);
+          }
+        }
+      } else {
+        // generic filterbanks: warp = filter, lane = frame
+        const int64_t t = t0 + lane;
+        const bool live = t < n_frames;
+        const float* prow = P + prow_offset(lane);
+        float* orow = out + (b * n_mels + wid) * n_frames + t;
+        for (int m = wid; m < n_mels; m += kThreads / 32, orow += (int64_t)(kThreads / 32) * n_frames) {
+          const int4 rc = sm.rec[m];
+          const float v = packed ? mel_log10_quads(prow + rc.x, reinterpret_cast<const float4*>(sm.wts + rc.z), rc.w)
+                                 : mel_log10(prow + rc.x, fb + (size_t)m * kBins + rc.x, rc.y);
+          if (live) {
+            *orow = v;
+            vmax = fmaxf(vmax, v);
+          }
         }
       }
     }
@@ -210,16 +312,25 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
   cp_async_wait<0>();
 }
 
+// max(x, clip_max - 8), (x + 4) / 4.  Silent tiles (flagged by the tile kernel) were never
+// written: their raw value is the constant log10(1e-10), so they are stored without a read.
 __global__ void __launch_bounds__(256)
 logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
-                       int64_t per_clip, int64_t total) {
-  if ((per_clip & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+                       const uint8_t* __restrict__ silent, int64_t n_frames, int n_mels,
+                       int64_t total) {
+  const int64_t per_clip = (int64_t)n_mels * n_frames;
+  const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
+  const float raw_silent = log10_floor(0.0f);
+  if ((n_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
     float4* o4 = reinterpret_cast<float4*>(out);
-    const int64_t n4 = total >> 2, per4 = per_clip >> 2;
+    const int64_t n4 = total >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (int64_t)gridDim.x * blockDim.x) {
-      const float floor_v = __fsub_rn(key_float(clip_max[i / per4]), 8.0f);
-      float4 x = o4[i];
+      const int64_t e = i << 2, b = e / per_clip, t = (e - b * per_clip) % n_frames;
+      const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
+      float4 x;
+      if (silent[b * tiles_per_clip + t / kTileFrames]) x = make_float4(raw_silent, raw_silent, raw_silent, raw_silent);
+      else x = o4[i];
       x.x = __fmul_rn(__fadd_rn(fmaxf(x.x, floor_v), 4.0f), 0.25f);
       x.y = __fmul_rn(__fadd_rn(fmaxf(x.y, floor_v), 4.0f), 0.25f);
       x.z = __fmul_rn(__fadd_rn(fmaxf(x.z, floor_v), 4.0f), 0.25f);
@@ -230,8 +341,9 @@ logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const float floor_v = __fsub_rn(key_float(clip_max[i / per_clip]), 8.0f);
-    const float x = fmaxf(out[i], floor_v);
+    const int64_t b = i / per_clip, t = (i - b * per_clip) % n_frames;
+    const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
+    const float x = fmaxf(silent[b * tiles_per_clip + t / kTileFrames] ? raw_silent : out[i], floor_v);
     out[i] = __fmul_rn(__fadd_rn(x, 4.0f), 0.25f);
   }
 }
@@ -307,31 +419,35 @@ extern "C" size_t avfe_logmel_workspace_bytes(int64_t B, int64_t L, int64_t padd
   (void)L; (void)padding;
   if (B < 0 || n_mels < 0) return 0;
   (void)n_mels;
-  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + 64;
+  if (L < 0 || padding < 0) return 0;
+  const size_t tiles = (size_t)B * (size_t)(((L + padding) / lm::kHop + lm::kTileFrames - 1) / lm::kTileFrames);
+  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + ((tiles + 15) & ~(size_t)15) + 64;
 }
 
-extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
-                               int n_mels, const float* mel_filters, float* out, void* workspace,
-                               size_t workspace_bytes, avfe_stream_t stream) {
-  if (B < 0 || L < 0 || padding < 0 || n_mels <= 0) return AVFE_ERR_INVALID_ARG;
+extern "C" size_t avfe_logmel_pack_bytes(void) { return sizeof(lm::MelPack); }
+
+extern "C" int avfe_logmel_prepare(const float* mel_filters, int n_mels, void* pack,
+                                   avfe_stream_t stream) {
+  if (n_mels <= 0) return AVFE_ERR_INVALID_ARG;
   if (n_mels > 128) return AVFE_ERR_UNSUPPORTED;
+  if (!mel_filters || !pack || !aligned16(pack)) return AVFE_ERR_INVALID_ARG;
+  lm::logmel_prep_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      mel_filters, n_mels, 0, nullptr, static_cast<lm::MelPack*>(pack));
+  count_launch();
+  return check_launch();
+}
+
+// shared tail of the two log-mel entry points: clip maxima <- -inf, tile kernel, finalize
+static int logmel_run(const float* audio, int64_t B, int64_t L, int64_t padding, int n_mels,
+                      const float* mel_filters, const lm::MelPack* pack, float* out,
+                      int* clip_max, uint8_t* silent, cudaStream_t s) {
   const int64_t Lp = L + padding;
   const int64_t n_frames = Lp / lm::kHop;
-  if (B == 0 || n_frames == 0) return AVFE_OK;
-  if (Lp <= lm::kNfft / 2) return AVFE_ERR_INVALID_ARG;   // reflect pad needs pad < length
-  if (!audio || !mel_filters || !out) return AVFE_ERR_INVALID_ARG;
-  if (!workspace || workspace_bytes < avfe_logmel_workspace_bytes(B, L, padding, n_mels) ||
-      !aligned16(workspace))
-    return AVFE_ERR_WORKSPACE;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int* clip_max = static_cast<int*>(workspace);
-  lm::MelPack* pack = reinterpret_cast<lm::MelPack*>(static_cast<char*>(workspace) +
-                                                     (((size_t)B * sizeof(int) + 15) & ~(size_t)15));
-
-  lm::logmel_prep_kernel<<<(unsigned)(1 + (B + 1023) / 1024), 1024, 0, s>>>(mel_filters, n_mels, B,
-                                                                           clip_max, pack);
-  count_launch();
-
+  // 0x80808080 as an ordered key is about -3.4e38: below every log10 value
+  if (cudaMemsetAsync(clip_max, 0x80, (size_t)B * sizeof(int), s) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
   // per-device attribute: set on every call (cheap) so multi-device processes stay correct
   if (cudaFuncSetAttribute(lm::logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(lm::Smem)) != cudaSuccess) {
@@ -341,15 +457,58 @@ extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t
   const int64_t n_tiles = B * ((n_frames + lm::kTileFrames - 1) / lm::kTileFrames);
   int64_t ctas = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;   // 2 resident CTAs per SM
   lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
-      audio, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max);
+      audio, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent);
   count_launch();
-
-  const int64_t per_clip = (int64_t)n_mels * n_frames, total = B * per_clip;
+  const int64_t total = B * (int64_t)n_mels * n_frames;
   int64_t fin = (total / 4 + 255) / 256 + 1;
   if (fin > (int64_t)kNumSMs * 16) fin = (int64_t)kNumSMs * 16;
-  lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, per_clip, total);
+  lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels, total);
   count_launch();
   return check_launch();
+}
+
+static int logmel_check(const float* audio, int64_t B, int64_t L, int64_t padding, int n_mels,
+                        const float* out, const void* workspace, size_t workspace_bytes) {
+  if (B < 0 || L < 0 || padding < 0 || n_mels <= 0) return AVFE_ERR_INVALID_ARG;
+  if (n_mels > 128) return AVFE_ERR_UNSUPPORTED;
+  const int64_t Lp = L + padding;
+  if (B == 0 || Lp / lm::kHop == 0) return 1;            // nothing to do
+  if (Lp <= lm::kNfft / 2) return AVFE_ERR_INVALID_ARG;  // reflect pad needs pad < length
+  if (!audio || !out) return AVFE_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < avfe_logmel_workspace_bytes(B, L, padding, n_mels) ||
+      !aligned16(workspace))
+    return AVFE_ERR_WORKSPACE;
+  return AVFE_OK;
+}
+
+extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
+                               int n_mels, const float* mel_filters, float* out, void* workspace,
+                               size_t workspace_bytes, avfe_stream_t stream) {
+  const int rc = logmel_check(audio, B, L, padding, n_mels, out, workspace, workspace_bytes);
+  if (rc != AVFE_OK) return rc > 0 ? AVFE_OK : rc;
+  if (!mel_filters) return AVFE_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* clip_max = static_cast<int*>(workspace);
+  lm::MelPack* pack = reinterpret_cast<lm::MelPack*>(static_cast<char*>(workspace) +
+                                                     (((size_t)B * sizeof(int) + 15) & ~(size_t)15));
+  uint8_t* silent = reinterpret_cast<uint8_t*>(pack) + sizeof(lm::MelPack);
+  lm::logmel_prep_kernel<<<1, 1024, 0, s>>>(mel_filters, n_mels, 0, nullptr, pack);
+  count_launch();
+  return logmel_run(audio, B, L, padding, n_mels, mel_filters, pack, out, clip_max, silent, s);
+}
+
+extern "C" int avfe_logmel_prepared_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
+                                        int n_mels, const float* mel_filters, const void* pack,
+                                        float* out, void* workspace, size_t workspace_bytes,
+                                        avfe_stream_t stream) {
+  const int rc = logmel_check(audio, B, L, padding, n_mels, out, workspace, workspace_bytes);
+  if (rc != AVFE_OK) return rc > 0 ? AVFE_OK : rc;
+  if (!mel_filters || !pack || !aligned16(pack)) return AVFE_ERR_INVALID_ARG;
+  int* clip_max = static_cast<int*>(workspace);
+  uint8_t* silent = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) +
+                                               (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack));
+  return logmel_run(audio, B, L, padding, n_mels, mel_filters, static_cast<const lm::MelPack*>(pack), out,
+                    clip_max, silent, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int avfe_pad_or_trim_f32(const float* in, int64_t B, int64_t L_in, int64_t L_out,

@@ -86,6 +86,19 @@ AVFE_API int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t p
                              int n_mels, const float* mel_filters, float* out,
                              void* workspace, size_t workspace_bytes, avfe_stream_t stream);
 
+/* The same with the filterbank analysed once: avfe_logmel_prepare turns the dense [n_mels,201]
+ * matrix into the sparse form the kernel uses (supports, quad-packed weights, balanced work
+ * table) in `pack` (avfe_logmel_pack_bytes() bytes, 16-byte aligned, device memory);
+ * avfe_logmel_prepared_f32 then skips that analysis on every call.  `mel_filters` must be the
+ * matrix `pack` was prepared from. */
+AVFE_API size_t avfe_logmel_pack_bytes(void);
+AVFE_API int avfe_logmel_prepare(const float* mel_filters, int n_mels, void* pack,
+                                 avfe_stream_t stream);
+AVFE_API int avfe_logmel_prepared_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
+                                      int n_mels, const float* mel_filters, const void* pack,
+                                      float* out, void* workspace, size_t workspace_bytes,
+                                      avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ video (V1..V8) */
 
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) — preprocess/video_process.py:201-214:

@@ -117,3 +117,32 @@ def test_pad_or_trim_and_peak_normalize():
     np.testing.assert_array_equal(A.peak_normalize(a), O.peak_normalize(a))
     both = np.stack([loud, a])
     np.testing.assert_array_equal(A.peak_normalize(both), np.stack([O.peak_normalize(loud), O.peak_normalize(a)]))
+
+
+def test_unprepared_entry_point_and_custom_filterbanks():
+    """avfe_logmel_f32 (dense filters analysed on every call) and filterbanks that are not the
+    sparse slaney triangles (dense rows -> generic projection path; wide triangles -> table with
+    coarser tiers) give the oracle's numbers too."""
+    from avsl_b200 import _lib
+    a = synth.audio_batch(3, 48000, 11)
+    rng = np.random.default_rng(0)
+    banks = {
+        "slaney80": O.mel_filters(80),
+        "dense20": np.abs(rng.normal(size=(20, 201))).astype(np.float32) * 1e-2,
+        "wide12": np.maximum(0, 1 - np.abs(np.arange(201)[None, :] - np.linspace(8, 190, 12)[:, None]) / 7.5).astype(np.float32),
+        "with_empty_row": np.concatenate([O.mel_filters(80)[:5], np.zeros((1, 201), np.float32)]),
+    }
+    for name, fb in banks.items():
+        n_mels = fb.shape[0]
+        ref = O.log_mel_spectrogram(a, n_mels, filters=fb)
+        got = A.log_mel_spectrogram(a, n_mels, filters=torch.from_numpy(fb).cuda()).cpu()
+        assert (got - ref).abs().max().item() <= TOL, name
+        # raw C-ABI entry without a prepared pack
+        d_a, d_fb = a.cuda(), torch.from_numpy(fb).cuda()
+        out = torch.empty((3, n_mels, 300), device="cuda")
+        lib = _lib.load()
+        nbytes = int(lib.avfe_logmel_workspace_bytes(3, 48000, 0, n_mels))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.call("avfe_logmel_f32", _lib.ptr(d_a), 3, 48000, 0, n_mels, _lib.ptr(d_fb), _lib.ptr(out),
+                  _lib.ptr(ws), nbytes, _lib.stream_ptr())
+        assert torch.equal(out.cpu(), got), name
