@@ -8,7 +8,7 @@ function raises if the library has not been built or no CUDA device is present.
 """
 from . import _lib  # noqa: F401
 from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram,
-                    mel_filters, pad_or_trim, peak_normalize)
+                    log_mel_spectrogram_ragged, mel_filters, pad_or_trim, peak_normalize)
 from .frontend import AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, pack_utterances, shard
 from .fusion import ModalityFusion, fuse_modalities, modality_dropout_flags, modality_dropout_mask
 from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,

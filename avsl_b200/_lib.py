@@ -28,6 +28,8 @@ _SIGNATURES = {
     "avfe_logmel_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "avfe_logmel_prepared_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avfe_logmel_ragged_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
     "avfe_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "avfe_warp_affine_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p]),

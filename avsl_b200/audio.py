@@ -168,6 +168,37 @@ def log_mel_spectrogram(audio: Union[np.ndarray, torch.Tensor], n_mels: int = 80
     return out
 
 
+def log_mel_spectrogram_ragged(audio: torch.Tensor, offsets: torch.Tensor, length: int = N_SAMPLES,
+                               n_mels: int = 80, filters: Optional[torch.Tensor] = None,
+                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``pad_or_trim(clip, length)`` + ``log_mel_spectrogram(clip, n_mels)`` for a batch of clips
+    stored back to back on the GPU (``audio`` float32 [sum L_i], ``offsets`` int64 [B+1]), in one
+    launch sequence: the zero padding is never written or read.  Returns [B, n_mels, length//160]."""
+    _lib.require_cuda()
+    if not (audio.is_cuda and offsets.is_cuda and audio.dtype == torch.float32 and offsets.dtype == torch.int64):
+        raise ValueError("audio (float32) and offsets (int64) must be CUDA tensors")
+    if n_mels <= 0 or n_mels > 128:
+        raise ValueError(f"Unsupported n_mels: {n_mels}")
+    if length <= N_FFT // 2:
+        raise RuntimeError("log_mel_spectrogram: reflect padding (200) needs more than 200 samples")
+    audio = audio.contiguous()
+    B = int(offsets.numel()) - 1
+    fb = filters if filters is not None else mel_filters(audio.device, n_mels)
+    shape = (B, n_mels, length // HOP_LENGTH)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=audio.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == shape):
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+    with torch.cuda.device(audio.device):
+        lib = _lib.load()
+        ws_bytes = int(lib.avfe_logmel_workspace_bytes(B, length, 0, n_mels))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=audio.device)
+        pack = _filter_pack(fb, n_mels)
+        _lib.call("avfe_logmel_ragged_f32", _lib.ptr(audio), _lib.ptr(offsets), B, length, n_mels, _lib.ptr(fb),
+                  _lib.ptr(pack), _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    return out
+
+
 def peak_normalize(audio: Union[np.ndarray, torch.Tensor]):
     """The waveform conditioning of ``preprocess_audio_for_whisper`` /
     ``process_audio_dual_encoder['waveform']`` (preprocess/audio_process.py:291-293,312-317)

@@ -55,6 +55,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -144,8 +148,8 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_t Lp,
-                   int64_t n_frames, int n_mels, const float* __restrict__ fb,
+logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets, int64_t B,
+                   int64_t L, int64_t Lp, int64_t n_frames, int n_mels, const float* __restrict__ fb,
                    const MelPack* __restrict__ pack, float* __restrict__ out,
                    int* __restrict__ clip_max, uint8_t* __restrict__ silent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -164,23 +168,46 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
   // (clip, tile-in-clip) pair is advanced incrementally in 32-bit arithmetic
   const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
   const int g = tid / 20, j = tid % 20;
-  const bool base_ok = ((reinterpret_cast<uintptr_t>(audio) & 15u) == 0) && (L % 4 == 0);
   const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
   const bool mel_fast = packed && pack->balanced != 0;
   const int step_b = (int)(gridDim.x / (unsigned)tiles_per_clip);
   const int step_t = (int)(gridDim.x % (unsigned)tiles_per_clip);
 
-  // Interior tiles (no reflection, no zero padding) are fetched with 16-byte cp.async one tile
-  // ahead; clip-edge tiles are assembled sample by sample when their turn comes.
-  auto is_fast = [&](int tt) -> bool {
-    const int64_t p0 = (int64_t)tt * (kTileFrames * kHop);
-    return base_ok && p0 >= kNfft / 2 && p0 - kNfft / 2 + kTileSamples <= L;
+  // Clip b is audio[b*L : (b+1)*L] (dense batch) or audio[offsets[b] : offsets[b+1]] cut to Lp
+  // samples (ragged batch: pad_or_trim fused in; the zero padding is never materialised).
+  auto clip_of = [&](int64_t b, int64_t& len) -> const float* {
+    if (offsets != nullptr) {
+      const int64_t o = offsets[b];
+      len = min(offsets[b + 1] - o, Lp);
+      return audio + o;
+    }
+    len = L;
+    return audio + b * L;
+  };
+  // Tile classes.  kSilent: every sample the tile touches (reflection included) lies in the zero
+  // padding, known from the clip length alone - nothing is read.  kFast16 / kFast4: interior tile
+  // (no reflection, no padding) fetched one tile ahead with 16- or 4-byte cp.async.  kEdge:
+  // assembled sample by sample when its turn comes.
+  enum { kSilent = 0, kFast16 = 1, kFast4 = 2, kEdge = 3 };
+  auto classify = [&](const float* clip, int64_t len, int tt) -> int {
+    const int64_t lo = (int64_t)tt * (kTileFrames * kHop) - kNfft / 2, hi = lo + kTileSamples;
+    if (lo >= len && (hi <= Lp || 2 * (Lp - 1) - (hi - 1) >= len)) return kSilent;
+    if (lo >= 0 && hi <= len)
+      return ((reinterpret_cast<uintptr_t>(clip + lo) & 15u) == 0) ? kFast16 : kFast4;
+    return kEdge;
   };
   auto prefetch = [&](int64_t b, int tt, int buf) {
-    if (b < B && is_fast(tt)) {
-      const float* src = audio + b * L + ((int64_t)tt * (kTileFrames * kHop) - kNfft / 2);
-      for (int i = tid; i < kTileSamples / 4; i += kThreads)
-        cp_async16(&sm.audio[buf][tile_pos(4 * i)], src + 4 * i);     // skew is a multiple of 4 floats
+    if (b < B) {
+      int64_t len;
+      const float* clip = clip_of(b, len);
+      const int cls = classify(clip, len, tt);
+      const float* src = clip + ((int64_t)tt * (kTileFrames * kHop) - kNfft / 2);
+      if (cls == kFast16) {
+        for (int i = tid; i < kTileSamples / 4; i += kThreads)
+          cp_async16(&sm.audio[buf][tile_pos(4 * i)], src + 4 * i);     // skew is a multiple of 4 floats
+      } else if (cls == kFast4) {
+        for (int i = tid; i < kTileSamples; i += kThreads) cp_async4(&sm.audio[buf][tile_pos(i)], src + i);
+      }
     }
     cp_async_commit();
   };
@@ -198,17 +225,21 @@ logmel_tile_kernel(const float* __restrict__ audio, int64_t B, int64_t L, int64_
     cp_async_wait<1>();                                  // this tile's group has landed
     const int64_t t0 = (int64_t)tt * kTileFrames;
     float* au = sm.audio[cur];
+    int64_t len;
+    const float* clip = clip_of(b, len);
+    const int cls = classify(clip, len, tt);
     bool nz = false;
-    if (is_fast(tt)) {
+    if (cls == kFast16) {
       for (int i = tid; i < kTileSamples / 4; i += kThreads) {   // the chunks this thread fetched
         const float4 q = *reinterpret_cast<const float4*>(&au[tile_pos(4 * i)]);
         nz |= (q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f) | (q.w != 0.0f);
       }
-    } else {
-      const float* clip = audio + b * L;
+    } else if (cls == kFast4) {
+      for (int i = tid; i < kTileSamples; i += kThreads) nz |= (au[tile_pos(i)] != 0.0f);
+    } else if (cls == kEdge) {
       const int64_t p0 = t0 * kHop;
       for (int i = tid; i < kTileSamples; i += kThreads) {
-        const float q = padded_sample(clip, L, Lp, p0 + i);
+        const float q = padded_sample(clip, len, Lp, p0 + i);
         au[tile_pos(i)] = q;
         nz |= (q != 0.0f);
       }
@@ -438,7 +469,7 @@ extern "C" int avfe_logmel_prepare(const float* mel_filters, int n_mels, void* p
 }
 
 // shared tail of the two log-mel entry points: clip maxima <- -inf, tile kernel, finalize
-static int logmel_run(const float* audio, int64_t B, int64_t L, int64_t padding, int n_mels,
+static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int64_t L, int64_t padding, int n_mels,
                       const float* mel_filters, const lm::MelPack* pack, float* out,
                       int* clip_max, uint8_t* silent, cudaStream_t s) {
   const int64_t Lp = L + padding;
@@ -457,7 +488,7 @@ static int logmel_run(const float* audio, int64_t B, int64_t L, int64_t padding,
   const int64_t n_tiles = B * ((n_frames + lm::kTileFrames - 1) / lm::kTileFrames);
   int64_t ctas = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;   // 2 resident CTAs per SM
   lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
-      audio, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent);
+      audio, offsets, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent);
   count_launch();
   const int64_t total = B * (int64_t)n_mels * n_frames;
   int64_t fin = (total / 4 + 255) / 256 + 1;
@@ -494,7 +525,7 @@ extern "C" int avfe_logmel_f32(const float* audio, int64_t B, int64_t L, int64_t
   uint8_t* silent = reinterpret_cast<uint8_t*>(pack) + sizeof(lm::MelPack);
   lm::logmel_prep_kernel<<<1, 1024, 0, s>>>(mel_filters, n_mels, 0, nullptr, pack);
   count_launch();
-  return logmel_run(audio, B, L, padding, n_mels, mel_filters, pack, out, clip_max, silent, s);
+  return logmel_run(audio, nullptr, B, L, padding, n_mels, mel_filters, pack, out, clip_max, silent, s);
 }
 
 extern "C" int avfe_logmel_prepared_f32(const float* audio, int64_t B, int64_t L, int64_t padding,
@@ -507,8 +538,32 @@ extern "C" int avfe_logmel_prepared_f32(const float* audio, int64_t B, int64_t L
   int* clip_max = static_cast<int*>(workspace);
   uint8_t* silent = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) +
                                                (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack));
-  return logmel_run(audio, B, L, padding, n_mels, mel_filters, static_cast<const lm::MelPack*>(pack), out,
+  return logmel_run(audio, nullptr, B, L, padding, n_mels, mel_filters, static_cast<const lm::MelPack*>(pack), out,
                     clip_max, silent, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, int64_t B,
+                                      int64_t length, int n_mels, const float* mel_filters,
+                                      const void* pack, float* out, void* workspace,
+                                      size_t workspace_bytes, avfe_stream_t stream) {
+  const int rc = logmel_check(audio, B, length, 0, n_mels, out, workspace, workspace_bytes);
+  if (rc != AVFE_OK) return rc > 0 ? AVFE_OK : rc;
+  if (!offsets || !mel_filters) return AVFE_ERR_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* clip_max = static_cast<int*>(workspace);
+  lm::MelPack* own = reinterpret_cast<lm::MelPack*>(static_cast<char*>(workspace) +
+                                                    (((size_t)B * sizeof(int) + 15) & ~(size_t)15));
+  uint8_t* silent = reinterpret_cast<uint8_t*>(own) + sizeof(lm::MelPack);
+  const lm::MelPack* use = static_cast<const lm::MelPack*>(pack);
+  if (use == nullptr) {                                   // no prepared pack: analyse the filters now
+    lm::logmel_prep_kernel<<<1, 1024, 0, s>>>(mel_filters, n_mels, 0, nullptr, own);
+    count_launch();
+    use = own;
+  } else if (!aligned16(pack)) {
+    return AVFE_ERR_INVALID_ARG;
+  }
+  // L = 0: clips come from `offsets`; the padded length is `length`
+  return logmel_run(audio, offsets, B, 0, length, n_mels, mel_filters, use, out, clip_max, silent, s);
 }
 
 extern "C" int avfe_pad_or_trim_f32(const float* in, int64_t B, int64_t L_in, int64_t L_out,

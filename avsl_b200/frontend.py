@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .audio import HOP_LENGTH, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, mel_filters
+from .audio import (HOP_LENGTH, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, log_mel_spectrogram_ragged,
+                    mel_filters)
 from .lips import IMAGE_CROP_SIZE, IMAGE_MEAN, IMAGE_STD, LipBatch, lip_roi_batch
 
 FPS = 25
@@ -119,8 +120,8 @@ class AVFrontEnd:
     # ---------------------------------------------------------------- device-resident path
     def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None,
                        mark=None) -> Dict[str, torch.Tensor]:
-        """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] skips
-        the pad_or_trim launch when the caller already holds the padded matrix.  ``mark(name)``
+        """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] makes the
+        log-mel read an already padded matrix instead of the ragged ``batch.audio``.  ``mark(name)``
         (optional) is called after each stage is enqueued (bench.py records CUDA events there).
         Returns device tensors: mel [U,n_mels,F], lip [N,88,88,1], gray [N,H,W] (optional),
         lip_u8 [N,96,96] (optional)."""
@@ -128,13 +129,13 @@ class AVFrontEnd:
         mark = mark or (lambda name: None)
         with torch.cuda.device(self.device):
             mark("start")
-            if padded_audio is None:
-                padded_audio = self._buf("audio", (U, L), torch.float32)
-                _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(batch.audio), _lib.ptr(batch.audio_offsets),
-                          U, L, _lib.ptr(padded_audio), _lib.stream_ptr())
-                mark("pad")
             mel = self._buf("mel", (U, self.n_mels, L // HOP_LENGTH), torch.float32)
-            log_mel_spectrogram(padded_audio, self.n_mels, filters=self.filters, out=mel)
+            if padded_audio is None:
+                # pad_or_trim is fused into the log-mel: the padded [U, L] matrix is never built
+                log_mel_spectrogram_ragged(batch.audio, batch.audio_offsets, L, self.n_mels,
+                                           filters=self.filters, out=mel)
+            else:
+                log_mel_spectrogram(padded_audio, self.n_mels, filters=self.filters, out=mel)
             mark("logmel")
             N, H, W = (int(s) for s in batch.frames.shape[:3])
             src = batch.frames

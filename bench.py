@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[4], "full AMI-shaped AV front-end sweep"): the 10,000 seeded
-synthetic utterances (durations clip(lognormal(ln 3, 0.9), 0.3, 30) s, 16 kHz audio zero-padded
-to 30 s as the reference's pad_or_trim does, 25 fps 224x224 BGR closeups with 68-point landmarks,
+synthetic utterances (durations clip(lognormal(ln 3, 0.9), 0.3, 30) s, 16 kHz audio that the path
+zero-pads to 30 s as the reference's pad_or_trim does, 25 fps 224x224 BGR closeups with 68-point landmarks,
 5% failed detections) are sharded i % world == rank; ONE STEP = one batch of U consecutive
 utterances of the rank's shard through log-mel (n_mels 80) + gray + lip-ROI warp/crop/normalise.
 The 10k sweep itself does not fit one GPU (169 GB of BGR frames), so a step is the largest unit
@@ -267,9 +267,6 @@ def main():
                             torch.from_numpy(np.concatenate(lms)).to(dev),
                             torch.from_numpy(np.concatenate(vals)).to(dev))
     fe = AVFrontEnd(n_mels=N_MELS, audio_max_length=AUDIO_LEN, device=dev, want_gray=True, fused=not args.unfused)
-    padded = torch.empty((U, AUDIO_LEN), dtype=torch.float32, device=dev)
-    _lib.call("avfe_pad_or_trim_ragged_f32", _lib.ptr(audio), _lib.ptr(batch_dev.audio_offsets), U, AUDIO_LEN,
-              _lib.ptr(padded), _lib.stream_ptr())
     torch.cuda.synchronize()
     audio_s = float(durs.sum())
     alg_bytes = algorithmic_bytes(U, N, H, W, N_MELS, AUDIO_LEN)
@@ -291,7 +288,7 @@ def main():
         return mark
 
     for _ in range(max(3, args.warmup)):
-        fe.forward_device(batch_dev, padded_audio=padded)
+        fe.forward_device(batch_dev)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -300,7 +297,7 @@ def main():
     barrier()
     t_start.record()
     for _ in range(args.steps):
-        fe.forward_device(batch_dev, padded_audio=padded, mark=make_mark(events))
+        fe.forward_device(batch_dev, mark=make_mark(events))
     t_end.record()
     barrier()
     sampler.pause()
@@ -435,7 +432,7 @@ def main():
     if fused:
         stage_names = ["logmel", "lip"]
         stage_ms.pop("gray", None)
-    kernel_names = {"logmel": "logmel_prep + logmel_tile_kernel + logmel_finalize (AMI batch: silent tiles take the exact zero-tile shortcut)",
+    kernel_names = {"logmel": "logmel_tile_kernel + logmel_finalize_kernel via avfe_logmel_ragged_f32 (pad_or_trim fused; AMI batch: frames inside the zero padding are not read, silent tiles skip the FFT - exact)",
                     "gray": "gray_vec_kernel",
                     "lip": ("tform_kernel + lip_fused_kernel<stream,88> (stream warps: BGR->gray; blend warps: ROI warp/crop/normalise)" if fused
                             else "tform_kernel + lip_fused_kernel<nostream,88> (ROI warp only, taps from the gray frames)")}

@@ -99,6 +99,17 @@ AVFE_API int avfe_logmel_prepared_f32(const float* audio, int64_t B, int64_t L, 
                                       float* out, void* workspace, size_t workspace_bytes,
                                       avfe_stream_t stream);
 
+/* pad_or_trim + log_mel_spectrogram fused for a ragged batch stored back to back
+ * (avsl/whisper_flamingo_ft_ami.py:209-213 in one call): clip b = audio[offsets[b] : offsets[b+1]],
+ * cut or zero-extended to `length` samples, then the log-mel of that.  The zero extension is
+ * never materialised and frames that lie entirely in it are not even read.  `pack` may be NULL
+ * (filters analysed on the fly).  out [B, n_mels, length/160]; workspace as for
+ * avfe_logmel_f32 with L = length, padding = 0. */
+AVFE_API int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, int64_t B,
+                                    int64_t length, int n_mels, const float* mel_filters,
+                                    const void* pack, float* out, void* workspace,
+                                    size_t workspace_bytes, avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ video (V1..V8) */
 
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) — preprocess/video_process.py:201-214:

@@ -146,3 +146,27 @@ def test_unprepared_entry_point_and_custom_filterbanks():
         _lib.call("avfe_logmel_f32", _lib.ptr(d_a), 3, 48000, 0, n_mels, _lib.ptr(d_fb), _lib.ptr(out),
                   _lib.ptr(ws), nbytes, _lib.stream_ptr())
         assert torch.equal(out.cpu(), got), name
+
+
+def test_ragged_fused_pad_or_trim():
+    """avfe_logmel_ragged_f32 == pad_or_trim + log_mel per clip, for lengths that are shorter,
+    equal and longer than the target, unaligned clip starts, a clip that is pure padding after a
+    few samples, and a clip of digital silence."""
+    L = 48000
+    lens = [48000, 12345, 60000, 201, 7, 30001]
+    clips = [synth.audio_clip(n, 40 + i) for i, n in enumerate(lens)]
+    clips[4] = np.zeros(7, np.float32) + 0.25
+    clips.append(np.zeros(20000, np.float32))
+    lens.append(20000)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    audio = torch.from_numpy(np.concatenate(clips)).cuda()
+    for n_mels in (80, 128):
+        got = A.log_mel_spectrogram_ragged(audio, torch.from_numpy(off).cuda(), L, n_mels).cpu()
+        assert got.shape == (len(lens), n_mels, 300)
+        for i, c in enumerate(clips):
+            ref = O.log_mel_spectrogram(O.pad_or_trim(c, L), n_mels)
+            assert (got[i] - ref).abs().max().item() <= TOL, (n_mels, i)
+    # the dense entry with a `padding` argument takes the same silent-by-length shortcut
+    a = synth.audio_clip(8000, 3)
+    x = A.log_mel_spectrogram(a, 80, padding=40000)
+    assert (x - O.log_mel_spectrogram(a, 80, padding=40000)).abs().max().item() <= TOL
