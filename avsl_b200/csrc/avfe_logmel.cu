@@ -147,11 +147,72 @@ logmel_prep_kernel(const float* __restrict__ fb, int n_mels, int64_t B, int* __r
   }
 }
 
+// clip b = audio[b*L : (b+1)*L] (dense batch) or audio[offsets[b] : offsets[b+1]] cut to Lp
+// samples (ragged batch: pad_or_trim fused in; the zero padding is never materialised)
+__device__ __forceinline__ const float* clip_of(const float* audio, const int64_t* offsets, int64_t b,
+                                                int64_t L, int64_t Lp, int64_t& len) {
+  if (offsets != nullptr) {
+    const int64_t o = offsets[b];
+    len = min(offsets[b + 1] - o, Lp);
+    return audio + o;
+  }
+  len = L;
+  return audio + b * L;
+}
+
+// Tile classes.  kSilent: every sample the tile touches (reflection included) lies in the zero
+// padding, known from the clip length alone - nothing is read.  kFast16 / kFast4: interior tile
+// (no reflection, no padding) fetched one tile ahead with 16- or 4-byte cp.async.  kEdge:
+// assembled sample by sample when its turn comes.
+enum { kSilent = 0, kFast16 = 1, kFast4 = 2, kEdge = 3 };
+__device__ __forceinline__ int classify_tile(const float* clip, int64_t len, int64_t Lp, int tt) {
+  const int64_t lo = (int64_t)tt * (kTileFrames * kHop) - kNfft / 2, hi = lo + kTileSamples;
+  if (lo >= len && (hi <= Lp || 2 * (Lp - 1) - (hi - 1) >= len)) return kSilent;
+  if (lo >= 0 && hi <= len)
+    return ((reinterpret_cast<uintptr_t>(clip + lo) & 15u) == 0) ? kFast16 : kFast4;
+  return kEdge;
+}
+
+// One warp per clip: list the tiles that have to be computed (everything that is not silent
+// by length), flag the others for logmel_finalize_kernel, and start the clip maximum at the
+// silent value when the clip has silent tiles (else at "-inf").
+__global__ void __launch_bounds__(256)
+logmel_live_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets, int64_t B,
+                   int64_t L, int64_t Lp, int tiles_per_clip, int* __restrict__ clip_max,
+                   uint8_t* __restrict__ silent, int* __restrict__ live_count,
+                   int2* __restrict__ live_list) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  int64_t len;
+  const float* clip = clip_of(audio, offsets, b, L, Lp, len);
+  int n_live = 0;
+  for (int t0 = 0; t0 < tiles_per_clip; t0 += 32) {
+    const int tt = t0 + lane;
+    const bool live = tt < tiles_per_clip && classify_tile(clip, len, Lp, tt) != kSilent;
+    n_live += __popc(__ballot_sync(0xffffffffu, live));
+  }
+  int base = 0;
+  if (lane == 0 && n_live) base = atomicAdd(live_count, n_live);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int t0 = 0; t0 < tiles_per_clip; t0 += 32) {
+    const int tt = t0 + lane;
+    const bool live = tt < tiles_per_clip && classify_tile(clip, len, Lp, tt) != kSilent;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (tt < tiles_per_clip) silent[b * tiles_per_clip + tt] = live ? 0 : 1;
+    if (live) live_list[base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)b, tt);
+    base += __popc(m);
+  }
+  // 0x80808080 as an ordered key is about -3.4e38: below every log10 value
+  if (lane == 0) clip_max[b] = (n_live < tiles_per_clip) ? float_key(log10_floor(0.0f)) : (int)0x80808080;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets, int64_t B,
                    int64_t L, int64_t Lp, int64_t n_frames, int n_mels, const float* __restrict__ fb,
                    const MelPack* __restrict__ pack, float* __restrict__ out,
-                   int* __restrict__ clip_max, uint8_t* __restrict__ silent) {
+                   int* __restrict__ clip_max, uint8_t* __restrict__ silent,
+                   const int* __restrict__ live_count, const int2* __restrict__ live_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -170,38 +231,17 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   const int g = tid / 20, j = tid % 20;
   const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
   const bool mel_fast = packed && pack->balanced != 0;
-  const int step_b = (int)(gridDim.x / (unsigned)tiles_per_clip);
-  const int step_t = (int)(gridDim.x % (unsigned)tiles_per_clip);
+  const int n_live = *live_count;                        // tiles to compute (logmel_live_kernel)
 
-  // Clip b is audio[b*L : (b+1)*L] (dense batch) or audio[offsets[b] : offsets[b+1]] cut to Lp
-  // samples (ragged batch: pad_or_trim fused in; the zero padding is never materialised).
-  auto clip_of = [&](int64_t b, int64_t& len) -> const float* {
-    if (offsets != nullptr) {
-      const int64_t o = offsets[b];
-      len = min(offsets[b + 1] - o, Lp);
-      return audio + o;
-    }
-    len = L;
-    return audio + b * L;
-  };
-  // Tile classes.  kSilent: every sample the tile touches (reflection included) lies in the zero
-  // padding, known from the clip length alone - nothing is read.  kFast16 / kFast4: interior tile
-  // (no reflection, no padding) fetched one tile ahead with 16- or 4-byte cp.async.  kEdge:
-  // assembled sample by sample when its turn comes.
-  enum { kSilent = 0, kFast16 = 1, kFast4 = 2, kEdge = 3 };
-  auto classify = [&](const float* clip, int64_t len, int tt) -> int {
-    const int64_t lo = (int64_t)tt * (kTileFrames * kHop) - kNfft / 2, hi = lo + kTileSamples;
-    if (lo >= len && (hi <= Lp || 2 * (Lp - 1) - (hi - 1) >= len)) return kSilent;
-    if (lo >= 0 && hi <= len)
-      return ((reinterpret_cast<uintptr_t>(clip + lo) & 15u) == 0) ? kFast16 : kFast4;
-    return kEdge;
-  };
-  auto prefetch = [&](int64_t b, int tt, int buf) {
-    if (b < B) {
+  // (clip, tile) records are read from the live list two tiles ahead so that the list load's
+  // latency never sits in front of a cp.async issue
+  const int2 none = make_int2(-1, 0);
+  auto prefetch = [&](int2 it, int buf) {
+    if (it.x >= 0) {
       int64_t len;
-      const float* clip = clip_of(b, len);
-      const int cls = classify(clip, len, tt);
-      const float* src = clip + ((int64_t)tt * (kTileFrames * kHop) - kNfft / 2);
+      const float* clip = clip_of(audio, offsets, it.x, L, Lp, len);
+      const int cls = classify_tile(clip, len, Lp, it.y);
+      const float* src = clip + ((int64_t)it.y * (kTileFrames * kHop) - kNfft / 2);
       if (cls == kFast16) {
         for (int i = tid; i < kTileSamples / 4; i += kThreads)
           cp_async16(&sm.audio[buf][tile_pos(4 * i)], src + 4 * i);     // skew is a multiple of 4 floats
@@ -211,23 +251,23 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
     }
     cp_async_commit();
   };
+  const int stride = (int)gridDim.x;
+  auto list_at = [&](int item) -> int2 { return item < n_live ? live_list[item] : none; };
 
-  int64_t b = blockIdx.x / (unsigned)tiles_per_clip;
-  int tt = (int)(blockIdx.x % (unsigned)tiles_per_clip);
   int cur = 0;
-  prefetch(b, tt, 0);
-  for (; b < B; cur ^= 1) {
-    // next tile of this CTA
-    int64_t bn = b + step_b;
-    int tn = tt + step_t;
-    if (tn >= tiles_per_clip) { tn -= tiles_per_clip; ++bn; }
-    prefetch(bn, tn, cur ^ 1);
+  int2 it = list_at((int)blockIdx.x), it_next = list_at((int)blockIdx.x + stride);
+  prefetch(it, 0);
+  for (int item = (int)blockIdx.x; item < n_live; item += stride, cur ^= 1) {
+    prefetch(it_next, cur ^ 1);                          // next tile of this CTA goes in flight
+    const int2 it_after = list_at(item + 2 * stride);
     cp_async_wait<1>();                                  // this tile's group has landed
+    const int64_t b = it.x;
+    const int tt = it.y;
     const int64_t t0 = (int64_t)tt * kTileFrames;
     float* au = sm.audio[cur];
     int64_t len;
-    const float* clip = clip_of(b, len);
-    const int cls = classify(clip, len, tt);
+    const float* clip = clip_of(audio, offsets, b, L, Lp, len);
+    const int cls = classify_tile(clip, len, Lp, tt);
     bool nz = false;
     if (cls == kFast16) {
       for (int i = tid; i < kTileSamples / 4; i += kThreads) {   // the chunks this thread fetched
@@ -236,7 +276,7 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
       }
     } else if (cls == kFast4) {
       for (int i = tid; i < kTileSamples; i += kThreads) nz |= (au[tile_pos(i)] != 0.0f);
-    } else if (cls == kEdge) {
+    } else {
       const int64_t p0 = t0 * kHop;
       for (int i = tid; i < kTileSamples; i += kThreads) {
         const float q = padded_sample(clip, len, Lp, p0 + i);
@@ -338,7 +378,8 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
       for (int w = 1; w < kThreads / 32; ++w) k = max(k, sm.red[w]);
       atomicMax(clip_max + b, k);
     }
-    b = bn; tt = tn;
+    it = it_next;
+    it_next = it_after;
   }
   cp_async_wait<0>();
 }
@@ -452,7 +493,9 @@ extern "C" size_t avfe_logmel_workspace_bytes(int64_t B, int64_t L, int64_t padd
   (void)n_mels;
   if (L < 0 || padding < 0) return 0;
   const size_t tiles = (size_t)B * (size_t)(((L + padding) / lm::kHop + lm::kTileFrames - 1) / lm::kTileFrames);
-  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + ((tiles + 15) & ~(size_t)15) + 64;
+  // clip maxima | MelPack | silent flags | live-tile count | live-tile list
+  return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + ((tiles + 15) & ~(size_t)15) + 16 +
+         tiles * sizeof(int2) + 64;
 }
 
 extern "C" size_t avfe_logmel_pack_bytes(void) { return sizeof(lm::MelPack); }
@@ -474,21 +517,29 @@ static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int
                       int* clip_max, uint8_t* silent, cudaStream_t s) {
   const int64_t Lp = L + padding;
   const int64_t n_frames = Lp / lm::kHop;
-  // 0x80808080 as an ordered key is about -3.4e38: below every log10 value
-  if (cudaMemsetAsync(clip_max, 0x80, (size_t)B * sizeof(int), s) != cudaSuccess) {
+  const int64_t tiles_per_clip = (n_frames + lm::kTileFrames - 1) / lm::kTileFrames;
+  const int64_t n_tiles = B * tiles_per_clip;
+  if (n_tiles > INT_MAX) return AVFE_ERR_UNSUPPORTED;
+  // live-tile count and list follow the silent flags in the workspace
+  int* live_count = reinterpret_cast<int*>(silent + (((size_t)n_tiles + 15) & ~(size_t)15));
+  int2* live_list = reinterpret_cast<int2*>(live_count + 4);
+  if (cudaMemsetAsync(live_count, 0, 16, s) != cudaSuccess) {
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
+  lm::logmel_live_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(
+      audio, offsets, B, L, Lp, (int)tiles_per_clip, clip_max, silent, live_count, live_list);
+  count_launch();
   // per-device attribute: set on every call (cheap) so multi-device processes stay correct
   if (cudaFuncSetAttribute(lm::logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(lm::Smem)) != cudaSuccess) {
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  const int64_t n_tiles = B * ((n_frames + lm::kTileFrames - 1) / lm::kTileFrames);
   int64_t ctas = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;   // 2 resident CTAs per SM
   lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
-      audio, offsets, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent);
+      audio, offsets, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent,
+      live_count, live_list);
   count_launch();
   const int64_t total = B * (int64_t)n_mels * n_frames;
   int64_t fin = (total / 4 + 255) / 256 + 1;
