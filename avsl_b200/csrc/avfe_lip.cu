@@ -136,24 +136,30 @@ __device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, 
 
 constexpr int kTformWarps = 4;
 
-__global__ void __launch_bounds__(kTformWarps * 32)
-tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
-             const int64_t* __restrict__ clip_offsets, int64_t n_clips, int64_t N,
-             const double* __restrict__ mean_face, const double* __restrict__ tforms_in,
-             int std_size, int roi, int window, int fp_lo, int fp_span, int H, int W, int fp_align,
-             FrameXform* __restrict__ xf, int32_t* __restrict__ crop_rc,
-             double* __restrict__ tforms_out, unsigned* __restrict__ queue_counter) {
-  if (queue_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0u;
+// everything tform_frame needs (the arguments of tform_kernel)
+struct TformArgs {
+  const double* lm;
+  const uint8_t* valid;
+  const int64_t* clip_offsets;
+  int64_t n_clips;
+  const double* mean_face;
+  const double* tforms_in;
+  int std_size, roi, window, fp_lo, fp_span, H, W, fp_align;
+  int32_t* crop_rc;
+  double* tforms_out;
+};
+
+// Window-smoothed similarity fit + cut_patch origin + footprint of frame f, computed by one warp
+// (V2 on the fly, V3, V4 fit, V6, V7).  The record is returned in every lane; lane 0 also writes
+// the optional crop_rc / tforms outputs.
+__device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f, int lane) {
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int64_t f = (int64_t)blockIdx.x * kTformWarps + (threadIdx.x >> 5);
-  if (f >= N) return;                                  // warp-uniform
-  const int64_t c = find_clip(clip_offsets, n_clips, f);
-  LmView v{lm, valid, clip_offsets[c], clip_offsets[c + 1]};
+  const int64_t c = find_clip(a.clip_offsets, a.n_clips, f);
+  LmView v{a.lm, a.valid, a.clip_offsets[c], a.clip_offsets[c + 1]};
   const int64_t T = v.end - v.beg;
   // margin = min(T, 12); frame i <= T-margin is fitted on mean(lm[i:i+margin]); later frames
   // reuse the transform of frame T-margin (preprocess/video_process.py:369-370,417-427,455-464)
-  const int margin = (int)(T < window ? T : window);   // window <= 31 is enforced by the caller
+  const int margin = (int)(T < a.window ? T : a.window);   // window <= 31 is enforced by the caller
   int64_t i0 = f - v.beg;
   if (i0 > T - margin) i0 = T - margin;
   const int64_t w0 = v.beg + i0;
@@ -163,8 +169,8 @@ tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
   lm_neighbours(v, mine, p, q);
 
   double fwd[6], inv[6];
-  if (tforms_in != nullptr) {
-    const double* ti = tforms_in + f * 18;
+  if (a.tforms_in != nullptr) {
+    const double* ti = a.tforms_in + f * 18;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { fwd[k] = ti[k]; inv[k] = ti[9 + k]; }
   } else {
@@ -183,8 +189,8 @@ tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
     for (int k = 0; k < kNumStable; ++k) {
       src[k][0] = __shfl_sync(full, mean, 2 * k);
       src[k][1] = __shfl_sync(full, mean, 2 * k + 1);
-      dst[k][0] = mean_face[(33 + 3 * k) * 2 + 0];
-      dst[k][1] = mean_face[(33 + 3 * k) * 2 + 1];
+      dst[k][0] = a.mean_face[(33 + 3 * k) * 2 + 0];
+      dst[k][1] = a.mean_face[(33 + 3 * k) * 2 + 1];
     }
     similarity_fit(src, dst, kNumStable, fwd);          // every lane computes the same fit
     affine_inverse(fwd, inv);
@@ -203,23 +209,34 @@ tform_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
   }
   cx = f64div(cx, 20.0);
   cy = f64div(cy, 20.0);
-  if (lane != 0) return;
   int r0, c0;
-  crop_origin(cx, cy, roi / 2, roi / 2, std_size, std_size, &r0, &c0);
+  crop_origin(cx, cy, a.roi / 2, a.roi / 2, a.std_size, a.std_size, &r0, &c0);
   FrameXform o;
 #pragma unroll
   for (int j = 0; j < 6; ++j) o.inv[j] = inv[j];
   o.r0 = r0; o.c0 = c0;
-  pack_footprint(o, fp_lo, fp_span, H, W, fp_align);
-  xf[f] = o;
-  if (crop_rc != nullptr) { crop_rc[2 * f] = r0; crop_rc[2 * f + 1] = c0; }
-  if (tforms_out != nullptr) {
-    double* to = tforms_out + f * 18;
+  pack_footprint(o, a.fp_lo, a.fp_span, a.H, a.W, a.fp_align);
+  if (lane == 0) {
+    if (a.crop_rc != nullptr) { a.crop_rc[2 * f] = r0; a.crop_rc[2 * f + 1] = c0; }
+    if (a.tforms_out != nullptr) {
+      double* to = a.tforms_out + f * 18;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { to[j] = fwd[j]; to[9 + j] = inv[j]; }
-    to[6] = 0.0; to[7] = 0.0; to[8] = 1.0;
-    to[15] = 0.0; to[16] = 0.0; to[17] = 1.0;
+      for (int j = 0; j < 6; ++j) { to[j] = fwd[j]; to[9 + j] = inv[j]; }
+      to[6] = 0.0; to[7] = 0.0; to[8] = 1.0;
+      to[15] = 0.0; to[16] = 0.0; to[17] = 1.0;
+    }
   }
+  return o;
+}
+
+__global__ void __launch_bounds__(kTformWarps * 32)
+tform_kernel(const TformArgs a, int64_t N, FrameXform* __restrict__ xf, unsigned* __restrict__ queue_counter) {
+  if (queue_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0u;
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * kTformWarps + (threadIdx.x >> 5);
+  if (f >= N) return;                                  // warp-uniform
+  const FrameXform o = tform_frame(a, f, lane);
+  if (lane == 0) xf[f] = o;
 }
 
 // ------------------------------------------------------------------ V1: BGR -> gray
@@ -320,6 +337,7 @@ static int launch_gray(const uint8_t* bgr, int64_t npx, uint8_t* gray, cudaStrea
 }  // namespace avfe
 
 #include "avfe_lip_queue.cuh"   // lip_fused_kernel: stream warps + compute warps
+#include "avfe_lip_frame.cuh"   // lip_frame_kernel: frame-owner CTAs, every BGR byte read once
 
 namespace avfe {
 
@@ -427,6 +445,19 @@ static int launch_fused(const LipJob& j, cudaStream_t s) {
   return AVFE_OK;
 }
 
+template <int SPAN>
+static int launch_frame(const FrameJob& j, cudaStream_t s) {
+  const int smem = (int)sizeof(FrameSmem<SPAN>);
+  if (cudaFuncSetAttribute(lip_frame_kernel<SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  const int64_t ctas = j.lip.N < kNumSMs ? j.lip.N : kNumSMs;          // one persistent CTA per SM
+  lip_frame_kernel<SPAN><<<(unsigned)ctas, 1024, smem, s>>>(j);
+  return AVFE_OK;
+}
+
 extern "C" int avfe_bgr2gray_u8(const uint8_t* bgr, int64_t N, int H, int W, uint8_t* gray,
                                 avfe_stream_t stream) {
   if (N < 0 || H < 0 || W < 0) return AVFE_ERR_INVALID_ARG;
@@ -488,9 +519,37 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
   else if (W % 4 == 0 && (fbase & 3u) == 0) fp_align = 4;
   (void)C;
   const int fp_lo = lip_u8 ? 0 : (roi - crop) / 2, fp_span = lip_u8 ? roi : crop;
-  tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(
-      landmarks, lm_valid, clip_offsets, n_clips, N, mean_face, tforms_in, std_size, roi, window,
-      fp_lo, fp_span, H, W, fp_align, xf, crop_rc, tforms, counter);
+  TformArgs ta;
+  ta.lm = landmarks; ta.valid = lm_valid; ta.clip_offsets = clip_offsets; ta.n_clips = n_clips;
+  ta.mean_face = mean_face; ta.tforms_in = tforms_in; ta.std_size = std_size; ta.roi = roi;
+  ta.window = window; ta.fp_lo = fp_lo; ta.fp_span = fp_span; ta.H = H; ta.W = W; ta.fp_align = fp_align;
+  ta.crop_rc = crop_rc; ta.tforms_out = tforms;
+
+  // window side known at compile time for the two standard configurations
+  const int span_sel = (lip_u8 != nullptr && roi == 96) ? 96
+                     : (lip_u8 == nullptr && lip_f32 != nullptr && crop == 88) ? 88 : 0;
+  // Standard case: BGR frames whose rows keep 16-byte alignment, gray frames wanted.  One launch
+  // in which each CTA owns whole frames (fit + gray + footprint + blend), every byte read once.
+  if (span_sel != 0 && channels == 3 && fp_align == 16 && gray_out != nullptr && aligned16(gray_out) &&
+      W >= 32 && W <= 8191 && H <= 8191 && (int64_t)H * W / 16 < (1 << 22)) {
+    FrameJob fj;
+    LipJob& j = fj.lip;
+    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = nullptr;
+    j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
+    j.gray_out = gray_out; j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = nullptr;
+    j.ngroups = 0; j.stage_align = fp_align;
+    fj.tf = ta;
+    fj.groups_per_frame = (int)((int64_t)H * W / 16);
+    fj.chunks_per_frame = (fj.groups_per_frame + 63) / 64;
+    fj.row_groups = W / 16;
+    fj.row_magic = (unsigned)(0x100000000ULL / (unsigned)fj.row_groups) + 1u;
+    const int rc = (span_sel == 96) ? launch_frame<96>(fj, s) : launch_frame<88>(fj, s);
+    if (rc != AVFE_OK) return rc;
+    count_launch();
+    return check_launch();
+  }
+
+  tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(ta, N, xf, counter);
   count_launch();
 
   const int64_t npx = (int64_t)H * W;
@@ -511,9 +570,6 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
     j.ngroups = (N * npx) / 512;
     j.stage_align = fp_align;
-    // window side known at compile time for the two standard configurations
-    const int span_sel = (lip_u8 != nullptr && roi == 96) ? 96
-                       : (lip_u8 == nullptr && lip_f32 != nullptr && crop == 88) ? 88 : 0;
     int rc = AVFE_OK;
     if (fuse_gray) {
       if (span_sel == 96) rc = launch_fused<true, 96>(j, s);

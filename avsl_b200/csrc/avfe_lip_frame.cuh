@@ -1,0 +1,323 @@
+// lip_frame_kernel: gray conversion, transform fit and ROI warp of a batch in ONE persistent
+// launch in which every BGR byte is read from HBM exactly once.  One 1024-thread CTA per SM owns
+// whole frames (f = blockIdx.x + k * gridDim.x); three warp roles, no CTA-wide barrier:
+//
+//   tform warps  (2) window-smoothed similarity fit, cut_patch origin and source footprint of
+//                the CTA's frames, a few frames ahead of everybody else (tform_frame, shared
+//                with tform_kernel), published through a 4-deep descriptor ring
+//   stream warps (8 for an 88-px window, 6 for 96) pull the frame through shared memory in
+//                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier) per
+//                chunk and a 6-deep ring per warp, convert BGR->gray (integer dp2a), store the
+//                gray frame with 16-byte streaming stores, and drop the gray pixels that lie
+//                inside the frame's ROI footprint into a double-buffered shared-memory tile
+//   blend warps  (22 / 24) float64 bilinear blend of the previous frame's ROI from that tile in
+//                skimage's operation order: u8 ROI and/or normalised f32 centre crop
+//
+// Hand-over is by mbarriers only (ring FULL per stage, descriptor FULL/EMPTY, tile FULL/EMPTY);
+// the FP64 work of frame k hides under the memory time of frame k+1.
+// Included by avfe_lip.cu only (after avfe_lip_queue.cuh, whose gray and blend helpers it uses).
+#pragma once
+
+namespace avfe {
+
+constexpr int kTformRoleWarps = 2;
+constexpr int kFrameRing = 6;               // bulk copies in flight per stream warp (x 3 KB)
+constexpr int kDescRing = 4;
+constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slot (u16 each)
+
+template <int SPAN>
+struct FrameRoles {
+  static constexpr int kSide = SPAN;
+  static constexpr int kBlendWarps = 8 * SPAN / 32;                    // 22 or 24
+  static constexpr int kBlendThreads = kBlendWarps * 32;
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 6
+  static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
+  static constexpr int kTformFirst = 32 - kTformRoleWarps;            // highest warp ids: scheduled first
+};
+
+struct FrameJob {
+  LipJob lip;                // frames, sizes, outputs (xf / counter unused)
+  TformArgs tf;
+  int chunks_per_frame;      // ceil(H*W / 1024)
+  int groups_per_frame;      // H*W / 16
+  int row_groups;            // W / 16
+  unsigned row_magic;        // exact g / row_groups for g < 2^22 (umulhi)
+};
+
+template <int SPAN>
+struct FrameSmem {
+  double lut255[256 * 16];                    // k / 255.0, 16 interleaved copies (see FusedSmem)
+  float lutn[256];                            // ((k/255) - mean) / std in float32
+  unsigned long long ring_full[FrameRoles<SPAN>::kStreamWarps][kFrameRing];
+  unsigned long long desc_full[kDescRing], desc_empty[kDescRing];
+  unsigned long long tile_full[2], tile_empty[2];
+  FrameXform desc[kDescRing];
+  __align__(16) uint16_t tile[2][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
+  __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][kFrameRing][kChunkVec];
+};
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "AVFE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra AVFE_DONE;\n"
+      "bra AVFE_WAIT;\n"
+      "AVFE_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------- tform warps
+template <int SPAN>
+__device__ __forceinline__ void frame_tform_run(const FrameJob& j, FrameSmem<SPAN>& sm, int tw, int lane,
+                                                int nk) {
+  for (int k = tw; k < nk; k += kTformRoleWarps) {
+    const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+    const FrameXform x = tform_frame(j.tf, f, lane);
+    const int slot = k % kDescRing, use = k / kDescRing;
+    if (use > 0) mbar_wait(&sm.desc_empty[slot], (unsigned)(use - 1) & 1u);   // every reader is done with it
+    if (lane == 0) {
+      sm.desc[slot] = x;
+      mbar_arrive(&sm.desc_full[slot]);                  // release: the record is visible to the waiters
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- stream warps
+// 16 packed gray bytes -> 16 x u16 (128 * k), two uint4
+__device__ __forceinline__ void gray16_to_tile(const uint4& g, uint4& lo, uint4& hi) {
+  auto pair_lo = [](uint32_t w) { return __byte_perm(w, 0u, 0x4140) << 7; };   // bytes 0,1
+  auto pair_hi = [](uint32_t w) { return __byte_perm(w, 0u, 0x4342) << 7; };   // bytes 2,3
+  lo = make_uint4(pair_lo(g.x), pair_hi(g.x), pair_lo(g.y), pair_hi(g.y));
+  hi = make_uint4(pair_lo(g.z), pair_hi(g.z), pair_lo(g.w), pair_hi(g.w));
+}
+
+template <int SPAN>
+__device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SPAN>& sm, int sw, int lane,
+                                                 int nk) {
+  using R = FrameRoles<SPAN>;
+  constexpr int S = R::kStreamWarps;
+  const LipJob& L = j.lip;
+  const int cpf = j.chunks_per_frame, gpf = j.groups_per_frame;
+  const int64_t frame_bytes = (int64_t)gpf * 48, frame_px = (int64_t)gpf * 16;
+  uint4(*ring)[kChunkVec] = sm.ring[sw];
+  unsigned long long* full = sm.ring_full[sw];
+
+  // issue side: (ik, ic) = next chunk to request; stage / use counter of the ring slot it goes to
+  int ik = (sw < cpf) ? 0 : nk, ic = sw, istage = 0;     // a frame may have fewer chunks than stream warps
+  auto issue = [&]() {
+    if (ik < nk) {
+      if (lane == 0) {
+        const int64_t f = (int64_t)blockIdx.x + (int64_t)ik * gridDim.x;
+        const int groups = min(64, gpf - ic * 64);
+        const unsigned bytes = (unsigned)groups * 48u;
+        mbar_arrive_expect_tx(&full[istage], bytes);
+        bulk_load(ring[istage], L.frames + f * frame_bytes + (int64_t)ic * (kChunkVec * 16), bytes, &full[istage]);
+      }
+      ic += S;
+      if (ic >= cpf) { ic = sw; ++ik; }
+    }
+    if (++istage == kFrameRing) istage = 0;
+  };
+#pragma unroll 1
+  for (int i = 0; i < kFrameRing - 1; ++i) issue();
+
+  int stage = 0;
+  unsigned phase = 0;                                    // parity of the current pass over the ring
+  for (int k = 0; k < nk; ++k) {
+    const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+    // this frame's footprint box (the tform warps are ahead) and its tile slot
+    const int dslot = k % kDescRing, slot = k & 1;
+    mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
+    const unsigned box_lo = sm.desc[dslot].box_lo, box_hi = sm.desc[dslot].box_hi;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.desc_empty[dslot]);
+    const bool staged = ((box_lo >> 27) & 1u) != 0;
+    const int br0 = (int)(box_lo & 0x1fffu), bcg = (int)((box_lo >> 13) & 0x1fffu) >> 4;
+    const int brows = staged ? (int)(box_hi & 0x1fffu) : 0, bpg = (int)((box_hi >> 13) & 0x1fffu) >> 4;
+    if (k >= 2) mbar_wait(&sm.tile_empty[slot], (unsigned)((k >> 1) - 1) & 1u);   // blend warps left the slot
+    uint4* tile = reinterpret_cast<uint4*>(sm.tile[slot]);
+    uint4* gout = reinterpret_cast<uint4*>(L.gray_out + f * frame_px);
+    for (int c = sw; c < cpf; c += S) {
+      mbar_wait(&full[stage], phase);                    // chunk landed
+      const uint4* s = ring[stage];
+      // lane owns 48 contiguous bytes (16 px) of each of the chunk's two halves
+      const uint4 p0 = s[3 * lane], p1 = s[3 * lane + 1], p2 = s[3 * lane + 2];
+      const uint4 q0 = s[96 + 3 * lane], q1 = s[96 + 3 * lane + 1], q2 = s[96 + 3 * lane + 2];
+      __syncwarp();                                      // every lane has read: the stage may be refilled
+      issue();                                           // into the stage consumed one iteration ago
+      const uint4 ga = gray16_dp2a(p0, p1, p2), gb = gray16_dp2a(q0, q1, q2);
+      const int g0 = c * 64 + lane, g1 = g0 + 32;        // 16-px group indices inside the frame
+      if (g0 < gpf) stg_stream(gout + g0, ga);
+      if (g1 < gpf) stg_stream(gout + g1, gb);
+      if (brows > 0) {
+        // groups never straddle rows (W % 16 == 0); deposit those inside the footprint box
+        const int ra = (int)__umulhi((unsigned)g0, j.row_magic), ca = g0 - ra * j.row_groups;
+        const int rb = (int)__umulhi((unsigned)g1, j.row_magic), cb = g1 - rb * j.row_groups;
+        if ((unsigned)(ra - br0) < (unsigned)brows && (unsigned)(ca - bcg) < (unsigned)bpg && g0 < gpf) {
+          uint4 lo, hi;
+          gray16_to_tile(ga, lo, hi);
+          uint4* t = tile + 2 * ((ra - br0) * bpg + (ca - bcg));
+          t[0] = lo; t[1] = hi;
+        }
+        if ((unsigned)(rb - br0) < (unsigned)brows && (unsigned)(cb - bcg) < (unsigned)bpg && g1 < gpf) {
+          uint4 lo, hi;
+          gray16_to_tile(gb, lo, hi);
+          uint4* t = tile + 2 * ((rb - br0) * bpg + (cb - bcg));
+          t[0] = lo; t[1] = hi;
+        }
+      }
+      if (++stage == kFrameRing) { stage = 0; phase ^= 1u; }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.tile_full[slot]);     // release: this warp's part of the footprint is in
+  }
+}
+
+// ---------------------------------------------------------------- blend warps
+template <int SPAN>
+__device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, const FrameXform& x,
+                                                 const uint16_t* tile, const double* lut255, const float* lutn,
+                                                 int tid) {
+  using R = FrameRoles<SPAN>;
+  const Footprint fp = unpack_footprint(x);
+  const double* lut = lut255 + (tid & 15);              // this lane's copy of the k/255 table
+  const int off = (j.roi - j.crop) / 2;
+  const int lo = j.lip_u8 ? 0 : off;
+  constexpr int S = SPAN;
+  uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
+  float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
+  auto emit = [&](int r, int c, uint32_t v) {
+    if (SPAN == 88) {                                   // centre crop only: window == f32 output
+      out_f32[r * 88 + c] = lutn[v];
+      return;
+    }
+    const int pr = lo + r, pc = lo + c;
+    if (out_u8) out_u8[pr * j.roi + pc] = (uint8_t)v;
+    if (out_f32) {
+      const int cr = pr - off, cc = pc - off;
+      if ((unsigned)cr < (unsigned)j.crop && (unsigned)cc < (unsigned)j.crop)
+        out_f32[cr * j.crop + cc] = lutn[v];
+    }
+  };
+  if (x.r0 < 0) {                                       // clip without any detection: zero ROI
+    for (int idx = tid; idx < S * S; idx += R::kBlendThreads) emit(idx / S, idx % S, 0u);
+    return;
+  }
+  // x_ = (M0*c + M1*r) + M2: two roundings per product as in skimage's _transform_affine; the
+  // integer coordinates are exact in float64, so tr + 8 is the next row of this thread exactly
+  const double m0 = x.inv[0], m1 = x.inv[1], m2 = x.inv[2], m3 = x.inv[3], m4 = x.inv[4], m5 = x.inv[5];
+  const int br0 = fp.r0, bc0 = fp.c0, pitch = fp.pitch;
+  const int rr = tid / S, c = tid - rr * S;             // thread = (column, row phase)
+  const double tc = (double)(x.c0 + lo + c);
+  const double cx = f64mul(m0, tc), cy = f64mul(m3, tc);
+  double tr = (double)(x.r0 + lo + rr);
+  if (fp.interior && fp.staged) {
+#pragma unroll
+    for (int i = 0; i < S / 8; ++i) {
+      const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
+      const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
+      emit(rr + 8 * i, c, bilinear_interior(sr, sc, tile, pitch, br0, bc0, lut));
+      tr = f64add(tr, 8.0);
+    }
+    return;
+  }
+  // ROI hanging over the frame border, or a footprint too large to stage: bounds-checked taps
+  const int H = j.H, W = j.W;
+  const uint8_t* img = j.frames + f * (int64_t)H * W * 3;
+  const int brows = fp.staged ? fp.rows : 0;
+  auto tap = [&](int r, int cc) -> double {
+    const int tr_ = r - br0, tc_ = cc - bc0;
+    if ((unsigned)tr_ < (unsigned)brows && (unsigned)tc_ < (unsigned)pitch) return lut_at(lut, tile[tr_ * pitch + tc_]);
+    const uint8_t* p = img + ((int64_t)r * W + cc) * 3;                 // not staged: global tap
+    return lut[16 * gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2))];
+  };
+  for (int i = 0; i < S / 8; ++i) {
+    const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
+    const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
+    emit(rr + 8 * i, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
+    tr = f64add(tr, 8.0);
+  }
+}
+
+template <int SPAN>
+__device__ __forceinline__ void frame_blend_run(const FrameJob& j, FrameSmem<SPAN>& sm, int tid, int nk) {
+  const int lane = tid & 31;
+  for (int k = 0; k < nk; ++k) {
+    const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+    const int dslot = k % kDescRing, slot = k & 1;
+    mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
+    const FrameXform x = sm.desc[dslot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.desc_empty[dslot]);
+    mbar_wait(&sm.tile_full[slot], (unsigned)(k >> 1) & 1u);   // the whole frame has been streamed
+    frame_blend_item<SPAN>(j.lip, f, x, sm.tile[slot], sm.lut255, sm.lutn, tid);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.tile_empty[slot]);
+  }
+}
+
+template <int SPAN>
+__global__ void __launch_bounds__(1024, 1)
+lip_frame_kernel(const FrameJob j) {
+  using R = FrameRoles<SPAN>;
+  extern __shared__ __align__(16) unsigned char frame_smem_raw[];
+  FrameSmem<SPAN>& sm = *reinterpret_cast<FrameSmem<SPAN>*>(frame_smem_raw);
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  // frames of this CTA: blockIdx.x, + gridDim.x, ...
+  const int64_t N = j.lip.N;
+  const int nk = (int)((N - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  if (tid == 0) {
+    for (int w = 0; w < R::kStreamWarps; ++w)
+      for (int s = 0; s < kFrameRing; ++s) mbar_init(&sm.ring_full[w][s], 1u);
+    for (int s = 0; s < kDescRing; ++s) {
+      mbar_init(&sm.desc_full[s], 1u);
+      mbar_init(&sm.desc_empty[s], (unsigned)(R::kStreamWarps + R::kBlendWarps));
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.tile_full[s], (unsigned)R::kStreamWarps);
+      mbar_init(&sm.tile_empty[s], (unsigned)R::kBlendWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < 256; k += 1024) {
+    const double q = f64div((double)k, 255.0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) sm.lut255[k * 16 + c] = q;
+    sm.lutn[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)k, 255.0f), j.lip.mean), j.lip.stdv);
+  }
+  __syncthreads();                                       // the only CTA-wide barrier
+  if (wid >= R::kTformFirst) {
+    frame_tform_run<SPAN>(j, sm, wid - R::kTformFirst, lane, nk);
+  } else if (wid >= R::kStreamFirst) {
+    frame_stream_run<SPAN>(j, sm, wid - R::kStreamFirst, lane, nk);
+  } else {
+    frame_blend_run<SPAN>(j, sm, tid, nk);
+  }
+}
+
+}  // namespace avfe
