@@ -58,6 +58,47 @@ __device__ __forceinline__ int64_t find_clip(const int64_t* __restrict__ clip_of
   return lo;
 }
 
+// lm_value in two phases so that a warp can put all its loads in flight before any arithmetic:
+// lm_taps issues the (at most two) loads, lm_blend applies landmarks_interpolate's rule.
+struct LmTaps { double s, t; };
+__device__ __forceinline__ LmTaps lm_taps(const LmView& v, int64_t f, int64_t p, int64_t q, int e) {
+  const bool has_p = p >= v.beg, has_q = q < v.end;
+  int64_t a = f, b = f;                               // p == f (a detection) or no detection at all
+  if (p != f && (has_p || has_q)) {
+    a = has_p ? p : q;                                // one-sided: replicate the nearest detection
+    b = has_q ? q : p;
+  }
+  LmTaps r;
+  r.s = v.lm[a * 136 + e];
+  r.t = (b != a) ? v.lm[b * 136 + e] : r.s;
+  return r;
+}
+__device__ __forceinline__ double lm_blend(const LmView& v, int64_t f, int64_t p, int64_t q, const LmTaps& x) {
+  if (p == f) return x.s;
+  const bool has_p = p >= v.beg, has_q = q < v.end;
+  if (!has_p && !has_q) return nan("");               // no detection in the whole clip
+  if (!has_p || !has_q) return x.s;
+  // start + idx/float(stop-start) * delta   (utils/lips_cropping.py:54-57)
+  const double w = f64div((double)(f - p), (double)(q - p));
+  return f64add(x.s, f64mul(w, f64sub(x.t, x.s)));
+}
+
+// find_clip by a whole warp: binary search down to <= 1024 candidates, then every lane counts
+// the boundaries <= f among its share (independent loads) and the counts are summed
+__device__ __forceinline__ int64_t find_clip_warp(const int64_t* __restrict__ clip_offsets, int64_t n_clips,
+                                                  int64_t f, int lane) {
+  int64_t lo = 0, hi = n_clips;
+  while (hi - lo > 1024) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (clip_offsets[mid] <= f) lo = mid; else hi = mid;
+  }
+  int cnt = 0;
+  for (int64_t i = lo + 1 + lane; i < hi; i += 32) cnt += (clip_offsets[i] <= f) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  return lo + cnt;
+}
+
 // V2 alone (avfe_landmarks_interpolate): one CTA per frame
 __global__ void __launch_bounds__(160)
 lm_fill_kernel(const double* __restrict__ lm, const uint8_t* __restrict__ valid,
@@ -154,7 +195,7 @@ struct TformArgs {
 // the optional crop_rc / tforms outputs.
 __device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f, int lane) {
   const unsigned full = 0xffffffffu;
-  const int64_t c = find_clip(a.clip_offsets, a.n_clips, f);
+  const int64_t c = find_clip_warp(a.clip_offsets, a.n_clips, f, lane);
   LmView v{a.lm, a.valid, a.clip_offsets[c], a.clip_offsets[c + 1]};
   const int64_t T = v.end - v.beg;
   // margin = min(T, 12); frame i <= T-margin is fitted on mean(lm[i:i+margin]); later frames
@@ -174,14 +215,41 @@ __device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f,
 #pragma unroll
     for (int k = 0; k < 6; ++k) { fwd[k] = ti[k]; inv[k] = ti[9 + k]; }
   } else {
-    // lanes 0..9 own one coordinate of one stable point (33,36,39,42,45); np.mean(axis=0) adds
-    // the window rows in order
-    const int slot = lane % 10;
+    // np.mean(axis=0) of the 5 stable points (33,36,39,42,45) adds the window rows in order.
+    // slot = one coordinate of one point.  Loads first: lane (slot, grp) fetches window frames
+    // grp, grp+3, grp+6, grp+9, so a 12-frame window costs one round of loads instead of twelve
+    // dependent ones; then lanes sum their slot's values in row order through shuffles.
+    const int grp = lane / 10, slot = lane - 10 * grp;  // lanes 30, 31 (grp 3) fetch nothing
     const int e = (33 + 3 * (slot >> 1)) * 2 + (slot & 1);
     double acc = 0.0;
-    for (int j = 0; j < margin; ++j) {
-      const int64_t pj = __shfl_sync(full, p, j), qj = __shfl_sync(full, q, j);
-      acc = f64add(acc, lm_value(v, w0 + j, pj, qj, e));
+    if (margin <= 12) {
+      LmTaps taps[4];
+      int64_t pj[4], qj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = 3 * u + grp;                      // <= 12
+        pj[u] = __shfl_sync(full, p, jj);
+        qj[u] = __shfl_sync(full, q, jj);
+        const bool mine_u = grp < 3 && jj < margin;
+        if (!mine_u) { pj[u] = f; qj[u] = f; }           // harmless in-range address
+        taps[u] = lm_taps(v, mine_u ? w0 + jj : f, pj[u], qj[u], e);
+      }
+      double vals[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = 3 * u + grp;
+        vals[u] = (grp < 3 && jj < margin) ? lm_blend(v, w0 + jj, pj[u], qj[u], taps[u]) : 0.0;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 12; ++jj) {
+        const double t = __shfl_sync(full, vals[jj / 3], slot + 10 * (jj % 3));
+        if (jj < margin) acc = f64add(acc, t);
+      }
+    } else {
+      for (int j = 0; j < margin; ++j) {
+        const int64_t pw = __shfl_sync(full, p, j), qw = __shfl_sync(full, q, j);
+        acc = f64add(acc, lm_value(v, w0 + j, pw, qw, e));
+      }
     }
     const double mean = f64div(acc, (double)margin);
     double src[kNumStable][2], dst[kNumStable][2];
@@ -198,7 +266,8 @@ __device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f,
   // trans(cur_landmarks)[48:68] -> mean -> cut_patch origin; lane k < 20 transforms point 48+k
   const int64_t pf = __shfl_sync(full, p, 31), qf = __shfl_sync(full, q, 31);
   const int k = 48 + (lane % 20);
-  const double x = lm_value(v, f, pf, qf, 2 * k), y = lm_value(v, f, pf, qf, 2 * k + 1);
+  const LmTaps xt = lm_taps(v, f, pf, qf, 2 * k), yt = lm_taps(v, f, pf, qf, 2 * k + 1);
+  const double x = lm_blend(v, f, pf, qf, xt), y = lm_blend(v, f, pf, qf, yt);
   const double tx = f64add(f64add(f64mul(x, fwd[0]), f64mul(y, fwd[1])), fwd[2]);
   const double ty = f64add(f64add(f64mul(x, fwd[3]), f64mul(y, fwd[4])), fwd[5]);
   double cx = 0.0, cy = 0.0;

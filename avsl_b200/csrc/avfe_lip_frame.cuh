@@ -73,12 +73,12 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       "{\n"
       ".reg .pred p;\n"
       "AVFE_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra AVFE_DONE;\n"
       "bra AVFE_WAIT;\n"
       "AVFE_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)                       // suspend-time hint (ns); the wait is re-armed if it expires
       : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D); completion is signalled on `bar` as transaction bytes
@@ -127,19 +127,23 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
   uint4(*ring)[kChunkVec] = sm.ring[sw];
   unsigned long long* full = sm.ring_full[sw];
 
-  // issue side: (ik, ic) = next chunk to request; stage / use counter of the ring slot it goes to
+  // issue side: (ik, ic) = next chunk to request and where it lives; the source pointer is
+  // advanced incrementally (S chunks ahead inside a frame, to this warp's first chunk of the
+  // CTA's next frame at a frame change)
   int ik = (sw < cpf) ? 0 : nk, ic = sw, istage = 0;     // a frame may have fewer chunks than stream warps
+  const uint8_t* isrc = L.frames + (int64_t)blockIdx.x * frame_bytes + (int64_t)sw * (kChunkVec * 16);
+  const int64_t next_frame = (int64_t)gridDim.x * frame_bytes;
+  const unsigned last_bytes = (unsigned)(gpf - (cpf - 1) * 64) * 48u;   // the frame's last chunk may be short
   auto issue = [&]() {
     if (ik < nk) {
       if (lane == 0) {
-        const int64_t f = (int64_t)blockIdx.x + (int64_t)ik * gridDim.x;
-        const int groups = min(64, gpf - ic * 64);
-        const unsigned bytes = (unsigned)groups * 48u;
+        const unsigned bytes = (ic == cpf - 1) ? last_bytes : (unsigned)(kChunkVec * 16);
         mbar_arrive_expect_tx(&full[istage], bytes);
-        bulk_load(ring[istage], L.frames + f * frame_bytes + (int64_t)ic * (kChunkVec * 16), bytes, &full[istage]);
+        bulk_load(ring[istage], isrc, bytes, &full[istage]);
       }
       ic += S;
-      if (ic >= cpf) { ic = sw; ++ik; }
+      isrc += S * (kChunkVec * 16);
+      if (ic >= cpf) { isrc += next_frame - (int64_t)(ic - sw) * (kChunkVec * 16); ic = sw; ++ik; }
     }
     if (++istage == kFrameRing) istage = 0;
   };
