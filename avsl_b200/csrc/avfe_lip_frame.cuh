@@ -13,7 +13,8 @@
 //   blend warps  (22 / 24) float64 bilinear blend of the previous frame's ROI from that tile in
 //                skimage's operation order: u8 ROI and/or normalised f32 centre crop
 //
-// Hand-over is by mbarriers only (ring FULL per stage, descriptor FULL/EMPTY, tile FULL/EMPTY);
+// Hand-over: mbarriers (ring FULL per stage, descriptor FULL/EMPTY, tile EMPTY) and one hardware
+// named barrier per tile slot for tile FULL, so that the 22 waiting blend warps do not poll;
 // the FP64 work of frame k hides under the memory time of frame k+1.
 // Included by avfe_lip.cu only (after avfe_lip_queue.cuh, whose gray and blend helpers it uses).
 #pragma once
@@ -23,6 +24,7 @@ namespace avfe {
 constexpr int kTformRoleWarps = 2;
 constexpr int kFrameRing = 6;               // bulk copies in flight per stream warp (x 3 KB)
 constexpr int kDescRing = 4;
+constexpr int kTileSlots = 3;               // footprint tiles: the stream may run this many frames ahead of the blend
 constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slot (u16 each)
 
 template <int SPAN>
@@ -33,6 +35,7 @@ struct FrameRoles {
   static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 6
   static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
   static constexpr int kTformFirst = 32 - kTformRoleWarps;            // highest warp ids: scheduled first
+  static constexpr int kHandoverThreads = 32 * (kBlendWarps + kStreamWarps);   // tile FULL barriers
 };
 
 struct FrameJob {
@@ -50,9 +53,9 @@ struct FrameSmem {
   float lutn[256];                            // ((k/255) - mean) / std in float32
   unsigned long long ring_full[FrameRoles<SPAN>::kStreamWarps][kFrameRing];
   unsigned long long desc_full[kDescRing], desc_empty[kDescRing];
-  unsigned long long tile_full[2], tile_empty[2];
+  unsigned long long tile_empty[kTileSlots];
   FrameXform desc[kDescRing];
-  __align__(16) uint16_t tile[2][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
+  __align__(16) uint16_t tile[kTileSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
   __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][kFrameRing][kChunkVec];
 };
 
@@ -155,7 +158,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
   for (int k = 0; k < nk; ++k) {
     const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
     // this frame's footprint box (the tform warps are ahead) and its tile slot
-    const int dslot = k % kDescRing, slot = k & 1;
+    const int dslot = k % kDescRing, slot = k % kTileSlots;
     mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
     const unsigned box_lo = sm.desc[dslot].box_lo, box_hi = sm.desc[dslot].box_hi;
     __syncwarp();
@@ -163,7 +166,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
     const bool staged = ((box_lo >> 27) & 1u) != 0;
     const int br0 = (int)(box_lo & 0x1fffu), bcg = (int)((box_lo >> 13) & 0x1fffu) >> 4;
     const int brows = staged ? (int)(box_hi & 0x1fffu) : 0, bpg = (int)((box_hi >> 13) & 0x1fffu) >> 4;
-    if (k >= 2) mbar_wait(&sm.tile_empty[slot], (unsigned)((k >> 1) - 1) & 1u);   // blend warps left the slot
+    if (k >= kTileSlots) mbar_wait(&sm.tile_empty[slot], (unsigned)(k / kTileSlots - 1) & 1u);   // blend warps left the slot
     uint4* tile = reinterpret_cast<uint4*>(sm.tile[slot]);
     uint4* gout = reinterpret_cast<uint4*>(L.gray_out + f * frame_px);
     for (int c = sw; c < cpf; c += S) {
@@ -197,8 +200,9 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
       }
       if (++stage == kFrameRing) { stage = 0; phase ^= 1u; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.tile_full[slot]);     // release: this warp's part of the footprint is in
+    // this warp's part of the footprint is in: hardware barrier 1 + slot, which the blend warps
+    // wait on without polling (stream warps only arrive)
+    bar_arrive(1 + slot, R::kHandoverThreads);
   }
 }
 
@@ -273,12 +277,12 @@ __device__ __forceinline__ void frame_blend_run(const FrameJob& j, FrameSmem<SPA
   const int lane = tid & 31;
   for (int k = 0; k < nk; ++k) {
     const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-    const int dslot = k % kDescRing, slot = k & 1;
+    const int dslot = k % kDescRing, slot = k % kTileSlots;
     mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
     const FrameXform x = sm.desc[dslot];
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.desc_empty[dslot]);
-    mbar_wait(&sm.tile_full[slot], (unsigned)(k >> 1) & 1u);   // the whole frame has been streamed
+    bar_sync(1 + slot, FrameRoles<SPAN>::kHandoverThreads);   // the whole frame has been streamed
     frame_blend_item<SPAN>(j.lip, f, x, sm.tile[slot], sm.lut255, sm.lutn, tid);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.tile_empty[slot]);
@@ -302,8 +306,7 @@ lip_frame_kernel(const FrameJob j) {
       mbar_init(&sm.desc_full[s], 1u);
       mbar_init(&sm.desc_empty[s], (unsigned)(R::kStreamWarps + R::kBlendWarps));
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.tile_full[s], (unsigned)R::kStreamWarps);
+    for (int s = 0; s < kTileSlots; ++s) {
       mbar_init(&sm.tile_empty[s], (unsigned)R::kBlendWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
