@@ -13,6 +13,8 @@
 // Frames, spectra and powers never touch HBM: traffic is the audio read plus the output.
 #include <limits.h>
 
+#include <type_traits>
+
 #include "avfe_common.cuh"
 #include "avfe_logmel_core.cuh"
 
@@ -229,23 +231,37 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   // (clip, tile-in-clip) pair is advanced incrementally in 32-bit arithmetic
   const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
   const int g = tid / 20, j = tid % 20;
-  const float floor_v = log10_floor(0.0f);               // value of every all-zero frame
   const bool mel_fast = packed && pack->balanced != 0;
   const int n_live = *live_count;                        // tiles to compute (logmel_live_kernel)
 
   // (clip, tile) records are read from the live list two tiles ahead so that the list load's
   // latency never sits in front of a cp.async issue
   const int2 none = make_int2(-1, 0);
-  auto prefetch = [&](int2 it, int buf) {
+  // this thread's 16-byte chunks of a tile: span samples 4*tid + 1280*k (k = 0..4); 1280 samples
+  // are four skew blocks, so the skewed position advances by 1280 + 4*kTileSkew per step
+  const int chunk0 = tile_pos(4 * tid);
+  constexpr int kChunkStep = 4 * kThreads + 4 * kTileSkew;
+  constexpr int kChunks = (kTileSamples / 4 + kThreads - 1) / kThreads;   // 5, the last one partial
+  struct TileRef { const float* clip; int64_t len; int cls; };
+  auto locate = [&](int2 it) -> TileRef {
+    TileRef r{nullptr, 0, kSilent};
     if (it.x >= 0) {
-      int64_t len;
-      const float* clip = clip_of(audio, offsets, it.x, L, Lp, len);
-      const int cls = classify_tile(clip, len, Lp, it.y);
-      const float* src = clip + ((int64_t)it.y * (kTileFrames * kHop) - kNfft / 2);
-      if (cls == kFast16) {
-        for (int i = tid; i < kTileSamples / 4; i += kThreads)
-          cp_async16(&sm.audio[buf][tile_pos(4 * i)], src + 4 * i);     // skew is a multiple of 4 floats
-      } else if (cls == kFast4) {
+      r.clip = clip_of(audio, offsets, it.x, L, Lp, r.len);
+      r.cls = classify_tile(r.clip, r.len, Lp, it.y);
+    }
+    return r;
+  };
+  auto prefetch = [&](int2 it, const TileRef& r, int buf) {
+    if (it.x >= 0) {
+      const float* src = r.clip + ((int64_t)it.y * (kTileFrames * kHop) - kNfft / 2);
+      if (r.cls == kFast16) {
+        float* dst = &sm.audio[buf][chunk0];
+        const float* s4 = src + 4 * tid;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+          if (k < kChunks - 1 || tid < kTileSamples / 4 - (kChunks - 1) * kThreads)
+            cp_async16(dst + k * kChunkStep, s4 + k * (4 * kThreads));   // skew is a multiple of 4 floats
+      } else if (r.cls == kFast4) {
         for (int i = tid; i < kTileSamples; i += kThreads) cp_async4(&sm.audio[buf][tile_pos(i)], src + i);
       }
     }
@@ -256,43 +272,26 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
 
   int cur = 0;
   int2 it = list_at((int)blockIdx.x), it_next = list_at((int)blockIdx.x + stride);
-  prefetch(it, 0);
+  TileRef ref = locate(it);
+  prefetch(it, ref, 0);
   for (int item = (int)blockIdx.x; item < n_live; item += stride, cur ^= 1) {
-    prefetch(it_next, cur ^ 1);                          // next tile of this CTA goes in flight
     const int2 it_after = list_at(item + 2 * stride);
-    cp_async_wait<1>();                                  // this tile's group has landed
+    const TileRef ref_next = locate(it_next);
+    cp_async_wait<0>();                                  // this tile's copies have landed
     const int64_t b = it.x;
     const int tt = it.y;
     const int64_t t0 = (int64_t)tt * kTileFrames;
     float* au = sm.audio[cur];
-    int64_t len;
-    const float* clip = clip_of(audio, offsets, b, L, Lp, len);
-    const int cls = classify_tile(clip, len, Lp, tt);
-    bool nz = false;
-    if (cls == kFast16) {
-      for (int i = tid; i < kTileSamples / 4; i += kThreads) {   // the chunks this thread fetched
-        const float4 q = *reinterpret_cast<const float4*>(&au[tile_pos(4 * i)]);
-        nz |= (q.x != 0.0f) | (q.y != 0.0f) | (q.z != 0.0f) | (q.w != 0.0f);
-      }
-    } else if (cls == kFast4) {
-      for (int i = tid; i < kTileSamples; i += kThreads) nz |= (au[tile_pos(i)] != 0.0f);
-    } else {
+    if (ref.cls == kEdge) {                              // clip edges: reflection / zero padding, sample by sample
       const int64_t p0 = t0 * kHop;
-      for (int i = tid; i < kTileSamples; i += kThreads) {
-        const float q = padded_sample(clip, len, Lp, p0 + i);
-        au[tile_pos(i)] = q;
-        nz |= (q != 0.0f);
-      }
+      for (int i = tid; i < kTileSamples; i += kThreads) au[tile_pos(i)] = padded_sample(ref.clip, ref.len, Lp, p0 + i);
     }
-    // barrier: tile visible to all, previous tile's power rows no longer needed
-    const int any = __syncthreads_or(nz ? 1 : 0);
+    // barrier: tile visible to all; every warp has left the previous tile (its power rows and its
+    // staged outputs, which sit in the buffer the next prefetch is about to overwrite)
+    __syncthreads();
+    prefetch(it_next, ref_next, cur ^ 1);                // next tile of this CTA goes in flight
     float vmax = -INFINITY;
-    if (tid == 0) silent[b * tiles_per_clip + tt] = any ? 0 : 1;
-    if (!any) {
-      // all 32 frames are digital silence: |X|^2 = 0 -> mel = 0 -> log10(1e-10).  No FFT and no
-      // store: logmel_finalize_kernel writes the final constant for silent tiles directly.
-      vmax = floor_v;
-    } else {
+    {
       // ---- 16 complex FFT-400: columns, twiddle, rows ----
       stage1(g, j, au, sm.hann, sm.tw, sm.Z);
       __syncthreads();
@@ -323,23 +322,41 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
           const float4 w2 = rc.w > 2 ? wq[2] : z4, w3 = rc.w > 3 ? wq[3] : z4;
           const float* prow = P + prow_offset(f0) + rc.x;
           float* so = stage_out + m * kTileFrames + f0;
-          for (int i = 0; i < nf; ++i, prow += kPStride) {
+          // one loop per support length (uniform within a warp: threads are sorted by quads),
+          // two frames per trip so that the second frame's loads overlap the first frame's FMAs
+          auto dot = [&](const float* pr, int quads) -> float {
             float a0 = 0.0f, a1 = 0.0f;
-            a0 = fmaf(w0.x, prow[0], a0); a1 = fmaf(w0.y, prow[1], a1);
-            a0 = fmaf(w0.z, prow[2], a0); a1 = fmaf(w0.w, prow[3], a1);
-            if (rc.w > 1) {                               // uniform within a warp (threads sorted by quads)
-              a0 = fmaf(w1.x, prow[4], a0); a1 = fmaf(w1.y, prow[5], a1);
-              a0 = fmaf(w1.z, prow[6], a0); a1 = fmaf(w1.w, prow[7], a1);
-              if (rc.w > 2) {
-                a0 = fmaf(w2.x, prow[8], a0); a1 = fmaf(w2.y, prow[9], a1);
-                a0 = fmaf(w2.z, prow[10], a0); a1 = fmaf(w2.w, prow[11], a1);
-                if (rc.w > 3) {
-                  a0 = fmaf(w3.x, prow[12], a0); a1 = fmaf(w3.y, prow[13], a1);
-                  a0 = fmaf(w3.z, prow[14], a0); a1 = fmaf(w3.w, prow[15], a1);
-                }
-              }
+            a0 = fmaf(w0.x, pr[0], a0); a1 = fmaf(w0.y, pr[1], a1);
+            a0 = fmaf(w0.z, pr[2], a0); a1 = fmaf(w0.w, pr[3], a1);
+            if (quads > 1) {
+              a0 = fmaf(w1.x, pr[4], a0); a1 = fmaf(w1.y, pr[5], a1);
+              a0 = fmaf(w1.z, pr[6], a0); a1 = fmaf(w1.w, pr[7], a1);
             }
-            so[i] = log10_floor(a0 + a1);
+            if (quads > 2) {
+              a0 = fmaf(w2.x, pr[8], a0); a1 = fmaf(w2.y, pr[9], a1);
+              a0 = fmaf(w2.z, pr[10], a0); a1 = fmaf(w2.w, pr[11], a1);
+            }
+            if (quads > 3) {
+              a0 = fmaf(w3.x, pr[12], a0); a1 = fmaf(w3.y, pr[13], a1);
+              a0 = fmaf(w3.z, pr[14], a0); a1 = fmaf(w3.w, pr[15], a1);
+            }
+            return a0 + a1;
+          };
+          auto run = [&](auto quads_c) {
+            constexpr int Q = decltype(quads_c)::value;
+            int i = 0;
+            for (; i + 2 <= nf; i += 2, prow += 2 * kPStride) {   // nf is even for every tier but the coarsest
+              const float s0 = dot(prow, Q), s1 = dot(prow + kPStride, Q);
+              so[i] = log10_floor(s0);
+              so[i + 1] = log10_floor(s1);
+            }
+            if (i < nf) so[i] = log10_floor(dot(prow, Q));
+          };
+          switch (rc.w) {
+            case 1:  run(std::integral_constant<int, 1>{}); break;
+            case 2:  run(std::integral_constant<int, 2>{}); break;
+            case 3:  run(std::integral_constant<int, 3>{}); break;
+            default: run(std::integral_constant<int, 4>{}); break;
           }
         }
         __syncthreads();
@@ -371,15 +388,10 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) sm.red[wid] = float_key(vmax);
-    __syncthreads();
-    if (tid == 0) {
-      int k = sm.red[0];
-      for (int w = 1; w < kThreads / 32; ++w) k = max(k, sm.red[w]);
-      atomicMax(clip_max + b, k);
-    }
+    if (lane == 0) atomicMax(clip_max + b, float_key(vmax));
     it = it_next;
     it_next = it_after;
+    ref = ref_next;
   }
   cp_async_wait<0>();
 }
