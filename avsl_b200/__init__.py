@@ -12,7 +12,7 @@ from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel
 from .frontend import AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, pack_utterances, shard
 from .fusion import ModalityFusion, fuse_modalities, modality_dropout_flags, modality_dropout_mask
 from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,
-                   landmarks_interpolate, lip_roi_batch, load_video_feats, mean_face_landmarks,
-                   trim_video_to_audio, warp_img)
+                   landmarks_interpolate, lip_roi_batch, lip_roi_collate, load_video_feats, mean_face_landmarks,
+                   trim_video_to_audio, video_frames_for_audio, warp_img)
 
 __version__ = "0.1.0"

@@ -38,6 +38,10 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avfe_lip_roi_collate": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "avfe_landmarks_interpolate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                            c_void_p]),
     "avfe_similarity_fit": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -188,16 +188,28 @@ struct TformArgs {
   int std_size, roi, window, fp_lo, fp_span, H, W, fp_align;
   int32_t* crop_rc;
   double* tforms_out;
+  // collation (avfe_lip_roi_collate): frame t of clip c goes to slot c*T_pad + t of the padded
+  // [n_clips, T_pad] video batch when t < min(keep[c], T_pad) and is dropped otherwise;
+  // T_pad == 0: packed output, frame f goes to slot f
+  const int64_t* keep;
+  int64_t T_pad;
 };
 
 // Window-smoothed similarity fit + cut_patch origin + footprint of frame f, computed by one warp
 // (V2 on the fly, V3, V4 fit, V6, V7).  The record is returned in every lane; lane 0 also writes
 // the optional crop_rc / tforms outputs.
-__device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f, int lane) {
+__device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f, int lane, int64_t& dst) {
   const unsigned full = 0xffffffffu;
   const int64_t c = find_clip_warp(a.clip_offsets, a.n_clips, f, lane);
   LmView v{a.lm, a.valid, a.clip_offsets[c], a.clip_offsets[c + 1]};
   const int64_t T = v.end - v.beg;
+  dst = f;
+  if (a.T_pad > 0) {
+    int64_t kept = a.keep != nullptr ? a.keep[c] : T;
+    if (kept > a.T_pad) kept = a.T_pad;
+    const int64_t t = f - v.beg;
+    dst = (t < kept) ? c * a.T_pad + t : -1;
+  }
   // margin = min(T, 12); frame i <= T-margin is fitted on mean(lm[i:i+margin]); later frames
   // reuse the transform of frame T-margin (preprocess/video_process.py:369-370,417-427,455-464)
   const int margin = (int)(T < a.window ? T : a.window);   // window <= 31 is enforced by the caller
@@ -299,13 +311,15 @@ __device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f,
 }
 
 __global__ void __launch_bounds__(kTformWarps * 32)
-tform_kernel(const TformArgs a, int64_t N, FrameXform* __restrict__ xf, unsigned* __restrict__ queue_counter) {
+tform_kernel(const TformArgs a, int64_t N, FrameXform* __restrict__ xf, int64_t* __restrict__ dst_slot,
+             unsigned* __restrict__ queue_counter) {
   if (queue_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *queue_counter = 0u;
   const int lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * kTformWarps + (threadIdx.x >> 5);
   if (f >= N) return;                                  // warp-uniform
-  const FrameXform o = tform_frame(a, f, lane);
-  if (lane == 0) xf[f] = o;
+  int64_t dst;
+  const FrameXform o = tform_frame(a, f, lane, dst);
+  if (lane == 0) { xf[f] = o; dst_slot[f] = dst; }
 }
 
 // ------------------------------------------------------------------ V1: BGR -> gray
@@ -495,6 +509,33 @@ cut_patch_kernel(const uint8_t* __restrict__ img, int H, int W, const double* __
   }
 }
 
+// Padded part of a collated video batch: frames [kept_c, T_pad) of every clip are zero (the
+// upstream collator's np.pad) and flagged in padding_mask (1 = padding).
+__global__ void __launch_bounds__(256)
+collate_tail_kernel(const int64_t* __restrict__ clip_offsets, const int64_t* __restrict__ keep, int64_t T_pad,
+                    int frame_floats, float* __restrict__ video, uint8_t* __restrict__ padding_mask) {
+  const int64_t c = blockIdx.y;
+  int64_t kept = clip_offsets[c + 1] - clip_offsets[c];
+  if (keep != nullptr && keep[c] < kept) kept = keep[c];
+  if (kept > T_pad) kept = T_pad;
+  if (kept < 0) kept = 0;
+  if (padding_mask != nullptr)
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T_pad; t += (int64_t)gridDim.x * blockDim.x)
+      padding_mask[c * T_pad + t] = t >= kept ? 1 : 0;
+  if (video == nullptr) return;
+  float* base = video + (c * T_pad + kept) * frame_floats;
+  const int64_t n = (T_pad - kept) * frame_floats;
+  if ((frame_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(video) & 15u) == 0) {
+    float4* b4 = reinterpret_cast<float4*>(base);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (int64_t)gridDim.x * blockDim.x)
+      b4[i] = z;
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      base[i] = 0.0f;
+  }
+}
+
 }  // namespace avfe
 
 // ====================================================================== C ABI
@@ -552,18 +593,18 @@ extern "C" int avfe_warp_affine_u8(const uint8_t* gray, int H, int W, const doub
 
 extern "C" size_t avfe_lip_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  // one FrameXform per frame + the work-queue counter
-  return (size_t)N * sizeof(FrameXform) + 256;
+  // work-queue counter + one FrameXform and one output slot index per frame
+  return (size_t)N * (sizeof(FrameXform) + sizeof(int64_t)) + 256;
 }
 
-extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N, int H, int W,
-                                  const int64_t* clip_offsets, int64_t n_clips,
-                                  const double* landmarks, const uint8_t* lm_valid,
-                                  const double* mean_face, const double* tforms_in,
-                                  int std_size, int roi, int crop, int window, float mean,
-                                  float std, uint8_t* gray_out, uint8_t* lip_u8, float* lip_f32,
-                                  int32_t* crop_rc, double* tforms, void* workspace,
-                                  size_t workspace_bytes, avfe_stream_t stream) {
+static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, int W,
+                        const int64_t* clip_offsets, int64_t n_clips,
+                        const double* landmarks, const uint8_t* lm_valid,
+                        const double* mean_face, const double* tforms_in,
+                        int std_size, int roi, int crop, int window, float mean,
+                        float std, uint8_t* gray_out, uint8_t* lip_u8, float* lip_f32,
+                        int32_t* crop_rc, double* tforms, const int64_t* keep, int64_t T_pad,
+                        void* workspace, size_t workspace_bytes, avfe_stream_t stream) {
   if (N < 0 || n_clips < 0 || H <= 0 || W <= 0) return AVFE_ERR_INVALID_ARG;
   if (channels != 1 && channels != 3) return AVFE_ERR_INVALID_ARG;
   if (roi <= 0 || (roi & 1) || crop <= 0 || crop > roi || ((roi - crop) & 1) || window <= 0 ||
@@ -580,6 +621,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
 
   unsigned* counter = static_cast<unsigned*>(workspace);
   FrameXform* xf = reinterpret_cast<FrameXform*>(static_cast<char*>(workspace) + 256);
+  int64_t* dst_slot = reinterpret_cast<int64_t*>(xf + N);
   // footprint staging: 16-byte cp.async when frame rows keep that alignment, else 4-byte, else none
   const int C = channels;
   const uintptr_t fbase = reinterpret_cast<uintptr_t>(frames);
@@ -592,7 +634,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
   ta.lm = landmarks; ta.valid = lm_valid; ta.clip_offsets = clip_offsets; ta.n_clips = n_clips;
   ta.mean_face = mean_face; ta.tforms_in = tforms_in; ta.std_size = std_size; ta.roi = roi;
   ta.window = window; ta.fp_lo = fp_lo; ta.fp_span = fp_span; ta.H = H; ta.W = W; ta.fp_align = fp_align;
-  ta.crop_rc = crop_rc; ta.tforms_out = tforms;
+  ta.crop_rc = crop_rc; ta.tforms_out = tforms; ta.keep = keep; ta.T_pad = T_pad;
 
   // window side known at compile time for the two standard configurations
   const int span_sel = (lip_u8 != nullptr && roi == 96) ? 96
@@ -603,7 +645,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
       W >= 32 && W <= 8191 && H <= 8191 && (int64_t)H * W / 16 < (1 << 22)) {
     FrameJob fj;
     LipJob& j = fj.lip;
-    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = nullptr;
+    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = nullptr; j.dst_slot = nullptr;
     j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
     j.gray_out = gray_out; j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = nullptr;
     j.ngroups = 0; j.stage_align = fp_align;
@@ -618,7 +660,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
     return check_launch();
   }
 
-  tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(ta, N, xf, counter);
+  tform_kernel<<<(unsigned)((N + kTformWarps - 1) / kTformWarps), kTformWarps * 32, 0, s>>>(ta, N, xf, dst_slot, counter);
   count_launch();
 
   const int64_t npx = (int64_t)H * W;
@@ -633,7 +675,7 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
   }
   if (want_roi) {
     LipJob j;
-    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = xf;
+    j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = xf; j.dst_slot = dst_slot;
     j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
     j.gray_out = fuse_gray ? gray_out : nullptr;
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
@@ -652,6 +694,48 @@ extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N
     if (rc != AVFE_OK) return rc;
     count_launch();
   }
+  return check_launch();
+}
+
+extern "C" int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N, int H, int W,
+                                  const int64_t* clip_offsets, int64_t n_clips,
+                                  const double* landmarks, const uint8_t* lm_valid,
+                                  const double* mean_face, const double* tforms_in,
+                                  int std_size, int roi, int crop, int window, float mean,
+                                  float std, uint8_t* gray_out, uint8_t* lip_u8, float* lip_f32,
+                                  int32_t* crop_rc, double* tforms, void* workspace,
+                                  size_t workspace_bytes, avfe_stream_t stream) {
+  return lip_roi_impl(frames, channels, N, H, W, clip_offsets, n_clips, landmarks, lm_valid, mean_face,
+                      tforms_in, std_size, roi, crop, window, mean, std, gray_out, lip_u8, lip_f32, crop_rc,
+                      tforms, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int avfe_lip_roi_collate(const uint8_t* frames, int channels, int64_t N, int H, int W,
+                                    const int64_t* clip_offsets, int64_t n_clips,
+                                    const double* landmarks, const uint8_t* lm_valid,
+                                    const double* mean_face, const double* tforms_in,
+                                    int std_size, int roi, int crop, int window, float mean,
+                                    float std, const int64_t* keep_frames, int64_t T_pad,
+                                    uint8_t* gray_out, float* video, uint8_t* padding_mask,
+                                    void* workspace, size_t workspace_bytes, avfe_stream_t stream) {
+  if (T_pad <= 0 || n_clips < 0 || crop <= 0) return AVFE_ERR_INVALID_ARG;
+  if (n_clips == 0) return AVFE_OK;
+  if (!video || !clip_offsets) return AVFE_ERR_INVALID_ARG;
+  if (n_clips > 65535) return AVFE_ERR_UNSUPPORTED;
+  if (N > 0) {
+    const int rc = lip_roi_impl(frames, channels, N, H, W, clip_offsets, n_clips, landmarks, lm_valid,
+                                mean_face, tforms_in, std_size, roi, crop, window, mean, std, gray_out,
+                                nullptr, video, nullptr, nullptr, keep_frames, T_pad, workspace,
+                                workspace_bytes, stream);
+    if (rc != AVFE_OK) return rc;
+  }
+  int64_t gx = (T_pad * (int64_t)crop * crop / 4 + 255) / 256;
+  if (gx > 8) gx = 8;                                     // the padded part is a few frames per clip
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)n_clips);
+  collate_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(clip_offsets, keep_frames, T_pad,
+                                                                       crop * crop, video, padding_mask);
+  count_launch();
   return check_launch();
 }
 

@@ -55,6 +55,7 @@ struct FrameSmem {
   unsigned long long desc_full[kDescRing], desc_empty[kDescRing];
   unsigned long long tile_empty[kTileSlots];
   FrameXform desc[kDescRing];
+  int64_t dst[kDescRing];                     // f32 output slot of the frame (collation), < 0: dropped
   __align__(16) uint16_t tile[kTileSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
   __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][kFrameRing][kChunkVec];
 };
@@ -93,17 +94,29 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
       : "memory");
 }
 
+// tile FULL: hardware barrier 1 + slot with a compile-time id (a register id would make ptxas
+// reserve all 16 barriers); stream warps arrive, blend warps sync
+template <bool SYNC>
+__device__ __forceinline__ void tile_bar(int slot, int count) {
+  static_assert(kTileSlots == 3, "one case per slot");
+  if (slot == 0)      { if (SYNC) bar_sync_id<1>(count); else bar_arrive_id<1>(count); }
+  else if (slot == 1) { if (SYNC) bar_sync_id<2>(count); else bar_arrive_id<2>(count); }
+  else                { if (SYNC) bar_sync_id<3>(count); else bar_arrive_id<3>(count); }
+}
+
 // ---------------------------------------------------------------- tform warps
 template <int SPAN>
 __device__ __forceinline__ void frame_tform_run(const FrameJob& j, FrameSmem<SPAN>& sm, int tw, int lane,
                                                 int nk) {
   for (int k = tw; k < nk; k += kTformRoleWarps) {
     const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-    const FrameXform x = tform_frame(j.tf, f, lane);
+    int64_t dst;
+    const FrameXform x = tform_frame(j.tf, f, lane, dst);
     const int slot = k % kDescRing, use = k / kDescRing;
     if (use > 0) mbar_wait(&sm.desc_empty[slot], (unsigned)(use - 1) & 1u);   // every reader is done with it
     if (lane == 0) {
       sm.desc[slot] = x;
+      sm.dst[slot] = dst;
       mbar_arrive(&sm.desc_full[slot]);                  // release: the record is visible to the waiters
     }
     __syncwarp();
@@ -202,13 +215,13 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
     }
     // this warp's part of the footprint is in: hardware barrier 1 + slot, which the blend warps
     // wait on without polling (stream warps only arrive)
-    bar_arrive(1 + slot, R::kHandoverThreads);
+    tile_bar<false>(slot, R::kHandoverThreads);
   }
 }
 
 // ---------------------------------------------------------------- blend warps
 template <int SPAN>
-__device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, const FrameXform& x,
+__device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int64_t slot_f32, const FrameXform& x,
                                                  const uint16_t* tile, const double* lut255, const float* lutn,
                                                  int tid) {
   using R = FrameRoles<SPAN>;
@@ -218,7 +231,8 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, con
   const int lo = j.lip_u8 ? 0 : off;
   constexpr int S = SPAN;
   uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
-  float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
+  float* out_f32 = (j.lip_f32 && slot_f32 >= 0) ? j.lip_f32 + slot_f32 * (int64_t)j.crop * j.crop : nullptr;
+  if (out_u8 == nullptr && out_f32 == nullptr) return;  // frame dropped by the collation trim
   auto emit = [&](int r, int c, uint32_t v) {
     if (SPAN == 88) {                                   // centre crop only: window == f32 output
       out_f32[r * 88 + c] = lutn[v];
@@ -280,10 +294,11 @@ __device__ __forceinline__ void frame_blend_run(const FrameJob& j, FrameSmem<SPA
     const int dslot = k % kDescRing, slot = k % kTileSlots;
     mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
     const FrameXform x = sm.desc[dslot];
+    const int64_t slot_f32 = sm.dst[dslot];
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.desc_empty[dslot]);
-    bar_sync(1 + slot, FrameRoles<SPAN>::kHandoverThreads);   // the whole frame has been streamed
-    frame_blend_item<SPAN>(j.lip, f, x, sm.tile[slot], sm.lut255, sm.lutn, tid);
+    tile_bar<true>(slot, FrameRoles<SPAN>::kHandoverThreads);   // the whole frame has been streamed
+    frame_blend_item<SPAN>(j.lip, f, slot_f32, x, sm.tile[slot], sm.lut255, sm.lutn, tid);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.tile_empty[slot]);
   }

@@ -43,6 +43,7 @@ struct LipJob {
   int channels, H, W;
   int64_t N;
   const FrameXform* xf;
+  const int64_t* dst_slot; // f32 output slot of each frame (collation); nullptr: slot = frame index
   int roi, crop;
   float mean, stdv;
   uint8_t* gray_out;       // stream group output (nullptr: no stream group)
@@ -84,6 +85,14 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 }
 __device__ __forceinline__ void bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_sync_id(int count) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void bar_arrive_id(int count) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -293,7 +302,9 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
   const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
   const int H = j.H, W = j.W;
   uint8_t* out_u8 = j.lip_u8 ? j.lip_u8 + f * (int64_t)j.roi * j.roi : nullptr;
-  float* out_f32 = j.lip_f32 ? j.lip_f32 + f * (int64_t)j.crop * j.crop : nullptr;
+  const int64_t slot_f32 = j.dst_slot ? j.dst_slot[f] : f;          // < 0: dropped by the collation trim
+  float* out_f32 = (j.lip_f32 && slot_f32 >= 0) ? j.lip_f32 + slot_f32 * (int64_t)j.crop * j.crop : nullptr;
+  if (out_u8 == nullptr && out_f32 == nullptr) return;
   const int npix = span * span;
   auto emit = [&](int r, int c, uint32_t v) {
     if (SPAN == 88) {                                   // centre crop only: window == f32 output

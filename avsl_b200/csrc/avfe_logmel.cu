@@ -229,7 +229,6 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
     for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
   // tiles are numbered clip-major; this CTA takes tiles blockIdx.x, +gridDim.x, ...; the
   // (clip, tile-in-clip) pair is advanced incrementally in 32-bit arithmetic
-  const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
   const int g = tid / 20, j = tid % 20;
   const bool mel_fast = packed && pack->balanced != 0;
   const int n_live = *live_count;                        // tiles to compute (logmel_live_kernel)

@@ -9,7 +9,7 @@ caller: every function here starts from decoded frames and 68-point landmarks.
 from __future__ import annotations
 
 from pathlib import Path
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -225,6 +225,71 @@ def lip_roi_batch(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: t
                   _lib.ptr(out.gray), _lib.ptr(out.lip_u8), _lib.ptr(out.lip_f32),
                   _lib.ptr(out.crop_rc), _lib.ptr(out.tforms), _lib.ptr(ws), ws_bytes,
                   _lib.stream_ptr())
+    return out
+
+
+def video_frames_for_audio(n_audio_samples: int, sample_rate: int = 16000, fps: int = 25) -> int:
+    """Frames the reference keeps for an audio of ``n_audio_samples``
+    (avsl/whisper_flamingo_ft_ami.py:299): Python ``round`` of the duration times 25."""
+    return round(n_audio_samples / sample_rate * fps)
+
+
+def lip_roi_collate(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: torch.Tensor,
+                    lm_valid: Optional[torch.Tensor] = None, *, T_pad: int,
+                    keep_frames: Optional[torch.Tensor] = None, mean_face=None,
+                    tforms_in: Optional[torch.Tensor] = None, want_gray: bool = True,
+                    roi: int = 96, crop: int = IMAGE_CROP_SIZE, std_size: int = 300,
+                    window: int = WINDOW_MARGIN, image_mean: float = IMAGE_MEAN,
+                    image_std: float = IMAGE_STD, out: Optional[Dict[str, torch.Tensor]] = None
+                    ) -> Dict[str, torch.Tensor]:
+    """:func:`lip_roi_batch` writing straight into the padded batch the encoder consumes
+    (``features, x_v = self.model.encoder(input_ids, video, ..., padding_mask=padding_mask)``,
+    avsl/whisper_flamingo_ft_ami.py:527): the per-sample trim of ``__getitem__`` (:299-302) and
+    the zero padding + mask of the upstream ``WhisperVideoCollatorWithPadding`` (:126, :686) are
+    folded into the kernel's output addressing, so the packed ``[N,88,88]`` tensor is never built.
+
+    keep_frames int64 [n_clips] (CUDA) = frames kept per clip after the trim (None: all);
+    T_pad = frames per clip in the batch (the collator uses the longest kept clip).
+    Returns ``video`` float32 [B,1,T_pad,88,88], ``padding_mask`` bool [B,T_pad] (True = padding)
+    and ``gray`` uint8 [N,H,W] (if wanted)."""
+    _lib.require_cuda()
+    if not frames.is_cuda or frames.dtype != torch.uint8 or not frames.is_contiguous():
+        raise ValueError("frames must be a contiguous CUDA uint8 tensor")
+    if frames.dim() == 4 and frames.shape[-1] == 3:
+        channels = 3
+    elif frames.dim() == 3:
+        channels = 1
+    else:
+        raise ValueError("frames must be [N,H,W,3] (BGR) or [N,H,W] (gray)")
+    if T_pad < 1:
+        raise ValueError("T_pad must be >= 1")
+    N, H, W = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+    dev = frames.device
+    n_clips = int(clip_offsets.numel()) - 1
+    if clip_offsets.dtype != torch.int64 or not clip_offsets.is_cuda:
+        raise ValueError("clip_offsets must be a CUDA int64 tensor")
+    if landmarks.dtype != torch.float64 or tuple(landmarks.shape) != (N, 68, 2) or not landmarks.is_contiguous():
+        raise ValueError("landmarks must be contiguous float64 [N,68,2]")
+    if keep_frames is not None and (keep_frames.dtype != torch.int64 or not keep_frames.is_cuda or
+                                    keep_frames.numel() != n_clips):
+        raise ValueError("keep_frames must be a CUDA int64 tensor [n_clips]")
+    mf = _mean_face_dev(dev, mean_face)
+    want_gray = want_gray and channels == 3
+    if out is None:
+        out = {"video": torch.empty((n_clips, 1, T_pad, crop, crop), dtype=torch.float32, device=dev),
+               "padding_mask_u8": torch.empty((n_clips, T_pad), dtype=torch.uint8, device=dev)}
+        if want_gray:
+            out["gray"] = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        ws_bytes = int(lib.avfe_lip_workspace_bytes(N))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.call("avfe_lip_roi_collate", _lib.ptr(frames), channels, N, H, W, _lib.ptr(clip_offsets),
+                  n_clips, _lib.ptr(landmarks), _lib.ptr(lm_valid), _lib.ptr(mf), _lib.ptr(tforms_in),
+                  std_size, roi, crop, window, float(image_mean), float(image_std),
+                  _lib.ptr(keep_frames), int(T_pad), _lib.ptr(out.get("gray")), _lib.ptr(out["video"]),
+                  _lib.ptr(out["padding_mask_u8"]), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    out["padding_mask"] = out["padding_mask_u8"].view(torch.bool)
     return out
 
 

@@ -163,6 +163,28 @@ AVFE_API int avfe_lip_roi_batch(const uint8_t* frames, int channels, int64_t N, 
                                 int32_t* crop_rc, double* tforms,
                                 void* workspace, size_t workspace_bytes, avfe_stream_t stream);
 
+/* The same path writing straight into the padded batch the Whisper-Flamingo encoder consumes,
+ * i.e. what AmiVideoHFDataset.__getitem__'s trim (avsl/whisper_flamingo_ft_ami.py:299-302:
+ * video_feats[:round(len(audio)/16000*25)]) and the upstream WhisperVideoCollatorWithPadding
+ * (imported at :126, used at :686; zero-pads every clip to the longest one and returns a boolean
+ * padding mask, read at :504) produce on the host:
+ *   keep_frames  [n_clips] int64 (device) or NULL: frames kept per clip after the trim
+ *   T_pad        frames per clip in the padded batch (>= 1)
+ *   video        [n_clips, T_pad, crop, crop] f32  == the collator's [B, 1, T, 88, 88]; frame t of
+ *                clip c is written for t < min(T_c, keep_frames[c], T_pad), zero otherwise
+ *   padding_mask [n_clips, T_pad] u8 (nullable), 1 = padded frame
+ *   gray_out     [N,H,W] u8 (nullable) as above (every frame, trimmed ones included)
+ * The ROI of a dropped frame is not computed.  Workspace as for avfe_lip_roi_batch. */
+AVFE_API int avfe_lip_roi_collate(const uint8_t* frames, int channels, int64_t N, int H, int W,
+                                  const int64_t* clip_offsets, int64_t n_clips,
+                                  const double* landmarks, const uint8_t* lm_valid,
+                                  const double* mean_face, const double* tforms_in,
+                                  int std_size, int roi, int crop, int window,
+                                  float mean, float std,
+                                  const int64_t* keep_frames, int64_t T_pad,
+                                  uint8_t* gray_out, float* video, uint8_t* padding_mask,
+                                  void* workspace, size_t workspace_bytes, avfe_stream_t stream);
+
 /* landmarks_interpolate — utils/lips_cropping.py:41-89 — alone: fills frames whose lm_valid is
  * 0 by linear interpolation between the neighbouring detections of the same clip
  * (start + idx/float(n) * delta) and by replication at the clip ends; a clip with no

@@ -169,3 +169,40 @@ def test_idempotence_and_clip_independence_full_size():
     assert torch.equal(a, b) and torch.equal(r1.gray[:250], r1.gray[310:])
     r2 = L.lip_roi_batch(F, off, LM, V, want_u8=True)
     assert torch.equal(r2.lip_f32[:250], a) and torch.equal(r2.lip_u8, r1.lip_u8)
+
+
+@pytest.mark.parametrize("shape,gray_in", [((224, 224), False), ((224, 224), True), ((120, 168), False)])
+def test_collate_matches_trim_plus_collator(shape, gray_in):
+    """avfe_lip_roi_collate == lip_roi_batch followed by the reference's trim
+    (whisper_flamingo_ft_ami.py:299-302) and the collator's zero padding + mask, on the frame-owner
+    kernel (224x224 BGR), on gray input and on a row length the bulk copies cannot take."""
+    from oracle import collate as OC
+    H, W = shape
+    lens = [30, 9, 1, 17]
+    clips = [synth.video_clip(t, H, W, seed=50 + t, invalid_frac=0.1) for t in lens]
+    frames = np.concatenate([c[0] for c in clips])
+    if gray_in:
+        frames = O.bgr2gray(frames)
+    lm = np.concatenate([c[1] for c in clips])
+    valid = np.concatenate([c[2] for c in clips])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    keep = np.array([12, 9, 5, 0], dtype=np.int64)       # trimmed, untouched, longer than the clip, dropped
+    d = dict(frames=torch.from_numpy(frames).cuda(), off=torch.from_numpy(off).cuda(),
+             lm=torch.from_numpy(lm).cuda(), valid=torch.from_numpy(valid).cuda())
+    packed = L.lip_roi_batch(d["frames"], d["off"], d["lm"], d["valid"], want_gray=not gray_in)
+    feats = packed.lip_f32.cpu().numpy()
+    kept = [feats[off[i]:off[i] + min(lens[i], keep[i])][..., None] for i in range(len(lens))]
+    for T_pad in (12, 16):
+        ref = OC.collate_video(kept, T_pad=T_pad)
+        got = L.lip_roi_collate(d["frames"], d["off"], d["lm"], d["valid"], T_pad=T_pad,
+                                keep_frames=torch.from_numpy(keep).cuda(), want_gray=not gray_in)
+        assert got["video"].shape == (4, 1, T_pad, 88, 88) and got["padding_mask"].dtype == torch.bool
+        np.testing.assert_array_equal(got["video"].cpu().numpy(), ref["video"])
+        np.testing.assert_array_equal(got["padding_mask"].cpu().numpy(), ref["padding_mask"])
+        if not gray_in:
+            assert torch.equal(got["gray"], packed.gray)
+    # no trim: every frame kept, T_pad = longest clip (the collator's own choice)
+    ref = OC.collate_video([feats[off[i]:off[i + 1]][..., None] for i in range(len(lens))])
+    got = L.lip_roi_collate(d["frames"], d["off"], d["lm"], d["valid"], T_pad=max(lens), want_gray=False)
+    np.testing.assert_array_equal(got["video"].cpu().numpy(), ref["video"])
+    np.testing.assert_array_equal(got["padding_mask"].cpu().numpy(), ref["padding_mask"])
