@@ -10,7 +10,8 @@ from . import _lib  # noqa: F401
 from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram,
                     log_mel_spectrogram_ragged, mel_filters, pad_or_trim, peak_normalize)
 from .frontend import AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, pack_utterances, shard
-from .fusion import ModalityFusion, fuse_modalities, modality_dropout_flags, modality_dropout_mask
+from .fusion import (ModalityFusion, fuse_modalities, fuse_transpose_layernorm, modality_dropout_flags,
+                     modality_dropout_mask)
 from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,
                    landmarks_interpolate, lip_roi_batch, lip_roi_collate, load_video_feats, mean_face_landmarks,
                    trim_video_to_audio, video_frames_for_audio, warp_img)

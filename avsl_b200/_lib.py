@@ -51,6 +51,8 @@ _SIGNATURES = {
                                     c_void_p, c_void_p]),
     "avfe_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,
                           c_int64, c_int64, c_void_p, c_void_p]),
+    "avfe_fuse_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,
+                                    c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

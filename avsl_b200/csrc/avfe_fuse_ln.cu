@@ -1,0 +1,265 @@
+// Fusion + transpose + LayerNorm in one pass: the tail of AVHuBERTEncoderWrapper.forward,
+// avsl/modules/av_hubert_encoder.py:315-330
+//     features = cat([fa, fv], 1) | fa + fv            (:315-326, missing modality zero-filled)
+//     features = features.transpose(1, 2)              (:329)
+//     features = self.layer_norm(features)             (:330; LayerNorm = nn.LayerNorm evaluated in
+//                                                       float32 and cast back, av_hubert_layers.py:438-440)
+// [B, C, T] x 2  ->  [B, T, C'] with C' = 2C (concat) or C (sum / weighted sum).
+//
+// HBM-bound: the unfused chain writes and re-reads the fused tensor twice (cat, transpose copy,
+// LayerNorm); here every input byte is read once and every output byte written once.  A CTA owns
+// a tile of TT consecutive time steps of one sample, all C' channels: rows are read along T
+// (TT elements = 32 or 64 contiguous bytes per channel row), parked in shared memory in the input
+// dtype (row stride padded to an odd number of words so that both the row-wise fill and the
+// column-wise drain are bank-conflict free), reduced to mean / rstd per time step in float32
+// (two passes over shared memory, like torch's RowwiseMoments), and drained channel-contiguous:
+// a warp writes 32 consecutive channels of one time step, i.e. full 128-byte lines.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "avfe_common.cuh"
+
+namespace avfe {
+namespace fln {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+constexpr int kThreads = 512;
+
+// elements of padding per tile row: the row stride in 32-bit words must be odd
+template <typename T> struct Pad { static constexpr int value = 4 / sizeof(T); };
+
+template <typename T, int TT>
+__host__ __device__ constexpr int row_stride() { return TT + Pad<T>::value; }
+
+struct Args {
+  const void* fa;
+  const void* fv;
+  const uint8_t* mask;      // [B,2] or nullptr
+  const float* gamma;       // [C'] or nullptr (= 1)
+  const float* beta;        // [C'] or nullptr (= 0)
+  void* out;                // [B, T, C']
+  float wa, wv, eps;
+  int64_t B;
+  int C, Cout, T, tiles_per_sample;
+};
+
+// VEC consecutive time steps (VEC * sizeof(T) = 8 bytes for float, 4 for the half types) as one load
+template <typename T, int VEC> struct Pack;
+template <> struct Pack<float, 2> { typedef float2 type; };
+template <> struct Pack<float, 1> { typedef float type; };
+template <> struct Pack<__half, 2> { typedef __half2 type; };
+template <> struct Pack<__half, 1> { typedef __half type; };
+template <> struct Pack<__nv_bfloat16, 2> { typedef __nv_bfloat162 type; };
+template <> struct Pack<__nv_bfloat16, 1> { typedef __nv_bfloat16 type; };
+
+template <typename T, int MODE>
+__device__ __forceinline__ T combine1(T x, T y, float wa, float wv) {
+  const float a = to_f32<T>(x), v = to_f32<T>(y);
+  return from_f32<T>((MODE == AVFE_FUSE_SUM) ? __fadd_rn(a, v) : __fadd_rn(__fmul_rn(wa, a), __fmul_rn(wv, v)));
+}
+
+// One CTA = one tile: time steps [t0, t0 + TT) of sample b, all Cout channels.
+template <typename T, int MODE, int TT, int VEC>
+__global__ void __launch_bounds__(kThreads)
+fuse_ln_kernel(const Args a) {
+  extern __shared__ __align__(16) unsigned char fln_smem[];
+  typedef typename Pack<T, VEC>::type P;
+  constexpr int RS = row_stride<T, TT>();
+  T* tile = reinterpret_cast<T*>(fln_smem);                       // [Cout][RS]
+  float* stat = reinterpret_cast<float*>(tile + (size_t)a.Cout * RS + (((size_t)a.Cout * RS) & 1));
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t b = blockIdx.x / a.tiles_per_sample;
+  const int t0 = (int)(blockIdx.x % a.tiles_per_sample) * TT;
+  const int nt = min(TT, a.T - t0);
+  unsigned m = 3u;
+  if (a.mask != nullptr) m = (a.mask[2 * b] ? 1u : 0u) | (a.mask[2 * b + 1] ? 2u : 0u);
+  const bool has_a = (m & 1u) != 0, has_v = (m & 2u) != 0;
+  const T* fa = static_cast<const T*>(a.fa) + b * (int64_t)a.C * a.T + t0;
+  const T* fv = static_cast<const T*>(a.fv) + b * (int64_t)a.C * a.T + t0;
+  const T zero = from_f32<T>(0.0f);
+
+  // ---- fill: thread = (row group, pack of VEC time steps); TT / VEC lanes cover one row's
+  // contiguous bytes, U rows per thread in flight before anything is stored
+  constexpr int kLanesPerRow = TT / VEC;
+  constexpr int kRowsPerPass = kThreads / kLanesPerRow;
+  const int tp = (tid % kLanesPerRow) * VEC, r0 = tid / kLanesPerRow;
+  constexpr int U = 8;
+  // with VEC == 2 (T even) a pack never straddles the end of the sample: tp + 1 < nt iff tp < nt
+  auto load = [&](const T* row, bool live) -> P {
+    if (live) return *reinterpret_cast<const P*>(row + tp);
+    P z;
+    T* zp = reinterpret_cast<T*>(&z);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) zp[i] = zero;
+    return z;
+  };
+  for (int c = r0; c < a.Cout; c += kRowsPerPass * U) {
+    P va[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int cc = c + u * kRowsPerPass;
+      const bool live = cc < a.Cout && tp < nt;
+      if (MODE == AVFE_FUSE_CONCAT) {                  // fused channel cc < C comes from fa, the rest from fv
+        const bool from_a = cc < a.C;
+        const T* row = from_a ? fa + (int64_t)cc * a.T : fv + (int64_t)(cc - a.C) * a.T;
+        va[u] = load(row, live && (from_a ? has_a : has_v));
+      } else {
+        va[u] = load(fa + (int64_t)cc * a.T, live && has_a);
+        vv[u] = load(fv + (int64_t)cc * a.T, live && has_v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int cc = c + u * kRowsPerPass;
+      if (cc < a.Cout) {
+        const T* pa = reinterpret_cast<const T*>(&va[u]);
+        const T* pv = reinterpret_cast<const T*>(&vv[u]);
+        T* dst = tile + cc * RS + tp;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          dst[i] = (MODE == AVFE_FUSE_CONCAT) ? pa[i] : combine1<T, MODE>(pa[i], pv[i], a.wa, a.wv);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- moments per time step (float32, two passes over the tile like torch's RowwiseMoments):
+  // thread (tt, rg) sums its share of the rows, partials are combined through shared memory
+  constexpr int kRowGroups = kThreads / TT;
+  const int tt = tid % TT, rg = tid / TT;
+  float* mean_s = stat;
+  float* rstd_s = stat + TT;
+  float* part = stat + 2 * TT;                                    // [kRowGroups][TT]
+  {
+    float s = 0.0f;
+    for (int c = rg; c < a.Cout; c += kRowGroups) s += to_f32<T>(tile[c * RS + tt]);
+    part[rg * TT + tt] = s;
+  }
+  __syncthreads();
+  if (tid < TT) {
+    float s = 0.0f;
+    for (int r = 0; r < kRowGroups; ++r) s += part[r * TT + tid];
+    mean_s[tid] = s / (float)a.Cout;
+  }
+  __syncthreads();
+  {
+    const float mu = mean_s[tt];
+    float s = 0.0f;
+    for (int c = rg; c < a.Cout; c += kRowGroups) {
+      const float d = to_f32<T>(tile[c * RS + tt]) - mu;
+      s = fmaf(d, d, s);
+    }
+    part[rg * TT + tt] = s;
+  }
+  __syncthreads();
+  if (tid < TT) {
+    float s = 0.0f;
+    for (int r = 0; r < kRowGroups; ++r) s += part[r * TT + tid];
+    rstd_s[tid] = rsqrtf(s / (float)a.Cout + a.eps);
+  }
+  __syncthreads();
+
+  // ---- drain: a warp takes 32 consecutive channels (their gamma / beta in registers) through
+  // all time steps of the tile: column reads of the tile are conflict-free (odd row stride) and
+  // every store instruction writes one full 128-byte line of out[b, t, :]
+  T* out = static_cast<T*>(a.out) + (b * (int64_t)a.T + t0) * a.Cout;
+  for (int c = wid * 32 + lane; c < a.Cout; c += kThreads) {
+    const float g = a.gamma ? a.gamma[c] : 1.0f, be = a.beta ? a.beta[c] : 0.0f;
+    const T* col = tile + c * RS;
+    T* o = out + c;
+#pragma unroll 4
+    for (int t = 0; t < nt; ++t) {
+      const float x = to_f32<T>(col[t]);
+      o[(int64_t)t * a.Cout] = from_f32<T>(fmaf((x - mean_s[t]) * rstd_s[t], g, be));
+    }
+  }
+}
+
+template <typename T, int TT>
+static size_t smem_bytes(int Cout) {
+  size_t tile = (size_t)Cout * row_stride<T, TT>();
+  tile += tile & 1;
+  return tile * sizeof(T) + (size_t)(2 * TT + (kThreads / TT) * TT) * sizeof(float);
+}
+
+template <typename T, int MODE, int TT, int VEC>
+static int launch_vec(const Args& a, cudaStream_t s) {
+  const size_t smem = smem_bytes<T, TT>(a.Cout);
+  if (smem > 227 * 1024) return AVFE_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(fuse_ln_kernel<T, MODE, TT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  const int64_t ctas = a.B * a.tiles_per_sample;
+  if (ctas > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  fuse_ln_kernel<T, MODE, TT, VEC><<<(unsigned)ctas, kThreads, smem, s>>>(a);
+  count_launch();
+  return check_launch();
+}
+
+// two time steps per load when every row keeps that alignment (T even, pointers aligned)
+template <typename T, int MODE, int TT>
+static int launch(const Args& a, cudaStream_t s) {
+  const uintptr_t al = 2 * sizeof(T) - 1;
+  const bool vec2 = (a.T % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.fa) & al) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(a.fv) & al) == 0);
+  return vec2 ? launch_vec<T, MODE, TT, 2>(a, s) : launch_vec<T, MODE, TT, 1>(a, s);
+}
+
+// TT = time steps per tile: 64 contiguous bytes per channel row when three tiles fit an SM, else 32
+template <typename T, int MODE>
+static int pick_tile(Args a, cudaStream_t s) {
+  constexpr int TT_WIDE = 64 / sizeof(T), TT_NARROW = 32 / sizeof(T);
+  if (smem_bytes<T, TT_WIDE>(a.Cout) <= 75 * 1024) {
+    a.tiles_per_sample = (a.T + TT_WIDE - 1) / TT_WIDE;
+    return launch<T, MODE, TT_WIDE>(a, s);
+  }
+  a.tiles_per_sample = (a.T + TT_NARROW - 1) / TT_NARROW;
+  return launch<T, MODE, TT_NARROW>(a, s);
+}
+
+template <typename T>
+static int pick_mode(int mode, const Args& a, cudaStream_t s) {
+  switch (mode) {
+    case AVFE_FUSE_CONCAT: return pick_tile<T, AVFE_FUSE_CONCAT>(a, s);
+    case AVFE_FUSE_SUM:    return pick_tile<T, AVFE_FUSE_SUM>(a, s);
+    case AVFE_FUSE_WSUM:   return pick_tile<T, AVFE_FUSE_WSUM>(a, s);
+    default: return AVFE_ERR_INVALID_ARG;
+  }
+}
+
+}  // namespace fln
+}  // namespace avfe
+
+extern "C" int avfe_fuse_layernorm(const void* fa, const void* fv, const uint8_t* mask, int mode,
+                                   float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
+                                   const float* gamma, const float* beta, float eps, void* out,
+                                   avfe_stream_t stream) {
+  using namespace avfe;
+  if (B < 0 || C < 0 || T < 0 || !(eps >= 0.0f)) return AVFE_ERR_INVALID_ARG;
+  if (mode != AVFE_FUSE_CONCAT && mode != AVFE_FUSE_SUM && mode != AVFE_FUSE_WSUM) return AVFE_ERR_INVALID_ARG;
+  if (B == 0 || C == 0 || T == 0) return AVFE_OK;
+  if (!fa || !fv || !out) return AVFE_ERR_INVALID_ARG;
+  if (C > (1 << 20) || T > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  fln::Args a;
+  a.fa = fa; a.fv = fv; a.mask = mask; a.gamma = gamma; a.beta = beta; a.out = out;
+  a.wa = w_a; a.wv = w_v; a.eps = eps; a.B = B; a.C = (int)C;
+  a.Cout = (int)(mode == AVFE_FUSE_CONCAT ? 2 * C : C);
+  a.T = (int)T; a.tiles_per_sample = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case AVFE_F32:  return fln::pick_mode<float>(mode, a, s);
+    case AVFE_F16:  return fln::pick_mode<__half>(mode, a, s);
+    case AVFE_BF16: return fln::pick_mode<__nv_bfloat16>(mode, a, s);
+    default: return AVFE_ERR_INVALID_ARG;
+  }
+}

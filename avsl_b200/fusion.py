@@ -50,6 +50,19 @@ def modality_dropout_mask(batch_size: int, training: bool, modality_dropout: flo
     return mask
 
 
+def _mask_tensor(mask, B: int, device) -> Optional[torch.Tensor]:
+    """[B,2] keep-mask as a uint8 device tensor (None stays None); a sample with both modalities
+    dropped raises like the reference (``av_hubert_encoder.py:301-302``)."""
+    if mask is None:
+        return None
+    m = torch.as_tensor(np.asarray(mask.cpu() if torch.is_tensor(mask) else mask) != 0).to(torch.uint8)
+    if tuple(m.shape) != (B, 2):
+        raise ValueError("mask must be [B, 2]")
+    if not bool((m.sum(dim=1) > 0).all()):
+        raise ValueError("At least one input modality must be provided and enabled")
+    return m.contiguous().to(device, non_blocking=True)
+
+
 def fuse_modalities(features_audio: torch.Tensor, features_video: torch.Tensor,
                     mask=None, fusion_type: str = "concat", weights: Tuple[float, float] = (0.5, 0.5),
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -74,17 +87,50 @@ def fuse_modalities(features_audio: torch.Tensor, features_video: torch.Tensor,
         out = torch.empty(shape, dtype=fa.dtype, device=fa.device)
     elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == shape):
         raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {shape}")
-    m = None
-    if mask is not None:
-        m = torch.as_tensor(np.asarray(mask.cpu() if torch.is_tensor(mask) else mask) != 0).to(torch.uint8)
-        if tuple(m.shape) != (B, 2):
-            raise ValueError("mask must be [B, 2]")
-        if not bool((m.sum(dim=1) > 0).all()):
-            raise ValueError("At least one input modality must be provided and enabled")
-        m = m.contiguous().to(fa.device, non_blocking=True)
+    m = _mask_tensor(mask, B, fa.device)
     with torch.cuda.device(fa.device):
         _lib.call("avfe_fuse", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
                   float(weights[1]), _DTYPES[fa.dtype], B, C, T, _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch.Tensor, mask=None,
+                             fusion_type: str = "concat", weight: Optional[torch.Tensor] = None,
+                             bias: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                             weights: Tuple[float, float] = (0.5, 0.5),
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fusion plus the two lines that follow it in ``AVHuBERTEncoderWrapper.forward``
+    (``av_hubert_encoder.py:329-330``): ``features.transpose(1, 2)`` and ``self.layer_norm``
+    (``LayerNorm`` of ``av_hubert_layers.py:438-440``: float32 arithmetic, result cast back), in
+    one kernel.  [B,C,T] x 2 -> [B,T,C'] (C' = 2C for "concat").  ``weight`` / ``bias`` are the
+    LayerNorm parameters (float32 [C'])."""
+    if fusion_type not in _MODES:
+        raise ValueError(f"Unsupported fusion type: {fusion_type}")
+    _lib.require_cuda()
+    fa, fv = features_audio, features_video
+    if not (fa.is_cuda and fv.is_cuda):
+        raise ValueError("fuse_transpose_layernorm takes CUDA tensors")
+    if fa.shape != fv.shape or fa.dim() != 3 or fa.dtype != fv.dtype:
+        raise ValueError("features_audio and features_video must both be [B, C, T] of one dtype")
+    if fa.dtype not in _DTYPES:
+        raise ValueError(f"unsupported dtype {fa.dtype}")
+    fa, fv = fa.contiguous(), fv.contiguous()
+    B, C, T = (int(s) for s in fa.shape)
+    mode = _MODES[fusion_type]
+    Cout = 2 * C if mode == _lib.FUSE_CONCAT else C
+    for name, prm in (("weight", weight), ("bias", bias)):
+        if prm is not None and not (prm.is_cuda and prm.dtype == torch.float32 and prm.is_contiguous()
+                                    and tuple(prm.shape) == (Cout,)):
+            raise ValueError(f"{name} must be a contiguous float32 CUDA tensor of shape ({Cout},)")
+    if out is None:
+        out = torch.empty((B, T, Cout), dtype=fa.dtype, device=fa.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == (B, T, Cout)):
+        raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {(B, T, Cout)}")
+    m = _mask_tensor(mask, B, fa.device)
+    with torch.cuda.device(fa.device):
+        _lib.call("avfe_fuse_layernorm", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
+                  float(weights[1]), _DTYPES[fa.dtype], B, C, T, _lib.ptr(weight), _lib.ptr(bias),
+                  float(eps), _lib.ptr(out), _lib.stream_ptr())
     return out
 
 

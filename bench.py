@@ -362,7 +362,35 @@ def main():
             nbytes = present * E1 + fout.numel() * 4
             side[f"fuse_{mode}"] = {"kernel": "fuse_vec_kernel (configs[3], masked: absent modalities not read)",
                                     "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+        # fusion + transpose + LayerNorm in one pass: same inputs, [B,T,C'] out
+        for mode, dt in (("concat", torch.float32), ("add", torch.float32), ("concat", torch.float16)):
+            xa, xv = fa.to(dt), fv.to(dt)
+            Cout = 2048 if mode == "concat" else 1024
+            w = torch.ones(Cout, device=dev)
+            bz = torch.zeros(Cout, device=dev)
+            lout = torch.empty((64, 750, Cout), device=dev, dtype=dt)
+            ms = time_op(lambda: A.fuse_transpose_layernorm(xa, xv, fmask, mode, w, bz, out=lout), 20)
+            esz = 4 if dt == torch.float32 else 2
+            nbytes = present * 1024 * 750 * esz + lout.numel() * esz
+            side[f"fuse_ln_{mode}_{'f32' if esz == 4 else 'f16'}"] = {
+                "kernel": "fuse_ln_kernel (fusion + transpose + LayerNorm, av_hubert_encoder.py:315-330; masked)",
+                "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+            del xa, xv, lout
         del fa, fv
+        # the lip stage writing the padded [B,1,T,88,88] batch + padding mask directly (8(f) rank 1)
+        T_pad = int((batch_dev.clip_offsets[1:] - batch_dev.clip_offsets[:-1]).max().item())
+        cout = None
+        def run_collate():
+            nonlocal cout
+            cout = A.lip_roi_collate(batch_dev.frames, batch_dev.clip_offsets, batch_dev.landmarks,
+                                     batch_dev.lm_valid, T_pad=T_pad, out=cout)
+        ms = time_op(run_collate, 10)
+        n_fr = int(batch_dev.frames.shape[0])
+        nbytes = n_fr * (H * W * 3 + 68 * 2 * 8 + H * W) + cout["video"].numel() * 4 + cout["padding_mask_u8"].numel()
+        side["lip_collated"] = {"kernel": "lip_frame_kernel + collate_tail_kernel: padded [U,1,T_pad,88,88] video + mask (trim + collator fused)",
+                                "ms": ms, "T_pad": T_pad, "algorithmic_bytes": nbytes,
+                                "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+        del cout
 
     # ---------------- end-to-end through host buffers ----------------
     e2e = None

@@ -223,6 +223,18 @@ AVFE_API int avfe_fuse(const void* fa, const void* fv, const uint8_t* mask, int 
                        float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
                        void* out, avfe_stream_t stream);
 
+/* The same fusion followed by the rest of the block's tail in one pass —
+ * avsl/modules/av_hubert_encoder.py:329-330: features.transpose(1, 2) then self.layer_norm
+ * (nn.LayerNorm over the fused channel dimension, evaluated in float32 and cast back to the
+ * input dtype, avsl/modules/av_hubert_layers.py:438-440).  The fused [B, C', T] tensor and its
+ * transposed copy are never materialised.
+ *   gamma, beta [C'] float32 (LayerNorm weight / bias; NULL = 1 / 0), eps (1e-5 in the reference)
+ *   out [B, T, C'] of `dtype`, C' = 2C for CONCAT, C otherwise. */
+AVFE_API int avfe_fuse_layernorm(const void* fa, const void* fv, const uint8_t* mask, int mode,
+                                 float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
+                                 const float* gamma, const float* beta, float eps, void* out,
+                                 avfe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,3 +55,15 @@ def fuse(fa: torch.Tensor, fv: torch.Tensor, mask=None, mode: str = "concat",
     wv = torch.tensor(w_v, dtype=torch.float32)
     # products rounded separately in fp32, then one add, result cast to the input dtype
     return (wa * fa.to(torch.float32) + wv * fv.to(torch.float32)).to(fa.dtype)
+
+
+def fuse_transpose_layernorm(fa: torch.Tensor, fv: torch.Tensor, mask=None, mode: str = "concat",
+                             weight=None, bias=None, eps: float = 1e-5, w_a: float = 0.5,
+                             w_v: float = 0.5) -> torch.Tensor:
+    """av_hubert_encoder.py:315-330: fusion, ``features.transpose(1, 2)``, ``self.layer_norm``.
+    ``LayerNorm`` is ``nn.LayerNorm`` run on ``x.float()`` and cast back to ``x.dtype``
+    (avsl/modules/av_hubert_layers.py:438-440); these are the reference's own torch ops, so the
+    oracle IS the reference arithmetic (CPU).  Returns [B, T, C']."""
+    x = fuse(fa, fv, mask, mode, w_a, w_v).transpose(1, 2)
+    y = torch.nn.functional.layer_norm(x.float(), (x.shape[-1],), weight, bias, eps)
+    return y.type(x.dtype).contiguous()

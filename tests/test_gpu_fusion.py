@@ -82,3 +82,50 @@ def test_modality_fusion_module_matches_reference_block():
     assert torch.equal(fuse(fa, fv, modality_override="visual")[:, :8].cpu(), torch.zeros(4, 8, 16))
     with pytest.raises(ValueError, match="At least one input modality"):
         A.ModalityFusion(use_audio=False)(fa, None)
+
+
+# tolerance of the fused LayerNorm against torch's CPU kernel (both float32 arithmetic, different
+# summation order): 2e-5 absolute on unit-variance output for fp32; one ulp of the output dtype
+# (fp16 2^-10, bf16 2^-7 relative) plus that for the half types
+_LN_TOL = {torch.float32: 2e-5, torch.float16: 2.5e-3, torch.bfloat16: 2e-2}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
+def test_fuse_transpose_layernorm_vs_reference_ops(dtype, mode):
+    B, C, T = 5, 72, 45                               # T not a multiple of the tile, C not of 32
+    fa, fv, mask = synth.fusion_inputs(B, C, T, seed=11, dtype=dtype)
+    fa = fa * 3.0 + 0.5                               # non-trivial mean and variance
+    Cout = 2 * C if mode == "concat" else C
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(Cout, generator=g) * 0.5 + 1.0
+    b = torch.randn(Cout, generator=g) * 0.1
+    for m in (None, mask):
+        ref = O.fuse_transpose_layernorm(fa, fv, m, mode, w, b, 1e-5, 0.3, 0.7)
+        got = A.fuse_transpose_layernorm(fa.cuda(), fv.cuda(), m, mode, w.cuda(), b.cuda(), 1e-5,
+                                         weights=(0.3, 0.7)).cpu()
+        assert got.shape == (B, T, Cout) and got.dtype == dtype
+        err = (got.float() - ref.float()).abs().max().item()
+        assert err <= _LN_TOL[dtype] * max(1.0, ref.float().abs().max().item()), err
+    # no affine parameters, and the unfused product path agrees
+    got = A.fuse_transpose_layernorm(fa.cuda(), fv.cuda(), None, mode, weights=(0.3, 0.7)).cpu()
+    ref = O.fuse_transpose_layernorm(fa, fv, None, mode, None, None, 1e-5, 0.3, 0.7)
+    assert (got.float() - ref.float()).abs().max().item() <= _LN_TOL[dtype] * max(1.0, ref.float().abs().max().item())
+
+
+def test_fuse_transpose_layernorm_config4_properties():
+    """Full size (B 64, C 1024, T 750): every output row has zero mean and unit variance (no affine),
+    a dropped modality contributes exact zeros before normalisation, and the result equals the
+    unfused GPU chain fuse -> transpose -> torch layer_norm to float32 round-off."""
+    fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
+    out = A.fuse_transpose_layernorm(fa, fv, mask, "concat")
+    assert out.shape == (64, 750, 2048)
+    assert out.mean(dim=-1).abs().max().item() < 1e-4
+    assert (out.var(dim=-1, unbiased=False) - 1.0).abs().max().item() < 1e-3
+    cat = A.fuse_modalities(fa, fv, mask, "concat")
+    ref = torch.nn.functional.layer_norm(cat.transpose(1, 2), (2048,), None, None, 1e-5)
+    assert (out - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 2e-5
+    add = A.fuse_transpose_layernorm(fa.half(), fv.half(), mask, "add")
+    ref = torch.nn.functional.layer_norm((A.fuse_modalities(fa.half(), fv.half(), mask, "add")).transpose(1, 2).float(),
+                                         (1024,), None, None, 1e-5).half()
+    assert (add.float() - ref.float()).abs().max().item() <= 2.5e-3 * ref.float().abs().max().item()
