@@ -49,9 +49,22 @@ def run_fuse(iters):
     torch.cuda.synchronize()
 
 
+def run_fuse_ln(iters):
+    fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
+    w, b = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
+    out = None
+    for _ in range(iters):
+        out = A.fuse_transpose_layernorm(fa, fv, mask, "concat", w, b, out=out)
+    out = None
+    fa, fv = fa.half(), fv.half()
+    for _ in range(iters):
+        out = A.fuse_transpose_layernorm(fa, fv, mask, "concat", w, b, out=out)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["logmel", "lip", "fuse", "all"])
+    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "all"])
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     if a.which in ("logmel", "all"):
@@ -60,4 +73,6 @@ if __name__ == "__main__":
         run_lip(a.iters)
     if a.which in ("fuse", "all"):
         run_fuse(a.iters)
+    if a.which in ("fuse_ln", "all"):
+        run_fuse_ln(a.iters)
     print("done", a.which)
