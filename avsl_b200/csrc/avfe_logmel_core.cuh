@@ -41,8 +41,20 @@ constexpr int kTileSkew = 20;
 constexpr int kTileFloats = kTileSamples + kTileSkew * (kTileSamples / 320 + 1);   // 5700
 constexpr int kBinsPerThread = 11;   // thread (g, j) untangles bins k = j + 20*m, m = 0..10
 
+// Complex add / subtract / scale as ONE packed instruction each on sm_100a (FADD2 / FFMA2 /
+// FMUL2: two float32 lanes per 64-bit register pair, Blackwell-only), with the same roundings as
+// the scalar form, which the host build (tests/hostcheck) uses.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+AVFE_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+AVFE_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }   // a - b, exact negation
+AVFE_HD float2 cscale(float s, float2 a) { return __fmul2_rn(make_float2(s, s), a); }             // s * a
+AVFE_HD float2 caxpy(float s, float2 a, float2 y) { return __ffma2_rn(make_float2(s, s), a, y); } // s * a + y
+#else
 AVFE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 AVFE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+AVFE_HD float2 cscale(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
+AVFE_HD float2 caxpy(float s, float2 a, float2 y) { return make_float2(fmaf(s, a.x, y.x), fmaf(s, a.y, y.y)); }
+#endif
 AVFE_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -61,11 +73,11 @@ AVFE_HD void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
   const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
   const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
   const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-  const float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-  const float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-  const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-  const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  const float2 m1 = caxpy(c2, t2, caxpy(c1, t1, x0));
+  const float2 m2 = caxpy(c1, t2, caxpy(c2, t1, x0));
+  const float2 n1 = caxpy(s2, t4, cscale(s1, t3));
+  const float2 n2 = caxpy(-s1, t4, cscale(s2, t3));
+  x0 = cadd(cadd(x0, t1), t2);
   x1 = make_float2(m1.x + n1.y, m1.y - n1.x);   // m1 - i*n1
   x4 = make_float2(m1.x - n1.y, m1.y + n1.x);   // m1 + i*n1
   x2 = make_float2(m2.x + n2.y, m2.y - n2.x);
