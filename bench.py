@@ -209,6 +209,9 @@ def workload_config(args, world, n_frames, n_utts):
 # ------------------------------------------------------------------------------- our arm
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: anything NCCL wants to say (its version banner when
+    # the environment sets NCCL_DEBUG) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, local, world = dist_env()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU
