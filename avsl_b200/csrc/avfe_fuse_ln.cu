@@ -11,9 +11,12 @@
 // a tile of TT consecutive time steps of one sample, all C' channels: rows are read along T
 // (TT elements = 32 or 64 contiguous bytes per channel row), parked in shared memory in the input
 // dtype (row stride padded to an odd number of words so that both the row-wise fill and the
-// column-wise drain are bank-conflict free), reduced to mean / rstd per time step in float32
-// (two passes over shared memory, like torch's RowwiseMoments), and drained channel-contiguous:
-// a warp writes 32 consecutive channels of one time step, i.e. full 128-byte lines.
+// column-wise drain are bank-conflict free) and drained channel-contiguous: a warp writes 32
+// consecutive channels of one time step, i.e. full 128-byte lines.  The kernel is bound by the
+// load/store pipe of the SM (every element crosses shared memory), so the moments are NOT taken
+// from the tile: each thread accumulates sum(x - K) and sum((x - K)^2) of the values it fills,
+// K = the time step's first channel (shifted moments: no cancellation), and the partials meet
+// through a few shuffles and one shared-memory round.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -101,6 +104,20 @@ fuse_ln_kernel(const Args a) {
     for (int i = 0; i < VEC; ++i) zp[i] = zero;
     return z;
   };
+  // fused value of (channel cc, time steps tp .. tp + VEC - 1) from its loaded packs
+  auto fused = [&](const P& xa, const P& xv, int i) -> T {
+    const T* pa = reinterpret_cast<const T*>(&xa);
+    const T* pv = reinterpret_cast<const T*>(&xv);
+    return (MODE == AVFE_FUSE_CONCAT) ? pa[i] : combine1<T, MODE>(pa[i], pv[i], a.wa, a.wv);
+  };
+  float K[VEC], s1[VEC], s2[VEC];
+  {
+    const bool live = tp < nt;
+    const P ka = load(fa, live && has_a);                // fused channel 0: fa row 0 (+ fv row 0 unless concat)
+    const P kv = (MODE == AVFE_FUSE_CONCAT) ? ka : load(fv, live && has_v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { K[i] = to_f32<T>(fused(ka, kv, i)); s1[i] = 0.0f; s2[i] = 0.0f; }
+  }
   for (int c = r0; c < a.Cout; c += kRowsPerPass * U) {
     P va[U], vv[U];
 #pragma unroll
@@ -120,50 +137,52 @@ fuse_ln_kernel(const Args a) {
     for (int u = 0; u < U; ++u) {
       const int cc = c + u * kRowsPerPass;
       if (cc < a.Cout) {
-        const T* pa = reinterpret_cast<const T*>(&va[u]);
-        const T* pv = reinterpret_cast<const T*>(&vv[u]);
         T* dst = tile + cc * RS + tp;
+        T f[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
-          dst[i] = (MODE == AVFE_FUSE_CONCAT) ? pa[i] : combine1<T, MODE>(pa[i], pv[i], a.wa, a.wv);
+        for (int i = 0; i < VEC; ++i) {
+          f[i] = fused(va[u], vv[u], i);
+          const float d = to_f32<T>(f[i]) - K[i];
+          s1[i] += d;
+          s2[i] = fmaf(d, d, s2[i]);
+        }
+        if (VEC == 2 && sizeof(T) == 2) {                // both time steps in one 32-bit store
+          *reinterpret_cast<P*>(dst) = *reinterpret_cast<const P*>(f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) dst[i] = f[i];
+        }
       }
     }
   }
-  __syncthreads();
-
-  // ---- moments per time step (float32, two passes over the tile like torch's RowwiseMoments):
-  // thread (tt, rg) sums its share of the rows, partials are combined through shared memory
-  constexpr int kRowGroups = kThreads / TT;
-  const int tt = tid % TT, rg = tid / TT;
+  // ---- moments per time step: lanes holding the same time steps are kLanesPerRow apart
+  constexpr int kWarps = kThreads / 32;
   float* mean_s = stat;
   float* rstd_s = stat + TT;
-  float* part = stat + 2 * TT;                                    // [kRowGroups][TT]
-  {
-    float s = 0.0f;
-    for (int c = rg; c < a.Cout; c += kRowGroups) s += to_f32<T>(tile[c * RS + tt]);
-    part[rg * TT + tt] = s;
-  }
-  __syncthreads();
-  if (tid < TT) {
-    float s = 0.0f;
-    for (int r = 0; r < kRowGroups; ++r) s += part[r * TT + tid];
-    mean_s[tid] = s / (float)a.Cout;
-  }
-  __syncthreads();
-  {
-    const float mu = mean_s[tt];
-    float s = 0.0f;
-    for (int c = rg; c < a.Cout; c += kRowGroups) {
-      const float d = to_f32<T>(tile[c * RS + tt]) - mu;
-      s = fmaf(d, d, s);
+  float* kref_s = stat + 2 * TT;
+  float* part = stat + 3 * TT;                                    // [2][TT][kWarps]
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+#pragma unroll
+    for (int o = 16; o >= kLanesPerRow; o >>= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
     }
-    part[rg * TT + tt] = s;
+    if (lane < kLanesPerRow) {
+      part[(tp + i) * kWarps + wid] = s1[i];
+      part[(TT + tp + i) * kWarps + wid] = s2[i];
+    }
+    if (tid < kLanesPerRow) kref_s[tp + i] = K[i];
   }
   __syncthreads();
   if (tid < TT) {
-    float s = 0.0f;
-    for (int r = 0; r < kRowGroups; ++r) s += part[r * TT + tid];
-    rstd_s[tid] = rsqrtf(s / (float)a.Cout + a.eps);
+    float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) { t1 += part[tid * kWarps + k]; t2 += part[(TT + tid) * kWarps + k]; }
+    const float n = (float)a.Cout;
+    const float md = t1 / n;                                       // mean - K
+    mean_s[tid] = kref_s[tid] + md;
+    rstd_s[tid] = rsqrtf(fmaxf((t2 - t1 * md) / n, 0.0f) + a.eps);
   }
   __syncthreads();
 
@@ -187,7 +206,7 @@ template <typename T, int TT>
 static size_t smem_bytes(int Cout) {
   size_t tile = (size_t)Cout * row_stride<T, TT>();
   tile += tile & 1;
-  return tile * sizeof(T) + (size_t)(2 * TT + (kThreads / TT) * TT) * sizeof(float);
+  return tile * sizeof(T) + (size_t)(3 * TT + 2 * TT * (kThreads / 32)) * sizeof(float);
 }
 
 template <typename T, int MODE, int TT, int VEC>
