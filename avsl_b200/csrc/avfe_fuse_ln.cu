@@ -71,13 +71,13 @@ __device__ __forceinline__ T combine1(T x, T y, float wa, float wv) {
 
 // One CTA = one tile: time steps [t0, t0 + TT) of sample b, all Cout channels.
 template <typename T, int MODE, int TT, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 fuse_ln_kernel(const Args a) {
   extern __shared__ __align__(16) unsigned char fln_smem[];
   typedef typename Pack<T, VEC>::type P;
   constexpr int RS = row_stride<T, TT>();
   T* tile = reinterpret_cast<T*>(fln_smem);                       // [Cout][RS]
-  float* stat = reinterpret_cast<float*>(tile + (size_t)a.Cout * RS + (((size_t)a.Cout * RS) & 1));
+  float* stat = reinterpret_cast<float*>(fln_smem + (((size_t)a.Cout * RS * sizeof(T) + 15) & ~(size_t)15));
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t b = blockIdx.x / a.tiles_per_sample;
   const int t0 = (int)(blockIdx.x % a.tiles_per_sample) * TT;
@@ -118,43 +118,68 @@ fuse_ln_kernel(const Args a) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { K[i] = to_f32<T>(fused(ka, kv, i)); s1[i] = 0.0f; s2[i] = 0.0f; }
   }
-  for (int c = r0; c < a.Cout; c += kRowsPerPass * U) {
-    P va[U], vv[U];
+  // Row pointers advance incrementally (one 64-bit add per U rows).  "concat" is two plain
+  // copies: fused channels [0, C) from fa, [C, 2C) from fv.
+  const bool t_live = tp < nt;
+  const int64_t pass_stride = (int64_t)kRowsPerPass * a.T;
+  auto put = [&](T* dst, const P& xa, const P& xv) {
+    T f[VEC];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int cc = c + u * kRowsPerPass;
-      const bool live = cc < a.Cout && tp < nt;
-      if (MODE == AVFE_FUSE_CONCAT) {                  // fused channel cc < C comes from fa, the rest from fv
-        const bool from_a = cc < a.C;
-        const T* row = from_a ? fa + (int64_t)cc * a.T : fv + (int64_t)(cc - a.C) * a.T;
-        va[u] = load(row, live && (from_a ? has_a : has_v));
-      } else {
-        va[u] = load(fa + (int64_t)cc * a.T, live && has_a);
-        vv[u] = load(fv + (int64_t)cc * a.T, live && has_v);
+    for (int i = 0; i < VEC; ++i) {
+      f[i] = fused(xa, xv, i);
+      const float d = to_f32<T>(f[i]) - K[i];
+      s1[i] += d;
+      s2[i] = fmaf(d, d, s2[i]);
+    }
+    if (VEC == 2 && sizeof(T) == 2) {                  // both time steps in one 32-bit store
+      *reinterpret_cast<P*>(dst) = *reinterpret_cast<const P*>(f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dst[i] = f[i];
+    }
+  };
+  P zpack;
+  {
+    T* zp = reinterpret_cast<T*>(&zpack);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) zp[i] = zero;
+  }
+  if (MODE == AVFE_FUSE_CONCAT) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const bool on = t_live && (half ? has_v : has_a);
+      const T* src = (half ? fv : fa) + (int64_t)r0 * a.T + tp;
+      T* dst = tile + (half * a.C + r0) * RS + tp;
+      for (int c = r0; c < a.C; c += kRowsPerPass * U, src += U * pass_stride, dst += U * kRowsPerPass * RS) {
+        P v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          v[u] = (on && c + u * kRowsPerPass < a.C) ? *reinterpret_cast<const P*>(src + u * pass_stride) : zpack;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (c + u * kRowsPerPass < a.C) put(dst + u * kRowsPerPass * RS, v[u], v[u]);
       }
     }
+  } else {
+    const T* pa = fa + (int64_t)r0 * a.T + tp;
+    const T* pv = fv + (int64_t)r0 * a.T + tp;
+    T* dst = tile + r0 * RS + tp;
+    for (int c = r0; c < a.C; c += kRowsPerPass * U, pa += U * pass_stride, pv += U * pass_stride,
+             dst += U * kRowsPerPass * RS) {
+      P va[U], vv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int cc = c + u * kRowsPerPass;
-      if (cc < a.Cout) {
-        T* dst = tile + cc * RS + tp;
-        T f[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          f[i] = fused(va[u], vv[u], i);
-          const float d = to_f32<T>(f[i]) - K[i];
-          s1[i] += d;
-          s2[i] = fmaf(d, d, s2[i]);
-        }
-        if (VEC == 2 && sizeof(T) == 2) {                // both time steps in one 32-bit store
-          *reinterpret_cast<P*>(dst) = *reinterpret_cast<const P*>(f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) dst[i] = f[i];
-        }
+      for (int u = 0; u < U; ++u) {
+        const bool on = t_live && c + u * kRowsPerPass < a.C;
+        va[u] = (on && has_a) ? *reinterpret_cast<const P*>(pa + u * pass_stride) : zpack;
+        vv[u] = (on && has_v) ? *reinterpret_cast<const P*>(pv + u * pass_stride) : zpack;
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c + u * kRowsPerPass < a.C) put(dst + u * kRowsPerPass * RS, va[u], vv[u]);
     }
   }
+  __syncthreads();
+
   // ---- moments per time step: lanes holding the same time steps are kLanesPerRow apart
   constexpr int kWarps = kThreads / 32;
   float* mean_s = stat;
@@ -188,25 +213,33 @@ fuse_ln_kernel(const Args a) {
 
   // ---- drain: a warp takes 32 consecutive channels (their gamma / beta in registers) through
   // all time steps of the tile: column reads of the tile are conflict-free (odd row stride) and
-  // every store instruction writes one full 128-byte line of out[b, t, :]
+  // every store instruction writes one full 128-byte line of out[b, t, :].  mean / rstd of four
+  // time steps come in as one 128-bit broadcast load each.
   T* out = static_cast<T*>(a.out) + (b * (int64_t)a.T + t0) * a.Cout;
+  const float4* mean4 = reinterpret_cast<const float4*>(mean_s);
+  const float4* rstd4 = reinterpret_cast<const float4*>(rstd_s);
   for (int c = wid * 32 + lane; c < a.Cout; c += kThreads) {
     const float g = a.gamma ? a.gamma[c] : 1.0f, be = a.beta ? a.beta[c] : 0.0f;
     const T* col = tile + c * RS;
     T* o = out + c;
-#pragma unroll 4
-    for (int t = 0; t < nt; ++t) {
-      const float x = to_f32<T>(col[t]);
-      o[(int64_t)t * a.Cout] = from_f32<T>(fmaf((x - mean_s[t]) * rstd_s[t], g, be));
+#pragma unroll
+    for (int q = 0; q < TT / 4; ++q) {
+      const float4 mu = mean4[q], rs = rstd4[q];
+      const float m[4] = {mu.x, mu.y, mu.z, mu.w}, r[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = 4 * q + i;
+        if (t < nt) *o = from_f32<T>(fmaf((to_f32<T>(col[t]) - m[i]) * r[i], g, be));
+        o += a.Cout;
+      }
     }
   }
 }
 
 template <typename T, int TT>
 static size_t smem_bytes(int Cout) {
-  size_t tile = (size_t)Cout * row_stride<T, TT>();
-  tile += tile & 1;
-  return tile * sizeof(T) + (size_t)(3 * TT + 2 * TT * (kThreads / 32)) * sizeof(float);
+  const size_t tile = ((size_t)Cout * row_stride<T, TT>() * sizeof(T) + 15) & ~(size_t)15;
+  return tile + (size_t)(3 * TT + 2 * TT * (kThreads / 32)) * sizeof(float);
 }
 
 template <typename T, int MODE, int TT, int VEC>
