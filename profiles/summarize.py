@@ -61,7 +61,7 @@ def full(rep, kernel_key, dst_dir, tag, lib):
                 f.write(",".join(r[i].replace(",", "") for _, i in idx) + "\n")
     names = sorted({r[hdr.index("Kernel Name")].split("(")[0] for r in rows[2:]}) if rows else []
     for n in names:
-        key = n.split("::")[-1].split("<")[0]
+        key = n.split("::")[-1].split("<")[0].replace("void ", "").strip()
         out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "sass_by_line.py"), rep, key, lib],
                              capture_output=True, text=True).stdout
         open(os.path.join(dst_dir, f"{key}_{tag}_by_line.txt"), "w").write(out)
@@ -77,14 +77,18 @@ def main():
     lc = os.path.join(src, f"{rnd}_launches_{tag}.csv")
     if os.path.exists(lc):
         launches(lc, dst, tag)
-    for key in ("lip", "logmel", "fuse"):
+    for key in ("lip", "logmel", "fuse", "fuseln"):
         rep = os.path.join(src, f"{rnd}_{key}_{tag}.ncu-rep")
         if os.path.exists(rep):
             full(rep, key, dst, tag, lib)
-    for name in ("bench_n1_default.json", "bench_n1_reference.json", "bench_n2.json", "bench_n2_ref.json"):
+    for name in ("bench_n1_default.json", "bench_n1_reference.json", "bench_n2.json", "bench_n2_ref.json",
+                 "bench_n4.json", "bench_n8.json"):
         p = os.path.join(src, name)
         if os.path.exists(p):
-            shutil.copy(p, os.path.join(dst, name.replace(".json", f"_{tag}.json")))
+            # keep the JSON line only (torchrun / NCCL banners may precede it)
+            lines = [l for l in open(p) if l.startswith("{")]
+            if lines:
+                open(os.path.join(dst, name.replace(".json", f"_{tag}.json")), "w").write(lines[-1])
 
 
 if __name__ == "__main__":
