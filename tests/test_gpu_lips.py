@@ -206,3 +206,46 @@ def test_collate_matches_trim_plus_collator(shape, gray_in):
     got = L.lip_roi_collate(d["frames"], d["off"], d["lm"], d["valid"], T_pad=max(lens), want_gray=False)
     np.testing.assert_array_equal(got["video"].cpu().numpy(), ref["video"])
     np.testing.assert_array_equal(got["padding_mask"].cpu().numpy(), ref["padding_mask"])
+
+
+def test_frame_kernel_edge_cases_in_one_batch():
+    """The frame-owner kernel (BGR, gray wanted) on a batch that mixes: a normal clip, a clip with
+    no detection at all (zero ROIs, crop_rc -1), a face mostly outside the frame (ROI hangs over the
+    border: taps outside read 0), a face so large that its source footprint exceeds the staged
+    tile (global-memory taps), and a single-frame clip.  Fewer frames than SMs in total."""
+    H = W = 224
+    specs = [("normal", 9), ("nodet", 4), ("offframe", 5), ("huge", 6), ("single", 1)]
+    frames, lms, valids, lens = [], [], [], []
+    for i, (kind, T) in enumerate(specs):
+        f, lm, v = synth.video_clip(T, H, W, seed=300 + i, invalid_frac=0.0)
+        if kind == "nodet":
+            v[:] = 0
+        elif kind == "offframe":
+            lm = lm + np.array([150.0, -120.0])
+        elif kind == "huge":
+            c = lm.mean(axis=(0, 1), keepdims=True)
+            lm = np.rint((lm - c) * 2.4 + c)              # inverse scale ~1.8: footprint ~165 x 176 px
+        frames.append(f); lms.append(lm); valids.append(v); lens.append(T)
+    F = np.concatenate(frames); LM = np.concatenate(lms); V = np.concatenate(valids)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for want_u8 in (False, True):
+        res = L.lip_roi_batch(torch.from_numpy(F).cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(LM).cuda(),
+                              torch.from_numpy(V).cuda(), want_gray=True, want_u8=want_u8, want_f32=True, want_meta=True)
+        gray_ref = O.bgr2gray(F)
+        np.testing.assert_array_equal(res.gray.cpu().numpy(), gray_ref)
+        mf = A.mean_face_landmarks()
+        for i, (kind, T) in enumerate(specs):
+            lo, hi = off[i], off[i + 1]
+            got_f32 = res.lip_f32[lo:hi].cpu().numpy()
+            if kind == "nodet":
+                assert (res.crop_rc[lo:hi].cpu().numpy() == -1).all()
+                np.testing.assert_array_equal(got_f32, O.video_feats_from_u8(np.zeros((T, 96, 96), np.uint8))[..., 0])
+                continue
+            ref, tf, org = O.extract_lip_frames_from_arrays(gray_ref[lo:hi], _as_list(lms[i], valids[i]), mf)
+            np.testing.assert_array_equal(res.crop_rc[lo:hi].cpu().numpy(), org)
+            feats_ref = O.video_feats_from_u8(ref)[..., 0]
+            assert np.abs(got_f32 - feats_ref).max() <= (1.0 / 255.0) / 0.165 + 1e-6, kind
+            assert (got_f32 != feats_ref).mean() < 2e-3, kind
+            if want_u8:
+                d = np.abs(res.lip_u8[lo:hi].cpu().numpy().astype(int) - ref.astype(int))
+                assert d.max() <= 1 and (d != 0).mean() < 2e-3, kind
