@@ -465,7 +465,7 @@ def main():
         stage_ms.pop("gray", None)
     kernel_names = {"logmel": "logmel_tile_kernel + logmel_finalize_kernel via avfe_logmel_ragged_f32 (pad_or_trim fused; AMI batch: frames inside the zero padding are not read, silent tiles skip the FFT - exact)",
                     "gray": "gray_vec_kernel",
-                    "lip": ("tform_kernel + lip_fused_kernel<stream,88> (stream warps: BGR->gray; blend warps: ROI warp/crop/normalise)" if fused
+                    "lip": ("lip_frame_kernel<88> (one launch: tform warps fit, TMA-staged stream warps BGR->gray + ROI footprint, blend warps warp/crop/normalise)" if fused
                             else "tform_kernel + lip_fused_kernel<nostream,88> (ROI warp only, taps from the gray frames)")}
     dominant = max(stage_ms, key=lambda k: stage_ms[k])
     stages = {}
