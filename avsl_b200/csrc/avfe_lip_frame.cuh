@@ -150,6 +150,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
   const uint8_t* isrc = L.frames + (int64_t)blockIdx.x * frame_bytes + (int64_t)sw * (kChunkVec * 16);
   const int64_t next_frame = (int64_t)gridDim.x * frame_bytes;
   const unsigned last_bytes = (unsigned)(gpf - (cpf - 1) * 64) * 48u;   // the frame's last chunk may be short
+  const bool full_chunks = (gpf & 63) == 0;
   auto issue = [&]() {
     if (ik < nk) {
       if (lane == 0) {
@@ -182,6 +183,13 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
     if (k >= kTileSlots) mbar_wait(&sm.tile_empty[slot], (unsigned)(k / kTileSlots - 1) & 1u);   // blend warps left the slot
     uint4* tile = reinterpret_cast<uint4*>(sm.tile[slot]);
     uint4* gout = reinterpret_cast<uint4*>(L.gray_out + f * frame_px);
+    // chunks that hold rows of the footprint box: [c_lo, c_hi] (warp-uniform, once per frame), so
+    // that the 68 % of the chunks outside it pay two compares instead of the per-lane box test
+    int c_lo = 1, c_hi = 0;
+    if (brows > 0) {
+      c_lo = (br0 * j.row_groups) >> 6;
+      c_hi = ((br0 + brows) * j.row_groups - 1) >> 6;
+    }
     for (int c = sw; c < cpf; c += S) {
       mbar_wait(&full[stage], phase);                    // chunk landed
       const uint4* s = ring[stage];
@@ -192,9 +200,9 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
       issue();                                           // into the stage consumed one iteration ago
       const uint4 ga = gray16_dp2a(p0, p1, p2), gb = gray16_dp2a(q0, q1, q2);
       const int g0 = c * 64 + lane, g1 = g0 + 32;        // 16-px group indices inside the frame
-      if (g0 < gpf) stg_stream(gout + g0, ga);
-      if (g1 < gpf) stg_stream(gout + g1, gb);
-      if (brows > 0) {
+      if (full_chunks || g0 < gpf) stg_stream(gout + g0, ga);
+      if (full_chunks || g1 < gpf) stg_stream(gout + g1, gb);
+      if (c >= c_lo && c <= c_hi) {
         // groups never straddle rows (W % 16 == 0); deposit those inside the footprint box
         const int ra = (int)__umulhi((unsigned)g0, j.row_magic), ca = g0 - ra * j.row_groups;
         const int rb = (int)__umulhi((unsigned)g1, j.row_magic), cb = g1 - rb * j.row_groups;
