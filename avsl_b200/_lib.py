@@ -30,6 +30,9 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "avfe_logmel_ragged_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
+    "avfe_logfbank_num_frames": (c_int64, [c_int64]),
+    "avfe_logfbank_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
+                                  c_int, c_void_p, c_void_p]),
     "avfe_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "avfe_warp_affine_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p]),

@@ -216,3 +216,75 @@ def peak_normalize(audio: Union[np.ndarray, torch.Tensor]):
     if kind == "numpy":
         return out.cpu().numpy()
     return out.cpu() if kind == "cpu" else out
+
+
+# ----------------------------------------------------------------------------- AV-HuBERT audio features
+@functools.lru_cache(maxsize=None)
+def _logfbank_filters_np(nfilt: int = 26, nfft: int = 512, samplerate: int = 16000) -> np.ndarray:
+    """python_speech_features.get_filterbanks(nfilt, nfft, samplerate, 0, samplerate/2): HTK mel
+    scale, triangular filters between floor((nfft + 1) * hz / samplerate) bins.  float32 [nfilt, 257]."""
+    def hz2mel(hz):
+        return 2595 * np.log10(1 + hz / 700.0)
+
+    def mel2hz(mel):
+        return 700 * (10 ** (mel / 2595.0) - 1)
+
+    melpoints = np.linspace(hz2mel(0.0), hz2mel(samplerate / 2), nfilt + 2)
+    bins = np.floor((nfft + 1) * mel2hz(melpoints) / samplerate)
+    fb = np.zeros([nfilt, nfft // 2 + 1])
+    for j in range(nfilt):
+        for i in range(int(bins[j]), int(bins[j + 1])):
+            fb[j, i] = (i - bins[j]) / (bins[j + 1] - bins[j])
+        for i in range(int(bins[j + 1]), int(bins[j + 2])):
+            fb[j, i] = (bins[j + 2] - i) / (bins[j + 2] - bins[j + 1])
+    return np.ascontiguousarray(fb.astype(np.float32))
+
+
+def logfbank_num_frames(n_samples: int) -> int:
+    """Frames python_speech_features makes of ``n_samples`` (25 ms / 10 ms at 16 kHz)."""
+    return int(_lib.load().avfe_logfbank_num_frames(int(n_samples)))
+
+
+def logfbank_batch(audio: torch.Tensor, offsets, stack_order: int = 4, normalize: bool = True,
+                   nfilt: int = 26):
+    """AV-HuBERT audio features of a packed batch on the GPU.  ``audio`` float32 CUDA [sum L_i],
+    ``offsets`` the [B+1] clip boundaries (host sequence or tensor).  Returns
+    ``(feats, row_offsets)``: float32 CUDA ``[sum rows_i, nfilt * stack_order]`` and the int64 numpy
+    row boundaries (``rows_i = ceil(frames_i / stack_order)``)."""
+    _lib.require_cuda()
+    if not (audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 1):
+        raise ValueError("audio must be a contiguous 1-D float32 CUDA tensor")
+    off = np.asarray(offsets.cpu() if torch.is_tensor(offsets) else offsets, dtype=np.int64)
+    B = len(off) - 1
+    lens = np.diff(off)
+    if B < 1 or (lens < 1).any():
+        raise ValueError("every clip needs at least one sample")
+    frames = np.where(lens <= 400, 1, 1 + -(-(lens - 400) // 160))
+    rows = -(-frames // stack_order)
+    row_off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+    dev = audio.device
+    out = torch.empty((int(row_off[-1]), nfilt * stack_order), dtype=torch.float32, device=dev)
+    key = (str(dev), nfilt)
+    fb = _FILTER_CACHE.get(("fbank",) + key)
+    if fb is None:
+        fb = torch.from_numpy(_logfbank_filters_np(nfilt)).to(dev)
+        _FILTER_CACHE[("fbank",) + key] = fb
+    d_off = torch.from_numpy(off).to(dev, non_blocking=True)
+    d_row = torch.from_numpy(row_off).to(dev, non_blocking=True)
+    with torch.cuda.device(dev):
+        _lib.call("avfe_logfbank_f32", _lib.ptr(audio), _lib.ptr(d_off), _lib.ptr(d_row), B, int(lens.max()),
+                  _lib.ptr(fb), nfilt, int(stack_order), 1 if normalize else 0, _lib.ptr(out), _lib.stream_ptr())
+    return out, row_off
+
+
+def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order: int = 1,
+                              normalize: bool = False) -> np.ndarray:
+    """``extract_logfbank_features`` (preprocess/audio_process.py:152-179) and, with
+    ``normalize=True``, ``audio_to_tensor`` (:181-197) on top of it, for one clip given as a host
+    array; float32 numpy ``[ceil(frames / stack_order), 26 * stack_order]`` like the reference."""
+    if sample_rate != SAMPLE_RATE:
+        raise ValueError("extract_logfbank_features is built for 16 kHz audio")
+    a = torch.from_numpy(np.ascontiguousarray(np.asarray(audio_data, dtype=np.float32).reshape(-1)))
+    _lib.require_cuda()
+    feats, _ = logfbank_batch(a.cuda(), [0, a.numel()], stack_order, normalize)
+    return feats.cpu().numpy()

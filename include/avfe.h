@@ -110,6 +110,24 @@ AVFE_API int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, 
                                     const void* pack, float* out, void* workspace,
                                     size_t workspace_bytes, avfe_stream_t stream);
 
+/* AV-HuBERT audio features — extract_logfbank_features + audio_to_tensor,
+ * preprocess/audio_process.py:152-197 (and utils/data_loading.py:181-201):
+ * python_speech_features.logfbank(audio, samplerate=16000) = pre-emphasis 0.97, 400-sample frames
+ * every 160 (rectangular window, zero-padded tail, 1 + ceil((L-400)/160) frames), 512-point power
+ * spectrum / 512, `nfilt` (26) triangular mel filters, zeros -> float64 eps, natural log; then
+ * `stack` (4) consecutive frames per row (zero rows appended to a multiple of `stack`) and, if
+ * `normalize`, (x - mean) / (std + 1e-5) per row with the population std.
+ *   audio       packed clips, clip b = audio[offsets[b] : offsets[b+1]] (float32, 16 kHz)
+ *   row_offsets [B+1] int64: first output row of clip b (clip b has
+ *               ceil(avfe_logfbank_num_frames(L_b) / stack) rows)
+ *   max_samples the longest clip (sizes the launch)
+ *   fbank       [nfilt, 257] float32 (python_speech_features.get_filterbanks)
+ *   out         [row_offsets[B], nfilt * stack] float32 */
+AVFE_API int64_t avfe_logfbank_num_frames(int64_t n_samples);
+AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
+                               int64_t B, int64_t max_samples, const float* fbank, int nfilt,
+                               int stack, int normalize, float* out, avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ video (V1..V8) */
 
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) — preprocess/video_process.py:201-214:

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "avfe_lip_math.cuh"
+#include "avfe_logfbank_core.cuh"
 #include "avfe_logmel_core.cuh"
 
 using namespace avfe;
@@ -57,6 +58,43 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
         out[m * kTileFrames + f] = mel_log10_quads(P + prow_offset(f) + lo, reinterpret_cast<const float4*>(wq), n4);
     }
   }
+}
+
+// raw log filterbank energies of frames fa, fb (two frames of one clip) -> out[2][nfilt]
+void hc_logfbank_pair(const float* clip, int64_t len, int64_t fa, int64_t fb, int nfilt, const float* fbank,
+                      float* out) {
+  using namespace fbk;
+  std::vector<float2> tw(kNfft);
+  for (int j = 0; j < kNfft; ++j)
+    tw[j] = make_float2((float)cos(-2.0 * M_PI * j / kNfft), (float)sin(-2.0 * M_PI * j / kNfft));
+  std::vector<float> ya(kFrame), yb(kFrame);
+  for (int n = 0; n < kFrame; ++n) {
+    ya[n] = preemph_sample(clip, len, fa * kHop + n);
+    yb[n] = preemph_sample(clip, len, fb * kHop + n);
+  }
+  std::vector<float2> S(kSFloat2), C(kNfft);
+  std::vector<float> P(2 * kPStride);
+  for (int t = 0; t < kFftThreads; ++t) step1(t, ya.data(), yb.data(), tw.data(), S.data());
+  std::vector<float2> regs(kFftThreads * 8);
+  for (int t = 0; t < kFftThreads; ++t) step2_load(t, S.data(), *reinterpret_cast<float2(*)[8]>(&regs[t * 8]));
+  for (int t = 0; t < kFftThreads; ++t) step2_store(t, tw.data(), *reinterpret_cast<float2(*)[8]>(&regs[t * 8]), S.data());
+  for (int t = 0; t < kFftThreads; ++t) step3(t, S.data(), C.data());
+  for (int t = 0; t < kFftThreads; ++t) power_rows(t, C.data(), P.data(), P.data() + kPStride);
+  for (int f = 0; f < 2; ++f)
+    for (int m = 0; m < nfilt; ++m) {
+      int lo = kBins, hi = 0;
+      for (int k = 0; k < kBins; ++k)
+        if (fbank[m * kBins + k] != 0.0f) { lo = lo < k ? lo : k; hi = k + 1; }
+      if (lo >= hi) { lo = 0; hi = 0; }
+      out[f * nfilt + m] = log_fbank(P.data() + f * kPStride, fbank + m * kBins, lo, hi);
+    }
+}
+
+void hc_dft8(const float* in_ri, float* out_ri) {
+  float2 x[8];
+  for (int i = 0; i < 8; ++i) x[i] = make_float2(in_ri[2 * i], in_ri[2 * i + 1]);
+  fbk::dft8(x);
+  for (int i = 0; i < 8; ++i) { out_ri[2 * i] = x[i].x; out_ri[2 * i + 1] = x[i].y; }
 }
 
 void hc_dft20(const float* in_ri, float* out_ri) {

@@ -49,6 +49,29 @@ def test_logmel_tile_codelets(hostcheck, n_mels, L, pad):
         assert np.abs(out[:, :nv] - ref).max() < 2e-5
 
 
+def test_dft8_and_logfbank_codelets(hostcheck):
+    """The 8 x 8 x 8 two-frames-per-FFT 512-point transform, pre-emphasis and the filterbank
+    against the oracle's restatement of python_speech_features.logfbank."""
+    from oracle import logfbank as OF
+    rng = np.random.default_rng(1)
+    x = (rng.normal(size=8) + 1j * rng.normal(size=8)).astype(np.complex64)
+    o = np.zeros(8, np.complex64)
+    hostcheck.hc_dft8(vp(x), vp(o))
+    assert np.abs(o - np.fft.fft(x.astype(np.complex128))).max() < 2e-6
+    fb = np.ascontiguousarray(OF.get_filterbanks().astype(np.float32))
+    for L in (16000, 5000, 401, 400, 37):
+        a = np.ascontiguousarray(synth.audio_clip(L, 7) * 3.0)
+        ref = OF.logfbank(a)
+        nfr = OF.num_frames(L)
+        for fa in sorted({0, nfr - 1, nfr // 2}):
+            fb_idx = min(fa + 1, nfr - 1)
+            out = np.zeros((2, 26), np.float32)
+            hostcheck.hc_logfbank_pair(vp(a), ctypes.c_int64(L), ctypes.c_int64(fa), ctypes.c_int64(fb_idx), 26,
+                                       vp(fb), vp(out))
+            assert np.abs(out[0] - ref[fa]).max() < 2e-4, (L, fa)
+            assert np.abs(out[1] - ref[fb_idx]).max() < 2e-4, (L, fb_idx)
+
+
 def test_float_key_order(hostcheck):
     hostcheck.hc_key_float.restype = ctypes.c_float
     vals = np.array([-np.inf, -10.0, -1e-3, -0.0, 0.0, 1e-10, 1.5, 3e38, np.inf], dtype=np.float32)
