@@ -7,7 +7,7 @@ AV-HuBERT modality fusion (``fusion``), as hand-written CUDA kernels behind a C 
 function raises if the library has not been built or no CUDA device is present.
 """
 from . import _lib  # noqa: F401
-from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, extract_logfbank_features,
+from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, LogfbankPlan, extract_logfbank_features,
                     log_mel_spectrogram, log_mel_spectrogram_ragged, logfbank_batch, logfbank_num_frames,
                     mel_filters, pad_or_trim, peak_normalize)
 from .frontend import AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, pack_utterances, shard

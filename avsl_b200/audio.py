@@ -245,36 +245,51 @@ def logfbank_num_frames(n_samples: int) -> int:
     return int(_lib.load().avfe_logfbank_num_frames(int(n_samples)))
 
 
-def logfbank_batch(audio: torch.Tensor, offsets, stack_order: int = 4, normalize: bool = True,
-                   nfilt: int = 26):
+class LogfbankPlan:
+    """Device-side bookkeeping of one packed batch layout (clip boundaries, output row boundaries,
+    workspace, output buffer), reusable for every batch with the same clip lengths."""
+
+    def __init__(self, offsets, stack_order: int, nfilt: int, device):
+        off = np.asarray(offsets.cpu() if torch.is_tensor(offsets) else offsets, dtype=np.int64)
+        lens = np.diff(off)
+        if len(off) < 2 or (lens < 1).any():
+            raise ValueError("every clip needs at least one sample")
+        frames = np.where(lens <= 400, 1, 1 + -(-(lens - 400) // 160))
+        rows = -(-frames // stack_order)
+        self.offsets, self.row_offsets = off, np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        self.B, self.max_len = len(lens), int(lens.max())
+        self.stack_order, self.nfilt, self.device = int(stack_order), int(nfilt), device
+        self.d_off = torch.from_numpy(self.offsets).to(device)
+        self.d_row = torch.from_numpy(self.row_offsets).to(device)
+        self.ws = torch.empty(int(_lib.load().avfe_logfbank_workspace_bytes()), dtype=torch.uint8, device=device)
+        self.out = torch.empty((int(self.row_offsets[-1]), nfilt * stack_order), dtype=torch.float32, device=device)
+
+
+def logfbank_batch(audio: torch.Tensor, offsets=None, stack_order: int = 4, normalize: bool = True,
+                   nfilt: int = 26, plan: Optional[LogfbankPlan] = None):
     """AV-HuBERT audio features of a packed batch on the GPU.  ``audio`` float32 CUDA [sum L_i],
-    ``offsets`` the [B+1] clip boundaries (host sequence or tensor).  Returns
+    ``offsets`` the [B+1] clip boundaries (host sequence or tensor), or a ``plan`` built once for
+    that layout (steady-state loops: no host-to-device traffic, output buffer reused).  Returns
     ``(feats, row_offsets)``: float32 CUDA ``[sum rows_i, nfilt * stack_order]`` and the int64 numpy
     row boundaries (``rows_i = ceil(frames_i / stack_order)``)."""
     _lib.require_cuda()
     if not (audio.is_cuda and audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 1):
         raise ValueError("audio must be a contiguous 1-D float32 CUDA tensor")
-    off = np.asarray(offsets.cpu() if torch.is_tensor(offsets) else offsets, dtype=np.int64)
-    B = len(off) - 1
-    lens = np.diff(off)
-    if B < 1 or (lens < 1).any():
-        raise ValueError("every clip needs at least one sample")
-    frames = np.where(lens <= 400, 1, 1 + -(-(lens - 400) // 160))
-    rows = -(-frames // stack_order)
-    row_off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
     dev = audio.device
-    out = torch.empty((int(row_off[-1]), nfilt * stack_order), dtype=torch.float32, device=dev)
-    key = (str(dev), nfilt)
-    fb = _FILTER_CACHE.get(("fbank",) + key)
+    if plan is None:
+        plan = LogfbankPlan(offsets, stack_order, nfilt, dev)
+    if int(plan.offsets[-1]) != audio.numel():
+        raise ValueError("offsets do not cover the audio tensor")
+    key = ("fbank", str(dev), plan.nfilt)
+    fb = _FILTER_CACHE.get(key)
     if fb is None:
-        fb = torch.from_numpy(_logfbank_filters_np(nfilt)).to(dev)
-        _FILTER_CACHE[("fbank",) + key] = fb
-    d_off = torch.from_numpy(off).to(dev, non_blocking=True)
-    d_row = torch.from_numpy(row_off).to(dev, non_blocking=True)
+        fb = torch.from_numpy(_logfbank_filters_np(plan.nfilt)).to(dev)
+        _FILTER_CACHE[key] = fb
     with torch.cuda.device(dev):
-        _lib.call("avfe_logfbank_f32", _lib.ptr(audio), _lib.ptr(d_off), _lib.ptr(d_row), B, int(lens.max()),
-                  _lib.ptr(fb), nfilt, int(stack_order), 1 if normalize else 0, _lib.ptr(out), _lib.stream_ptr())
-    return out, row_off
+        _lib.call("avfe_logfbank_f32", _lib.ptr(audio), _lib.ptr(plan.d_off), _lib.ptr(plan.d_row), plan.B,
+                  plan.max_len, _lib.ptr(fb), plan.nfilt, plan.stack_order, 1 if normalize else 0,
+                  _lib.ptr(plan.out), _lib.ptr(plan.ws), plan.ws.numel(), _lib.stream_ptr())
+    return plan.out, plan.row_offsets
 
 
 def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order: int = 1,

@@ -40,30 +40,42 @@ __host__ __device__ inline int64_t num_frames(int64_t len) {
   return len <= kFrame ? 1 : 1 + (len - kFrame + kHop - 1) / kHop;
 }
 
+// filter supports [first, last + 1) of the nonzero weights, once per call: one warp per filter
+__global__ void __launch_bounds__(256)
+logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, int* __restrict__ supports) {
+  const int lane = threadIdx.x & 31;
+  for (int m = threadIdx.x >> 5; m < nfilt; m += blockDim.x >> 5) {
+    int lo = kBins, hi = 0;
+    for (int k = lane; k < kBins; k += 32)
+      if (fb[(size_t)m * kBins + k] != 0.0f) { lo = min(lo, k); hi = max(hi, k + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { supports[2 * m] = lo < hi ? lo : 0; supports[2 * m + 1] = lo < hi ? hi : 0; }
+  }
+}
+
+// grid = (tile slots, clips): a CTA walks the tiles blockIdx.x, + gridDim.x, ... of its clip, so
+// that the twiddle table and the filter supports are set up once per CTA, not once per 8 frames
 __global__ void __launch_bounds__(kThreads)
 logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets,
                 const int64_t* __restrict__ row_offsets, const float* __restrict__ fb, int nfilt,
-                int stack, int normalize, float* __restrict__ out) {
+                const int* __restrict__ supports, int stack, int normalize, float* __restrict__ out) {
   __shared__ Smem sm;
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.y;
   const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
   const int64_t nfr = num_frames(len);
   const int64_t rows = (nfr + stack - 1) / stack;               // stacked rows (zero-padded tail)
-  const int64_t f0 = (int64_t)blockIdx.x * kTileFrames;
-  if (f0 >= rows * stack) return;                               // CTA-uniform
+  if ((int64_t)blockIdx.x * kTileFrames >= rows * stack) return;   // CTA-uniform
   const float* clip = audio + beg;
-
-  for (int i = tid; i < kSpan; i += kThreads) sm.y[i] = preemph_sample(clip, len, f0 * kHop + i);
   for (int i = tid; i < kNfft; i += kThreads) sm.tw[i] = make_float2(kTw512Re[i], kTw512Im[i]);
-  if (tid < nfilt) {                                            // support of filter tid
-    const float* w = fb + (size_t)tid * kBins;
-    int lo = kBins, hi = 0;
-    for (int k = 0; k < kBins; ++k)
-      if (w[k] != 0.0f) { lo = min(lo, k); hi = k + 1; }
-    sm.lo[tid] = lo < hi ? lo : 0;
-    sm.hi[tid] = lo < hi ? hi : 0;
-  }
+  if (tid < nfilt) { sm.lo[tid] = supports[2 * tid]; sm.hi[tid] = supports[2 * tid + 1]; }
+
+  for (int64_t f0 = (int64_t)blockIdx.x * kTileFrames; f0 < rows * stack; f0 += (int64_t)gridDim.x * kTileFrames) {
+  for (int i = tid; i < kSpan; i += kThreads) sm.y[i] = preemph_sample(clip, len, f0 * kHop + i);
   __syncthreads();
 
   const int g = tid / kFftThreads, t = tid % kFftThreads;       // FFT g: tile frames 2g, 2g + 1
@@ -121,6 +133,8 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     if (normalize) v = __fdiv_rn(v - sm.stat[r][0], sm.stat[r][1]);
     o[i] = v;
   }
+  __syncthreads();                                              // staging buffers are reused
+  }
 }
 
 }  // namespace fbk
@@ -132,21 +146,32 @@ extern "C" int64_t avfe_logfbank_num_frames(int64_t n_samples) {
   return n_samples < 0 ? 0 : fbk::num_frames(n_samples);
 }
 
+extern "C" size_t avfe_logfbank_workspace_bytes(void) { return 2 * fbk::kMaxFilt * sizeof(int); }
+
 extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
                                  int64_t B, int64_t max_samples, const float* fbank, int nfilt,
-                                 int stack, int normalize, float* out, avfe_stream_t stream) {
+                                 int stack, int normalize, float* out, void* workspace,
+                                 size_t workspace_bytes, avfe_stream_t stream) {
   if (B < 0 || nfilt <= 0 || stack <= 0 || max_samples < 0) return AVFE_ERR_INVALID_ARG;
   if (nfilt > fbk::kMaxFilt || (fbk::kTileFrames % stack) != 0) return AVFE_ERR_UNSUPPORTED;
   if (B == 0) return AVFE_OK;
   if (!audio || !offsets || !row_offsets || !fbank || !out) return AVFE_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < avfe_logfbank_workspace_bytes()) return AVFE_ERR_WORKSPACE;
   if (B > 65535) return AVFE_ERR_UNSUPPORTED;
   const int64_t nfr = fbk::num_frames(max_samples);
   const int64_t padded = (nfr + stack - 1) / stack * stack;
   const int64_t tiles = (padded + fbk::kTileFrames - 1) / fbk::kTileFrames;
   if (tiles > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)tiles, (unsigned)B);
-  fbk::logfbank_kernel<<<grid, fbk::kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      audio, offsets, row_offsets, fbank, nfilt, stack, normalize, out);
-  count_launch();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* supports = static_cast<int*>(workspace);
+  fbk::logfbank_prep_kernel<<<1, 256, 0, s>>>(fbank, nfilt, supports);
+  // about 4 resident CTAs per SM in total, each walking several tiles of its clip
+  int64_t slots = (4 * (int64_t)kNumSMs + B - 1) / B;
+  if (slots > tiles) slots = tiles;
+  if (slots < 1) slots = 1;
+  dim3 grid((unsigned)slots, (unsigned)B);
+  fbk::logfbank_kernel<<<grid, fbk::kThreads, 0, s>>>(audio, offsets, row_offsets, fbank, nfilt, supports, stack,
+                                                      normalize, out);
+  count_launch(2);
   return check_launch();
 }

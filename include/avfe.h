@@ -122,11 +122,14 @@ AVFE_API int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, 
  *               ceil(avfe_logfbank_num_frames(L_b) / stack) rows)
  *   max_samples the longest clip (sizes the launch)
  *   fbank       [nfilt, 257] float32 (python_speech_features.get_filterbanks)
- *   out         [row_offsets[B], nfilt * stack] float32 */
+ *   out         [row_offsets[B], nfilt * stack] float32
+ *   workspace   avfe_logfbank_workspace_bytes() bytes (filter supports) */
 AVFE_API int64_t avfe_logfbank_num_frames(int64_t n_samples);
+AVFE_API size_t avfe_logfbank_workspace_bytes(void);
 AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
                                int64_t B, int64_t max_samples, const float* fbank, int nfilt,
-                               int stack, int normalize, float* out, avfe_stream_t stream);
+                               int stack, int normalize, float* out, void* workspace,
+                               size_t workspace_bytes, avfe_stream_t stream);
 
 /* ------------------------------------------------------------------ video (V1..V8) */
 

@@ -49,6 +49,14 @@ def run_fuse(iters):
     torch.cuda.synchronize()
 
 
+def run_logfbank(iters, batch=64):
+    a = synth.audio_batch(batch, 480000, 3407, device="cuda").reshape(-1)
+    plan = A.LogfbankPlan(np.arange(batch + 1, dtype=np.int64) * 480000, 4, 26, a.device)
+    for _ in range(iters):
+        A.logfbank_batch(a, plan=plan, normalize=True)
+    torch.cuda.synchronize()
+
+
 def run_fuse_ln(iters):
     fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
     w, b = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
@@ -64,7 +72,7 @@ def run_fuse_ln(iters):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "all"])
+    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "logfbank", "all"])
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     if a.which in ("logmel", "all"):
@@ -73,6 +81,8 @@ if __name__ == "__main__":
         run_lip(a.iters)
     if a.which in ("fuse", "all"):
         run_fuse(a.iters)
+    if a.which in ("logfbank", "all"):
+        run_logfbank(a.iters)
     if a.which in ("fuse_ln", "all"):
         run_fuse_ln(a.iters)
     print("done", a.which)
