@@ -25,14 +25,25 @@ constexpr int kThreads = kFfts * kFftThreads;                 // 256
 constexpr int kSpan = (kTileFrames - 1) * kHop + kFrame;       // 1520 samples per tile
 constexpr int kMaxFilt = 64;
 
+constexpr int kMaxTaps = 640;             // packed nonzero filter weights (26 HTK filters: 2 x 257 at most)
+
 struct Smem {
   float y[kSpan];                       // pre-emphasised samples of the tile (zero past the clip)
   float2 tw[kNfft];
   float2 S[kFfts][kSFloat2];            // exchange storage; the power rows overwrite it
   float2 C[kFfts][kNfft];               // spectra
-  float feat[kTileFrames][kMaxFilt];    // log energies, frame-major = the stacked row layout
-  int lo[kMaxFilt], hi[kMaxFilt];       // filter supports
+  float feat[kTileFrames * kMaxFilt];   // log energies [frame][nfilt] packed = the stacked row layout
+  float wts[kMaxTaps];                  // filter weights, supports back to back
+  int lo[kMaxFilt], hi[kMaxFilt], woff[kMaxFilt];   // filter supports and weight offsets
   float stat[kTileFrames][2];
+};
+
+// workspace: supports [kMaxFilt][2], weight offsets [kMaxFilt], total, packed weights [kMaxTaps]
+struct FilterPack {
+  int support[kMaxFilt][2];
+  int woff[kMaxFilt];
+  int total, pad[3];
+  float wts[kMaxTaps];
 };
 
 // number of frames framesig makes of `len` samples (python_speech_features.sigproc.framesig)
@@ -40,9 +51,11 @@ __host__ __device__ inline int64_t num_frames(int64_t len) {
   return len <= kFrame ? 1 : 1 + (len - kFrame + kHop - 1) / kHop;
 }
 
-// filter supports [first, last + 1) of the nonzero weights, once per call: one warp per filter
+// filter supports [first, last + 1) of the nonzero weights and the weights packed back to back,
+// once per call: one warp per filter, then a serial prefix over <= 64 lengths
 __global__ void __launch_bounds__(256)
-logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, int* __restrict__ supports) {
+logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __restrict__ pack) {
+  __shared__ int s_lo[kMaxFilt], s_hi[kMaxFilt], s_off[kMaxFilt + 1];
   const int lane = threadIdx.x & 31;
   for (int m = threadIdx.x >> 5; m < nfilt; m += blockDim.x >> 5) {
     int lo = kBins, hi = 0;
@@ -53,7 +66,21 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, int* __restrict__ 
       lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) { supports[2 * m] = lo < hi ? lo : 0; supports[2 * m + 1] = lo < hi ? hi : 0; }
+    if (lane == 0) { s_lo[m] = lo < hi ? lo : 0; s_hi[m] = lo < hi ? hi : 0; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int m = 0; m < nfilt; ++m) { s_off[m] = acc; acc += s_hi[m] - s_lo[m]; }
+    s_off[nfilt] = acc;
+    pack->total = acc;
+  }
+  __syncthreads();
+  const bool fits = s_off[nfilt] <= kMaxTaps;
+  for (int m = threadIdx.x >> 5; m < nfilt; m += blockDim.x >> 5) {
+    if (lane == 0) { pack->support[m][0] = s_lo[m]; pack->support[m][1] = s_hi[m]; pack->woff[m] = s_off[m]; }
+    if (fits)
+      for (int k = s_lo[m] + lane; k < s_hi[m]; k += 32) pack->wts[s_off[m] + k - s_lo[m]] = fb[(size_t)m * kBins + k];
   }
 }
 
@@ -62,8 +89,9 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, int* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets,
                 const int64_t* __restrict__ row_offsets, const float* __restrict__ fb, int nfilt,
-                const int* __restrict__ supports, int stack, int normalize, float* __restrict__ out) {
-  __shared__ Smem sm;
+                const FilterPack* __restrict__ pack, int stack, int normalize, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char fbk_smem[];
+  Smem& sm = *reinterpret_cast<Smem*>(fbk_smem);
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.y;
   const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
@@ -72,10 +100,41 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   if ((int64_t)blockIdx.x * kTileFrames >= rows * stack) return;   // CTA-uniform
   const float* clip = audio + beg;
   for (int i = tid; i < kNfft; i += kThreads) sm.tw[i] = make_float2(kTw512Re[i], kTw512Im[i]);
-  if (tid < nfilt) { sm.lo[tid] = supports[2 * tid]; sm.hi[tid] = supports[2 * tid + 1]; }
+  if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.woff[tid] = pack->woff[tid]; }
+  const bool packed = pack->total <= kMaxTaps;
+  if (packed)
+    for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
+  // tile-invariant work split of the filterbank stage: item = (frame, filter)
+  constexpr int kItems = (kTileFrames * kMaxFilt + kThreads - 1) / kThreads;   // 2
+  int it_f[kItems], it_m[kItems];
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int i = tid + q * kThreads;
+    it_f[q] = (i < kTileFrames * nfilt) ? i / nfilt : -1;
+    it_m[q] = (i < kTileFrames * nfilt) ? i % nfilt : 0;
+  }
+  const int rows_here = kTileFrames / stack, width = stack * nfilt;
 
   for (int64_t f0 = (int64_t)blockIdx.x * kTileFrames; f0 < rows * stack; f0 += (int64_t)gridDim.x * kTileFrames) {
-  for (int i = tid; i < kSpan; i += kThreads) sm.y[i] = preemph_sample(clip, len, f0 * kHop + i);
+  // raw samples of the span (one coalesced load each, plus the sample before the span), then the
+  // pre-emphasis y[n] = x[n] - 0.97 x[n-1] from registers; beyond the clip: framesig's zeros
+  {
+    const int64_t s0 = f0 * kHop;
+    constexpr int kPer = (kSpan + kThreads - 1) / kThreads;       // 6
+    float cur[kPer], prev[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int64_t n = s0 + tid + q * kThreads;
+      cur[q] = (n < len) ? clip[n] : 0.0f;
+      prev[q] = (n >= 1 && n < len) ? clip[n - 1] : 0.0f;       // a neighbouring lane's line: L1 hit
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = tid + q * kThreads;
+      const int64_t n = s0 + i;
+      if (i < kSpan) sm.y[i] = (n == 0 || n >= len) ? cur[q] : __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));
+    }
+  }
   __syncthreads();
 
   const int g = tid / kFftThreads, t = tid % kFftThreads;       // FFT g: tile frames 2g, 2g + 1
@@ -94,28 +153,36 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   power_rows(t, C, P, P + kPStride);
   __syncthreads();
 
-  // log filterbank energies: thread = (frame, filter); frames past the clip's last one are the
+  // log filterbank energies: item = (frame, filter); frames past the clip's last one are the
   // zero rows extract_logfbank_features appends before stacking
-  for (int i = tid; i < kTileFrames * nfilt; i += kThreads) {
-    const int f = i / nfilt, m = i - f * nfilt;
+#pragma unroll
+  for (int q = 0; q < kItems; ++q) {
+    const int f = it_f[q], m = it_m[q];
+    if (f < 0) continue;
     const float* Pf = reinterpret_cast<const float*>(sm.S[f >> 1]) + (f & 1) * kPStride;
-    sm.feat[f][m] = (f0 + f < nfr) ? log_fbank(Pf, fb + (size_t)m * kBins, sm.lo[m], sm.hi[m]) : 0.0f;
+    float v = 0.0f;
+    if (f0 + f < nfr) {
+      const int lo = sm.lo[m], hi = sm.hi[m];
+      v = packed ? log_fbank(Pf + lo, sm.wts + sm.woff[m], 0, hi - lo) : log_fbank(Pf, fb + (size_t)m * kBins, lo, hi);
+    }
+    sm.feat[f * nfilt + m] = v;
   }
   __syncthreads();
 
-  // rows of `stack` consecutive frames; audio_to_tensor: (x - mean) / (std + 1e-5), population std
-  const int rows_here = kTileFrames / stack, width = stack * nfilt;
+  // rows of `stack` consecutive frames (contiguous in feat); audio_to_tensor:
+  // (x - mean) / (std + 1e-5), population std
   if (normalize) {
     const int lane = tid & 31, wid = tid >> 5;
     for (int r = wid; r < rows_here; r += kThreads / 32) {
-      float s = 0.0f;
-      for (int i = lane; i < width; i += 32) s += sm.feat[r * stack + i / nfilt][i % nfilt];
+      const float* row = sm.feat + r * width;
+      float sum = 0.0f;
+      for (int i = lane; i < width; i += 32) sum += row[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s / (float)width;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / (float)width;
       float v = 0.0f;
       for (int i = lane; i < width; i += 32) {
-        const float d = sm.feat[r * stack + i / nfilt][i % nfilt] - mean;
+        const float d = row[i] - mean;
         v = fmaf(d, d, v);
       }
 #pragma unroll
@@ -126,12 +193,13 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   }
   const int64_t row0 = f0 / stack;
   float* o = out + (row_offsets[b] + row0) * width;
-  for (int i = tid; i < rows_here * width; i += kThreads) {
-    const int r = i / width, c = i - r * width;
-    if (row0 + r >= rows) continue;
-    float v = sm.feat[r * stack + c / nfilt][c % nfilt];
-    if (normalize) v = __fdiv_rn(v - sm.stat[r][0], sm.stat[r][1]);
-    o[i] = v;
+  for (int r = 0; r < rows_here; ++r) {
+    if (row0 + r >= rows) break;
+    const float mean = normalize ? sm.stat[r][0] : 0.0f, sd = normalize ? sm.stat[r][1] : 1.0f;
+    for (int c = tid; c < width; c += kThreads) {
+      const float v = sm.feat[r * width + c];
+      o[r * width + c] = normalize ? __fdiv_rn(v - mean, sd) : v;
+    }
   }
   __syncthreads();                                              // staging buffers are reused
   }
@@ -146,7 +214,7 @@ extern "C" int64_t avfe_logfbank_num_frames(int64_t n_samples) {
   return n_samples < 0 ? 0 : fbk::num_frames(n_samples);
 }
 
-extern "C" size_t avfe_logfbank_workspace_bytes(void) { return 2 * fbk::kMaxFilt * sizeof(int); }
+extern "C" size_t avfe_logfbank_workspace_bytes(void) { return sizeof(fbk::FilterPack); }
 
 extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
                                  int64_t B, int64_t max_samples, const float* fbank, int nfilt,
@@ -163,14 +231,20 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
   const int64_t tiles = (padded + fbk::kTileFrames - 1) / fbk::kTileFrames;
   if (tiles > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int* supports = static_cast<int*>(workspace);
-  fbk::logfbank_prep_kernel<<<1, 256, 0, s>>>(fbank, nfilt, supports);
+  if (!aligned16(workspace)) return AVFE_ERR_WORKSPACE;
+  fbk::FilterPack* pack = static_cast<fbk::FilterPack*>(workspace);
+  fbk::logfbank_prep_kernel<<<1, 256, 0, s>>>(fbank, nfilt, pack);
   // about 4 resident CTAs per SM in total, each walking several tiles of its clip
   int64_t slots = (4 * (int64_t)kNumSMs + B - 1) / B;
   if (slots > tiles) slots = tiles;
   if (slots < 1) slots = 1;
   dim3 grid((unsigned)slots, (unsigned)B);
-  fbk::logfbank_kernel<<<grid, fbk::kThreads, 0, s>>>(audio, offsets, row_offsets, fbank, nfilt, supports, stack,
+  if (cudaFuncSetAttribute(fbk::logfbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(fbk::Smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  fbk::logfbank_kernel<<<grid, fbk::kThreads, sizeof(fbk::Smem), s>>>(audio, offsets, row_offsets, fbank, nfilt, pack, stack,
                                                       normalize, out);
   count_launch(2);
   return check_launch();

@@ -7,8 +7,10 @@
 // shared-memory exchanges.  With n = 64a + m, k = r + 8s (and inside the 64-point step
 // m = 8b + c, s = u + 8v):
 //   step 1  thread m       Y[m][r] = sum_a x[64a+m] W8^(ar),  times W512^(mr)      -> S[r][m]
-//   step 2  thread (r,c)   T[u]    = sum_b S[r][8b+c] W8^(bu), times W512^(8cu)    -> S'[r][c][u]
-//   step 3  thread (r,u)   X[r + 8u + 64v] = sum_c S'[r][c][u] W8^(cv)              -> C[k]
+//   step 2  thread (r,c)   T[u]    = sum_b S[r][8b+c] W8^(bu), times W512^(8cu)    -> S'[u][c][r]
+//   step 3  thread (u,r)   X[r + 8u + 64v] = sum_c S'[u][c][r] W8^(cv)              -> C[k]
+// (layouts chosen so that every 64-bit exchange is bank-conflict free and the spectrum is written
+// in natural order by consecutive lanes)
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -92,20 +94,20 @@ AVFE_HD void step2_load(int t, const float2* S, float2 (&x)[8]) {
 AVFE_HD void step2_store(int t, const float2* tw, float2 (&x)[8], float2* S) {
   const int r = t >> 3, c = t & 7;
   dft8(x);
-  S[r * kRow + 9 * c] = x[0];
+  S[9 * c + r] = x[0];
 #pragma unroll
-  for (int u = 1; u < 8; ++u) S[r * kRow + 9 * c + u] = cmul(x[u], tw[(8 * c * u) & (kNfft - 1)]);
+  for (int u = 1; u < 8; ++u) S[u * kRow + 9 * c + r] = cmul(x[u], tw[(8 * c * u) & (kNfft - 1)]);
 }
 
 // step 3: spectrum in natural order
 AVFE_HD void step3(int t, const float2* S, float2* C) {
-  const int r = t >> 3, u = t & 7;
+  const int r = t & 7, u = t >> 3;                   // consecutive lanes write consecutive bins
   float2 x[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) x[c] = S[r * kRow + 9 * c + u];
+  for (int c = 0; c < 8; ++c) x[c] = S[u * kRow + 9 * c + r];
   dft8(x);
 #pragma unroll
-  for (int v = 0; v < 8; ++v) C[r + 8 * u + 64 * v] = x[v];
+  for (int v = 0; v < 8; ++v) C[t + 64 * v] = x[v];
 }
 
 // power spectra 1/512 |X|^2 of the two real frames packed in C: thread t owns bins t + 64 j
