@@ -9,7 +9,7 @@ function raises if the library has not been built or no CUDA device is present.
 from . import _lib  # noqa: F401
 from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, LogfbankPlan, extract_logfbank_features,
                     log_mel_spectrogram, log_mel_spectrogram_ragged, logfbank_batch, logfbank_num_frames,
-                    mel_filters, pad_or_trim, peak_normalize)
+                    mel_filters, pad_or_trim, peak_normalize, spec_augment, spec_augment_bands)
 from .frontend import AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, pack_utterances, shard
 from .fusion import (ModalityFusion, fuse_modalities, fuse_transpose_layernorm, modality_dropout_flags,
                      modality_dropout_mask)

@@ -303,3 +303,70 @@ def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order:
     _lib.require_cuda()
     feats, _ = logfbank_batch(a.cuda(), [0, a.numel()], stack_order, normalize)
     return feats.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- SpecAugment masks
+# LibriSpeech policies of the SpecAugment paper (Park et al. 2019, table 1), the names the
+# reference passes as ``spec_augment_config`` (avsl/whisper_flamingo_ft_ami.py:165,217-220):
+# frequency mask parameter F, number of frequency masks, time mask parameter T, upper bound p on
+# the masked fraction of the utterance, number of time masks.  Time warping (W = 80) is not applied.
+SPEC_AUGMENT_POLICIES = {"ls-basic": dict(F=27, n_freq_mask=1, T=100, p=1.0, n_time_mask=1),
+                         "ls-double": dict(F=27, n_freq_mask=2, T=100, p=1.0, n_time_mask=2)}
+
+
+def spec_augment_bands(audio_frames, n_mels: int = 80, policy: str = "ls-double", rng=None,
+                       n_freq_mask: Optional[int] = None, n_time_mask: Optional[int] = None) -> np.ndarray:
+    """Draw the mask rectangles for a batch on the host: int32 ``[B, n_bands, 4]`` rows
+    ``(f0, f1, t0, t1)``.  ``audio_frames[b]`` is the clip's frame count before padding
+    (``audio_frames_before_pad``, whisper_flamingo_ft_ami.py:206): time masks stay inside it.
+    Per clip, in this order: for every frequency mask ``f ~ U{0..F}``, ``f0 ~ U{0..n_mels-f}``; then for
+    every time mask ``t ~ U{0..min(T, floor(p*tau))}``, ``t0 ~ U{0..tau-t}`` (the paper's sampling)."""
+    if policy not in SPEC_AUGMENT_POLICIES:
+        raise NotImplementedError(policy)                      # as the reference (:221-222)
+    cfg = dict(SPEC_AUGMENT_POLICIES[policy])
+    if n_freq_mask is not None:
+        cfg["n_freq_mask"] = n_freq_mask
+    if n_time_mask is not None:
+        cfg["n_time_mask"] = n_time_mask
+    rng = rng if rng is not None else np.random.default_rng()
+    frames = np.atleast_1d(np.asarray(audio_frames, dtype=np.int64))
+    nb = cfg["n_freq_mask"] + cfg["n_time_mask"]
+    bands = np.zeros((len(frames), nb, 4), dtype=np.int32)
+    for b, tau in enumerate(frames):
+        k = 0
+        for _ in range(cfg["n_freq_mask"]):
+            f = int(rng.integers(0, min(cfg["F"], n_mels) + 1))
+            f0 = int(rng.integers(0, n_mels - f + 1))
+            bands[b, k] = (f0, f0 + f, 0, np.iinfo(np.int32).max)
+            k += 1
+        for _ in range(cfg["n_time_mask"]):
+            t_max = int(min(cfg["T"], np.floor(cfg["p"] * tau)))
+            t = int(rng.integers(0, max(t_max, 0) + 1))
+            t0 = int(rng.integers(0, max(int(tau) - t, 0) + 1))
+            bands[b, k] = (0, n_mels, t0, t0 + t)
+            k += 1
+    return bands
+
+
+def spec_augment(mel: torch.Tensor, audio_frames=None, policy: str = "ls-double", rng=None,
+                 bands: Optional[np.ndarray] = None, fill: float = 0.0) -> torch.Tensor:
+    """Apply SpecAugment masks in place to ``mel`` float32 CUDA ``[B, n_mels, n_frames]`` (or
+    ``[n_mels, n_frames]``).  Either pass ``bands`` (from :func:`spec_augment_bands`) or
+    ``audio_frames`` + ``policy`` to draw them here."""
+    _lib.require_cuda()
+    if not (mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous() and mel.dim() in (2, 3)):
+        raise ValueError("mel must be a contiguous float32 CUDA tensor [B, n_mels, n_frames]")
+    m3 = mel if mel.dim() == 3 else mel.unsqueeze(0)
+    B, n_mels, n_frames = (int(s) for s in m3.shape)
+    if bands is None:
+        if audio_frames is None:
+            audio_frames = [n_frames] * B
+        bands = spec_augment_bands(audio_frames, n_mels, policy, rng)
+    bands = np.ascontiguousarray(bands, dtype=np.int32)
+    if bands.shape[0] != B or bands.shape[-1] != 4:
+        raise ValueError("bands must be [B, n_bands, 4]")
+    d_bands = torch.from_numpy(bands).to(mel.device)
+    with torch.cuda.device(mel.device):
+        _lib.call("avfe_spec_mask_f32", _lib.ptr(m3), B, n_mels, n_frames, _lib.ptr(d_bands), int(bands.shape[1]),
+                  float(fill), _lib.stream_ptr())
+    return mel

@@ -110,6 +110,14 @@ AVFE_API int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, 
                                     const void* pack, float* out, void* workspace,
                                     size_t workspace_bytes, avfe_stream_t stream);
 
+/* SpecAugment masks on a log-mel batch, in place — the spec_augment call of
+ * AmiVideoHFDataset.__getitem__, avsl/whisper_flamingo_ft_ami.py:216-224 (upstream
+ * whisper_flamingo.spec_augment, policies "ls-double" / "ls-basic").  The rectangles are drawn on
+ * the host; bands [B, n_bands, 4] int32 = (f0, f1, t0, t1): mel[b, f0:f1, t0:t1] = fill (empty or
+ * out-of-range parts are clipped / ignored).  mel [B, n_mels, n_frames] float32. */
+AVFE_API int avfe_spec_mask_f32(float* mel, int64_t B, int n_mels, int64_t n_frames, const int32_t* bands,
+                                int n_bands, float fill, avfe_stream_t stream);
+
 /* AV-HuBERT audio features — extract_logfbank_features + audio_to_tensor,
  * preprocess/audio_process.py:152-197 (and utils/data_loading.py:181-201):
  * python_speech_features.logfbank(audio, samplerate=16000) = pre-emphasis 0.97, 400-sample frames
