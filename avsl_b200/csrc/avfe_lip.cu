@@ -4,13 +4,14 @@
 // utils/hf_video_utils.py:113-138.
 //
 // Kernels
-//   tform_kernel      one WARP per frame: failed detections are interpolated on the fly (V2),
-//                     12-frame window mean of the 5 stable points (V3), closed-form similarity
-//                     fit + inverse (V4), mouth-centre transform (V6) and cut_patch origin (V7)
-//   lip_fused_kernel  (avfe_lip_queue.cuh) persistent, warp-specialised: stream warps convert
-//                     BGR->gray at HBM speed while compute warps pull one frame's ROI at a time
-//                     from a work queue (footprint staged in shared memory, float64 bilinear
-//                     blend in skimage's operation order, u8 ROI + normalised f32 centre crop)
+//   lip_frame_kernel  (avfe_lip_frame.cuh) the standard case in ONE launch: persistent CTAs own
+//                     whole frames; tform warps fit the transforms (tform_frame: V2 on the fly, V3,
+//                     V4 fit, V6, V7), stream warps pull the BGR frame through shared memory with
+//                     TMA bulk copies, write the gray frame and deposit the ROI's source footprint,
+//                     blend warps do the float64 bilinear blend, crop and normalisation
+//   tform_kernel +    the generic path (gray input, rows not 16-byte aligned, other ROI sizes, no
+//   lip_fused_kernel  gray output): one warp per frame for the transforms, then a warp-specialised
+//                     (avfe_lip_queue.cuh) work-queue kernel that stages each footprint itself
 //   gray_vec_kernel   the gray conversion alone (avfe_bgr2gray_u8)
 //   small single-purpose kernels for the per-function entry points (warp_full, cut_patch, ...)
 #include <stddef.h>

@@ -152,7 +152,8 @@ class AVFrontEnd:
                              self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
                              self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
                              batch.clip_offsets)
-            # fused: one work-queue launch interleaves the streaming gray items with the FP64 warp items
+            # fused: one launch does the transform fits, the gray frames and the ROI warp (every
+            # frame byte is read once)
             lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid,
                           want_gray=self.fused and gray is not None, want_u8=self.want_lip_u8,
                           crop=self.crop, image_mean=self.mean, image_std=self.std, out=reuse)

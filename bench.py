@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = auto (bounded to ~10-30 s)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--unfused", action="store_true", help="gray and warp as two passes instead of one work queue")
+    ap.add_argument("--unfused", action="store_true", help="gray and warp as two passes (generic kernels) instead of the frame-owner kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
