@@ -395,8 +395,45 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   cp_async_wait<0>();
 }
 
-// max(x, clip_max - 8), (x + 4) / 4.  Silent tiles (flagged by the tile kernel) were never
+// max(x, clip_max - 8), (x + 4) / 4.  Silent tiles (flagged by logmel_live_kernel) were never
 // written: their raw value is the constant log10(1e-10), so they are stored without a read.
+// Row form (frame count a multiple of 4, 16-byte aligned output): one CTA per (clip, mel) row,
+// no per-element index arithmetic, every thread's float4s issued before any is used.
+__global__ void __launch_bounds__(256)
+logmel_finalize_rows_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
+                            const uint8_t* __restrict__ silent, int64_t n_frames, int n_mels) {
+  const int64_t row = blockIdx.x, b = row / n_mels;
+  const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
+  const uint8_t* flags = silent + b * tiles_per_clip;
+  const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
+  const float raw_silent = log10_floor(0.0f);
+  float4* o4 = reinterpret_cast<float4*>(out + row * n_frames);
+  const int n4 = (int)(n_frames >> 2);
+  constexpr int U = 4;
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 256 * U) {
+    float4 x[U];
+    bool sil[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 256;
+      sil[u] = i < n4 ? flags[(4 * i) / kTileFrames] != 0 : true;   // a float4 never straddles a 32-frame tile
+      x[u] = sil[u] ? make_float4(raw_silent, raw_silent, raw_silent, raw_silent) : o4[i];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 256;
+      if (i >= n4) break;
+      float4 v = x[u];
+      v.x = __fmul_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 0.25f);
+      v.y = __fmul_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 0.25f);
+      v.z = __fmul_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 0.25f);
+      v.w = __fmul_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 0.25f);
+      o4[i] = v;
+    }
+  }
+}
+
+// generic form (any frame count / alignment)
 __global__ void __launch_bounds__(256)
 logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
                        const uint8_t* __restrict__ silent, int64_t n_frames, int n_mels,
@@ -404,24 +441,6 @@ logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max
   const int64_t per_clip = (int64_t)n_mels * n_frames;
   const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
   const float raw_silent = log10_floor(0.0f);
-  if ((n_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-    float4* o4 = reinterpret_cast<float4*>(out);
-    const int64_t n4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t e = i << 2, b = e / per_clip, t = (e - b * per_clip) % n_frames;
-      const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
-      float4 x;
-      if (silent[b * tiles_per_clip + t / kTileFrames]) x = make_float4(raw_silent, raw_silent, raw_silent, raw_silent);
-      else x = o4[i];
-      x.x = __fmul_rn(__fadd_rn(fmaxf(x.x, floor_v), 4.0f), 0.25f);
-      x.y = __fmul_rn(__fadd_rn(fmaxf(x.y, floor_v), 4.0f), 0.25f);
-      x.z = __fmul_rn(__fadd_rn(fmaxf(x.z, floor_v), 4.0f), 0.25f);
-      x.w = __fmul_rn(__fadd_rn(fmaxf(x.w, floor_v), 4.0f), 0.25f);
-      o4[i] = x;
-    }
-    return;
-  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / per_clip, t = (i - b * per_clip) % n_frames;
@@ -553,9 +572,13 @@ static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int
       live_count, live_list);
   count_launch();
   const int64_t total = B * (int64_t)n_mels * n_frames;
-  int64_t fin = (total / 4 + 255) / 256 + 1;
-  if (fin > (int64_t)kNumSMs * 16) fin = (int64_t)kNumSMs * 16;
-  lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels, total);
+  if ((n_frames & 3) == 0 && aligned16(out) && B * n_mels <= 0x7fffffffLL) {
+    lm::logmel_finalize_rows_kernel<<<(unsigned)(B * n_mels), 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels);
+  } else {
+    int64_t fin = (total + 255) / 256;
+    if (fin > (int64_t)kNumSMs * 16) fin = (int64_t)kNumSMs * 16;
+    lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels, total);
+  }
   count_launch();
   return check_launch();
 }
