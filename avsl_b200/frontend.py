@@ -165,6 +165,22 @@ class AVFrontEnd:
             out["lip_u8"] = reuse.lip_u8
         return out
 
+    # ---------------------------------------------------------------- CUDA graph of one step
+    def capture(self, batch: PackedBatch):
+        """Capture the device-resident step on ``batch``'s buffers into a CUDA graph (the step is a
+        handful of launches plus two memsets; replaying the graph removes their launch gaps, which
+        matters for small batches).  Returns ``(graph, outputs)``: refill the tensors of ``batch``
+        in place (same shapes), call ``graph.replay()``, read ``outputs`` (same tensors every time)."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.forward_device(batch)                  # warm-up: buffers, filter packs, attributes
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward_device(batch)
+        return graph, out
+
     # ---------------------------------------------------------------- host-buffer path (e2e)
     def forward_host(self, batch: PackedBatch, host_out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``batch`` lives in (pinned) host memory: H2D copy of every input, the kernels, and a

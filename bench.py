@@ -395,6 +395,13 @@ def main():
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
             del xa, xv, lout
         del fa, fv
+        # the same step replayed from a CUDA graph (no launch gaps)
+        graph, _ = fe.capture(batch_dev)
+        ms_graph = time_op(graph.replay, 20)
+        side["step_cuda_graph"] = {"kernel": "AVFrontEnd.capture(): the device-resident step as one CUDA graph", "ms": ms_graph,
+                                   "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (ms_graph * 1e-3) / 1e9,
+                                   "audio_s_per_s": audio_s / (ms_graph * 1e-3)}
+        del graph
         # the lip stage writing the padded [B,1,T,88,88] batch + padding mask directly (8(f) rank 1)
         T_pad = int((batch_dev.clip_offsets[1:] - batch_dev.clip_offsets[:-1]).max().item())
         cout = None
