@@ -72,3 +72,30 @@ def test_no_cpu_fallback_without_cuda():
         avsl_b200.log_mel_spectrogram(np.zeros(16000, np.float32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.bgr2gray(np.zeros((4, 4, 3), np.uint8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.extract_logfbank_features(np.zeros(16000, np.float32), stack_order=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.spec_augment(torch.zeros(1, 80, 3000))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.fuse_transpose_layernorm(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.lip_roi_collate(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), torch.zeros(2, dtype=torch.int64),
+                                  torch.zeros(1, 68, 2, dtype=torch.float64), T_pad=1)
+
+
+def test_argument_validation_of_the_widened_entry_points(libavfe_path):
+    """Status codes of the rows added after the hot path (collation, SpecAugment masks, logfbank,
+    fused LayerNorm) for invalid arguments, before anything touches CUDA."""
+    from avsl_b200 import _lib
+    lib = _lib.load()
+    assert lib.avfe_fuse_layernorm(None, None, None, 0, 0.5, 0.5, 0, 4, 8, 8, None, None, 1e-5, None, None) == -1
+    assert lib.avfe_fuse_layernorm(None, None, None, 9, 0.5, 0.5, 0, 4, 8, 8, None, None, 1e-5, None, None) == -1
+    assert lib.avfe_fuse_layernorm(None, None, None, 0, 0.5, 0.5, 0, 0, 8, 8, None, None, 1e-5, None, None) == 0
+    assert lib.avfe_spec_mask_f32(None, 2, 80, 3000, None, 4, 0.0, None) == -1
+    assert lib.avfe_spec_mask_f32(None, 2, 80, 3000, None, 0, 0.0, None) == 0           # no bands: no-op
+    assert lib.avfe_logfbank_f32(None, None, None, 1, 16000, None, 26, 3, 1, None, None, 0, None) == -2   # 8 % 3 != 0
+    assert lib.avfe_logfbank_f32(None, None, None, 1, 16000, None, 26, 4, 1, None, None, 0, None) == -1
+    assert lib.avfe_logfbank_num_frames(16000) == 99 and lib.avfe_logfbank_num_frames(400) == 1
+    assert lib.avfe_logfbank_workspace_bytes() >= 26 * 12
+    assert lib.avfe_lip_roi_collate(None, 3, 1, 8, 8, None, 1, None, None, None, None, 300, 96, 88, 12, 0.421, 0.165,
+                                    None, 0, None, None, None, None, 0, None) == -1           # T_pad < 1
