@@ -34,15 +34,12 @@ def trim_video(video_feats: np.ndarray, n_audio_samples: int) -> np.ndarray:
 
 
 def align_audio_video_features(audio_features, video_features):
-    """preprocess/audio_process.py:238-264."""
+    """Semantics of preprocess/audio_process.py:238-264: both sequences are cut to the shorter
+    length; a missing stream leaves the other untouched."""
     if audio_features is None or video_features is None:
         return audio_features, video_features
-    a, v = len(audio_features), len(video_features)
-    if a > v:
-        audio_features = audio_features[:v]
-    elif a < v:
-        video_features = video_features[:a]
-    return audio_features, video_features
+    n = min(len(audio_features), len(video_features))
+    return audio_features[:n], video_features[:n]
 
 
 def collate_video(videos: Sequence[np.ndarray], mels: Optional[Sequence[np.ndarray]] = None,

@@ -71,22 +71,24 @@ def logfbank(signal: np.ndarray, samplerate: int = 16000) -> np.ndarray:
 
 
 def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order: int = 1) -> np.ndarray:
-    """preprocess/audio_process.py:152-179."""
-    audio_feats = logfbank(audio_data, samplerate=sample_rate).astype(np.float32)
-    if stack_order > 1:
-        feat_dim = audio_feats.shape[1]
-        if len(audio_feats) % stack_order != 0:
-            res = stack_order - len(audio_feats) % stack_order
-            res = np.zeros([res, feat_dim]).astype(audio_feats.dtype)
-            audio_feats = np.concatenate([audio_feats, res], axis=0)
-        audio_feats = audio_feats.reshape((-1, stack_order, feat_dim)).reshape(-1, stack_order * feat_dim)
-    return audio_feats
+    """Semantics of preprocess/audio_process.py:152-179: float32 log filterbank frames; with
+    ``stack_order`` > 1, zero frames are appended up to a multiple of it and every ``stack_order``
+    consecutive frames become one row."""
+    frames = logfbank(audio_data, samplerate=sample_rate).astype(np.float32)
+    if stack_order <= 1:
+        return frames
+    n, dim = frames.shape
+    short = (-n) % stack_order
+    if short:
+        frames = np.pad(frames, ((0, short), (0, 0)))
+    return frames.reshape(-1, stack_order * dim)
 
 
 def audio_to_tensor(audio_features: np.ndarray, normalize: bool = True) -> np.ndarray:
-    """preprocess/audio_process.py:181-197."""
-    if normalize:
-        mean = np.mean(audio_features, axis=1, keepdims=True)
-        std = np.std(audio_features, axis=1, keepdims=True)
-        audio_features = (audio_features - mean) / (std + 1e-5)
-    return audio_features
+    """Semantics of preprocess/audio_process.py:181-197: per row, subtract the mean and divide by
+    (population standard deviation + 1e-5)."""
+    if not normalize:
+        return audio_features
+    mu = audio_features.mean(axis=1, keepdims=True)
+    sd = audio_features.std(axis=1, keepdims=True)
+    return (audio_features - mu) / (sd + 1e-5)
