@@ -249,3 +249,25 @@ def test_frame_kernel_edge_cases_in_one_batch():
             if want_u8:
                 d = np.abs(res.lip_u8[lo:hi].cpu().numpy().astype(int) - ref.astype(int))
                 assert d.max() <= 1 and (d != 0).mean() < 2e-3, kind
+
+
+@pytest.mark.parametrize("H,W,T", [(288, 352, 40), (120, 176, 33), (96, 128, 150), (240, 320, 149), (224, 224, 297)])
+def test_frame_kernel_equals_generic_path(H, W, T):
+    """The frame-owner kernel (gray wanted) and the generic work-queue path (no gray) are two
+    implementations of the same arithmetic: identical ROI bytes, crop origins and transforms on
+    frame sizes with partial last chunks, more / fewer frames than SMs, several clips."""
+    cuts = sorted({0, T // 3, T // 3 + 1, T})
+    lens = np.diff(cuts)
+    clips = [synth.video_clip(int(n), H, W, seed=700 + i, invalid_frac=0.15) for i, n in enumerate(lens)]
+    F = torch.from_numpy(np.concatenate([c[0] for c in clips])).cuda()
+    LM = torch.from_numpy(np.concatenate([c[1] for c in clips])).cuda()
+    V = torch.from_numpy(np.concatenate([c[2] for c in clips])).cuda()
+    off = torch.tensor(cuts, dtype=torch.int64).cuda()
+    for want_u8 in (False, True):
+        a = L.lip_roi_batch(F, off, LM, V, want_gray=True, want_u8=want_u8, want_meta=True)
+        b = L.lip_roi_batch(F, off, LM, V, want_gray=False, want_u8=want_u8, want_meta=True)
+        assert torch.equal(a.lip_f32, b.lip_f32)
+        assert torch.equal(a.crop_rc, b.crop_rc) and torch.equal(a.tforms, b.tforms)
+        if want_u8:
+            assert torch.equal(a.lip_u8, b.lip_u8)
+    np.testing.assert_array_equal(a.gray.cpu().numpy(), O.bgr2gray(F.cpu().numpy()))
