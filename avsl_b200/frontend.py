@@ -165,6 +165,39 @@ class AVFrontEnd:
             out["lip_u8"] = reuse.lip_u8
         return out
 
+    # ---------------------------------------------------------------- the training batch, collated
+    def forward_collated(self, batch: PackedBatch, clip_frames: Sequence[int], audio_lengths: Sequence[int],
+                         spec_augment_config: Optional[str] = None, train: bool = False,
+                         rng=None) -> Dict[str, torch.Tensor]:
+        """The batch dict the reference's training step reads (``batch["input_ids"]``,
+        ``batch["video"]``, ``batch["padding_mask"]``, avsl/whisper_flamingo_ft_ami.py:499-504,527),
+        built on the GPU from a packed batch: what ``AmiVideoHFDataset.__getitem__`` (:187-313) does
+        per sample -- pad_or_trim + log-mel, SpecAugment when ``train`` and a policy is set (:216-224),
+        lip features trimmed to ``round(len(audio) / 16000 * 25)`` frames (:299-302; ``audio`` is the
+        padded clip there) -- followed by the collator's zero padding and mask (:686).
+        ``clip_frames`` / ``audio_lengths`` are the host-side frame and sample counts of the clips
+        (``audio_frames_before_pad`` = samples // 160 bounds the time masks, :206)."""
+        from .audio import spec_augment
+        from .lips import lip_roi_collate, video_frames_for_audio
+        U, L = batch.n_utts, self.audio_max_length
+        keep_n = video_frames_for_audio(L)
+        kept = [min(int(t), keep_n) for t in clip_frames]
+        T_pad = max(max(kept), 1)
+        with torch.cuda.device(self.device):
+            mel = self._buf("mel", (U, self.n_mels, L // HOP_LENGTH), torch.float32)
+            log_mel_spectrogram_ragged(batch.audio, batch.audio_offsets, L, self.n_mels, filters=self.filters, out=mel)
+            if train and spec_augment_config:
+                frames_before_pad = [min(int(n), L) // HOP_LENGTH for n in audio_lengths]
+                spec_augment(mel, audio_frames=frames_before_pad, policy=spec_augment_config, rng=rng)
+            keep = torch.full((U,), keep_n, dtype=torch.int64, device=self.device)
+            col = lip_roi_collate(batch.frames, batch.clip_offsets, batch.landmarks, batch.lm_valid, T_pad=T_pad,
+                                  keep_frames=keep, want_gray=self.want_gray, crop=self.crop,
+                                  image_mean=self.mean, image_std=self.std)
+        out = {"input_ids": mel, "video": col["video"], "padding_mask": col["padding_mask"]}
+        if "gray" in col:
+            out["gray"] = col["gray"]
+        return out
+
     # ---------------------------------------------------------------- CUDA graph of one step
     def capture(self, batch: PackedBatch):
         """Capture the device-resident step on ``batch``'s buffers into a CUDA graph (the step is a

@@ -101,3 +101,31 @@ def test_cuda_graph_replay_matches_eager():
     torch.cuda.synchronize()
     for k in eager2:
         assert torch.equal(out[k], eager2[k]), k
+
+
+def test_forward_collated_is_getitem_plus_collator():
+    """forward_collated == per-sample pad_or_trim + log-mel (+ SpecAugment with the same bands) and
+    lip features trimmed to round(L/16000*25) frames, then the collator's padding and mask."""
+    from oracle import collate as OC
+    from oracle import specaug as OS
+    audios, vids, lms, vals = _utts(3)
+    L = 16000                                            # 1 s: keeps 25 frames, the 2.52 s clip (63 frames) is trimmed
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=L)
+    batch = A.pack_utterances(audios, vids, lms, vals, audio_max_length=None)
+    frames = [len(v) for v in vids]
+    lens = [len(a) for a in audios]
+    out = fe.forward_collated(batch.to("cuda"), frames, lens, "ls-double", train=True, rng=np.random.default_rng(9))
+    out = {k: v.clone() for k, v in out.items()}         # the front-end reuses its output buffers
+    plain = fe.forward_device(batch.to("cuda"))
+    lips = fe.split_lip(plain["lip"].cpu(), batch.clip_offsets)
+    keep = OC.video_frames_for_audio(L)
+    assert keep == 25
+    ref = OC.collate_video([OC.trim_video(x.numpy(), L) for x in lips])
+    assert out["video"].shape == (3, 1, 25, 88, 88)
+    np.testing.assert_array_equal(out["video"].cpu().numpy(), ref["video"])
+    np.testing.assert_array_equal(out["padding_mask"].cpu().numpy(), ref["padding_mask"])
+    bands = A.spec_augment_bands([min(n, L) // 160 for n in lens], 80, "ls-double", np.random.default_rng(9))
+    np.testing.assert_array_equal(out["input_ids"].cpu().numpy(), OS.apply_bands(plain["mel"].cpu().numpy(), bands))
+    # eval: no augmentation
+    ev = fe.forward_collated(batch.to("cuda"), frames, lens, "ls-double", train=False)["input_ids"].clone()
+    assert torch.equal(ev, fe.forward_device(batch.to("cuda"))["mel"])
