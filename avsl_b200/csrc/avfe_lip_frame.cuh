@@ -86,12 +86,19 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D); completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar) {
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar,
+                                          unsigned long long policy) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
           smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
+}
+// frames are read exactly once: ask L2 to evict them first
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 
 // tile FULL: hardware barrier 1 + slot with a compile-time id (a register id would make ptxas
@@ -151,12 +158,13 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
   const int64_t next_frame = (int64_t)gridDim.x * frame_bytes;
   const unsigned last_bytes = (unsigned)(gpf - (cpf - 1) * 64) * 48u;   // the frame's last chunk may be short
   const bool full_chunks = (gpf & 63) == 0;
+  const unsigned long long l2_policy = l2_evict_first_policy();
   auto issue = [&]() {
     if (ik < nk) {
       if (lane == 0) {
         const unsigned bytes = (ic == cpf - 1) ? last_bytes : (unsigned)(kChunkVec * 16);
         mbar_arrive_expect_tx(&full[istage], bytes);
-        bulk_load(ring[istage], isrc, bytes, &full[istage]);
+        bulk_load(ring[istage], isrc, bytes, &full[istage], l2_policy);
       }
       ic += S;
       isrc += S * (kChunkVec * 16);
