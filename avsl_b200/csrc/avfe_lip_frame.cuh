@@ -208,8 +208,8 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
       issue();                                           // into the stage consumed one iteration ago
       const uint4 ga = gray16_dp2a(p0, p1, p2), gb = gray16_dp2a(q0, q1, q2);
       const int g0 = c * 64 + lane, g1 = g0 + 32;        // 16-px group indices inside the frame
-      if (full_chunks || g0 < gpf) stg_stream(gout + g0, ga);
-      if (full_chunks || g1 < gpf) stg_stream(gout + g1, gb);
+      if (full_chunks || g0 < gpf) gout[g0] = ga;
+      if (full_chunks || g1 < gpf) gout[g1] = gb;
       if (c >= c_lo && c <= c_hi) {
         // groups never straddle rows (W % 16 == 0); deposit those inside the footprint box
         const int ra = (int)__umulhi((unsigned)g0, j.row_magic), ca = g0 - ra * j.row_groups;
