@@ -63,6 +63,34 @@ template <> struct Pack<__half, 1> { typedef __half type; };
 template <> struct Pack<__nv_bfloat16, 2> { typedef __nv_bfloat162 type; };
 template <> struct Pack<__nv_bfloat16, 1> { typedef __nv_bfloat16 type; };
 
+// A tile touches 32 or 64 bytes of every channel row; the rest of the 128-byte line belongs to the
+// neighbouring tiles, which other CTAs are reading at about the same time: ask L2 to fetch the
+// whole line (ld.global.L2::128B) so that DRAM sees full-line bursts and the neighbours hit.
+__device__ __forceinline__ float2 ld_line(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.L2::128B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_line(const float* p) {
+  float v;
+  asm volatile("ld.global.L2::128B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_line_u32(const void* p) {
+  unsigned v;
+  asm volatile("ld.global.L2::128B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned short ld_line_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.L2::128B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ __half2 ld_line(const __half2* p) { const unsigned v = ld_line_u32(p); return *reinterpret_cast<const __half2*>(&v); }
+__device__ __forceinline__ __half ld_line(const __half* p) { const unsigned short v = ld_line_u16(p); return *reinterpret_cast<const __half*>(&v); }
+__device__ __forceinline__ __nv_bfloat162 ld_line(const __nv_bfloat162* p) { const unsigned v = ld_line_u32(p); return *reinterpret_cast<const __nv_bfloat162*>(&v); }
+__device__ __forceinline__ __nv_bfloat16 ld_line(const __nv_bfloat16* p) { const unsigned short v = ld_line_u16(p); return *reinterpret_cast<const __nv_bfloat16*>(&v); }
+
 template <typename T, int MODE>
 __device__ __forceinline__ T combine1(T x, T y, float wa, float wv) {
   const float a = to_f32<T>(x), v = to_f32<T>(y);
@@ -154,7 +182,7 @@ fuse_ln_kernel(const Args a) {
         P v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          v[u] = (on && c + u * kRowsPerPass < a.C) ? *reinterpret_cast<const P*>(src + u * pass_stride) : zpack;
+          v[u] = (on && c + u * kRowsPerPass < a.C) ? ld_line(reinterpret_cast<const P*>(src + u * pass_stride)) : zpack;
 #pragma unroll
         for (int u = 0; u < U; ++u)
           if (c + u * kRowsPerPass < a.C) put(dst + u * kRowsPerPass * RS, v[u], v[u]);
@@ -170,8 +198,8 @@ fuse_ln_kernel(const Args a) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const bool on = t_live && c + u * kRowsPerPass < a.C;
-        va[u] = (on && has_a) ? *reinterpret_cast<const P*>(pa + u * pass_stride) : zpack;
-        vv[u] = (on && has_v) ? *reinterpret_cast<const P*>(pv + u * pass_stride) : zpack;
+        va[u] = (on && has_a) ? ld_line(reinterpret_cast<const P*>(pa + u * pass_stride)) : zpack;
+        vv[u] = (on && has_v) ? ld_line(reinterpret_cast<const P*>(pv + u * pass_stride)) : zpack;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
