@@ -395,6 +395,16 @@ def main():
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
             del xa, xv, lout
         del fa, fv
+        # SpecAugment masks (8(f) rank 2) on the step's mel batch: only the masked elements are written
+        mel_b = fe.forward_device(batch_dev)["mel"]
+        frames_before_pad = [int(x) for x in ((batch_dev.audio_offsets[1:] - batch_dev.audio_offsets[:-1]) // 160).tolist()]
+        bands = A.spec_augment_bands(frames_before_pad, N_MELS, "ls-double", np.random.default_rng(SEED))
+        ms = time_op(lambda: A.spec_augment(mel_b, bands=bands), 20)
+        masked = 0
+        for bnd in bands.reshape(-1, 4):
+            masked += max(0, min(int(bnd[1]), N_MELS) - max(int(bnd[0]), 0)) * max(0, min(int(bnd[3]), AUDIO_LEN // 160) - max(int(bnd[2]), 0))
+        side["spec_augment_ls_double"] = {"kernel": "spec_mask_kernel on mel [U,80,3000] (bands drawn on the host, H2D of the band table included)",
+                                          "ms": ms, "algorithmic_bytes": masked * 4, "achieved_gbs": masked * 4 / (ms * 1e-3) / 1e9}
         # the same step replayed from a CUDA graph (no launch gaps)
         graph, _ = fe.capture(batch_dev)
         ms_graph = time_op(graph.replay, 20)
