@@ -22,7 +22,6 @@
 namespace avfe {
 
 constexpr int kTformRoleWarps = 2;
-constexpr int kFrameRing = 6;               // bulk copies in flight per stream warp (x 3 KB)
 constexpr int kDescRing = 4;
 constexpr int kTileSlots = 3;               // footprint tiles: the stream may run this many frames ahead of the blend
 constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slot (u16 each)
@@ -30,7 +29,12 @@ constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slo
 template <int SPAN>
 struct FrameRoles {
   static constexpr int kSide = SPAN;
-  static constexpr int kBlendWarps = 8 * SPAN / 32;                    // 22 or 24
+  // thread = (column, row phase): 8 phases of 11 rows for the 88-px window (22 warps); 6 phases of
+  // 16 rows for the 96-px one (18 warps), which leaves 12 warps for the stream instead of 6
+  static constexpr int kPhases = (SPAN == 96) ? 6 : 8;
+  static constexpr int kBlendWarps = kPhases * SPAN / 32;             // 22 or 18
+  // bulk copies in flight per stream warp (x 3 KB): 144 KB per SM either way
+  static constexpr int kRing = (SPAN == 96) ? 4 : 6;
   static constexpr int kBlendThreads = kBlendWarps * 32;
   static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 6
   static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
@@ -51,13 +55,13 @@ template <int SPAN>
 struct FrameSmem {
   double lut255[256 * 16];                    // k / 255.0, 16 interleaved copies (see FusedSmem)
   float lutn[256];                            // ((k/255) - mean) / std in float32
-  unsigned long long ring_full[FrameRoles<SPAN>::kStreamWarps][kFrameRing];
+  unsigned long long ring_full[FrameRoles<SPAN>::kStreamWarps][FrameRoles<SPAN>::kRing];
   unsigned long long desc_full[kDescRing], desc_empty[kDescRing];
   unsigned long long tile_empty[kTileSlots];
   FrameXform desc[kDescRing];
   int64_t dst[kDescRing];                     // f32 output slot of the frame (collation), < 0: dropped
   __align__(16) uint16_t tile[kTileSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
-  __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][kFrameRing][kChunkVec];
+  __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][FrameRoles<SPAN>::kRing][kChunkVec];
 };
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
@@ -170,10 +174,10 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
       isrc += S * (kChunkVec * 16);
       if (ic >= cpf) { isrc += next_frame - (int64_t)(ic - sw) * (kChunkVec * 16); ic = sw; ++ik; }
     }
-    if (++istage == kFrameRing) istage = 0;
+    if (++istage == R::kRing) istage = 0;
   };
 #pragma unroll 1
-  for (int i = 0; i < kFrameRing - 1; ++i) issue();
+  for (int i = 0; i < R::kRing - 1; ++i) issue();
 
   int stage = 0;
   unsigned phase = 0;                                    // parity of the current pass over the ring
@@ -227,7 +231,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
           t[0] = lo; t[1] = hi;
         }
       }
-      if (++stage == kFrameRing) { stage = 0; phase ^= 1u; }
+      if (++stage == R::kRing) { stage = 0; phase ^= 1u; }
     }
     // this warp's part of the footprint is in: hardware barrier 1 + slot, which the blend warps
     // wait on without polling (stream warps only arrive)
@@ -267,7 +271,7 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
     return;
   }
   // x_ = (M0*c + M1*r) + M2: two roundings per product as in skimage's _transform_affine; the
-  // integer coordinates are exact in float64, so tr + 8 is the next row of this thread exactly
+  // integer coordinates are exact in float64, so tr + kPhases is the next row of this thread exactly
   const double m0 = x.inv[0], m1 = x.inv[1], m2 = x.inv[2], m3 = x.inv[3], m4 = x.inv[4], m5 = x.inv[5];
   const int br0 = fp.r0, bc0 = fp.c0, pitch = fp.pitch;
   const int rr = tid / S, c = tid - rr * S;             // thread = (column, row phase)
@@ -276,11 +280,11 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
   double tr = (double)(x.r0 + lo + rr);
   if (fp.interior && fp.staged) {
 #pragma unroll
-    for (int i = 0; i < S / 8; ++i) {
+    for (int i = 0; i < S / R::kPhases; ++i) {
       const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
       const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
-      emit(rr + 8 * i, c, bilinear_interior(sr, sc, tile, pitch, br0, bc0, lut));
-      tr = f64add(tr, 8.0);
+      emit(rr + R::kPhases * i, c, bilinear_interior(sr, sc, tile, pitch, br0, bc0, lut));
+      tr = f64add(tr, (double)R::kPhases);
     }
     return;
   }
@@ -294,11 +298,11 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
     const uint8_t* p = img + ((int64_t)r * W + cc) * 3;                 // not staged: global tap
     return lut[16 * gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2))];
   };
-  for (int i = 0; i < S / 8; ++i) {
+  for (int i = 0; i < S / R::kPhases; ++i) {
     const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
     const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
-    emit(rr + 8 * i, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
-    tr = f64add(tr, 8.0);
+    emit(rr + R::kPhases * i, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
+    tr = f64add(tr, (double)R::kPhases);
   }
 }
 
@@ -332,7 +336,7 @@ lip_frame_kernel(const FrameJob j) {
   const int nk = (int)((N - blockIdx.x + gridDim.x - 1) / gridDim.x);
   if (tid == 0) {
     for (int w = 0; w < R::kStreamWarps; ++w)
-      for (int s = 0; s < kFrameRing; ++s) mbar_init(&sm.ring_full[w][s], 1u);
+      for (int s = 0; s < R::kRing; ++s) mbar_init(&sm.ring_full[w][s], 1u);
     for (int s = 0; s < kDescRing; ++s) {
       mbar_init(&sm.desc_full[s], 1u);
       mbar_init(&sm.desc_empty[s], (unsigned)(R::kStreamWarps + R::kBlendWarps));

@@ -395,6 +395,20 @@ def main():
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
             del xa, xv, lout
         del fa, fv
+        # the lip stage with the 96x96 u8 ROI (what extract_lip_frames returns) as a third output
+        from avsl_b200.lips import lip_roi_batch
+        r96 = None
+
+        def run_96():
+            nonlocal r96
+            r96 = lip_roi_batch(batch_dev.frames, batch_dev.clip_offsets, batch_dev.landmarks, batch_dev.lm_valid,
+                                want_gray=True, want_u8=True, want_f32=True, out=r96)
+        ms = time_op(run_96, 10)
+        n_fr = int(batch_dev.frames.shape[0])
+        nbytes = n_fr * (H * W * 3 + 68 * 2 * 8 + H * W + 88 * 88 * 4 + 96 * 96)
+        side["lip_with_u8_roi"] = {"kernel": "lip_frame_kernel<96>: gray + 96x96 u8 ROI + 88x88 f32 crop (6 stream, 24 blend warps)",
+                                   "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+        del r96
         # SpecAugment masks (8(f) rank 2) on the step's mel batch: only the masked elements are written
         mel_b = fe.forward_device(batch_dev)["mel"]
         frames_before_pad = [int(x) for x in ((batch_dev.audio_offsets[1:] - batch_dev.audio_offsets[:-1]) // 160).tolist()]
