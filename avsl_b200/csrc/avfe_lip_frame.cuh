@@ -5,12 +5,12 @@
 //   tform warps  (2) window-smoothed similarity fit, cut_patch origin and source footprint of
 //                the CTA's frames, a few frames ahead of everybody else (tform_frame, shared
 //                with tform_kernel), published through a 4-deep descriptor ring
-//   stream warps (8 for an 88-px window, 6 for 96) pull the frame through shared memory in
+//   stream warps (8 for an 88-px window, 12 for 96) pull the frame through shared memory in
 //                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier) per
-//                chunk and a 6-deep ring per warp, convert BGR->gray (integer dp2a), store the
+//                chunk and a 6- / 4-deep ring per warp, convert BGR->gray (integer dp2a), store the
 //                gray frame with 16-byte streaming stores, and drop the gray pixels that lie
 //                inside the frame's ROI footprint into a double-buffered shared-memory tile
-//   blend warps  (22 / 24) float64 bilinear blend of the previous frame's ROI from that tile in
+//   blend warps  (22 / 18) float64 bilinear blend of the previous frame's ROI from that tile in
 //                skimage's operation order: u8 ROI and/or normalised f32 centre crop
 //
 // Hand-over: mbarriers (ring FULL per stage, descriptor FULL/EMPTY, tile EMPTY) and one hardware
@@ -23,20 +23,25 @@ namespace avfe {
 
 constexpr int kTformRoleWarps = 2;
 constexpr int kDescRing = 4;
-constexpr int kTileSlots = 3;               // footprint tiles: the stream may run this many frames ahead of the blend
 constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slot (u16 each)
 
 template <int SPAN>
 struct FrameRoles {
   static constexpr int kSide = SPAN;
-  // thread = (column, row phase): 8 phases of 11 rows for the 88-px window (22 warps); 6 phases of
-  // 16 rows for the 96-px one (18 warps), which leaves 12 warps for the stream instead of 6
+  // thread = (column, row phase): 8 phases of 11 rows for the 88-px window (22 blend warps, 8
+  // stream warps); 6 phases of 16 rows for the 96-px one (18 blend warps), which leaves 12 warps
+  // for the stream instead of 6 (-11 % time).  Measured for 88: 6 phases (17 blend / 13 stream
+  // warps, shallower rings) is 1-2 % slower than 8 phases.
   static constexpr int kPhases = (SPAN == 96) ? 6 : 8;
-  static constexpr int kBlendWarps = kPhases * SPAN / 32;             // 22 or 18
+  static constexpr int kBlendActive = kPhases * SPAN;                 // 704 or 576 threads with pixels
+  static constexpr int kBlendWarps = (kBlendActive + 31) / 32;        // 22 or 18
+  static constexpr int kRowsMax = (SPAN + kPhases - 1) / kPhases;     // 11 or 16
   // bulk copies in flight per stream warp (x 3 KB): 144 KB per SM either way
   static constexpr int kRing = (SPAN == 96) ? 4 : 6;
+  // footprint tiles: the stream may run this many frames ahead of the blend (what fits)
+  static constexpr int kSlots = 3;
   static constexpr int kBlendThreads = kBlendWarps * 32;
-  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 6
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 12
   static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
   static constexpr int kTformFirst = 32 - kTformRoleWarps;            // highest warp ids: scheduled first
   static constexpr int kHandoverThreads = 32 * (kBlendWarps + kStreamWarps);   // tile FULL barriers
@@ -57,10 +62,10 @@ struct FrameSmem {
   float lutn[256];                            // ((k/255) - mean) / std in float32
   unsigned long long ring_full[FrameRoles<SPAN>::kStreamWarps][FrameRoles<SPAN>::kRing];
   unsigned long long desc_full[kDescRing], desc_empty[kDescRing];
-  unsigned long long tile_empty[kTileSlots];
+  unsigned long long tile_empty[FrameRoles<SPAN>::kSlots];
   FrameXform desc[kDescRing];
   int64_t dst[kDescRing];                     // f32 output slot of the frame (collation), < 0: dropped
-  __align__(16) uint16_t tile[kTileSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
+  __align__(16) uint16_t tile[FrameRoles<SPAN>::kSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
   __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][FrameRoles<SPAN>::kRing][kChunkVec];
 };
 
@@ -109,7 +114,6 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
 // reserve all 16 barriers); stream warps arrive, blend warps sync
 template <bool SYNC>
 __device__ __forceinline__ void tile_bar(int slot, int count) {
-  static_assert(kTileSlots == 3, "one case per slot");
   if (slot == 0)      { if (SYNC) bar_sync_id<1>(count); else bar_arrive_id<1>(count); }
   else if (slot == 1) { if (SYNC) bar_sync_id<2>(count); else bar_arrive_id<2>(count); }
   else                { if (SYNC) bar_sync_id<3>(count); else bar_arrive_id<3>(count); }
@@ -184,7 +188,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
   for (int k = 0; k < nk; ++k) {
     const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
     // this frame's footprint box (the tform warps are ahead) and its tile slot
-    const int dslot = k % kDescRing, slot = k % kTileSlots;
+    const int dslot = k % kDescRing, slot = k % R::kSlots;
     mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
     const unsigned box_lo = sm.desc[dslot].box_lo, box_hi = sm.desc[dslot].box_hi;
     __syncwarp();
@@ -192,7 +196,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
     const bool staged = ((box_lo >> 27) & 1u) != 0;
     const int br0 = (int)(box_lo & 0x1fffu), bcg = (int)((box_lo >> 13) & 0x1fffu) >> 4;
     const int brows = staged ? (int)(box_hi & 0x1fffu) : 0, bpg = (int)((box_hi >> 13) & 0x1fffu) >> 4;
-    if (k >= kTileSlots) mbar_wait(&sm.tile_empty[slot], (unsigned)(k / kTileSlots - 1) & 1u);   // blend warps left the slot
+    if (k >= R::kSlots) mbar_wait(&sm.tile_empty[slot], (unsigned)(k / R::kSlots - 1) & 1u);   // blend warps left the slot
     uint4* tile = reinterpret_cast<uint4*>(sm.tile[slot]);
     uint4* gout = reinterpret_cast<uint4*>(L.gray_out + f * frame_px);
     // chunks that hold rows of the footprint box: [c_lo, c_hi] (warp-uniform, once per frame), so
@@ -274,13 +278,15 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
   // integer coordinates are exact in float64, so tr + kPhases is the next row of this thread exactly
   const double m0 = x.inv[0], m1 = x.inv[1], m2 = x.inv[2], m3 = x.inv[3], m4 = x.inv[4], m5 = x.inv[5];
   const int br0 = fp.r0, bc0 = fp.c0, pitch = fp.pitch;
+  if (tid >= R::kBlendActive) return;                   // idle lanes of the last blend warp
   const int rr = tid / S, c = tid - rr * S;             // thread = (column, row phase)
   const double tc = (double)(x.c0 + lo + c);
   const double cx = f64mul(m0, tc), cy = f64mul(m3, tc);
   double tr = (double)(x.r0 + lo + rr);
   if (fp.interior && fp.staged) {
 #pragma unroll
-    for (int i = 0; i < S / R::kPhases; ++i) {
+    for (int i = 0; i < R::kRowsMax; ++i) {
+      if (S % R::kPhases != 0 && rr + R::kPhases * i >= S) break;     // 88 = 14 * 6 + 4
       const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
       const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
       emit(rr + R::kPhases * i, c, bilinear_interior(sr, sc, tile, pitch, br0, bc0, lut));
@@ -298,7 +304,8 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
     const uint8_t* p = img + ((int64_t)r * W + cc) * 3;                 // not staged: global tap
     return lut[16 * gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2))];
   };
-  for (int i = 0; i < S / R::kPhases; ++i) {
+  for (int i = 0; i < R::kRowsMax; ++i) {
+    if (rr + R::kPhases * i >= S) break;
     const double sc = f64add(f64add(cx, f64mul(m1, tr)), m2);
     const double sr = f64add(f64add(cy, f64mul(m4, tr)), m5);
     emit(rr + R::kPhases * i, c, (uint32_t)bilinear_u8(sr, sc, H, W, tap));
@@ -311,7 +318,7 @@ __device__ __forceinline__ void frame_blend_run(const FrameJob& j, FrameSmem<SPA
   const int lane = tid & 31;
   for (int k = 0; k < nk; ++k) {
     const int64_t f = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-    const int dslot = k % kDescRing, slot = k % kTileSlots;
+    const int dslot = k % kDescRing, slot = k % FrameRoles<SPAN>::kSlots;
     mbar_wait(&sm.desc_full[dslot], (unsigned)(k / kDescRing) & 1u);
     const FrameXform x = sm.desc[dslot];
     const int64_t slot_f32 = sm.dst[dslot];
@@ -341,7 +348,7 @@ lip_frame_kernel(const FrameJob j) {
       mbar_init(&sm.desc_full[s], 1u);
       mbar_init(&sm.desc_empty[s], (unsigned)(R::kStreamWarps + R::kBlendWarps));
     }
-    for (int s = 0; s < kTileSlots; ++s) {
+    for (int s = 0; s < R::kSlots; ++s) {
       mbar_init(&sm.tile_empty[s], (unsigned)R::kBlendWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
