@@ -279,6 +279,36 @@ class HostPipeline:
                 ev.synchronize()
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs closest to GPU ``device_index`` (NVML's ideal affinity),
+    so that the pinned staging buffers it allocates afterwards are first-touched on the NUMA node
+    the GPU hangs off and host-to-device copies do not cross the socket interconnect.  One process
+    per GPU calls this once, before allocating pinned memory.  Returns the CPU list, or ``None`` when
+    NVML or the scheduler call is unavailable (nothing is changed then)."""
+    try:
+        import os
+
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def shard(n_items: int, rank: int, world_size: int) -> np.ndarray:
     """Indices of the utterances rank ``rank`` of ``world_size`` processes owns."""
     if not (0 <= rank < world_size):

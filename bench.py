@@ -248,6 +248,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host side of the e2e path: this rank's pinned buffers live on the GPU's own NUMA node
+    numa_cpus = A.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -487,6 +489,8 @@ def main():
                "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_pipe / e2e_steps, "steps": e2e_steps,
                "api": "avsl_b200.HostPipeline(depth=2).submit(i, pinned PackedBatch) -> result(i): H2D of every input and D2H of mel+lip for every step, two slots in flight",
+               "host_binding": (f"rank pinned to the {len(numa_cpus)} CPUs of its GPU's NUMA node (NVML ideal affinity) before allocating pinned buffers"
+                                if numa_cpus else "none"),
                "serial": {"value": audio_s_all * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
                           "api": "AVFrontEnd.forward_host (H2D -> kernels -> D2H -> sync, one step at a time)"}}
         del pipe
