@@ -1,20 +1,21 @@
 // lip_frame_kernel: gray conversion, transform fit and ROI warp of a batch in ONE persistent
 // launch in which every BGR byte is read from HBM exactly once.  One 1024-thread CTA per SM owns
-// whole frames (f = blockIdx.x + k * gridDim.x); three warp roles, no CTA-wide barrier:
+// whole frames (f = blockIdx.x + k * gridDim.x); three warp roles, one CTA-wide barrier at start-up:
 //
 //   tform warps  (2) window-smoothed similarity fit, cut_patch origin and source footprint of
 //                the CTA's frames, a few frames ahead of everybody else (tform_frame, shared
 //                with tform_kernel), published through a 4-deep descriptor ring
 //   stream warps (8 for an 88-px window, 12 for 96) pull the frame through shared memory in
-//                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier) per
-//                chunk and a 6- / 4-deep ring per warp, convert BGR->gray (integer dp2a), store the
-//                gray frame with 16-byte streaming stores, and drop the gray pixels that lie
-//                inside the frame's ROI footprint into a double-buffered shared-memory tile
+//                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier, L2
+//                evict-first hint) per chunk and a 6- / 4-deep ring per warp, convert BGR->gray
+//                (integer dp2a), store the gray frame with 16-byte stores, and drop the gray
+//                pixels that lie inside the frame's ROI footprint into one of three
+//                shared-memory footprint tiles
 //   blend warps  (22 / 18) float64 bilinear blend of the previous frame's ROI from that tile in
 //                skimage's operation order: u8 ROI and/or normalised f32 centre crop
 //
 // Hand-over: mbarriers (ring FULL per stage, descriptor FULL/EMPTY, tile EMPTY) and one hardware
-// named barrier per tile slot for tile FULL, so that the 22 waiting blend warps do not poll;
+// named barrier per tile slot for tile FULL, so that the waiting blend warps do not poll;
 // the FP64 work of frame k hides under the memory time of frame k+1.
 // Included by avfe_lip.cu only (after avfe_lip_queue.cuh, whose gray and blend helpers it uses).
 #pragma once
