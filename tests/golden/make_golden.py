@@ -12,6 +12,12 @@ transformers / cv2 are available):
 * video_feats_golden.npz  the reference's own load_video_feats_from_decord_reader
                        (utils/hf_video_utils.py:73-145), imported by file path from
                        /root/reference and fed a duck-typed reader.
+* noise_golden.npz      the reference's own add_noise (preprocess/audio_process.py:110-150), taken
+                       out of its module by function name (the module's top-level imports --
+                       librosa, python_speech_features -- are not installable here) and run on
+                       seeded int16-scale and [-1, 1] waveforms: tiled / cut / equal-length noise,
+                       both clipping branches, lengths below 8 and around 128, one 30 s clip
+                       (slices + SHA-256 of the whole output).
 The similarity-fit / warp path has no golden: scikit-image is not installable here
 ("parity unpinned", see oracle/lips.py).
 """
@@ -107,7 +113,74 @@ def video_feats():
     print("video_feats:", feats.shape, feats.dtype, float(feats.min()), float(feats.max()))
 
 
+def noise_cases():
+    """name -> (clean f32, noise f32, snr); int16-scale unless said otherwise.  Shared with the tests
+    (tests/test_oracle_noise.py regenerates the 30 s case from its seed)."""
+    rng = np.random.default_rng(3407)
+
+    def wav(n, amp):
+        return np.clip(np.rint(rng.standard_normal(n) * amp), -32768, 32767).astype(np.int16).astype(np.float32)
+
+    cases = {
+        "tile": (wav(24000, 3000), wav(7345, 800), 10),
+        "cut": (wav(12000, 2500), wav(26000, 4000), 0),
+        "equal": (wav(9000, 1000), wav(9000, 1000), -5),
+        "multiple": (wav(3 * 4096, 2000), wav(4096, 500), 7.5),
+        "tiny": (wav(5, 3000), wav(3, 1000), 5),
+        "n130": (wav(130, 3000), wav(129, 1000), 3),
+        "n8": (wav(8, 3000), wav(300, 1000), 20),
+        "unit_range": ((rng.standard_normal(8000) * 0.1).astype(np.float32),
+                       (rng.standard_normal(3000) * 0.1).astype(np.float32), 10),
+    }
+    hot = wav(12000, 9000)
+    hot[2345] = 32000.0
+    cases["clip_pos"] = (hot, wav(7000, 6000), -6)
+    cold = wav(12000, 9000)
+    cold[777] = -32700.0
+    cold[778] = -32768.0
+    cases["clip_neg"] = (cold, wav(13000, 6000), -6)
+    return cases
+
+
+def noise_long_case():
+    rng = np.random.default_rng(99)
+    clean = rng.integers(-12000, 12001, size=480000).astype(np.float32)
+    noise = rng.integers(-3000, 3001, size=160007).astype(np.float32)
+    return clean, noise, 4
+
+
+NOISE_SEL = np.r_[0:256, 160000:160256, 479744:480000]
+
+
+def noise_mix():
+    import ast
+    import hashlib
+    path = "/root/reference/preprocess/audio_process.py"
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "add_noise"]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)   # the reference's function, unmodified
+    add_noise = ns["add_noise"]
+    out = {}
+    for name, (clean, noise, snr) in noise_cases().items():
+        small = (lambda a: a.astype(np.int16) if name != "unit_range" else a)   # int16-valued: store as int16
+        out[f"{name}_clean"], out[f"{name}_noise"], out[f"{name}_snr"] = small(clean), small(noise), np.float64(snr)
+        out[f"{name}_mixed"] = add_noise(clean.copy(), noise.copy(), snr)
+        assert out[f"{name}_mixed"].dtype == np.int16
+    clean, noise, snr = noise_long_case()
+    mixed = add_noise(clean, noise, snr)
+    out["long_sel"] = NOISE_SEL
+    out["long_mixed_sel"] = mixed[NOISE_SEL]
+    out["long_sha256"] = np.frombuffer(hashlib.sha256(mixed.tobytes()).digest(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "noise_golden.npz"), **out)
+    print("noise:", {k: (v.shape, int(np.abs(v).max()) if v.size else 0) for k, v in out.items() if k.endswith("_mixed")})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "noise":
+        noise_mix()
+        sys.exit(0)
     logmel()
     gray()
     video_feats()
+    noise_mix()

@@ -1,0 +1,70 @@
+"""SNR noise mixing: the oracle against the golden outputs of the reference's own add_noise
+(tests/golden/noise_golden.npz, made by tests/golden/make_golden.py::noise_mix), and the spelled-out
+pairwise sum against numpy's."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import noise as ON
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden as MG  # noqa: E402  (seeded input generators only)
+
+CASES = ["tile", "cut", "equal", "multiple", "tiny", "n130", "n8", "unit_range", "clip_pos", "clip_neg"]
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "noise_golden.npz"))
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 127, 128, 129, 136, 143, 144, 1000, 4097, 70001])
+def test_pairwise_sum_is_numpys(n):
+    x = (np.random.default_rng(n).standard_normal(n) * 3000).astype(np.float32)
+    sq = np.square(x)
+    assert ON.pairwise_sum(sq) == np.sum(sq)
+    if n:
+        assert ON.rms(x) == np.sqrt(np.mean(sq, axis=-1))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_output(golden, name):
+    clean = golden[f"{name}_clean"].astype(np.float32)
+    noise = golden[f"{name}_noise"].astype(np.float32)
+    out, info = ON.add_noise(clean, noise, float(golden[f"{name}_snr"]), return_info=True)
+    assert out.dtype == np.int16
+    np.testing.assert_array_equal(out, golden[f"{name}_mixed"])
+    if name == "clip_pos":
+        assert info["rate"] is not None and info["max"] >= abs(info["min"])
+    if name == "clip_neg":
+        assert info["rate"] is not None and info["max"] < abs(info["min"])
+    if name == "unit_range":
+        assert not out.any()          # the reference's int16 cast zeroes [-1, 1] waveforms
+
+
+def test_golden_inputs_are_reproducible(golden):
+    for name, (clean, noise, snr) in MG.noise_cases().items():
+        np.testing.assert_array_equal(clean, golden[f"{name}_clean"].astype(np.float32))
+        np.testing.assert_array_equal(noise, golden[f"{name}_noise"].astype(np.float32))
+
+
+def test_oracle_long_clip(golden):
+    clean, noise, snr = MG.noise_long_case()
+    out = ON.add_noise(clean, noise, snr)
+    np.testing.assert_array_equal(out[golden["long_sel"]], golden["long_mixed_sel"])
+    assert hashlib.sha256(out.tobytes()).digest() == golden["long_sha256"].tobytes()
+
+
+def test_batch_is_per_clip(golden):
+    names = ["tile", "tiny", "clip_neg"]
+    cl = [golden[f"{n}_clean"].astype(np.float32) for n in names]
+    nz = [golden[f"{n}_noise"].astype(np.float32) for n in names]
+    co = np.cumsum([0] + [len(c) for c in cl])
+    no = np.cumsum([0] + [len(c) for c in nz])
+    out = ON.add_noise_batch(np.concatenate(cl), co, np.concatenate(nz), no, [float(golden[f"{n}_snr"]) for n in names])
+    for i, n in enumerate(names):
+        np.testing.assert_array_equal(out[co[i]:co[i + 1]], golden[f"{n}_mixed"])
