@@ -305,6 +305,84 @@ def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order:
     return feats.cpu().numpy()
 
 
+# ----------------------------------------------------------------------------- SNR noise mixing
+def snr_ratio(snr) -> np.float32:
+    """``float32(10 ** (snr / 20))``: the divisor of preprocess/audio_process.py:135 as numpy 2
+    evaluates it next to a float32 scalar (the Python float takes the scalar's type)."""
+    return np.float32(10 ** (snr / 20))
+
+
+class NoisePlan:
+    """Device-side bookkeeping of one packed clean / noise layout (clip boundaries, per-clip SNR
+    divisors, workspace, output buffer), reusable for every batch with the same clip lengths."""
+
+    def __init__(self, clean_offsets, noise_offsets, snr, device, out_dtype=torch.int16):
+        if out_dtype not in (torch.int16, torch.float32):
+            raise ValueError("out_dtype must be torch.int16 or torch.float32")
+        co = np.asarray(clean_offsets, dtype=np.int64)
+        no = np.asarray(noise_offsets, dtype=np.int64)
+        B = len(co) - 1
+        if B < 0 or len(no) != B + 1 or (np.diff(co) < 0).any() or (np.diff(no) < 0).any():
+            raise ValueError("clean_offsets / noise_offsets must be non-decreasing and of equal length")
+        if ((np.diff(co) > 0) & (np.diff(no) == 0)).any():
+            raise ZeroDivisionError("a clean clip has an empty noise clip")     # the reference's ceil(Lc / 0), :128
+        ratios = np.broadcast_to(np.asarray([snr_ratio(v) for v in np.atleast_1d(snr)], dtype=np.float32), (B,))
+        self.co, self.no, self.B, self.out_dtype, self.device = co, no, B, out_dtype, device
+        self.max_len = int(np.diff(co).max()) if B else 0
+        self.d_co, self.d_no = torch.from_numpy(co).to(device), torch.from_numpy(no).to(device)
+        self.d_ratio = torch.from_numpy(np.ascontiguousarray(ratios)).to(device)
+        nbytes = int(_lib.load().avfe_add_noise_workspace_bytes(B, self.max_len))
+        if nbytes == 0:
+            raise ValueError("clip too long for avfe_add_noise")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.out = None
+
+
+def add_noise_batch(clean: torch.Tensor, clean_offsets=None, noise: torch.Tensor = None, noise_offsets=None,
+                    snr=0, out_dtype=torch.int16, plan: Optional[NoisePlan] = None) -> torch.Tensor:
+    """``add_noise`` (preprocess/audio_process.py:110-150) for a packed batch on the GPU, bit-exact
+    with the reference's float32 numpy arithmetic.  ``clean`` / ``noise``: contiguous 1-D float32 CUDA
+    tensors holding the clips back to back, ``*_offsets`` their [B+1] boundaries (host sequences),
+    ``snr`` a number or one per clip (dB) -- or a ``plan`` built once for that layout (steady-state
+    loops: no host-to-device traffic, output buffer reused).  A noise clip is repeated or cut to its
+    clean clip's length like the reference does.  Returns the mixed clips packed like ``clean``:
+    int16 (the reference's return type) or, with ``out_dtype=torch.float32``, the same integers as
+    float32 -- what ``logfbank_batch`` takes next (:224-227)."""
+    _lib.require_cuda()
+    for name, t in (("clean", clean), ("noise", noise)):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 1):
+            raise ValueError(f"{name} must be a contiguous 1-D float32 CUDA tensor")
+    dev = clean.device
+    if plan is None:
+        plan = NoisePlan(clean_offsets, noise_offsets, snr, dev, out_dtype)
+    co, no = plan.co, plan.no
+    if plan.B and (int(co[-1]) > clean.numel() or int(no[-1]) > noise.numel()):
+        raise ValueError("offsets run past the end of the tensors")
+    if plan.out is None or plan.out.numel() != clean.numel():
+        plan.out = torch.empty(clean.numel(), dtype=plan.out_dtype, device=dev)
+    out = plan.out
+    if plan.B == 0 or clean.numel() == 0:
+        return out
+    with torch.cuda.device(dev):
+        _lib.call("avfe_add_noise", _lib.ptr(clean), _lib.ptr(plan.d_co), _lib.ptr(noise), _lib.ptr(plan.d_no),
+                  _lib.ptr(plan.d_ratio), plan.B, plan.max_len, _lib.ptr(out) if plan.out_dtype == torch.int16 else None,
+                  _lib.ptr(out) if plan.out_dtype == torch.float32 else None, _lib.ptr(plan.ws), plan.ws.numel(),
+                  _lib.stream_ptr())
+    if int(co[0]) > 0 or int(co[-1]) < clean.numel():      # samples outside every clip pass through unmixed
+        out[:int(co[0])] = clean[:int(co[0])].to(plan.out_dtype)
+        out[int(co[-1]):] = clean[int(co[-1]):].to(plan.out_dtype)
+    return out
+
+
+def add_noise(clean_wav, noise_wav, snr) -> np.ndarray:
+    """``add_noise(clean_wav, noise_wav, snr)`` of preprocess/audio_process.py:110-150 for one clip
+    given as host arrays: int16 numpy like the reference."""
+    c = torch.from_numpy(np.ascontiguousarray(np.asarray(clean_wav).astype(np.float32).reshape(-1)))
+    z = torch.from_numpy(np.ascontiguousarray(np.asarray(noise_wav).astype(np.float32).reshape(-1)))
+    _lib.require_cuda()
+    return add_noise_batch(c.cuda(), [0, c.numel()], z.cuda(), [0, z.numel()], snr).cpu().numpy()
+
+
 # ----------------------------------------------------------------------------- SpecAugment masks
 # LibriSpeech policies of the SpecAugment paper (Park et al. 2019, table 1), the names the
 # reference passes as ``spec_augment_config`` (avsl/whisper_flamingo_ft_ami.py:165,217-220):

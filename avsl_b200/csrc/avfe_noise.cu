@@ -1,0 +1,247 @@
+// SNR noise mixing on the GPU, bit-exact with the reference's numpy code: add_noise(clean_wav,
+// noise_wav, snr), preprocess/audio_process.py:110-150 (called by process_audio_for_av_hubert,
+// :222-224, in front of the logfbank features).
+//
+//   clean_rms = sqrt(mean(clean^2));  noise'[i] = noise[i mod Ln], i < Lc;  noise_rms likewise
+//   mixed = clean + noise' * ((clean_rms / 10^(snr/20)) / noise_rms)
+//   if it leaves the int16 range: mixed *= 32767 / max  (or -32768 / min);   int16 by truncation
+//
+// Every step is float32 in the reference, so the only thing that decides the last bit of the gain
+// is the ORDER of the two sums of squares.  numpy adds pairwise: the array is halved (at n/2
+// rounded down to a multiple of 8) until a piece has at most 128 elements, a piece is summed in 8
+// interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail.
+// The kernels below rebuild exactly that tree:
+//
+//   noise_leaf_kernel     the tree is addressed like a heap (root 1, children 2k / 2k+1); a heap
+//                         index is turned into (offset, length) by walking down from the root.
+//                         Eight lanes own one <= 128-element piece, one numpy accumulator each,
+//                         and combine them with three xor-shuffles (the same parenthesisation).
+//   noise_combine_kernel  one CTA per clip adds the children level by level, bottom-up, then
+//                         takes the two rms values and the gain and arms the clip's max / min.
+//   noise_mix_kernel      mixed = clean + noise' * gain with a rounded product and a rounded sum
+//                         (no FMA), provisional int16 / float output, per-clip max / min through
+//                         order-preserving integer atomics.
+//   noise_rescale_kernel  exits at once unless the clip left the int16 range; otherwise recomputes
+//                         the mix, applies the reduction rate and rewrites the clip.
+//
+// Algorithmic bytes per sample: 4 (clean) + 4 (noise, at most Ln of them) + 2 (int16 out); the
+// design reads both waveforms twice (sum of squares, then the mix), which bounds it near half of
+// the HBM roofline; the tiled noise of a short noise clip is served by L2.
+#include "avfe_common.cuh"
+#include "avfe_noise_core.cuh"
+
+namespace avfe {
+
+constexpr int kMixChunk = 4096;     // samples per CTA of the mix / rescale kernels
+
+struct NoiseClip {        // per-clip scalars in the workspace
+  float gain;
+  uint32_t max_key, min_key;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ int16_t to_i16(float v) {
+  // C cast as x86 executes it (cvttss2si, low 16 bits); NaN / out of int32 range -> 0
+  if (!(fabsf(v) < 2147483648.f)) return 0;
+  return (int16_t)__float2int_rz(v);
+}
+
+struct NoiseArgs {
+  const float* clean;
+  const int64_t* clean_offsets;
+  const float* noise;
+  const int64_t* noise_offsets;
+  const float* snr_ratio;
+  float* heap;            // [B][2][heap_slots]
+  NoiseClip* clips;       // [B]
+  uint32_t heap_slots;    // 2^(depth+1)
+  int depth;
+};
+
+__global__ void __launch_bounds__(256)
+noise_leaf_kernel(NoiseArgs a) {
+  const int64_t b = blockIdx.z;
+  const int sig = blockIdx.y;
+  const int lane = threadIdx.x & 31, j = lane & 7;
+  const uint32_t k = blockIdx.x * 32u + (threadIdx.x >> 3);
+  const int64_t c0 = a.clean_offsets[b];
+  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
+  const int64_t z0 = a.noise_offsets[b];
+  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
+  uint32_t off = 0, len = 0;
+  const bool leaf = k >= 1 && k < a.heap_slots && n > 0 && (sig == 0 || period > 0) &&
+                    locate_node(k, n, off, len) == 1;
+  const float* src = sig ? a.noise + z0 : a.clean + c0;
+  const uint32_t wrap = sig ? period : 0xffffffffu;       // clean: never wraps (off + i < n < 2^32 - 1)
+  float r = 0.f;
+  const uint32_t body = len & ~7u;
+  if (leaf && len >= 8) {
+    uint32_t pos = (off + (uint32_t)j) % wrap;
+    float v = src[pos];
+    r = __fmul_rn(v, v);
+    for (uint32_t i = 8; i < body; i += 8) {
+      pos += 8;
+      if (pos >= wrap) pos %= wrap;
+      v = src[pos];
+      r = __fadd_rn(r, __fmul_rn(v, v));
+    }
+  }
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  if (leaf && j == 0) {
+    if (len < 8) r = 0.f;
+    for (uint32_t i = (len < 8 ? 0u : body); i < len; ++i) {
+      const float v = src[(off + i) % wrap];
+      r = __fadd_rn(r, __fmul_rn(v, v));
+    }
+    a.heap[(b * 2 + sig) * (int64_t)a.heap_slots + k] = r;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+noise_combine_kernel(NoiseArgs a) {
+  const int64_t b = blockIdx.x;
+  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - a.clean_offsets[b]);
+  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - a.noise_offsets[b]);
+  float* heap = a.heap + b * 2 * (int64_t)a.heap_slots;
+  if (n > 0) {
+    for (int d = a.depth - 1; d >= 0; --d) {
+      const uint32_t first = 1u << d;
+      for (uint32_t t = threadIdx.x; t < 2 * first; t += blockDim.x) {
+        const uint32_t k = first + (t >> 1);
+        float* h = heap + (t & 1u) * (int64_t)a.heap_slots;
+        uint32_t off, len;
+        if (locate_node(k, n, off, len) == 2) h[k] = __fadd_rn(h[2 * k], h[2 * k + 1]);
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    NoiseClip c;
+    c.gain = 0.f;
+    c.max_key = 0u;
+    c.min_key = 0xffffffffu;
+    c.pad = 0u;
+    if (n > 0 && period > 0) {
+      const float clean_ms = __double2float_rn(__ddiv_rn((double)heap[1], (double)n));
+      const float noise_ms = __double2float_rn(__ddiv_rn((double)heap[a.heap_slots + 1], (double)n));
+      const float clean_rms = __fsqrt_rn(clean_ms), noise_rms = __fsqrt_rn(noise_ms);
+      c.gain = __fdiv_rn(__fdiv_rn(clean_rms, a.snr_ratio[b]), noise_rms);
+    }
+    a.clips[b] = c;
+  }
+}
+
+struct MixArgs {
+  NoiseArgs n;
+  int16_t* out_i16;
+  float* out_f32;
+};
+
+template <bool RESCALE>
+__global__ void __launch_bounds__(256)
+noise_mix_kernel(MixArgs m) {
+  const NoiseArgs& a = m.n;
+  const int64_t b = blockIdx.y;
+  const int64_t c0 = a.clean_offsets[b];
+  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
+  const uint32_t begin = blockIdx.x * (uint32_t)kMixChunk;
+  if (begin >= n) return;
+  const int64_t z0 = a.noise_offsets[b];
+  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
+  const NoiseClip clip = a.clips[b];
+  float rate = 1.f;
+  if (RESCALE) {
+    const float hi = key_float(clip.max_key), lo = key_float(clip.min_key);
+    if (!(hi > 32767.f || lo < -32768.f)) return;
+    rate = (hi >= fabsf(lo)) ? __fdiv_rn(32767.f, hi) : __fdiv_rn(-32768.f, lo);
+  }
+  const uint32_t end = min(begin + (uint32_t)kMixChunk, n);
+  const float* clean = a.clean + c0;
+  const float* noise = a.noise + z0;
+  float vmax = -INFINITY, vmin = INFINITY;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += 256) {
+    float v = clean[i];
+    if (period > 0) v = __fadd_rn(v, __fmul_rn(noise[i < period ? i : i % period], clip.gain));
+    if (RESCALE) {
+      v = __fmul_rn(v, rate);
+    } else {
+      vmax = fmaxf(vmax, v);
+      vmin = fminf(vmin, v);
+    }
+    const int16_t q = to_i16(v);
+    if (m.out_i16) m.out_i16[c0 + i] = q;
+    if (m.out_f32) m.out_f32[c0 + i] = (float)q;
+  }
+  if (!RESCALE) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s));
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+    }
+    if ((threadIdx.x & 31) == 0 && vmax >= vmin) {
+      atomicMax(&a.clips[b].max_key, float_key(vmax));
+      atomicMin(&a.clips[b].min_key, float_key(vmin));
+    }
+  }
+}
+
+inline size_t noise_heap_bytes(int64_t B, int depth) {
+  return (size_t)B * 2 * ((size_t)2 << depth) * sizeof(float);
+}
+
+}  // namespace avfe
+
+extern "C" size_t avfe_add_noise_workspace_bytes(int64_t B, int64_t max_len) {
+  using namespace avfe;
+  if (B <= 0 || max_len <= 0) return 256;
+  const int depth = tree_depth(max_len);
+  if (depth > kMaxDepth) return 0;
+  return 256 + noise_heap_bytes(B, depth) + (size_t)B * sizeof(NoiseClip);
+}
+
+extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, const float* noise,
+                              const int64_t* noise_offsets, const float* snr_ratio, int64_t B,
+                              int64_t max_len, int16_t* out_i16, float* out_f32, void* workspace,
+                              size_t workspace_bytes, avfe_stream_t stream) {
+  using namespace avfe;
+  if (B < 0 || max_len < 0) return AVFE_ERR_INVALID_ARG;
+  if (B == 0 || max_len == 0) return AVFE_OK;
+  if (!clean || !clean_offsets || !noise || !noise_offsets || !snr_ratio || !workspace) return AVFE_ERR_INVALID_ARG;
+  if (!out_i16 && !out_f32) return AVFE_ERR_INVALID_ARG;
+  if (B > 65535 || max_len >= ((int64_t)1 << 31)) return AVFE_ERR_UNSUPPORTED;
+  const int depth = tree_depth(max_len);
+  if (depth > kMaxDepth) return AVFE_ERR_UNSUPPORTED;
+  uintptr_t p = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  const size_t need = (p - reinterpret_cast<uintptr_t>(workspace)) + noise_heap_bytes(B, depth) + (size_t)B * sizeof(NoiseClip);
+  if (workspace_bytes < need) return AVFE_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MixArgs m;
+  m.n.clean = clean;
+  m.n.clean_offsets = clean_offsets;
+  m.n.noise = noise;
+  m.n.noise_offsets = noise_offsets;
+  m.n.snr_ratio = snr_ratio;
+  m.n.heap = reinterpret_cast<float*>(p);
+  m.n.clips = reinterpret_cast<NoiseClip*>(p + noise_heap_bytes(B, depth));
+  m.n.heap_slots = 2u << depth;
+  m.n.depth = depth;
+  m.out_i16 = out_i16;
+  m.out_f32 = out_f32;
+  noise_leaf_kernel<<<dim3((m.n.heap_slots + 31) / 32, 2, (unsigned)B), 256, 0, s>>>(m.n);
+  noise_combine_kernel<<<(unsigned)B, 512, 0, s>>>(m.n);
+  const dim3 grid((unsigned)((max_len + kMixChunk - 1) / kMixChunk), (unsigned)B);
+  noise_mix_kernel<false><<<grid, 256, 0, s>>>(m);
+  noise_mix_kernel<true><<<grid, 256, 0, s>>>(m);
+  count_launch(4);
+  return check_launch();
+}

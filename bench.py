@@ -372,6 +372,20 @@ def main():
         side["logfbank_dense"] = {"kernel": "logfbank_kernel, 64 x 30 s dense noise: logfbank(26) + stack 4 + normalise -> [rows, 104]",
                                   "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
                                   "audio_s_per_s": 64 * 30.0 / (ms * 1e-3)}
+        # SNR noise mixing (SURVEY 8(f) rank 4 prologue, add_noise): 64 x 30 s int16-scale clips, 10 s noise each
+        wav = flat * 8000.0
+        nz = synth.audio_batch(64, AUDIO_LEN // 3, SEED + 1, device=dev).reshape(-1) * 3000.0
+        nz_plan = A.NoisePlan(offs, np.arange(65, dtype=np.int64) * (AUDIO_LEN // 3), 10, dev)
+
+        def run_mix():
+            flush.zero_()
+            A.add_noise_batch(wav, noise=nz, plan=nz_plan)
+        ms = time_op(run_mix, 10) - ms_flush
+        nbytes = 64 * (4 * AUDIO_LEN + 4 * (AUDIO_LEN // 3) + 2 * AUDIO_LEN)
+        side["add_noise"] = {"kernel": "noise_leaf+combine+mix+rescale, 64 x 30 s clean + 10 s noise -> int16 (bit-exact numpy pairwise sums)",
+                             "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                             "audio_s_per_s": 64 * 30.0 / (ms * 1e-3)}
+        del wav, nz, nz_plan
         del dense, flush, flat, lf_rows, lf_plan
         fa, fv, fmask = synth.fusion_inputs(64, 1024, 750, seed=SEED, device=dev)
         present = int(fmask.sum())

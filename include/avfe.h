@@ -139,6 +139,30 @@ AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const
                                int stack, int normalize, float* out, void* workspace,
                                size_t workspace_bytes, avfe_stream_t stream);
 
+/* SNR noise mixing — add_noise(clean_wav, noise_wav, snr), preprocess/audio_process.py:110-150
+ * (the optional augmentation of process_audio_for_av_hubert, :222-224, in front of the logfbank
+ * features), for a packed batch and BIT-EXACT with the reference's float32 numpy arithmetic
+ * (its pairwise sums of squares are re-created in the same order):
+ *   noise'[i] = noise_b[i mod Ln], i < Lc;  gain = (rms(clean_b) / snr_ratio[b]) / rms(noise')
+ *   mixed = clean_b + noise' * gain;  if max > 32767 or min < -32768: mixed *= 32767 / max when
+ *   max >= |min|, else -32768 / min;  int16 by truncation toward zero.
+ *   clean / noise   packed float32 waveforms (the reference's .astype(np.float32) is the
+ *                   caller's), clip b = clean[clean_offsets[b] : clean_offsets[b+1]], noise
+ *                   likewise; offsets are [B+1] int64 on the device
+ *   snr_ratio       [B] float32 = (float)10^(snr_b / 20), evaluated by the caller in double like
+ *                   the reference's Python expression
+ *   max_len         the longest clean clip (sizes the launch and the workspace), < 2^31
+ *   out_i16/out_f32 packed like `clean`; either may be NULL; out_f32 holds the same integers as
+ *                   float32 (what logfbank takes)
+ * A clip whose noise is empty is cast unmixed (the reference raises ZeroDivisionError; the Python
+ * shim raises too).  NaN / inf samples and a silent noise clip are outside the contract, as in
+ * the reference. */
+AVFE_API size_t avfe_add_noise_workspace_bytes(int64_t B, int64_t max_len);
+AVFE_API int avfe_add_noise(const float* clean, const int64_t* clean_offsets, const float* noise,
+                            const int64_t* noise_offsets, const float* snr_ratio, int64_t B,
+                            int64_t max_len, int16_t* out_i16, float* out_f32, void* workspace,
+                            size_t workspace_bytes, avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ video (V1..V8) */
 
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) — preprocess/video_process.py:201-214:

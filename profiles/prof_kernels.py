@@ -57,6 +57,16 @@ def run_logfbank(iters, batch=64):
     torch.cuda.synchronize()
 
 
+def run_noise(iters, batch=64):
+    wav = synth.audio_batch(batch, 480000, 3407, device="cuda").reshape(-1) * 8000.0
+    nz = synth.audio_batch(batch, 160000, 3408, device="cuda").reshape(-1) * 3000.0
+    plan = A.NoisePlan(np.arange(batch + 1, dtype=np.int64) * 480000, np.arange(batch + 1, dtype=np.int64) * 160000,
+                       10, wav.device)
+    for _ in range(iters):
+        A.add_noise_batch(wav, noise=nz, plan=plan)
+    torch.cuda.synchronize()
+
+
 def run_fuse_ln(iters):
     fa, fv, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
     w, b = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
@@ -72,7 +82,7 @@ def run_fuse_ln(iters):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "logfbank", "all"])
+    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "logfbank", "noise", "all"])
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     if a.which in ("logmel", "all"):
@@ -83,6 +93,8 @@ if __name__ == "__main__":
         run_fuse(a.iters)
     if a.which in ("logfbank", "all"):
         run_logfbank(a.iters)
+    if a.which in ("noise", "all"):
+        run_noise(a.iters)
     if a.which in ("fuse_ln", "all"):
         run_fuse_ln(a.iters)
     print("done", a.which)

@@ -13,6 +13,7 @@
 #include "avfe_lip_math.cuh"
 #include "avfe_logfbank_core.cuh"
 #include "avfe_logmel_core.cuh"
+#include "avfe_noise_core.cuh"
 
 using namespace avfe;
 
@@ -134,6 +135,43 @@ void hc_warp_window(const uint8_t* gray, int H, int W, const double* inv6, int r
 void hc_gray(const uint8_t* bgr, int64_t n, uint8_t* gray) {
   for (int64_t i = 0; i < n; ++i)
     gray[i] = (uint8_t)gray_from_bgr(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+}
+
+// The sum of squares of x[(i) % period], i < n, evaluated the way noise_leaf_kernel +
+// noise_combine_kernel do it: heap-addressed tree, 8 "lanes" per leaf joined by xor steps 1, 2, 4,
+// a sequential tail, children added bottom-up.  Returns the root; *leaves counts the leaf nodes.
+float hc_noise_tree_sumsq(const float* x, uint32_t n, uint32_t period, int64_t max_len, int* leaves) {
+  const int depth = tree_depth(max_len);
+  const uint32_t slots = 2u << depth;
+  std::vector<float> heap(slots, NAN);
+  *leaves = 0;
+  for (uint32_t k = 1; k < slots; ++k) {
+    uint32_t off, len;
+    if (locate_node(k, n, off, len) != 1) continue;
+    ++*leaves;
+    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t body = len & ~7u;
+    auto sq = [&](uint32_t i) { const float v = x[(off + i) % period]; return v * v; };
+    if (len >= 8)
+      for (int j = 0; j < 8; ++j) {
+        r[j] = sq(j);
+        for (uint32_t i = 8; i < body; i += 8) r[j] = r[j] + sq(i + j);
+      }
+    for (int step = 1; step < 8; step <<= 1) {
+      float t[8];
+      for (int j = 0; j < 8; ++j) t[j] = r[j] + r[j ^ step];
+      memcpy(r, t, sizeof(r));
+    }
+    float res = len < 8 ? 0.f : r[0];
+    for (uint32_t i = (len < 8 ? 0u : body); i < len; ++i) res = res + sq(i);
+    heap[k] = res;
+  }
+  for (int d = depth - 1; d >= 0; --d)
+    for (uint32_t k = 1u << d; k < (2u << d); ++k) {
+      uint32_t off, len;
+      if (locate_node(k, n, off, len) == 2) heap[k] = heap[2 * k] + heap[2 * k + 1];
+    }
+  return heap[1];
 }
 
 }  // extern "C"

@@ -77,6 +77,8 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.spec_augment(torch.zeros(1, 80, 3000))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.add_noise(np.zeros(100, np.float32), np.ones(10, np.float32), 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.fuse_transpose_layernorm(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.lip_roi_collate(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), torch.zeros(2, dtype=torch.int64),
@@ -99,3 +101,10 @@ def test_argument_validation_of_the_widened_entry_points(libavfe_path):
     assert lib.avfe_logfbank_workspace_bytes() >= 26 * 12
     assert lib.avfe_lip_roi_collate(None, 3, 1, 8, 8, None, 1, None, None, None, None, 300, 96, 88, 12, 0.421, 0.165,
                                     None, 0, None, None, None, None, 0, None) == -1           # T_pad < 1
+    assert lib.avfe_add_noise(None, None, None, None, None, 0, 100, None, None, None, 0, None) == 0     # empty batch
+    assert lib.avfe_add_noise(None, None, None, None, None, 2, 100, None, None, None, 0, None) == -1
+    assert lib.avfe_add_noise(None, None, None, None, None, -1, 100, None, None, None, 0, None) == -1
+    # workspace: two heaps of 2^(depth+1) floats per clip; 30 s clips need depth 13
+    assert lib.avfe_add_noise_workspace_bytes(64, 480000) == 256 + 64 * 2 * (2 << 13) * 4 + 64 * 16
+    assert lib.avfe_add_noise_workspace_bytes(1, 128) == 256 + 2 * 2 * 4 + 16
+    assert lib.avfe_add_noise_workspace_bytes(1, 1 << 40) == 0                                           # unsupported length

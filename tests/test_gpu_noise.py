@@ -1,0 +1,111 @@
+"""GPU parity of the SNR noise mixing (avfe_add_noise through avsl_b200.audio) -- int16 results,
+so the bar is bit-exact: against the golden outputs of the reference's own add_noise
+(tests/golden/noise_golden.npz) and against the oracle on seeded ragged batches."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import noise as ON
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden as MG  # noqa: E402  (seeded input generators only)
+
+pytestmark = pytest.mark.gpu
+CASES = ["tile", "cut", "equal", "multiple", "tiny", "n130", "n8", "unit_range", "clip_pos", "clip_neg"]
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "noise_golden.npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_single_clip_equals_reference_output(golden, name):
+    import avsl_b200 as A
+    out = A.add_noise(golden[f"{name}_clean"], golden[f"{name}_noise"], float(golden[f"{name}_snr"]))
+    assert out.dtype == np.int16
+    np.testing.assert_array_equal(out, golden[f"{name}_mixed"])
+
+
+def test_long_clip_equals_reference_output(golden):
+    import avsl_b200 as A
+    clean, noise, snr = MG.noise_long_case()
+    out = A.add_noise(clean, noise, snr)
+    np.testing.assert_array_equal(out[golden["long_sel"]], golden["long_mixed_sel"])
+    assert hashlib.sha256(out.tobytes()).digest() == golden["long_sha256"].tobytes()
+
+
+def test_packed_batch_of_all_golden_cases(golden):
+    import torch
+    import avsl_b200 as A
+    cl = [golden[f"{n}_clean"].astype(np.float32) for n in CASES]
+    nz = [golden[f"{n}_noise"].astype(np.float32) for n in CASES]
+    co = np.cumsum([0] + [len(c) for c in cl])
+    no = np.cumsum([0] + [len(c) for c in nz])
+    snr = [float(golden[f"{n}_snr"]) for n in CASES]
+    c, z = torch.from_numpy(np.concatenate(cl)).cuda(), torch.from_numpy(np.concatenate(nz)).cuda()
+    out = A.add_noise_batch(c, co, z, no, snr).cpu().numpy()
+    outf = A.add_noise_batch(c, co, z, no, snr, out_dtype=torch.float32).cpu().numpy()
+    for i, n in enumerate(CASES):
+        np.testing.assert_array_equal(out[co[i]:co[i + 1]], golden[f"{n}_mixed"], err_msg=n)
+    np.testing.assert_array_equal(outf, out.astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ragged_batch_equals_oracle(seed):
+    import torch
+    import avsl_b200 as A
+    rng = np.random.default_rng(seed)
+    lens = [1, 7, 8, 127, 128, 129, 143, 144, 257, 0, 5000, 16001, 48000, 99999, 31, 272]
+    nlens = [3, 1, 100, 128, 50, 129, 1000, 7, 256, 4, 5000, 900, 160000, 33333, 31, 17]
+    amps = rng.choice([300.0, 3000.0, 15000.0, 40000.0], size=len(lens))     # 40000: beyond int16 -> rescale
+    cl = [(rng.standard_normal(n) * a).astype(np.float32) for n, a in zip(lens, amps)]
+    nz = [(rng.standard_normal(n) * 2000).astype(np.float32) for n in nlens]
+    snr = list(rng.choice([-10, -5, 0, 2.5, 10, 20], size=len(lens)))
+    co = np.cumsum([0] + lens)
+    no = np.cumsum([0] + nlens)
+    want = ON.add_noise_batch(np.concatenate(cl), co, np.concatenate(nz), no, snr)
+    got = A.add_noise_batch(torch.from_numpy(np.concatenate(cl)).cuda(), co,
+                            torch.from_numpy(np.concatenate(nz)).cuda(), no, snr).cpu().numpy()
+    for i in range(len(lens)):
+        np.testing.assert_array_equal(got[co[i]:co[i + 1]], want[co[i]:co[i + 1]], err_msg=f"clip {i} len {lens[i]}")
+    assert (np.abs(want.astype(np.int32)) >= 32767).any()       # a rescaled clip is among them
+
+
+def test_edge_cases():
+    import torch
+    import avsl_b200 as A
+    e = torch.empty(0, dtype=torch.float32, device="cuda")
+    assert A.add_noise_batch(e, [0], e, [0], 0).numel() == 0
+    c = torch.ones(10, dtype=torch.float32, device="cuda") * 100
+    with pytest.raises(ZeroDivisionError):
+        A.add_noise_batch(c, [0, 10], e, [0, 0], 0)
+    with pytest.raises(ValueError):
+        A.add_noise_batch(c.double(), [0, 10], c, [0, 10], 0)
+    # samples outside the clips pass through unmixed
+    z = torch.full((4,), 50.0, device="cuda")
+    out = A.add_noise_batch(c, [2, 8], z, [0, 4], 0).cpu().numpy()
+    np.testing.assert_array_equal(out[:2], [100, 100])
+    np.testing.assert_array_equal(out[8:], [100, 100])
+    np.testing.assert_array_equal(out[2:8], ON.add_noise(np.full(6, 100.0), np.full(4, 50.0), 0))
+
+
+def test_noise_then_logfbank_chain():
+    """process_audio_for_av_hubert, preprocess/audio_process.py:222-230: the mixed int16 signal is what
+    logfbank sees; the float32 output of the mix feeds logfbank_batch without a host round trip."""
+    import torch
+    import avsl_b200 as A
+    from oracle import logfbank as OF
+    clean, noise, snr = MG.noise_long_case()
+    clean, noise = clean[:48000], noise[:20000]
+    mixed = ON.add_noise(clean, noise, snr)
+    want = OF.extract_logfbank_features(mixed.astype(np.float32), stack_order=4)
+    m = A.add_noise_batch(torch.from_numpy(clean).cuda(), [0, len(clean)], torch.from_numpy(noise).cuda(),
+                          [0, len(noise)], snr, out_dtype=torch.float32)
+    np.testing.assert_array_equal(m.cpu().numpy(), mixed.astype(np.float32))
+    feats, _ = A.logfbank_batch(m, [0, len(clean)], stack_order=4, normalize=False)
+    np.testing.assert_allclose(feats.cpu().numpy(), want, atol=2e-4, rtol=0)

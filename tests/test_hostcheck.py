@@ -134,3 +134,24 @@ def test_warp_window_bit_exact_vs_oracle(hostcheck):
             inv6 = np.ascontiguousarray(M[:2].reshape(-1))
             hostcheck.hc_warp_window(vp(np.ascontiguousarray(gray[f])), 224, 224, vp(inv6), r0, c0, 96, 96, vp(out))
             np.testing.assert_array_equal(out, ref)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 136, 143, 144, 255, 257, 272, 1000, 4097, 16000, 70001, 480000])
+def test_noise_tree_sum_is_numpys_pairwise_sum(hostcheck, n):
+    """The heap-addressed tree of avfe_noise.cu adds in numpy's order: same float32 bits as np.sum of
+    the squares, for the plain signal and for a tiled (i mod period) one, at a launch depth sized
+    for a longer clip as well."""
+    hostcheck.hc_noise_tree_sumsq.restype = ctypes.c_float
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 3000).astype(np.float32)
+    leaves = ctypes.c_int(0)
+    for max_len in (n, 2 * n + 77):
+        got = hostcheck.hc_noise_tree_sumsq(vp(x), ctypes.c_uint32(n), ctypes.c_uint32(n), ctypes.c_int64(max_len),
+                                            ctypes.byref(leaves))
+        assert np.float32(got) == np.sum(np.square(x)), (n, max_len)
+    period = max(1, n // 3 + 1)
+    tiled = x[np.arange(n) % period]
+    got = hostcheck.hc_noise_tree_sumsq(vp(x), ctypes.c_uint32(n), ctypes.c_uint32(period), ctypes.c_int64(n),
+                                        ctypes.byref(leaves))
+    assert np.float32(got) == np.sum(np.square(tiled))
+    assert leaves.value >= max(1, n // 128)
