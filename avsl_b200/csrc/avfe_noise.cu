@@ -12,17 +12,20 @@
 // interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail.
 // The kernels below rebuild exactly that tree:
 //
-//   noise_leaf_kernel     the tree is addressed like a heap (root 1, children 2k / 2k+1); a heap
-//                         index is turned into (offset, length) by walking down from the root.
-//                         Eight lanes own one <= 128-element piece, one numpy accumulator each,
-//                         and combine them with three xor-shuffles (the same parenthesisation).
-//   noise_combine_kernel  one CTA per clip adds the children level by level, bottom-up, then
-//                         takes the two rms values and the gain and arms the clip's max / min.
+//   noise_leaf_kernel     the tree is addressed like a heap (root 1, children 2k / 2k+1).  A piece
+//                         has 64..128 elements, so the 8-lane group standing on the first
+//                         multiple of 64 inside it owns it (found by walking down from the root):
+//                         one numpy accumulator per lane, joined by three xor-shuffles (the
+//                         same parenthesisation), then the sequential tail.
+//   noise_combine_kernel  one CTA per clip copies the clip's two heaps to shared memory, adds the
+//                         children level by level, bottom-up, then takes the two rms values
+//                         and the gain and arms the clip's max / min.
 //   noise_mix_kernel      mixed = clean + noise' * gain with a rounded product and a rounded sum
 //                         (no FMA), provisional int16 / float output, per-clip max / min through
 //                         order-preserving integer atomics.
-//   noise_rescale_kernel  exits at once unless the clip left the int16 range; otherwise recomputes
-//                         the mix, applies the reduction rate and rewrites the clip.
+//   noise_mix_kernel<1>   the rescale pass: exits at once unless the clip left the int16 range;
+//                         otherwise recomputes the mix, applies the reduction rate and rewrites
+//                         the clip.
 //
 // Algorithmic bytes per sample: 4 (clean) + 4 (noise, at most Ln of them) + 2 (int16 out); the
 // design reads both waveforms twice (sum of squares, then the mix), which bounds it near half of
@@ -33,6 +36,7 @@
 namespace avfe {
 
 constexpr int kMixChunk = 4096;     // samples per CTA of the mix / rescale kernels
+constexpr size_t kCombineSmemMax = 160 * 1024;   // both heaps of a clip up to ~57 s (depth 13) fit in shared memory
 
 struct NoiseClip {        // per-clip scalars in the workspace
   float gain;
@@ -70,27 +74,32 @@ __global__ void __launch_bounds__(256)
 noise_leaf_kernel(NoiseArgs a) {
   const int64_t b = blockIdx.z;
   const int sig = blockIdx.y;
-  const int lane = threadIdx.x & 31, j = lane & 7;
-  const uint32_t k = blockIdx.x * 32u + (threadIdx.x >> 3);
+  const int j = threadIdx.x & 7;
+  // a piece of the tree has 64..128 elements (or is the whole clip), so it holds one or two
+  // multiples of 64: the 8-lane group standing on the first of them owns the piece
+  const uint32_t pos = (blockIdx.x * 32u + (threadIdx.x >> 3)) * 64u;
   const int64_t c0 = a.clean_offsets[b];
   const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
   const int64_t z0 = a.noise_offsets[b];
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
-  uint32_t off = 0, len = 0;
-  const bool leaf = k >= 1 && k < a.heap_slots && n > 0 && (sig == 0 || period > 0) &&
-                    locate_node(k, n, off, len) == 1;
+  uint32_t k = 1, off = 0, len = 0;
+  bool leaf = pos < n && (sig == 0 || period > 0);
+  if (leaf) {
+    k = locate_piece(pos, n, off, len);
+    leaf = pos - off < 64u;
+  }
   const float* src = sig ? a.noise + z0 : a.clean + c0;
-  const uint32_t wrap = sig ? period : 0xffffffffu;       // clean: never wraps (off + i < n < 2^32 - 1)
+  const uint32_t wrap = sig ? period : 0xffffffffu;       // clean: never wraps (off + i < n < 2^31)
   float r = 0.f;
   const uint32_t body = len & ~7u;
   if (leaf && len >= 8) {
-    uint32_t pos = (off + (uint32_t)j) % wrap;
-    float v = src[pos];
+    uint32_t p = (off + (uint32_t)j) % wrap;
+    float v = src[p];
     r = __fmul_rn(v, v);
     for (uint32_t i = 8; i < body; i += 8) {
-      pos += 8;
-      if (pos >= wrap) pos %= wrap;
-      v = src[pos];
+      p += 8;
+      if (p >= wrap) p %= wrap;
+      v = src[p];
       r = __fadd_rn(r, __fmul_rn(v, v));
     }
   }
@@ -107,13 +116,24 @@ noise_leaf_kernel(NoiseArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(512)
+// SMEM: both heaps of the clip are copied to shared memory first (2 x heap_slots floats), so the
+// level-by-level additions wait on shared memory instead of L2.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
 noise_combine_kernel(NoiseArgs a) {
+  extern __shared__ float heap_s[];
   const int64_t b = blockIdx.x;
   const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - a.clean_offsets[b]);
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - a.noise_offsets[b]);
-  float* heap = a.heap + b * 2 * (int64_t)a.heap_slots;
-  if (n > 0) {
+  float* heap_g = a.heap + b * 2 * (int64_t)a.heap_slots;
+  float* heap = SMEM ? heap_s : heap_g;
+  if (n > (uint32_t)kLeafMax) {
+    if (SMEM) {
+      // pieces live on the two deepest levels that exist for this clip; copying every slot from
+      // the first possible one keeps the loop free of tree walks
+      for (uint32_t t = threadIdx.x; t < 2 * a.heap_slots; t += blockDim.x) heap_s[t] = heap_g[t];
+      __syncthreads();
+    }
     for (int d = a.depth - 1; d >= 0; --d) {
       const uint32_t first = 1u << d;
       for (uint32_t t = threadIdx.x; t < 2 * first; t += blockDim.x) {
@@ -124,6 +144,8 @@ noise_combine_kernel(NoiseArgs a) {
       }
       __syncthreads();
     }
+  } else {
+    heap = heap_g;          // the clip is one piece: the root was written by the leaf kernel
   }
   if (threadIdx.x == 0) {
     NoiseClip c;
@@ -237,8 +259,19 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   m.n.depth = depth;
   m.out_i16 = out_i16;
   m.out_f32 = out_f32;
-  noise_leaf_kernel<<<dim3((m.n.heap_slots + 31) / 32, 2, (unsigned)B), 256, 0, s>>>(m.n);
-  noise_combine_kernel<<<(unsigned)B, 512, 0, s>>>(m.n);
+  noise_leaf_kernel<<<dim3((unsigned)((max_len + 64 * 32 - 1) / (64 * 32)), 2, (unsigned)B), 256, 0, s>>>(m.n);
+  const size_t heap_smem = 2 * (size_t)m.n.heap_slots * sizeof(float);
+  if (heap_smem <= kCombineSmemMax) {
+    if (heap_smem > 48 * 1024 &&
+        cudaFuncSetAttribute(noise_combine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kCombineSmemMax) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+    noise_combine_kernel<true><<<(unsigned)B, 1024, heap_smem, s>>>(m.n);
+  } else {
+    noise_combine_kernel<false><<<(unsigned)B, 1024, 0, s>>>(m.n);
+  }
   const dim3 grid((unsigned)((max_len + kMixChunk - 1) / kMixChunk), (unsigned)B);
   noise_mix_kernel<false><<<grid, 256, 0, s>>>(m);
   noise_mix_kernel<true><<<grid, 256, 0, s>>>(m);

@@ -32,6 +32,25 @@ __host__ __device__ inline int locate_node(uint32_t k, uint32_t n, uint32_t& off
   return len <= (uint32_t)kLeafMax ? 1 : 2;
 }
 
+// The leaf piece that holds element `pos` (< n): heap index, offset and length.
+__host__ __device__ inline uint32_t locate_piece(uint32_t pos, uint32_t n, uint32_t& off, uint32_t& len) {
+  uint32_t k = 1;
+  off = 0;
+  len = n;
+  while (len > (uint32_t)kLeafMax) {
+    const uint32_t half = (len >> 1) & ~7u;
+    if (pos < off + half) {
+      len = half;
+      k = 2 * k;
+    } else {
+      off += half;
+      len -= half;
+      k = 2 * k + 1;
+    }
+  }
+  return k;
+}
+
 // A depth at which every node of every clip up to max_len samples is a leaf: the larger child of
 // an m-element node has at most m/2 + 8 elements.
 inline int tree_depth(int64_t max_len) {

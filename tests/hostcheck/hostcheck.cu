@@ -145,9 +145,11 @@ float hc_noise_tree_sumsq(const float* x, uint32_t n, uint32_t period, int64_t m
   const uint32_t slots = 2u << depth;
   std::vector<float> heap(slots, NAN);
   *leaves = 0;
-  for (uint32_t k = 1; k < slots; ++k) {
+  for (uint32_t pos = 0; pos < n; pos += 64) {          // one 8-lane group per multiple of 64
     uint32_t off, len;
-    if (locate_node(k, n, off, len) != 1) continue;
+    const uint32_t k = locate_piece(pos, n, off, len);
+    if (pos - off >= 64u) continue;                       // the piece belongs to the group before
+    if (k >= slots || locate_node(k, n, off, len) != 1 || !isnan(heap[k])) return NAN;
     ++*leaves;
     float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t body = len & ~7u;
