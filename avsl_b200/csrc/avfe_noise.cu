@@ -93,15 +93,20 @@ noise_leaf_kernel(NoiseArgs a) {
   float r = 0.f;
   const uint32_t body = len & ~7u;
   if (leaf && len >= 8) {
+    // a lane's (at most 16) elements are fetched before the first addition: the chain of
+    // additions is short, the latency of dependent loads was the cost
+    float v[kLeafMax / 8];
     uint32_t p = (off + (uint32_t)j) % wrap;
-    float v = src[p];
-    r = __fmul_rn(v, v);
-    for (uint32_t i = 8; i < body; i += 8) {
+#pragma unroll
+    for (int t = 0; t < kLeafMax / 8; ++t) {
+      v[t] = (uint32_t)(8 * t) < body ? src[p] : 0.f;
       p += 8;
       if (p >= wrap) p %= wrap;
-      v = src[p];
-      r = __fadd_rn(r, __fmul_rn(v, v));
     }
+    r = __fmul_rn(v[0], v[0]);
+#pragma unroll
+    for (int t = 1; t < kLeafMax / 8; ++t)          // r >= +0, so adding the +0 of an absent element is exact
+      r = __fadd_rn(r, __fmul_rn(v[t], v[t]));
   }
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
@@ -131,7 +136,18 @@ noise_combine_kernel(NoiseArgs a) {
     if (SMEM) {
       // pieces live on the two deepest levels that exist for this clip; copying every slot from
       // the first possible one keeps the loop free of tree walks
-      for (uint32_t t = threadIdx.x; t < 2 * a.heap_slots; t += blockDim.x) heap_s[t] = heap_g[t];
+      const float4* g4 = reinterpret_cast<const float4*>(heap_g);      // 256-byte aligned, slots % 4 == 0
+      float4* s4 = reinterpret_cast<float4*>(heap_s);
+      const uint32_t quads = a.heap_slots / 2;
+      for (uint32_t t = threadIdx.x; t < quads; t += 8 * blockDim.x) {
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t + u * blockDim.x < quads) q[u] = g4[t + u * blockDim.x];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t + u * blockDim.x < quads) s4[t + u * blockDim.x] = q[u];
+      }
       __syncthreads();
     }
     for (int d = a.depth - 1; d >= 0; --d) {
@@ -176,8 +192,7 @@ noise_mix_kernel(MixArgs m) {
   const int64_t b = blockIdx.y;
   const int64_t c0 = a.clean_offsets[b];
   const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
-  const uint32_t begin = blockIdx.x * (uint32_t)kMixChunk;
-  if (begin >= n) return;
+  if (blockIdx.x * (uint32_t)kMixChunk >= n) return;
   const int64_t z0 = a.noise_offsets[b];
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
   const NoiseClip clip = a.clips[b];
@@ -187,22 +202,37 @@ noise_mix_kernel(MixArgs m) {
     if (!(hi > 32767.f || lo < -32768.f)) return;
     rate = (hi >= fabsf(lo)) ? __fdiv_rn(32767.f, hi) : __fdiv_rn(-32768.f, lo);
   }
-  const uint32_t end = min(begin + (uint32_t)kMixChunk, n);
   const float* clean = a.clean + c0;
   const float* noise = a.noise + z0;
   float vmax = -INFINITY, vmin = INFINITY;
-  for (uint32_t i = begin + threadIdx.x; i < end; i += 256) {
-    float v = clean[i];
-    if (period > 0) v = __fadd_rn(v, __fmul_rn(noise[i < period ? i : i % period], clip.gain));
-    if (RESCALE) {
-      v = __fmul_rn(v, rate);
-    } else {
-      vmax = fmaxf(vmax, v);
-      vmin = fminf(vmin, v);
+  constexpr int kBatch = 8;                 // loads in flight per thread
+  for (uint32_t begin = blockIdx.x * (uint32_t)kMixChunk; begin < n; begin += gridDim.x * (uint32_t)kMixChunk) {
+    const uint32_t end = min(begin + (uint32_t)kMixChunk, n);
+    for (uint32_t i0 = begin + threadIdx.x; i0 < end; i0 += kBatch * 256) {
+      float x[kBatch], z[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const uint32_t i = i0 + u * 256;
+        x[u] = i < end ? clean[i] : 0.f;
+        z[u] = (i < end && period > 0) ? noise[i < period ? i : i % period] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const uint32_t i = i0 + u * 256;
+        if (i >= end) break;
+        float v = x[u];
+        if (period > 0) v = __fadd_rn(v, __fmul_rn(z[u], clip.gain));
+        if (RESCALE) {
+          v = __fmul_rn(v, rate);
+        } else {
+          vmax = fmaxf(vmax, v);
+          vmin = fminf(vmin, v);
+        }
+        const int16_t q = to_i16(v);
+        if (m.out_i16) m.out_i16[c0 + i] = q;
+        if (m.out_f32) m.out_f32[c0 + i] = (float)q;
+      }
     }
-    const int16_t q = to_i16(v);
-    if (m.out_i16) m.out_i16[c0 + i] = q;
-    if (m.out_f32) m.out_f32[c0 + i] = (float)q;
   }
   if (!RESCALE) {
 #pragma unroll
@@ -272,9 +302,10 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   } else {
     noise_combine_kernel<false><<<(unsigned)B, 1024, 0, s>>>(m.n);
   }
-  const dim3 grid((unsigned)((max_len + kMixChunk - 1) / kMixChunk), (unsigned)B);
-  noise_mix_kernel<false><<<grid, 256, 0, s>>>(m);
-  noise_mix_kernel<true><<<grid, 256, 0, s>>>(m);
+  const unsigned chunks = (unsigned)((max_len + kMixChunk - 1) / kMixChunk);
+  noise_mix_kernel<false><<<dim3(chunks, (unsigned)B), 256, 0, s>>>(m);
+  // the rescale pass is a no-op for a clip that stayed inside int16: a few CTAs per clip, striding
+  noise_mix_kernel<true><<<dim3(chunks < 16u ? chunks : 16u, (unsigned)B), 256, 0, s>>>(m);
   count_launch(4);
   return check_launch();
 }
