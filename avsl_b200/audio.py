@@ -352,6 +352,8 @@ def add_noise_batch(clean: torch.Tensor, clean_offsets=None, noise: torch.Tensor
     for name, t in (("clean", clean), ("noise", noise)):
         if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 1):
             raise ValueError(f"{name} must be a contiguous 1-D float32 CUDA tensor")
+    if clean.data_ptr() % 16:
+        raise ValueError("clean must start on a 16-byte boundary (pass the packed buffer, not a slice of it)")
     dev = clean.device
     if plan is None:
         plan = NoisePlan(clean_offsets, noise_offsets, snr, dev, out_dtype)

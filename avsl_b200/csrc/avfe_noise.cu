@@ -108,17 +108,19 @@ noise_leaf_kernel(NoiseArgs a) {
     for (int t = 1; t < kLeafMax / 8; ++t)          // r >= +0, so adding the +0 of an absent element is exact
       r = __fadd_rn(r, __fmul_rn(v[t], v[t]));
   }
+  // the (< 8) leftover elements are fetched by lanes 0..6 along with the rest and handed to lane 0
+  // one by one afterwards: again no load waits behind an addition
+  float tail = 0.f;
+  if (leaf && body + (uint32_t)j < len) {
+    const float v = src[(off + body + (uint32_t)j) % wrap];
+    tail = __fmul_rn(v, v);
+  }
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-  if (leaf && j == 0) {
-    if (len < 8) r = 0.f;
-    for (uint32_t i = (len < 8 ? 0u : body); i < len; ++i) {
-      const float v = src[(off + i) % wrap];
-      r = __fadd_rn(r, __fmul_rn(v, v));
-    }
-    a.heap[(b * 2 + sig) * (int64_t)a.heap_slots + k] = r;
-  }
+#pragma unroll
+  for (int u = 0; u < 7; ++u) r = __fadd_rn(r, __shfl_sync(0xffffffffu, tail, u, 8));   // absent: + 0, exact
+  if (leaf && j == 0) a.heap[(b * 2 + sig) * (int64_t)a.heap_slots + k] = r;
 }
 
 // SMEM: both heaps of the clip are copied to shared memory first (2 x heap_slots floats), so the
@@ -185,14 +187,19 @@ struct MixArgs {
   float* out_f32;
 };
 
+// Samples are handled in groups of four on ABSOLUTE 16-byte boundaries of the packed buffers (a
+// clip may start anywhere): an inner group is one float4 load of the clean signal, one 8-byte
+// int16 (16-byte float) store and one `mod period` for its four noise samples; the groups that
+// straddle the ends of the clip go sample by sample.
 template <bool RESCALE>
 __global__ void __launch_bounds__(256)
 noise_mix_kernel(MixArgs m) {
   const NoiseArgs& a = m.n;
   const int64_t b = blockIdx.y;
   const int64_t c0 = a.clean_offsets[b];
-  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
-  if (blockIdx.x * (uint32_t)kMixChunk >= n) return;
+  const int64_t c1 = a.clean_offsets[b + 1];
+  const int64_t g0 = c0 & ~(int64_t)3;                    // first group of the clip (may start before it)
+  if (g0 + (int64_t)blockIdx.x * kMixChunk >= c1) return;
   const int64_t z0 = a.noise_offsets[b];
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
   const NoiseClip clip = a.clips[b];
@@ -202,35 +209,76 @@ noise_mix_kernel(MixArgs m) {
     if (!(hi > 32767.f || lo < -32768.f)) return;
     rate = (hi >= fabsf(lo)) ? __fdiv_rn(32767.f, hi) : __fdiv_rn(-32768.f, lo);
   }
-  const float* clean = a.clean + c0;
   const float* noise = a.noise + z0;
+  const bool noise_vec = ((reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
   float vmax = -INFINITY, vmin = INFINITY;
-  constexpr int kBatch = 8;                 // loads in flight per thread
-  for (uint32_t begin = blockIdx.x * (uint32_t)kMixChunk; begin < n; begin += gridDim.x * (uint32_t)kMixChunk) {
-    const uint32_t end = min(begin + (uint32_t)kMixChunk, n);
-    for (uint32_t i0 = begin + threadIdx.x; i0 < end; i0 += kBatch * 256) {
-      float x[kBatch], z[kBatch];
+  constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk, all fetched up front
+  for (int64_t base = g0 + (int64_t)blockIdx.x * kMixChunk; base < c1; base += (int64_t)gridDim.x * kMixChunk) {
+    float4 x[kRounds], z[kRounds];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const uint32_t i = i0 + u * 256;
-        x[u] = i < end ? clean[i] : 0.f;
-        z[u] = (i < end && period > 0) ? noise[i < period ? i : i % period] : 0.f;
+    for (int r = 0; r < kRounds; ++r) {
+      const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
+      x[r] = z[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g >= c1) continue;
+      if (g >= c0 && g + 4 <= c1) {
+        x[r] = *reinterpret_cast<const float4*>(a.clean + g);
+        if (period > 0) {
+          const uint32_t i = (uint32_t)(g - c0);
+          const uint32_t p = i < period ? i : i % period;
+          if (noise_vec && (p & 3u) == 0 && p + 4 <= period) {
+            z[r] = *reinterpret_cast<const float4*>(noise + p);
+          } else if (p + 4 <= period) {
+            z[r] = make_float4(noise[p], noise[p + 1], noise[p + 2], noise[p + 3]);
+          } else {
+            z[r] = make_float4(noise[p], noise[(p + 1) % period], noise[(p + 2) % period], noise[(p + 3) % period]);
+          }
+        }
+      } else {
+        float* xs = reinterpret_cast<float*>(&x[r]);
+        float* zs = reinterpret_cast<float*>(&z[r]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (g + q >= c0 && g + q < c1) {
+            xs[q] = a.clean[g + q];
+            if (period > 0) zs[q] = noise[(uint32_t)(g + q - c0) % period];
+          }
       }
+    }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const uint32_t i = i0 + u * 256;
-        if (i >= end) break;
-        float v = x[u];
-        if (period > 0) v = __fadd_rn(v, __fmul_rn(z[u], clip.gain));
+    for (int r = 0; r < kRounds; ++r) {
+      const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
+      if (g >= c1) continue;
+      const float xs[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+      const float zs[4] = {z[r].x, z[r].y, z[r].z, z[r].w};
+      int16_t q16[4];
+      const bool full = g >= c0 && g + 4 <= c1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = xs[q];
+        if (period > 0) v = __fadd_rn(v, __fmul_rn(zs[q], clip.gain));
         if (RESCALE) {
           v = __fmul_rn(v, rate);
-        } else {
+        } else if (full || (g + q >= c0 && g + q < c1)) {
           vmax = fmaxf(vmax, v);
           vmin = fminf(vmin, v);
         }
-        const int16_t q = to_i16(v);
-        if (m.out_i16) m.out_i16[c0 + i] = q;
-        if (m.out_f32) m.out_f32[c0 + i] = (float)q;
+        q16[q] = to_i16(v);
+      }
+      if (full) {
+        if (m.out_i16) {
+          const uint32_t lo = (uint16_t)q16[0] | ((uint32_t)(uint16_t)q16[1] << 16);
+          const uint32_t hi = (uint16_t)q16[2] | ((uint32_t)(uint16_t)q16[3] << 16);
+          *reinterpret_cast<uint2*>(m.out_i16 + g) = make_uint2(lo, hi);
+        }
+        if (m.out_f32)
+          *reinterpret_cast<float4*>(m.out_f32 + g) = make_float4((float)q16[0], (float)q16[1], (float)q16[2], (float)q16[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (g + q >= c0 && g + q < c1) {
+            if (m.out_i16) m.out_i16[g + q] = q16[q];
+            if (m.out_f32) m.out_f32[g + q] = (float)q16[q];
+          }
       }
     }
   }
@@ -271,6 +319,8 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   if (!clean || !clean_offsets || !noise || !noise_offsets || !snr_ratio || !workspace) return AVFE_ERR_INVALID_ARG;
   if (!out_i16 && !out_f32) return AVFE_ERR_INVALID_ARG;
   if (B > 65535 || max_len >= ((int64_t)1 << 31)) return AVFE_ERR_UNSUPPORTED;
+  if (!aligned16(clean) || (out_i16 && (reinterpret_cast<uintptr_t>(out_i16) & 7u)) || (out_f32 && !aligned16(out_f32)))
+    return AVFE_ERR_INVALID_ARG;                       // packed buffers: 16-byte aligned (int16 output: 8)
   const int depth = tree_depth(max_len);
   if (depth > kMaxDepth) return AVFE_ERR_UNSUPPORTED;
   uintptr_t p = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
@@ -302,7 +352,7 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   } else {
     noise_combine_kernel<false><<<(unsigned)B, 1024, 0, s>>>(m.n);
   }
-  const unsigned chunks = (unsigned)((max_len + kMixChunk - 1) / kMixChunk);
+  const unsigned chunks = (unsigned)((max_len + 3 + kMixChunk - 1) / kMixChunk);   // + 3: a clip may start 3 past a group boundary
   noise_mix_kernel<false><<<dim3(chunks, (unsigned)B), 256, 0, s>>>(m);
   // the rescale pass is a no-op for a clip that stayed inside int16: a few CTAs per clip, striding
   noise_mix_kernel<true><<<dim3(chunks < 16u ? chunks : 16u, (unsigned)B), 256, 0, s>>>(m);

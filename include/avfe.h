@@ -147,12 +147,12 @@ AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const
  *   mixed = clean_b + noise' * gain;  if max > 32767 or min < -32768: mixed *= 32767 / max when
  *   max >= |min|, else -32768 / min;  int16 by truncation toward zero.
  *   clean / noise   packed float32 waveforms (the reference's .astype(np.float32) is the
- *                   caller's), clip b = clean[clean_offsets[b] : clean_offsets[b+1]], noise
+ *                   caller's; `clean` 16-byte aligned), clip b = clean[clean_offsets[b] : clean_offsets[b+1]], noise
  *                   likewise; offsets are [B+1] int64 on the device
  *   snr_ratio       [B] float32 = (float)10^(snr_b / 20), evaluated by the caller in double like
  *                   the reference's Python expression
  *   max_len         the longest clean clip (sizes the launch and the workspace), < 2^31
- *   out_i16/out_f32 packed like `clean`; either may be NULL; out_f32 holds the same integers as
+ *   out_i16/out_f32 packed like `clean` (8- / 16-byte aligned); either may be NULL; out_f32 holds the same integers as
  *                   float32 (what logfbank takes)
  * A clip whose noise is empty is cast unmixed (the reference raises ZeroDivisionError; the Python
  * shim raises too).  NaN / inf samples and a silent noise clip are outside the contract, as in
