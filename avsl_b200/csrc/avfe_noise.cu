@@ -35,8 +35,8 @@
 
 namespace avfe {
 
-constexpr int kMixChunk = 4096;     // samples per CTA of the mix / rescale kernels
-constexpr size_t kCombineSmemMax = 160 * 1024;   // both heaps of a clip up to ~57 s (depth 13) fit in shared memory
+constexpr int kMixChunk = 2048;     // samples per CTA and step of the mix / rescale kernels
+constexpr size_t kCombineSmemMax = 160 * 1024;   // both heaps and the node lengths of a clip up to ~57 s (depth 13)
 
 struct NoiseClip {        // per-clip scalars in the workspace
   float gain;
@@ -70,61 +70,88 @@ struct NoiseArgs {
   int depth;
 };
 
-__global__ void __launch_bounds__(256)
-noise_leaf_kernel(NoiseArgs a) {
-  const int64_t b = blockIdx.z;
-  const int sig = blockIdx.y;
-  const int j = threadIdx.x & 7;
-  // a piece of the tree has 64..128 elements (or is the whole clip), so it holds one or two
-  // multiples of 64: the 8-lane group standing on the first of them owns the piece
-  const uint32_t pos = (blockIdx.x * 32u + (threadIdx.x >> 3)) * 64u;
-  const int64_t c0 = a.clean_offsets[b];
-  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
-  const int64_t z0 = a.noise_offsets[b];
-  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
-  uint32_t k = 1, off = 0, len = 0;
-  bool leaf = pos < n && (sig == 0 || period > 0);
-  if (leaf) {
-    k = locate_piece(pos, n, off, len);
-    leaf = pos - off < 64u;
-  }
-  const float* src = sig ? a.noise + z0 : a.clean + c0;
-  const uint32_t wrap = sig ? period : 0xffffffffu;       // clean: never wraps (off + i < n < 2^31)
-  float r = 0.f;
+// One piece (<= 128 elements from `src`, contiguous) summed the numpy way by 8 lanes: lane j owns
+// accumulator j.  All loads are issued before the first addition (the chain of additions is short;
+// loads waiting behind additions were the cost), the (< 8) leftover elements are fetched by lanes
+// 0..6 and handed over by shuffle.  WRAP: the piece crosses the end of a repeated noise clip, every
+// index goes through `mod period`.  Returns the piece's sum in every lane of the group.
+template <bool WRAP>
+__device__ __forceinline__ void piece_loads(const float* __restrict__ src, uint32_t start, uint32_t len, uint32_t period,
+                                            int j, float (&v)[kLeafMax / 8], float& tail) {
   const uint32_t body = len & ~7u;
-  if (leaf && len >= 8) {
-    // a lane's (at most 16) elements are fetched before the first addition: the chain of
-    // additions is short, the latency of dependent loads was the cost
-    float v[kLeafMax / 8];
-    uint32_t p = (off + (uint32_t)j) % wrap;
 #pragma unroll
-    for (int t = 0; t < kLeafMax / 8; ++t) {
-      v[t] = (uint32_t)(8 * t) < body ? src[p] : 0.f;
-      p += 8;
-      if (p >= wrap) p %= wrap;
-    }
-    r = __fmul_rn(v[0], v[0]);
+  for (int t = 0; t < kLeafMax / 8; ++t) {
+    const uint32_t i = (uint32_t)(8 * t + j);
+    v[t] = 0.f;
+    if (i < body) v[t] = src[WRAP ? (start + i) % period : start + i];
+  }
+  tail = 0.f;
+  if (body + (uint32_t)j < len) tail = src[WRAP ? (start + body + (uint32_t)j) % period : start + body + (uint32_t)j];
+}
+
+__device__ __forceinline__ float piece_sum(const float (&v)[kLeafMax / 8], float tail) {
+  float r = __fmul_rn(v[0], v[0]);
 #pragma unroll
-    for (int t = 1; t < kLeafMax / 8; ++t)          // r >= +0, so adding the +0 of an absent element is exact
-      r = __fadd_rn(r, __fmul_rn(v[t], v[t]));
-  }
-  // the (< 8) leftover elements are fetched by lanes 0..6 along with the rest and handed to lane 0
-  // one by one afterwards: again no load waits behind an addition
-  float tail = 0.f;
-  if (leaf && body + (uint32_t)j < len) {
-    const float v = src[(off + body + (uint32_t)j) % wrap];
-    tail = __fmul_rn(v, v);
-  }
+  for (int t = 1; t < kLeafMax / 8; ++t) r = __fadd_rn(r, __fmul_rn(v[t], v[t]));   // r >= +0: an absent element adds +0, exact
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  tail = __fmul_rn(tail, tail);
 #pragma unroll
-  for (int u = 0; u < 7; ++u) r = __fadd_rn(r, __shfl_sync(0xffffffffu, tail, u, 8));   // absent: + 0, exact
-  if (leaf && j == 0) a.heap[(b * 2 + sig) * (int64_t)a.heap_slots + k] = r;
+  for (int u = 0; u < 7; ++u) r = __fadd_rn(r, __shfl_sync(0xffffffffu, tail, u, 8));
+  return r;
 }
 
-// SMEM: both heaps of the clip are copied to shared memory first (2 x heap_slots floats), so the
-// level-by-level additions wait on shared memory instead of L2.
+// A warp covers 32 consecutive multiples of 64 samples of one clip.  Phase 1: every lane walks the
+// tree down to the piece that holds its own multiple (the clean signal and the repeated noise have
+// the same length, hence the same tree: one walk serves both).  Phase 2: eight rounds; in a round
+// each 8-lane group takes over one lane's piece -- if that lane stands on the piece's FIRST
+// multiple of 64 (a piece has 64..128 elements, so one or two multiples) -- and sums it for both
+// signals.
+__global__ void __launch_bounds__(256)
+noise_leaf_kernel(NoiseArgs a) {
+  const int64_t b = blockIdx.y;
+  const int lane = threadIdx.x & 31, j = lane & 7, grp = lane >> 3;
+  const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const int64_t c0 = a.clean_offsets[b];
+  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
+  if ((uint64_t)warp * 2048u >= n) return;
+  const int64_t z0 = a.noise_offsets[b];
+  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
+  const float* __restrict__ clean = a.clean + c0;
+  const float* __restrict__ noise = a.noise + z0;
+  const uint32_t pos = (warp * 32u + (uint32_t)lane) * 64u;
+  uint32_t k = 0, off = 0, len = 0, p0 = 0;
+  if (pos < n) {
+    k = locate_piece(pos, n, off, len);
+    if (pos - off >= 64u) k = 0;                       // the piece belongs to the lane before
+    if (period > 0) p0 = off % period;
+  }
+  float* heap = a.heap + b * 2 * (int64_t)a.heap_slots;
+#pragma unroll 1
+  for (int r = 0; r < 8; ++r) {
+    const int cand = r * 4 + grp;
+    const uint32_t kk = __shfl_sync(0xffffffffu, k, cand);
+    if (!__any_sync(0xffffffffu, kk != 0)) continue;
+    const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
+    const uint32_t l = kk ? __shfl_sync(0xffffffffu, len, cand) : 0u;      // l = 0: every load predicated off
+    const uint32_t q = __shfl_sync(0xffffffffu, p0, cand);
+    float vc[kLeafMax / 8], vz[kLeafMax / 8], tc, tz;
+    piece_loads<false>(clean, o, l, 0u, j, vc, tc);
+    const uint32_t lz = period > 0 ? l : 0u;
+    if (q + lz <= period) {
+      piece_loads<false>(noise, q, lz, period, j, vz, tz);
+    } else {
+      piece_loads<true>(noise, q, lz, period, j, vz, tz);
+    }
+    const float sc = piece_sum(vc, tc);
+    const float sz = piece_sum(vz, tz);
+    if (kk != 0 && j < 2) heap[(int64_t)j * a.heap_slots + kk] = j ? sz : sc;
+  }
+}
+
+// One CTA per clip.  Shared memory: the lengths of the tree's nodes (top-down, so that no node has
+// to be located by a walk) and both heaps; the children are added level by level, bottom-up.
 template <bool SMEM>
 __global__ void __launch_bounds__(1024)
 noise_combine_kernel(NoiseArgs a) {
@@ -133,11 +160,11 @@ noise_combine_kernel(NoiseArgs a) {
   const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - a.clean_offsets[b]);
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - a.noise_offsets[b]);
   float* heap_g = a.heap + b * 2 * (int64_t)a.heap_slots;
-  float* heap = SMEM ? heap_s : heap_g;
+  float* heap = heap_g;
   if (n > (uint32_t)kLeafMax) {
     if (SMEM) {
-      // pieces live on the two deepest levels that exist for this clip; copying every slot from
-      // the first possible one keeps the loop free of tree walks
+      heap = heap_s;
+      uint32_t* len_s = reinterpret_cast<uint32_t*>(heap_s + 2 * a.heap_slots);   // nodes above the last level
       const float4* g4 = reinterpret_cast<const float4*>(heap_g);      // 256-byte aligned, slots % 4 == 0
       float4* s4 = reinterpret_cast<float4*>(heap_s);
       const uint32_t quads = a.heap_slots / 2;
@@ -150,20 +177,37 @@ noise_combine_kernel(NoiseArgs a) {
         for (int u = 0; u < 8; ++u)
           if (t + u * blockDim.x < quads) s4[t + u * blockDim.x] = q[u];
       }
+      if (threadIdx.x == 0) len_s[1] = n;
       __syncthreads();
-    }
-    for (int d = a.depth - 1; d >= 0; --d) {
-      const uint32_t first = 1u << d;
-      for (uint32_t t = threadIdx.x; t < 2 * first; t += blockDim.x) {
-        const uint32_t k = first + (t >> 1);
-        float* h = heap + (t & 1u) * (int64_t)a.heap_slots;
-        uint32_t off, len;
-        if (locate_node(k, n, off, len) == 2) h[k] = __fadd_rn(h[2 * k], h[2 * k + 1]);
+      for (int d = 0; d + 1 < a.depth; ++d) {             // lengths of the levels 1 .. depth-1
+        for (uint32_t k = (1u << d) + threadIdx.x; k < (2u << d); k += blockDim.x) {
+          const uint32_t len = len_s[k];
+          const uint32_t half = len > (uint32_t)kLeafMax ? (len >> 1) & ~7u : 0u;
+          len_s[2 * k] = half;
+          len_s[2 * k + 1] = len > (uint32_t)kLeafMax ? len - half : 0u;
+        }
+        __syncthreads();
       }
-      __syncthreads();
+      for (int d = a.depth - 1; d >= 0; --d) {
+        for (uint32_t k = (1u << d) + threadIdx.x; k < (2u << d); k += blockDim.x)
+          if (len_s[k] > (uint32_t)kLeafMax) {
+            heap_s[k] = __fadd_rn(heap_s[2 * k], heap_s[2 * k + 1]);
+            heap_s[a.heap_slots + k] = __fadd_rn(heap_s[a.heap_slots + 2 * k], heap_s[a.heap_slots + 2 * k + 1]);
+          }
+        __syncthreads();
+      }
+    } else {
+      for (int d = a.depth - 1; d >= 0; --d) {
+        const uint32_t first = 1u << d;
+        for (uint32_t t = threadIdx.x; t < 2 * first; t += blockDim.x) {
+          const uint32_t k = first + (t >> 1);
+          float* h = heap_g + (t & 1u) * (int64_t)a.heap_slots;
+          uint32_t off, len;
+          if (locate_node(k, n, off, len) == 2) h[k] = __fadd_rn(h[2 * k], h[2 * k + 1]);
+        }
+        __syncthreads();
+      }
     }
-  } else {
-    heap = heap_g;          // the clip is one piece: the root was written by the leaf kernel
   }
   if (threadIdx.x == 0) {
     NoiseClip c;
@@ -212,9 +256,9 @@ noise_mix_kernel(MixArgs m) {
   const float* noise = a.noise + z0;
   const bool noise_vec = ((reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
   float vmax = -INFINITY, vmin = INFINITY;
-  constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk, all fetched up front
-  for (int64_t base = g0 + (int64_t)blockIdx.x * kMixChunk; base < c1; base += (int64_t)gridDim.x * kMixChunk) {
-    float4 x[kRounds], z[kRounds];
+  constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk
+
+  auto fetch = [&](int64_t base, float4 (&x)[kRounds], float4 (&z)[kRounds]) {
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
@@ -244,6 +288,9 @@ noise_mix_kernel(MixArgs m) {
           }
       }
     }
+  };
+
+  auto process = [&](int64_t base, const float4 (&x)[kRounds], const float4 (&z)[kRounds]) {
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
@@ -281,6 +328,24 @@ noise_mix_kernel(MixArgs m) {
           }
       }
     }
+  };
+
+  // the CTA strides over the clip's chunks; the next chunk is in flight while this one is mixed
+  const int64_t stride = (int64_t)gridDim.x * kMixChunk;
+  int64_t base = g0 + (int64_t)blockIdx.x * kMixChunk;
+  float4 xa[kRounds], za[kRounds], xb[kRounds], zb[kRounds];
+  fetch(base, xa, za);
+  for (;;) {
+    bool more = base + stride < c1;
+    if (more) fetch(base + stride, xb, zb);
+    process(base, xa, za);
+    if (!more) break;
+    base += stride;
+    more = base + stride < c1;
+    if (more) fetch(base + stride, xa, za);
+    process(base, xb, zb);
+    if (!more) break;
+    base += stride;
   }
   if (!RESCALE) {
 #pragma unroll
@@ -339,8 +404,8 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   m.n.depth = depth;
   m.out_i16 = out_i16;
   m.out_f32 = out_f32;
-  noise_leaf_kernel<<<dim3((unsigned)((max_len + 64 * 32 - 1) / (64 * 32)), 2, (unsigned)B), 256, 0, s>>>(m.n);
-  const size_t heap_smem = 2 * (size_t)m.n.heap_slots * sizeof(float);
+  noise_leaf_kernel<<<dim3((unsigned)((max_len + 16383) / 16384), (unsigned)B), 256, 0, s>>>(m.n);
+  const size_t heap_smem = (2 * (size_t)m.n.heap_slots + m.n.heap_slots / 2) * sizeof(float);     // heaps + node lengths
   if (heap_smem <= kCombineSmemMax) {
     if (heap_smem > 48 * 1024 &&
         cudaFuncSetAttribute(noise_combine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -353,7 +418,11 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
     noise_combine_kernel<false><<<(unsigned)B, 1024, 0, s>>>(m.n);
   }
   const unsigned chunks = (unsigned)((max_len + 3 + kMixChunk - 1) / kMixChunk);   // + 3: a clip may start 3 past a group boundary
-  noise_mix_kernel<false><<<dim3(chunks, (unsigned)B), 256, 0, s>>>(m);
+  // one wave: at most 5 CTAs are resident per SM (48 registers x 256 threads), each strides over its clip's chunks
+  unsigned per_clip = (unsigned)(5 * (int64_t)kNumSMs / B);
+  if (per_clip < 1) per_clip = 1;
+  if (per_clip > chunks) per_clip = chunks;
+  noise_mix_kernel<false><<<dim3(per_clip, (unsigned)B), 256, 0, s>>>(m);
   // the rescale pass is a no-op for a clip that stayed inside int16: a few CTAs per clip, striding
   noise_mix_kernel<true><<<dim3(chunks < 16u ? chunks : 16u, (unsigned)B), 256, 0, s>>>(m);
   count_launch(4);
