@@ -134,7 +134,8 @@ noise_leaf_kernel(NoiseArgs a) {
     const uint32_t kk = __shfl_sync(0xffffffffu, k, cand);
     if (!__any_sync(0xffffffffu, kk != 0)) continue;
     const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
-    const uint32_t l = kk ? __shfl_sync(0xffffffffu, len, cand) : 0u;      // l = 0: every load predicated off
+    const uint32_t l_any = __shfl_sync(0xffffffffu, len, cand);
+    const uint32_t l = kk ? l_any : 0u;                                    // l = 0: every load predicated off
     const uint32_t q = __shfl_sync(0xffffffffu, p0, cand);
     float vc[kLeafMax / 8], vz[kLeafMax / 8], tc, tz;
     piece_loads<false>(clean, o, l, 0u, j, vc, tc);
