@@ -79,14 +79,14 @@ template <bool WRAP>
 __device__ __forceinline__ void piece_loads(const float* __restrict__ src, uint32_t start, uint32_t len, uint32_t period,
                                             int j, float (&v)[kLeafMax / 8], float& tail) {
   const uint32_t body = len & ~7u;
+  const float* __restrict__ mine = src + start + j;        // one address per lane, constant offsets from it
 #pragma unroll
   for (int t = 0; t < kLeafMax / 8; ++t) {
-    const uint32_t i = (uint32_t)(8 * t + j);
     v[t] = 0.f;
-    if (i < body) v[t] = src[WRAP ? (start + i) % period : start + i];
+    if ((uint32_t)(8 * t) < body) v[t] = WRAP ? src[(start + (uint32_t)(8 * t + j)) % period] : mine[8 * t];
   }
   tail = 0.f;
-  if (body + (uint32_t)j < len) tail = src[WRAP ? (start + body + (uint32_t)j) % period : start + body + (uint32_t)j];
+  if (body + (uint32_t)j < len) tail = WRAP ? src[(start + body + (uint32_t)j) % period] : mine[body];
 }
 
 __device__ __forceinline__ float piece_sum(const float (&v)[kLeafMax / 8], float tail) {
@@ -259,13 +259,14 @@ noise_mix_kernel(MixArgs m) {
   float vmax = -INFINITY, vmin = INFINITY;
   constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk
 
+  // `inner`: the whole chunk lies inside the clip (CTA-uniform), no per-group bounds logic
   auto fetch = [&](int64_t base, float4 (&x)[kRounds], float4 (&z)[kRounds]) {
+    const bool inner = base >= c0 && base + kMixChunk <= c1;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
       x[r] = z[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g >= c1) continue;
-      if (g >= c0 && g + 4 <= c1) {
+      if (inner || (g >= c0 && g + 4 <= c1)) {
         x[r] = *reinterpret_cast<const float4*>(a.clean + g);
         if (period > 0) {
           const uint32_t i = (uint32_t)(g - c0);
@@ -278,7 +279,7 @@ noise_mix_kernel(MixArgs m) {
             z[r] = make_float4(noise[p], noise[(p + 1) % period], noise[(p + 2) % period], noise[(p + 3) % period]);
           }
         }
-      } else {
+      } else if (g < c1) {
         float* xs = reinterpret_cast<float*>(&x[r]);
         float* zs = reinterpret_cast<float*>(&z[r]);
 #pragma unroll
@@ -292,14 +293,15 @@ noise_mix_kernel(MixArgs m) {
   };
 
   auto process = [&](int64_t base, const float4 (&x)[kRounds], const float4 (&z)[kRounds]) {
+    const bool inner = base >= c0 && base + kMixChunk <= c1;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
-      if (g >= c1) continue;
+      if (!inner && g >= c1) continue;
       const float xs[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
       const float zs[4] = {z[r].x, z[r].y, z[r].z, z[r].w};
       int16_t q16[4];
-      const bool full = g >= c0 && g + 4 <= c1;
+      const bool full = inner || (g >= c0 && g + 4 <= c1);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v = xs[q];
@@ -419,8 +421,13 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
     noise_combine_kernel<false><<<(unsigned)B, 1024, 0, s>>>(m.n);
   }
   const unsigned chunks = (unsigned)((max_len + 3 + kMixChunk - 1) / kMixChunk);   // + 3: a clip may start 3 past a group boundary
-  // one wave: at most 5 CTAs are resident per SM (48 registers x 256 threads), each strides over its clip's chunks
-  unsigned per_clip = (unsigned)(5 * (int64_t)kNumSMs / B);
+  // one wave of CTAs, each striding over its clip's chunks
+  int resident = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, noise_mix_kernel<false>, 256, 0) != cudaSuccess || resident < 1) {
+    cudaGetLastError();
+    resident = 1;
+  }
+  unsigned per_clip = (unsigned)((int64_t)resident * kNumSMs / B);
   if (per_clip < 1) per_clip = 1;
   if (per_clip > chunks) per_clip = chunks;
   noise_mix_kernel<false><<<dim3(per_clip, (unsigned)B), 256, 0, s>>>(m);
