@@ -112,42 +112,43 @@ __global__ void __launch_bounds__(256)
 noise_leaf_kernel(NoiseArgs a) {
   const int64_t b = blockIdx.y;
   const int lane = threadIdx.x & 31, j = lane & 7, grp = lane >> 3;
-  const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
   const int64_t c0 = a.clean_offsets[b];
   const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
-  if ((uint64_t)warp * 2048u >= n) return;
   const int64_t z0 = a.noise_offsets[b];
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
   const float* __restrict__ clean = a.clean + c0;
   const float* __restrict__ noise = a.noise + z0;
-  const uint32_t pos = (warp * 32u + (uint32_t)lane) * 64u;
-  uint32_t k = 0, off = 0, len = 0, p0 = 0;
-  if (pos < n) {
-    k = locate_piece(pos, n, off, len);
-    if (pos - off >= 64u) k = 0;                       // the piece belongs to the lane before
-    if (period > 0) p0 = off % period;
-  }
   float* heap = a.heap + b * 2 * (int64_t)a.heap_slots;
-#pragma unroll 1
-  for (int r = 0; r < 8; ++r) {
-    const int cand = r * 4 + grp;
-    const uint32_t kk = __shfl_sync(0xffffffffu, k, cand);
-    if (!__any_sync(0xffffffffu, kk != 0)) continue;
-    const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
-    const uint32_t l_any = __shfl_sync(0xffffffffu, len, cand);
-    const uint32_t l = kk ? l_any : 0u;                                    // l = 0: every load predicated off
-    const uint32_t q = __shfl_sync(0xffffffffu, p0, cand);
-    float vc[kLeafMax / 8], vz[kLeafMax / 8], tc, tz;
-    piece_loads<false>(clean, o, l, 0u, j, vc, tc);
-    const uint32_t lz = period > 0 ? l : 0u;
-    if (q + lz <= period) {
-      piece_loads<false>(noise, q, lz, period, j, vz, tz);
-    } else {
-      piece_loads<true>(noise, q, lz, period, j, vz, tz);
+  // the clip's CTAs stride over its 2048-sample warp spans (one resident wave for the whole batch)
+  for (uint64_t warp = blockIdx.x * 8u + (threadIdx.x >> 5); warp * 2048u < n; warp += gridDim.x * 8u) {
+    const uint32_t pos = ((uint32_t)warp * 32u + (uint32_t)lane) * 64u;
+    uint32_t k = 0, off = 0, len = 0, p0 = 0;
+    if (pos < n) {
+      k = locate_piece(pos, n, off, len);
+      if (pos - off >= 64u) k = 0;                       // the piece belongs to the lane before
+      if (period > 0) p0 = off % period;
     }
-    const float sc = piece_sum(vc, tc);
-    const float sz = piece_sum(vz, tz);
-    if (kk != 0 && j < 2) heap[(int64_t)j * a.heap_slots + kk] = j ? sz : sc;
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+      const int cand = r * 4 + grp;
+      const uint32_t kk = __shfl_sync(0xffffffffu, k, cand);
+      if (!__any_sync(0xffffffffu, kk != 0)) continue;
+      const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
+      const uint32_t l_any = __shfl_sync(0xffffffffu, len, cand);
+      const uint32_t l = kk ? l_any : 0u;                                    // l = 0: every load predicated off
+      const uint32_t q = __shfl_sync(0xffffffffu, p0, cand);
+      float vc[kLeafMax / 8], vz[kLeafMax / 8], tc, tz;
+      piece_loads<false>(clean, o, l, 0u, j, vc, tc);
+      const uint32_t lz = period > 0 ? l : 0u;
+      if (q + lz <= period) {
+        piece_loads<false>(noise, q, lz, period, j, vz, tz);
+      } else {
+        piece_loads<true>(noise, q, lz, period, j, vz, tz);
+      }
+      const float sc = piece_sum(vc, tc);
+      const float sz = piece_sum(vz, tz);
+      if (kk != 0 && j < 2) heap[(int64_t)j * a.heap_slots + kk] = j ? sz : sc;
+    }
   }
 }
 
@@ -233,9 +234,11 @@ struct MixArgs {
 };
 
 // Samples are handled in groups of four on ABSOLUTE 16-byte boundaries of the packed buffers (a
-// clip may start anywhere): an inner group is one float4 load of the clean signal, one 8-byte
-// int16 (16-byte float) store and one `mod period` for its four noise samples; the groups that
-// straddle the ends of the clip go sample by sample.
+// clip may start anywhere).  A CTA strides over the clip's chunks of kMixChunk samples with the
+// next chunk's loads in flight while the current one is mixed.  A chunk that lies wholly inside
+// the clip (CTA-uniform test) takes the lean path: one float4 of clean signal and one 8-byte int16
+// (16-byte float) store per group, the noise position carried along incrementally instead of a
+// `mod period` per group.  The chunks at the two ends of the clip go sample by sample.
 template <bool RESCALE>
 __global__ void __launch_bounds__(256)
 noise_mix_kernel(MixArgs m) {
@@ -254,23 +257,33 @@ noise_mix_kernel(MixArgs m) {
     if (!(hi > 32767.f || lo < -32768.f)) return;
     rate = (hi >= fabsf(lo)) ? __fdiv_rn(32767.f, hi) : __fdiv_rn(-32768.f, lo);
   }
-  const float* noise = a.noise + z0;
+  const float* __restrict__ noise = a.noise + z0;
   const bool noise_vec = ((reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
   float vmax = -INFINITY, vmin = INFINITY;
   constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk
+  const int64_t stride = (int64_t)gridDim.x * kMixChunk;
+  // noise position of this thread's first group of the chunk to be fetched next, kept in
+  // [0, period); it advances by 1024 per round and by `stride` per chunk, both reduced once
+  const uint32_t per = period ? period : 1u;
+  const uint32_t step_round = 1024u % per, step_chunk = (uint32_t)(stride % per);
+  uint32_t pos;
+  {
+    const int64_t i0 = g0 + (int64_t)blockIdx.x * kMixChunk + 4 * (int)threadIdx.x - c0;      // >= -3
+    pos = (uint32_t)(((i0 % (int64_t)per) + per) % per);
+  }
 
-  // `inner`: the whole chunk lies inside the clip (CTA-uniform), no per-group bounds logic
   auto fetch = [&](int64_t base, float4 (&x)[kRounds], float4 (&z)[kRounds]) {
     const bool inner = base >= c0 && base + kMixChunk <= c1;
+    uint32_t p = pos;
+    pos += step_chunk;
+    if (pos >= per) pos -= per;
+    if (inner) {
 #pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-      const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
-      x[r] = z[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (inner || (g >= c0 && g + 4 <= c1)) {
+      for (int r = 0; r < kRounds; ++r) {
+        const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
         x[r] = *reinterpret_cast<const float4*>(a.clean + g);
+        z[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (period > 0) {
-          const uint32_t i = (uint32_t)(g - c0);
-          const uint32_t p = i < period ? i : i % period;
           if (noise_vec && (p & 3u) == 0 && p + 4 <= period) {
             z[r] = *reinterpret_cast<const float4*>(noise + p);
           } else if (p + 4 <= period) {
@@ -279,7 +292,14 @@ noise_mix_kernel(MixArgs m) {
             z[r] = make_float4(noise[p], noise[(p + 1) % period], noise[(p + 2) % period], noise[(p + 3) % period]);
           }
         }
-      } else if (g < c1) {
+        p += step_round;
+        if (p >= per) p -= per;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
+        x[r] = z[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         float* xs = reinterpret_cast<float*>(&x[r]);
         float* zs = reinterpret_cast<float*>(&z[r]);
 #pragma unroll
@@ -292,29 +312,31 @@ noise_mix_kernel(MixArgs m) {
     }
   };
 
+  auto mix4 = [&](const float4& x, const float4& z, int16_t (&q16)[4], float (&v)[4]) {
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = xs[q];
+      if (period > 0) v[q] = __fadd_rn(v[q], __fmul_rn(zs[q], clip.gain));
+      if (RESCALE) v[q] = __fmul_rn(v[q], rate);
+      q16[q] = to_i16(v[q]);
+    }
+  };
+
   auto process = [&](int64_t base, const float4 (&x)[kRounds], const float4 (&z)[kRounds]) {
     const bool inner = base >= c0 && base + kMixChunk <= c1;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
       const int64_t g = base + r * 1024 + 4 * (int)threadIdx.x;
-      if (!inner && g >= c1) continue;
-      const float xs[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
-      const float zs[4] = {z[r].x, z[r].y, z[r].z, z[r].w};
       int16_t q16[4];
-      const bool full = inner || (g >= c0 && g + 4 <= c1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v = xs[q];
-        if (period > 0) v = __fadd_rn(v, __fmul_rn(zs[q], clip.gain));
-        if (RESCALE) {
-          v = __fmul_rn(v, rate);
-        } else if (full || (g + q >= c0 && g + q < c1)) {
-          vmax = fmaxf(vmax, v);
-          vmin = fminf(vmin, v);
+      float v[4];
+      mix4(x[r], z[r], q16, v);
+      if (inner) {
+        if (!RESCALE) {
+          vmax = fmaxf(fmaxf(vmax, fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
+          vmin = fminf(fminf(vmin, fminf(v[0], v[1])), fminf(v[2], v[3]));
         }
-        q16[q] = to_i16(v);
-      }
-      if (full) {
         if (m.out_i16) {
           const uint32_t lo = (uint16_t)q16[0] | ((uint32_t)(uint16_t)q16[1] << 16);
           const uint32_t hi = (uint16_t)q16[2] | ((uint32_t)(uint16_t)q16[3] << 16);
@@ -326,6 +348,10 @@ noise_mix_kernel(MixArgs m) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (g + q >= c0 && g + q < c1) {
+            if (!RESCALE) {
+              vmax = fmaxf(vmax, v[q]);
+              vmin = fminf(vmin, v[q]);
+            }
             if (m.out_i16) m.out_i16[g + q] = q16[q];
             if (m.out_f32) m.out_f32[g + q] = (float)q16[q];
           }
@@ -333,8 +359,6 @@ noise_mix_kernel(MixArgs m) {
     }
   };
 
-  // the CTA strides over the clip's chunks; the next chunk is in flight while this one is mixed
-  const int64_t stride = (int64_t)gridDim.x * kMixChunk;
   int64_t base = g0 + (int64_t)blockIdx.x * kMixChunk;
   float4 xa[kRounds], za[kRounds], xb[kRounds], zb[kRounds];
   fetch(base, xa, za);
@@ -407,7 +431,16 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   m.n.depth = depth;
   m.out_i16 = out_i16;
   m.out_f32 = out_f32;
-  noise_leaf_kernel<<<dim3((unsigned)((max_len + 16383) / 16384), (unsigned)B), 256, 0, s>>>(m.n);
+  int resident = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, noise_leaf_kernel, 256, 0) != cudaSuccess || resident < 1) {
+    cudaGetLastError();
+    resident = 1;
+  }
+  unsigned leaf_ctas = (unsigned)((int64_t)resident * kNumSMs / B);
+  const unsigned leaf_max = (unsigned)((max_len + 16383) / 16384);
+  if (leaf_ctas < 1) leaf_ctas = 1;
+  if (leaf_ctas > leaf_max) leaf_ctas = leaf_max;
+  noise_leaf_kernel<<<dim3(leaf_ctas, (unsigned)B), 256, 0, s>>>(m.n);
   const size_t heap_smem = (2 * (size_t)m.n.heap_slots + m.n.heap_slots / 2) * sizeof(float);     // heaps + node lengths
   if (heap_smem <= kCombineSmemMax) {
     if (heap_smem > 48 * 1024 &&
@@ -422,7 +455,6 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   }
   const unsigned chunks = (unsigned)((max_len + 3 + kMixChunk - 1) / kMixChunk);   // + 3: a clip may start 3 past a group boundary
   // one wave of CTAs, each striding over its clip's chunks
-  int resident = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, noise_mix_kernel<false>, 256, 0) != cudaSuccess || resident < 1) {
     cudaGetLastError();
     resident = 1;
