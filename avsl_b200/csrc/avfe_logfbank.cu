@@ -27,6 +27,8 @@ constexpr int kMaxFilt = 64;
 
 constexpr int kMaxTaps = 640;             // packed nonzero filter weights (26 HTK filters: 2 x 257 at most)
 
+constexpr int kPRow = 268;            // floats between the power rows of consecutive tile frames (= 12 banks)
+
 struct Smem {
   float y[kSpan];                       // pre-emphasised samples of the tile (zero past the clip)
   float2 tw[kNfft];
@@ -110,8 +112,11 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
 #pragma unroll
   for (int q = 0; q < kItems; ++q) {
     const int i = tid + q * kThreads;
-    it_f[q] = (i < kTileFrames * nfilt) ? i / nfilt : -1;
-    it_m[q] = (i < kTileFrames * nfilt) ? i % nfilt : 0;
+    // the 8 frames of one filter sit in adjacent lanes: a warp holds 4 neighbouring filters, whose
+    // supports have similar lengths (a warp runs as long as its widest filter), and the 8 power rows
+    // are kPRow = 268 floats apart, i.e. 12 banks: same-bin reads of the 8 frames do not collide
+    it_f[q] = (i < kTileFrames * nfilt) ? i % kTileFrames : -1;
+    it_m[q] = (i < kTileFrames * nfilt) ? i / kTileFrames : 0;
   }
   const int rows_here = kTileFrames / stack, width = stack * nfilt;
 
@@ -149,8 +154,8 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   __syncthreads();
   step3(t, S, C);
   __syncthreads();
-  float* P = reinterpret_cast<float*>(S);                       // two power rows per FFT
-  power_rows(t, C, P, P + kPStride);
+  float* Pall = reinterpret_cast<float*>(sm.S);                 // the tile's power rows overwrite the exchange storage
+  power_rows(t, C, Pall + (2 * g) * kPRow, Pall + (2 * g + 1) * kPRow);
   __syncthreads();
 
   // log filterbank energies: item = (frame, filter); frames past the clip's last one are the
@@ -159,7 +164,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   for (int q = 0; q < kItems; ++q) {
     const int f = it_f[q], m = it_m[q];
     if (f < 0) continue;
-    const float* Pf = reinterpret_cast<const float*>(sm.S[f >> 1]) + (f & 1) * kPStride;
+    const float* Pf = Pall + f * kPRow;
     float v = 0.0f;
     if (f0 + f < nfr) {
       const int lo = sm.lo[m], hi = sm.hi[m];

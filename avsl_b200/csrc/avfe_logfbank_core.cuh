@@ -127,6 +127,7 @@ AVFE_HD void power_rows(int t, const float2* C, float* Pa, float* Pb) {
 // log of one filterbank energy: feat = fb_row . pspec, zero -> float64 eps (numpy.finfo(float).eps)
 AVFE_HD float log_fbank(const float* P, const float* w, int lo, int hi) {
   float acc = 0.0f;
+#pragma unroll 4
   for (int k = lo; k < hi; ++k) acc = fmaf(w[k], P[k], acc);
   if (acc == 0.0f) acc = 2.220446049250313e-16f;
   return logf(acc);
