@@ -10,7 +10,8 @@ from . import _lib  # noqa: F401
 from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, LogfbankPlan, NoisePlan, add_noise, add_noise_batch,
                     extract_logfbank_features,
                     log_mel_spectrogram, log_mel_spectrogram_ragged, logfbank_batch, logfbank_num_frames,
-                    mel_filters, pad_or_trim, peak_normalize, spec_augment, spec_augment_bands)
+                    mel_filters, pad_or_trim, peak_normalize, process_audio_for_av_hubert, spec_augment,
+                    spec_augment_bands)
 from .frontend import (AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, bind_to_gpu_numa_node,
                        pack_utterances, shard)
 from .fusion import (ModalityFusion, fuse_modalities, fuse_transpose_layernorm, modality_dropout_flags,

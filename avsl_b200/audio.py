@@ -385,6 +385,30 @@ def add_noise(clean_wav, noise_wav, snr) -> np.ndarray:
     return add_noise_batch(c.cuda(), [0, c.numel()], z.cuda(), [0, z.numel()], snr).cpu().numpy()
 
 
+def process_audio_for_av_hubert(audio, stack_order: int = 1, normalize: bool = True, add_noise_prob: float = 0.0,
+                                noise=None, noise_snr=0, rng=None):
+    """``process_audio_for_av_hubert`` (preprocess/audio_process.py:199-236) from the point where the
+    waveforms are in memory (the reference's ``librosa.load`` of ``audio_path`` / ``noise_file`` is the
+    caller's; pass the 16 kHz arrays): optional SNR noise mixing with probability ``add_noise_prob``
+    (:222-224, drawn like the reference from ``np.random.rand()`` unless ``rng`` is given), logfbank
+    features stacked ``stack_order`` at a time (:227), per-row normalisation (:230).  Everything after
+    the draw runs on the GPU without a host round trip.  float32 numpy
+    ``[ceil(frames / stack_order), 26 * stack_order]``; like the reference, any failure is reported
+    and answered with ``None`` (:234-236)."""
+    _lib.require_cuda()
+    try:
+        a = torch.from_numpy(np.ascontiguousarray(np.asarray(audio).astype(np.float32).reshape(-1))).cuda()
+        draw = (rng.random() if rng is not None else np.random.rand()) if add_noise_prob > 0 and noise is not None else 1.0
+        if add_noise_prob > 0 and noise is not None and draw < add_noise_prob:
+            z = torch.from_numpy(np.ascontiguousarray(np.asarray(noise).astype(np.float32).reshape(-1))).cuda()
+            a = add_noise_batch(a, [0, a.numel()], z, [0, z.numel()], noise_snr, out_dtype=torch.float32)
+        feats, _ = logfbank_batch(a, [0, a.numel()], stack_order, normalize)
+        return feats.cpu().numpy()
+    except Exception as e:                                  # the reference's catch-all, :234-236
+        print(f"Error processing audio for AV-HuBERT: {str(e)}")
+        return None
+
+
 # ----------------------------------------------------------------------------- SpecAugment masks
 # LibriSpeech policies of the SpecAugment paper (Park et al. 2019, table 1), the names the
 # reference passes as ``spec_augment_config`` (avsl/whisper_flamingo_ft_ami.py:165,217-220):

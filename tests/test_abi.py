@@ -79,6 +79,8 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.add_noise(np.zeros(100, np.float32), np.ones(10, np.float32), 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
+        avsl_b200.process_audio_for_av_hubert(np.zeros(16000, np.float32), stack_order=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.fuse_transpose_layernorm(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         avsl_b200.lip_roi_collate(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), torch.zeros(2, dtype=torch.int64),

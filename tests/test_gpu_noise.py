@@ -109,3 +109,31 @@ def test_noise_then_logfbank_chain():
     np.testing.assert_array_equal(m.cpu().numpy(), mixed.astype(np.float32))
     feats, _ = A.logfbank_batch(m, [0, len(clean)], stack_order=4, normalize=False)
     np.testing.assert_allclose(feats.cpu().numpy(), want, atol=2e-4, rtol=0)
+
+
+def test_process_audio_for_av_hubert_chain():
+    """preprocess/audio_process.py:199-236 from the loaded waveforms on: the noise draw, the mix, the
+    stacked logfbank features and the row normalisation against the oracle chain."""
+    import avsl_b200 as A
+    from oracle import logfbank as OF
+    clean, noise, snr = MG.noise_long_case()
+    clean, noise = clean[:32000], noise[:9000]
+
+    class Fixed:
+        def __init__(self, v):
+            self.v = v
+
+        def random(self):
+            return self.v
+    want_mix = OF.audio_to_tensor(OF.extract_logfbank_features(ON.add_noise(clean, noise, snr).astype(np.float32),
+                                                               stack_order=4), normalize=True)
+    want_plain = OF.audio_to_tensor(OF.extract_logfbank_features(clean, stack_order=4), normalize=True)
+    got_mix = A.process_audio_for_av_hubert(clean, stack_order=4, add_noise_prob=0.5, noise=noise, noise_snr=snr, rng=Fixed(0.1))
+    got_skip = A.process_audio_for_av_hubert(clean, stack_order=4, add_noise_prob=0.5, noise=noise, noise_snr=snr, rng=Fixed(0.9))
+    got_off = A.process_audio_for_av_hubert(clean, stack_order=4)
+    assert got_mix.dtype == np.float32 and got_mix.shape == want_mix.shape
+    np.testing.assert_allclose(got_mix, want_mix, atol=1e-3, rtol=0)
+    np.testing.assert_allclose(got_skip, want_plain, atol=1e-3, rtol=0)
+    np.testing.assert_array_equal(got_off, got_skip)
+    assert np.abs(want_mix - want_plain).max() > 0.05            # the mix does change the features
+    assert A.process_audio_for_av_hubert(np.zeros(0, np.float32)) is None      # the reference's catch-all
