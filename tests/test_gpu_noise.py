@@ -137,3 +137,29 @@ def test_process_audio_for_av_hubert_chain():
     np.testing.assert_array_equal(got_off, got_skip)
     assert np.abs(want_mix - want_plain).max() > 0.05            # the mix does change the features
     assert A.process_audio_for_av_hubert(np.zeros(0, np.float32)) is None      # the reference's catch-all
+
+
+def test_full_size_batch_two_clips_checked():
+    """BASELINE-sized batch (64 x 30 s, noise 10 s each, one packed buffer): every clip is compared
+    through a size-independent property -- the mix of clip b must not depend on its neighbours, so a
+    batch made of one clip repeated has 64 identical answers -- and two clips against the oracle."""
+    import torch
+    import avsl_b200 as A
+    rng = np.random.default_rng(7)
+    L, Ln, B = 480000, 160000, 64
+    one = rng.integers(-9000, 9001, size=L).astype(np.float32)
+    nz = rng.integers(-2500, 2501, size=Ln).astype(np.float32)
+    other = rng.integers(-30000, 30001, size=L).astype(np.float32)          # loud: takes the rescale branch at -10 dB
+    clean = np.tile(one, B)
+    clean[5 * L:6 * L] = other
+    snr = [6.0] * B
+    snr[5] = -10.0
+    got = A.add_noise_batch(torch.from_numpy(clean).cuda(), np.arange(B + 1) * L, torch.from_numpy(np.tile(nz, B)).cuda(),
+                            np.arange(B + 1) * Ln, snr).cpu().numpy().reshape(B, L)
+    for b in range(B):
+        if b != 5:
+            assert np.array_equal(got[b], got[0]), b
+    np.testing.assert_array_equal(got[0], ON.add_noise(one, nz, 6.0))
+    want5, info = ON.add_noise(other, nz, -10.0, return_info=True)
+    assert info["rate"] is not None
+    np.testing.assert_array_equal(got[5], want5)
