@@ -330,7 +330,7 @@ class NoisePlan:
         self.co, self.no, self.B, self.out_dtype, self.device = co, no, B, out_dtype, device
         self.max_len = int(np.diff(co).max()) if B else 0
         self.d_co, self.d_no = torch.from_numpy(co).to(device), torch.from_numpy(no).to(device)
-        self.d_ratio = torch.from_numpy(np.ascontiguousarray(ratios)).to(device)
+        self.d_ratio = torch.from_numpy(np.array(ratios, dtype=np.float32)).to(device)     # broadcast_to is read-only: copy
         nbytes = int(_lib.load().avfe_add_noise_workspace_bytes(B, self.max_len))
         if nbytes == 0:
             raise ValueError("clip too long for avfe_add_noise")
