@@ -128,11 +128,16 @@ noise_leaf_kernel(NoiseArgs a) {
       if (pos - off >= 64u) k = 0;                       // the piece belongs to the lane before
       if (period > 0) p0 = off % period;
     }
+    // only about 17 of the 32 lanes own a piece (a piece holds one or two multiples of 64): the
+    // groups walk the owners, four per round, instead of all 32 lanes
+    const uint32_t owners = __ballot_sync(0xffffffffu, k != 0);
+    const int n_own = __popc(owners);
 #pragma unroll 1
-    for (int r = 0; r < 8; ++r) {
-      const int cand = r * 4 + grp;
-      const uint32_t kk = __shfl_sync(0xffffffffu, k, cand);
-      if (!__any_sync(0xffffffffu, kk != 0)) continue;
+    for (int r = 0; 4 * r < n_own; ++r) {
+      const int nth = 4 * r + grp;
+      const int cand = nth < n_own ? (int)__fns(owners, 0, nth + 1) : lane;     // an idle group reads its own lane, kk := 0
+      const uint32_t k_any = __shfl_sync(0xffffffffu, k, cand);
+      const uint32_t kk = nth < n_own ? k_any : 0u;
       const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
       const uint32_t l_any = __shfl_sync(0xffffffffu, len, cand);
       const uint32_t l = kk ? l_any : 0u;                                    // l = 0: every load predicated off
