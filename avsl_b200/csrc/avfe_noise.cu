@@ -252,9 +252,17 @@ noise_mix_kernel(MixArgs m) {
   const int64_t c0 = a.clean_offsets[b];
   const int64_t c1 = a.clean_offsets[b + 1];
   const int64_t g0 = c0 & ~(int64_t)3;                    // first group of the clip (may start before it)
-  if (g0 + (int64_t)blockIdx.x * kMixChunk >= c1) return;
+  const int64_t total = (c1 - g0 + kMixChunk - 1) / kMixChunk;      // chunks of this clip
   const int64_t z0 = a.noise_offsets[b];
   const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
+  // Chunk order.  A repeated noise clip is read once from HBM if its repeats are mixed back to back:
+  // the clip's chunks form `cols` columns (chunk c belongs to column c mod cols, cols = the noise
+  // period in chunks), a CTA takes the columns blockIdx.x, + gridDim.x, ... and walks each column
+  // down (c, c + cols, c + 2 cols, ...: the same stretch of noise, give or take a chunk's rounding).
+  // Without repetition (or with a period so short that L2 keeps it anyway) every column is one chunk.
+  int64_t cols = ((int64_t)period + kMixChunk / 2) / kMixChunk;
+  if (period == 0 || cols < (int64_t)gridDim.x || cols >= total) cols = total;
+  if ((int64_t)blockIdx.x >= cols) return;
   const NoiseClip clip = a.clips[b];
   float rate = 1.f;
   if (RESCALE) {
@@ -266,22 +274,40 @@ noise_mix_kernel(MixArgs m) {
   const bool noise_vec = ((reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
   float vmax = -INFINITY, vmin = INFINITY;
   constexpr int kRounds = kMixChunk / 1024;               // groups per thread and chunk
-  const int64_t stride = (int64_t)gridDim.x * kMixChunk;
-  // noise position of this thread's first group of the chunk to be fetched next, kept in
-  // [0, period); it advances by 1024 per round and by `stride` per chunk, both reduced once
+  // noise position of this thread's first group of a chunk, kept in [0, period): it advances by
+  // 1024 per round, by `cols` chunks down a column and by gridDim.x chunks to the next column, each
+  // step reduced mod period once
   const uint32_t per = period ? period : 1u;
-  const uint32_t step_round = 1024u % per, step_chunk = (uint32_t)(stride % per);
-  uint32_t pos;
+  const uint32_t step_round = 1024u % per;
+  const uint32_t step_down = (uint32_t)((cols * kMixChunk) % per);
+  const uint32_t step_col = (uint32_t)(((int64_t)gridDim.x * kMixChunk) % per);
+  struct Walk {
+    int64_t col, c;          // column, chunk
+    uint32_t pos_col, pos;   // noise position at the head of the column / at chunk c
+  };
+  auto advance = [&](Walk& w) {
+    w.c += cols;
+    w.pos += step_down;
+    if (w.pos >= per) w.pos -= per;
+    if (w.c >= total) {
+      w.col += gridDim.x;
+      w.c = w.col;
+      w.pos_col += step_col;
+      if (w.pos_col >= per) w.pos_col -= per;
+      w.pos = w.pos_col;
+    }
+  };
+  Walk cur;
+  cur.col = cur.c = blockIdx.x;
   {
     const int64_t i0 = g0 + (int64_t)blockIdx.x * kMixChunk + 4 * (int)threadIdx.x - c0;      // >= -3
-    pos = (uint32_t)(((i0 % (int64_t)per) + per) % per);
+    cur.pos_col = cur.pos = (uint32_t)(((i0 % (int64_t)per) + per) % per);
   }
 
-  auto fetch = [&](int64_t base, float4 (&x)[kRounds], float4 (&z)[kRounds]) {
+  auto fetch = [&](const Walk& w, float4 (&x)[kRounds], float4 (&z)[kRounds]) {
+    const int64_t base = g0 + w.c * kMixChunk;
     const bool inner = base >= c0 && base + kMixChunk <= c1;
-    uint32_t p = pos;
-    pos += step_chunk;
-    if (pos >= per) pos -= per;
+    uint32_t p = w.pos;
     if (inner) {
 #pragma unroll
       for (int r = 0; r < kRounds; ++r) {
@@ -329,7 +355,8 @@ noise_mix_kernel(MixArgs m) {
     }
   };
 
-  auto process = [&](int64_t base, const float4 (&x)[kRounds], const float4 (&z)[kRounds]) {
+  auto process = [&](const Walk& w, const float4 (&x)[kRounds], const float4 (&z)[kRounds]) {
+    const int64_t base = g0 + w.c * kMixChunk;
     const bool inner = base >= c0 && base + kMixChunk <= c1;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
@@ -364,20 +391,22 @@ noise_mix_kernel(MixArgs m) {
     }
   };
 
-  int64_t base = g0 + (int64_t)blockIdx.x * kMixChunk;
   float4 xa[kRounds], za[kRounds], xb[kRounds], zb[kRounds];
-  fetch(base, xa, za);
+  fetch(cur, xa, za);
   for (;;) {
-    bool more = base + stride < c1;
-    if (more) fetch(base + stride, xb, zb);
-    process(base, xa, za);
+    Walk nxt = cur;
+    advance(nxt);
+    bool more = nxt.col < cols;
+    if (more) fetch(nxt, xb, zb);
+    process(cur, xa, za);
     if (!more) break;
-    base += stride;
-    more = base + stride < c1;
-    if (more) fetch(base + stride, xa, za);
-    process(base, xb, zb);
+    cur = nxt;
+    advance(nxt);
+    more = nxt.col < cols;
+    if (more) fetch(nxt, xa, za);
+    process(cur, xb, zb);
     if (!more) break;
-    base += stride;
+    cur = nxt;
   }
   if (!RESCALE) {
 #pragma unroll
