@@ -163,3 +163,18 @@ def test_full_size_batch_two_clips_checked():
     want5, info = ON.add_noise(other, nz, -10.0, return_info=True)
     assert info["rate"] is not None
     np.testing.assert_array_equal(got[5], want5)
+
+
+def test_clip_longer_than_the_shared_memory_heap():
+    """A 70 s clip needs a depth-14 tree: its heaps no longer fit in shared memory and the combine
+    kernel takes the global-memory path; a second, short clip in the same batch shares the launch."""
+    import torch
+    import avsl_b200 as A
+    rng = np.random.default_rng(11)
+    L = 70 * 16000 + 13
+    clean = rng.integers(-8000, 8001, size=L + 4000).astype(np.float32)
+    noise = rng.integers(-2000, 2001, size=50001 + 977).astype(np.float32)
+    co, no = [0, L, L + 4000], [0, 50001, 50001 + 977]
+    want = ON.add_noise_batch(clean, co, noise, no, [3.0, -2.0])
+    got = A.add_noise_batch(torch.from_numpy(clean).cuda(), co, torch.from_numpy(noise).cuda(), no, [3.0, -2.0]).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
