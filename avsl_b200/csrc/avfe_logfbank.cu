@@ -23,17 +23,17 @@ constexpr int kTileFrames = 8;
 constexpr int kFfts = kTileFrames / 2;
 constexpr int kThreads = kFfts * kFftThreads;                 // 256
 constexpr int kSpan = (kTileFrames - 1) * kHop + kFrame;       // 1520 samples per tile
-constexpr int kMaxFilt = 64;
+constexpr int kMaxFilt = 40;             // filters per bank (python_speech_features: 26; fbank-40 fits)
 
 constexpr int kMaxTaps = 640;             // packed nonzero filter weights (26 HTK filters: 2 x 257 at most)
 
 constexpr int kPRow = 268;            // floats between the power rows of consecutive tile frames (= 12 banks)
 
 struct Smem {
-  float y[kSpan];                       // pre-emphasised samples of the tile (zero past the clip)
   float2 tw[kNfft];
   float2 S[kFfts][kSFloat2];            // exchange storage; the power rows overwrite it
-  float2 C[kFfts][kNfft];               // spectra
+  float2 C[kFfts][kNfft];               // spectra; the tile's pre-emphasised samples (kSpan floats, zero past
+                                        // the clip) live here until step 1 has consumed them
   float feat[kTileFrames * kMaxFilt];   // log energies [frame][nfilt] packed = the stacked row layout
   float wts[kMaxTaps];                  // filter weights, supports back to back
   int lo[kMaxFilt], hi[kMaxFilt], woff[kMaxFilt];   // filter supports and weight offsets
@@ -119,6 +119,8 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     it_m[q] = (i < kTileFrames * nfilt) ? i / kTileFrames : 0;
   }
   const int rows_here = kTileFrames / stack, width = stack * nfilt;
+  float* tile_y = reinterpret_cast<float*>(sm.C);               // dead between power_rows and the next step 3
+  static_assert(kSpan * sizeof(float) <= sizeof(sm.C), "the tile's samples must fit in the spectrum storage");
 
   for (int64_t f0 = (int64_t)blockIdx.x * kTileFrames; f0 < rows * stack; f0 += (int64_t)gridDim.x * kTileFrames) {
   // raw samples of the span (one coalesced load each, plus the sample before the span), then the
@@ -137,7 +139,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     for (int q = 0; q < kPer; ++q) {
       const int i = tid + q * kThreads;
       const int64_t n = s0 + i;
-      if (i < kSpan) sm.y[i] = (n == 0 || n >= len) ? cur[q] : __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));
+      if (i < kSpan) tile_y[i] = (n == 0 || n >= len) ? cur[q] : __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));
     }
   }
   __syncthreads();
@@ -145,7 +147,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   const int g = tid / kFftThreads, t = tid % kFftThreads;       // FFT g: tile frames 2g, 2g + 1
   float2* S = sm.S[g];
   float2* C = sm.C[g];
-  step1(t, sm.y + (2 * g) * kHop, sm.y + (2 * g + 1) * kHop, sm.tw, S);
+  step1(t, tile_y + (2 * g) * kHop, tile_y + (2 * g + 1) * kHop, sm.tw, S);
   __syncthreads();
   float2 x[8];
   step2_load(t, S, x);
