@@ -86,21 +86,19 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
   }
 }
 
-// grid = (tile slots, clips): a CTA walks the tiles blockIdx.x, + gridDim.x, ... of its clip, so
-// that the twiddle table and the filter supports are set up once per CTA, not once per 8 frames
+// One wave of CTAs; the tiles of the whole (ragged) batch form one list that the CTAs stride over,
+// so that the twiddle table and the filter supports are set up once per CTA and a long clip does not
+// leave the CTAs of the short ones idle.  The list is virtual: clip b's tiles start at unit
+// V_b = row_offsets[b] / rows_per_tile + b (monotone, and V_{b+1} - V_b >= the clip's tile count), a
+// unit that falls into the slack between two clips is skipped; the clip of a unit is found by a
+// binary search over row_offsets.
 __global__ void __launch_bounds__(kThreads)
 logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets,
-                const int64_t* __restrict__ row_offsets, const float* __restrict__ fb, int nfilt,
+                const int64_t* __restrict__ row_offsets, int64_t B, const float* __restrict__ fb, int nfilt,
                 const FilterPack* __restrict__ pack, int stack, int normalize, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char fbk_smem[];
   Smem& sm = *reinterpret_cast<Smem*>(fbk_smem);
   const int tid = threadIdx.x;
-  const int64_t b = blockIdx.y;
-  const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
-  const int64_t nfr = num_frames(len);
-  const int64_t rows = (nfr + stack - 1) / stack;               // stacked rows (zero-padded tail)
-  if ((int64_t)blockIdx.x * kTileFrames >= rows * stack) return;   // CTA-uniform
-  const float* clip = audio + beg;
   for (int i = tid; i < kNfft; i += kThreads) sm.tw[i] = make_float2(kTw512Re[i], kTw512Im[i]);
   if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.woff[tid] = pack->woff[tid]; }
   const bool packed = pack->total <= kMaxTaps;
@@ -122,7 +120,19 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   float* tile_y = reinterpret_cast<float*>(sm.C);               // dead between power_rows and the next step 3
   static_assert(kSpan * sizeof(float) <= sizeof(sm.C), "the tile's samples must fit in the spectrum storage");
 
-  for (int64_t f0 = (int64_t)blockIdx.x * kTileFrames; f0 < rows * stack; f0 += (int64_t)gridDim.x * kTileFrames) {
+  const int64_t units = row_offsets[B] / rows_here + B;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+  int64_t b = 0;
+  for (int64_t hi = B - 1; b < hi;) {                           // largest b with V_b <= u (CTA-uniform)
+    const int64_t mid = (b + hi + 1) >> 1;
+    if (row_offsets[mid] / rows_here + mid <= u) b = mid; else hi = mid - 1;
+  }
+  const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
+  const int64_t nfr = num_frames(len);
+  const int64_t rows = (nfr + stack - 1) / stack;               // stacked rows (zero-padded tail)
+  const int64_t f0 = (u - (row_offsets[b] / rows_here + b)) * kTileFrames;
+  if (len <= 0 || f0 < 0 || f0 >= rows * stack) continue;       // slack unit
+  const float* clip = audio + beg;
   // raw samples of the span (one coalesced load each, plus the sample before the span), then the
   // pre-emphasis y[n] = x[n] - 0.97 x[n-1] from registers; beyond the clip: framesig's zeros
   {
@@ -241,18 +251,23 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
   if (!aligned16(workspace)) return AVFE_ERR_WORKSPACE;
   fbk::FilterPack* pack = static_cast<fbk::FilterPack*>(workspace);
   fbk::logfbank_prep_kernel<<<1, 256, 0, s>>>(fbank, nfilt, pack);
-  // about 4 resident CTAs per SM in total, each walking several tiles of its clip
-  int64_t slots = (4 * (int64_t)kNumSMs + B - 1) / B;
-  if (slots > tiles) slots = tiles;
-  if (slots < 1) slots = 1;
-  dim3 grid((unsigned)slots, (unsigned)B);
   if (cudaFuncSetAttribute(fbk::logfbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(fbk::Smem)) != cudaSuccess) {
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  fbk::logfbank_kernel<<<grid, fbk::kThreads, sizeof(fbk::Smem), s>>>(audio, offsets, row_offsets, fbank, nfilt, pack, stack,
-                                                      normalize, out);
+  // one resident wave (5 CTAs per SM: shared memory), each CTA striding over the batch's tile list
+  int resident = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fbk::logfbank_kernel, fbk::kThreads, sizeof(fbk::Smem)) !=
+          cudaSuccess || resident < 1) {
+    cudaGetLastError();
+    resident = 1;
+  }
+  int64_t ctas = (int64_t)resident * kNumSMs;
+  if (ctas > tiles * B) ctas = tiles * B;
+  if (ctas < 1) ctas = 1;
+  fbk::logfbank_kernel<<<(unsigned)ctas, fbk::kThreads, sizeof(fbk::Smem), s>>>(audio, offsets, row_offsets, B, fbank, nfilt,
+                                                                              pack, stack, normalize, out);
   count_launch(2);
   return check_launch();
 }
