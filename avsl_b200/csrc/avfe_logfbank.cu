@@ -120,18 +120,20 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
   float* tile_y = reinterpret_cast<float*>(sm.C);               // dead between power_rows and the next step 3
   static_assert(kSpan * sizeof(float) <= sizeof(sm.C), "the tile's samples must fit in the spectrum storage");
 
-  const int64_t units = row_offsets[B] / rows_here + B;
+  const int rpt_shift = 31 - __clz(rows_here);                   // rows per tile is 1, 2, 4 or 8 (8 % stack == 0)
+  const int stack_shift = 31 - __clz(stack);                     // ... and so is stack: shifts, not 64-bit divisions per tile
+  const int64_t units = (row_offsets[B] >> rpt_shift) + B;
   for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
   int64_t b = 0;
   for (int64_t hi = B - 1; b < hi;) {                           // largest b with V_b <= u (CTA-uniform)
     const int64_t mid = (b + hi + 1) >> 1;
-    if (row_offsets[mid] / rows_here + mid <= u) b = mid; else hi = mid - 1;
+    if ((row_offsets[mid] >> rpt_shift) + mid <= u) b = mid; else hi = mid - 1;
   }
   const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
   const int64_t nfr = num_frames(len);
-  const int64_t rows = (nfr + stack - 1) / stack;               // stacked rows (zero-padded tail)
-  const int64_t f0 = (u - (row_offsets[b] / rows_here + b)) * kTileFrames;
-  if (len <= 0 || f0 < 0 || f0 >= rows * stack) continue;       // slack unit
+  const int64_t rows = (nfr + stack - 1) >> stack_shift;        // stacked rows (zero-padded tail)
+  const int64_t f0 = (u - ((row_offsets[b] >> rpt_shift) + b)) * kTileFrames;
+  if (len <= 0 || f0 < 0 || f0 >= (rows << stack_shift)) continue;   // slack unit
   const float* clip = audio + beg;
   // raw samples of the span (one coalesced load each, plus the sample before the span), then the
   // pre-emphasis y[n] = x[n] - 0.97 x[n-1] from registers; beyond the clip: framesig's zeros
@@ -208,7 +210,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     }
     __syncthreads();
   }
-  const int64_t row0 = f0 / stack;
+  const int64_t row0 = f0 >> stack_shift;
   float* o = out + (row_offsets[b] + row0) * width;
   for (int r = 0; r < rows_here; ++r) {
     if (row0 + r >= rows) break;
