@@ -129,7 +129,7 @@ AVFE_API int avfe_spec_mask_f32(float* mel, int64_t B, int n_mels, int64_t n_fra
  *   row_offsets [B+1] int64: first output row of clip b (clip b has
  *               ceil(avfe_logfbank_num_frames(L_b) / stack) rows)
  *   max_samples the longest clip (sizes the launch)
- *   fbank       [nfilt, 257] float32 (python_speech_features.get_filterbanks)
+ *   fbank       [nfilt, 257] float32 (python_speech_features.get_filterbanks), nfilt <= 40
  *   out         [row_offsets[B], nfilt * stack] float32
  *   workspace   avfe_logfbank_workspace_bytes() bytes (filter supports) */
 AVFE_API int64_t avfe_logfbank_num_frames(int64_t n_samples);
