@@ -124,7 +124,7 @@ struct FrameXform {
   uint32_t box_hi;   //                   rows | pitch << 13
 };
 
-constexpr int kTilePx = 8192;   // staged footprint capacity (e.g. 80 x 96 source pixels + alignment)
+constexpr int kTilePx = 8192;   // staged footprint capacity of the generic kernel (e.g. 80 x 96 source pixels + alignment)
 constexpr int kMaxRoi = 128;
 
 // Source footprint of one ROI window, frame-clipped and aligned for cp.async staging.
@@ -145,8 +145,9 @@ __device__ __forceinline__ Footprint unpack_footprint(const FrameXform& x) {
   return fp;
 }
 
-// align = pixel alignment of the box's first column and pitch (16 or 4; 0 = do not stage)
-__device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, int H, int W, int align) {
+// align = pixel alignment of the box's first column and pitch (16 or 4; 0 = do not stage);
+// cap = pixels the consumer's shared-memory tile holds
+__device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, int H, int W, int align, int cap) {
   x.box_lo = 0u; x.box_hi = 0u;
   if (x.r0 < 0 || align == 0 || H > 8191 || W > 8191) return;
   // an affine map takes its extrema at the window corners
@@ -171,7 +172,7 @@ __device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, 
   const int cols = (int)fmin(fc1, (double)(W - 1)) - c0 + 1;
   if (rows <= 0 || cols <= 0) return;                       // window entirely off-frame
   const int pitch = min((cols + align - 1) & ~(align - 1), W - c0);   // W % align == 0
-  if (rows * pitch > kTilePx) return;                       // too large: taps from global memory
+  if (rows * pitch > cap) return;                           // too large: taps from global memory
   x.box_lo = (uint32_t)r0 | ((uint32_t)c0 << 13) | (interior ? (1u << 26) : 0u) | (1u << 27);
   x.box_hi = (uint32_t)rows | ((uint32_t)pitch << 13);
 }
@@ -186,7 +187,7 @@ struct TformArgs {
   int64_t n_clips;
   const double* mean_face;
   const double* tforms_in;
-  int std_size, roi, window, fp_lo, fp_span, H, W, fp_align;
+  int std_size, roi, window, fp_lo, fp_span, H, W, fp_align, fp_cap;
   int32_t* crop_rc;
   double* tforms_out;
   // collation (avfe_lip_roi_collate): frame t of clip c goes to slot c*T_pad + t of the padded
@@ -297,7 +298,7 @@ __device__ __forceinline__ FrameXform tform_frame(const TformArgs& a, int64_t f,
 #pragma unroll
   for (int j = 0; j < 6; ++j) o.inv[j] = inv[j];
   o.r0 = r0; o.c0 = c0;
-  pack_footprint(o, a.fp_lo, a.fp_span, a.H, a.W, a.fp_align);
+  pack_footprint(o, a.fp_lo, a.fp_span, a.H, a.W, a.fp_align, a.fp_cap);
   if (lane == 0) {
     if (a.crop_rc != nullptr) { a.crop_rc[2 * f] = r0; a.crop_rc[2 * f + 1] = c0; }
     if (a.tforms_out != nullptr) {
@@ -635,6 +636,7 @@ static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, i
   ta.lm = landmarks; ta.valid = lm_valid; ta.clip_offsets = clip_offsets; ta.n_clips = n_clips;
   ta.mean_face = mean_face; ta.tforms_in = tforms_in; ta.std_size = std_size; ta.roi = roi;
   ta.window = window; ta.fp_lo = fp_lo; ta.fp_span = fp_span; ta.H = H; ta.W = W; ta.fp_align = fp_align;
+  ta.fp_cap = kTilePx;
   ta.crop_rc = crop_rc; ta.tforms_out = tforms; ta.keep = keep; ta.T_pad = T_pad;
 
   // window side known at compile time for the two standard configurations
@@ -651,6 +653,7 @@ static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, i
     j.gray_out = gray_out; j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = nullptr;
     j.ngroups = 0; j.stage_align = fp_align;
     fj.tf = ta;
+    fj.tf.fp_cap = kFrameTilePx;                            // u8 tiles: twice the generic kernel's capacity
     fj.groups_per_frame = (int)((int64_t)H * W / 16);
     fj.chunks_per_frame = (fj.groups_per_frame + 63) / 64;
     fj.row_groups = W / 16;

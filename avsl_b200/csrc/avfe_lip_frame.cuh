@@ -24,7 +24,7 @@ namespace avfe {
 
 constexpr int kTformRoleWarps = 2;
 constexpr int kDescRing = 4;
-constexpr int kFrameTilePx = 8192;          // staged footprint capacity per slot (u16 each)
+constexpr int kFrameTilePx = 16384;         // staged footprint capacity per slot (one byte per pixel)
 
 template <int SPAN>
 struct FrameRoles {
@@ -66,7 +66,7 @@ struct FrameSmem {
   unsigned long long tile_empty[FrameRoles<SPAN>::kSlots];
   FrameXform desc[kDescRing];
   int64_t dst[kDescRing];                     // f32 output slot of the frame (collation), < 0: dropped
-  __align__(16) uint16_t tile[FrameRoles<SPAN>::kSlots][kFrameTilePx];   // gray footprint as 128*k (byte offset of lut255 row k)
+  __align__(16) uint8_t tile[FrameRoles<SPAN>::kSlots][kFrameTilePx];    // gray footprint, one byte per pixel
   __align__(16) uint4 ring[FrameRoles<SPAN>::kStreamWarps][FrameRoles<SPAN>::kRing][kChunkVec];
 };
 
@@ -140,14 +140,6 @@ __device__ __forceinline__ void frame_tform_run(const FrameJob& j, FrameSmem<SPA
 }
 
 // ---------------------------------------------------------------- stream warps
-// 16 packed gray bytes -> 16 x u16 (128 * k), two uint4
-__device__ __forceinline__ void gray16_to_tile(const uint4& g, uint4& lo, uint4& hi) {
-  auto pair_lo = [](uint32_t w) { return __byte_perm(w, 0u, 0x4140) << 7; };   // bytes 0,1
-  auto pair_hi = [](uint32_t w) { return __byte_perm(w, 0u, 0x4342) << 7; };   // bytes 2,3
-  lo = make_uint4(pair_lo(g.x), pair_hi(g.x), pair_lo(g.y), pair_hi(g.y));
-  hi = make_uint4(pair_lo(g.z), pair_hi(g.z), pair_lo(g.w), pair_hi(g.w));
-}
-
 template <int SPAN>
 __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SPAN>& sm, int sw, int lane,
                                                  int nk) {
@@ -224,16 +216,10 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
         const int ra = (int)__umulhi((unsigned)g0, j.row_magic), ca = g0 - ra * j.row_groups;
         const int rb = (int)__umulhi((unsigned)g1, j.row_magic), cb = g1 - rb * j.row_groups;
         if ((unsigned)(ra - br0) < (unsigned)brows && (unsigned)(ca - bcg) < (unsigned)bpg && g0 < gpf) {
-          uint4 lo, hi;
-          gray16_to_tile(ga, lo, hi);
-          uint4* t = tile + 2 * ((ra - br0) * bpg + (ca - bcg));
-          t[0] = lo; t[1] = hi;
+          tile[(ra - br0) * bpg + (ca - bcg)] = ga;
         }
         if ((unsigned)(rb - br0) < (unsigned)brows && (unsigned)(cb - bcg) < (unsigned)bpg && g1 < gpf) {
-          uint4 lo, hi;
-          gray16_to_tile(gb, lo, hi);
-          uint4* t = tile + 2 * ((rb - br0) * bpg + (cb - bcg));
-          t[0] = lo; t[1] = hi;
+          tile[(rb - br0) * bpg + (cb - bcg)] = gb;
         }
       }
       if (++stage == R::kRing) { stage = 0; phase ^= 1u; }
@@ -247,7 +233,7 @@ __device__ __forceinline__ void frame_stream_run(const FrameJob& j, FrameSmem<SP
 // ---------------------------------------------------------------- blend warps
 template <int SPAN>
 __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int64_t slot_f32, const FrameXform& x,
-                                                 const uint16_t* tile, const double* lut255, const float* lutn,
+                                                 const uint8_t* tile, const double* lut255, const float* lutn,
                                                  int tid) {
   using R = FrameRoles<SPAN>;
   const Footprint fp = unpack_footprint(x);
@@ -301,7 +287,7 @@ __device__ __forceinline__ void frame_blend_item(const LipJob& j, int64_t f, int
   const int brows = fp.staged ? fp.rows : 0;
   auto tap = [&](int r, int cc) -> double {
     const int tr_ = r - br0, tc_ = cc - bc0;
-    if ((unsigned)tr_ < (unsigned)brows && (unsigned)tc_ < (unsigned)pitch) return lut_at(lut, tile[tr_ * pitch + tc_]);
+    if ((unsigned)tr_ < (unsigned)brows && (unsigned)tc_ < (unsigned)pitch) return lut_at(lut, tile_off(tile[tr_ * pitch + tc_]));
     const uint8_t* p = img + ((int64_t)r * W + cc) * 3;                 // not staged: global tap
     return lut[16 * gray_from_bgr(__ldg(p), __ldg(p + 1), __ldg(p + 2))];
   };

@@ -272,18 +272,23 @@ __device__ __forceinline__ void producer_run(const LipJob& j, FusedSmem& sm, int
 __device__ __forceinline__ double lut_at(const double* lut, uint32_t off8) {   // off8 = 128 * k
   return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(lut) + off8);
 }
+// tile element -> byte offset of its lut255 row: the generic kernel stores 128 * k as u16, the frame
+// kernel the gray level itself as u8 (twice the pixels in the same shared memory, one shift per tap)
+__device__ __forceinline__ uint32_t tile_off(uint16_t v) { return v; }
+__device__ __forceinline__ uint32_t tile_off(uint8_t v) { return (uint32_t)v << 7; }
 
 // One output pixel whose four taps are known to lie inside the staged tile (interior ROI):
 // no bounds tests, tap offsets by increment.  Same roundings as bilinear_u8.
-__device__ __forceinline__ uint32_t bilinear_interior(double r, double c, const uint16_t* tile, int pitch,
+template <typename T>
+__device__ __forceinline__ uint32_t bilinear_interior(double r, double c, const T* tile, int pitch,
                                                       int br0, int bc0, const double* lut) {
   const double fr = floor(r), fc = floor(c);
   const double dr = f64sub(r, fr), dc = f64sub(c, fc);
-  const uint16_t* p = tile + ((int)fr - br0) * pitch + ((int)fc - bc0);
+  const T* p = tile + ((int)fr - br0) * pitch + ((int)fc - bc0);
   const int oc = (dc != 0.0) ? 1 : 0;                 // ceil(c) - floor(c)
   const int orow = (dr != 0.0) ? pitch : 0;           // (ceil(r) - floor(r)) * pitch
-  const double tl = lut_at(lut, p[0]), tr = lut_at(lut, p[oc]);
-  const double bl = lut_at(lut, p[orow]), br = lut_at(lut, p[orow + oc]);
+  const double tl = lut_at(lut, tile_off(p[0])), tr = lut_at(lut, tile_off(p[oc]));
+  const double bl = lut_at(lut, tile_off(p[orow])), br = lut_at(lut, tile_off(p[orow + oc]));
   const double omc = f64sub(1.0, dc), omr = f64sub(1.0, dr);
   const double top = f64add(f64mul(omc, tl), f64mul(dc, tr));
   const double bot = f64add(f64mul(omc, bl), f64mul(dc, br));
