@@ -425,6 +425,23 @@ def main():
         side["lip_with_u8_roi"] = {"kernel": "lip_frame_kernel<96>: gray + 96x96 u8 ROI + 88x88 f32 crop (6 stream, 24 blend warps)",
                                    "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
         del r96
+        # the same lip stage on the reference's real frame shape (AMI closeups are 352 x 288): 32 clips x 250 frames
+        H2, W2, T2, C2 = 288, 352, 250, 32
+        fr2 = synth.video_frames_cuda(C2 * T2, H2, W2, SEED + 2, device=dev)
+        lm2 = [synth.landmarks_for_clip(T2, H2, W2, seed=SEED + 10 + c) for c in range(C2)]
+        lmt = torch.from_numpy(np.concatenate([x[0] for x in lm2])).to(dev)
+        vt = torch.from_numpy(np.concatenate([x[1] for x in lm2])).to(dev)
+        off2 = torch.arange(C2 + 1, dtype=torch.int64, device=dev) * T2
+        r2 = None
+
+        def run_352():
+            nonlocal r2
+            r2 = lip_roi_batch(fr2, off2, lmt, vt, want_gray=True, want_u8=False, want_f32=True, out=r2)
+        ms = time_op(run_352, 10)
+        nbytes = C2 * T2 * (H2 * W2 * 3 + 68 * 2 * 8 + H2 * W2 + 88 * 88 * 4)
+        side["lip_352x288"] = {"kernel": "lip_frame_kernel<88> on 8000 frames of 352 x 288 (AMI closeup shape; footprint ~ 88 x 112 px per frame)",
+                               "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
+        del fr2, lmt, vt, r2
         # SpecAugment masks (8(f) rank 2) on the step's mel batch: only the masked elements are written
         mel_b = fe.forward_device(batch_dev)["mel"]
         frames_before_pad = [int(x) for x in ((batch_dev.audio_offsets[1:] - batch_dev.audio_offsets[:-1]) // 160).tolist()]
