@@ -157,7 +157,7 @@ noise_leaf_kernel(NoiseArgs a) {
       }
       const float sc = piece_sum(vc, tc);
       const float sz = piece_sum(vz, tz);
-      if (kk != 0 && j < 2) heap[(int64_t)j * a.heap_slots + kk] = j ? sz : sc;
+      if (kk != 0 && kk < a.heap_slots && j < 2) heap[(int64_t)j * a.heap_slots + kk] = j ? sz : sc;   // kk >= slots: a clip longer than the max_len the caller promised
     }
   }
 }

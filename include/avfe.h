@@ -151,7 +151,8 @@ AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const
  *                   likewise; offsets are [B+1] int64 on the device
  *   snr_ratio       [B] float32 = (float)10^(snr_b / 20), evaluated by the caller in double like
  *                   the reference's Python expression
- *   max_len         the longest clean clip (sizes the launch and the workspace), < 2^31
+ *   max_len         the longest clean clip (sizes the launch and the workspace), < 2^31; a clip
+ *                   longer than this is mixed with a wrong gain (never out of bounds)
  *   out_i16/out_f32 packed like `clean` (8- / 16-byte aligned); either may be NULL; out_f32 holds the same integers as
  *                   float32 (what logfbank takes)
  * A clip whose noise is empty is cast unmixed (the reference raises ZeroDivisionError; the Python
