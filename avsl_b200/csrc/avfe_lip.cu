@@ -166,13 +166,19 @@ __device__ __forceinline__ void pack_footprint(FrameXform& x, int lo, int span, 
   // one pixel of slack each side (covers the rounding of the hoisted evaluation)
   const double fr0 = floor(rmin) - 1.0, fr1 = ceil(rmax) + 1.0;
   const double fc0 = floor(cmin) - 1.0, fc1 = ceil(cmax) + 1.0;
-  const bool interior = fr0 >= 0.0 && fc0 >= 0.0 && fr1 <= (double)(H - 1) && fc1 <= (double)(W - 1);
+  bool interior = fr0 >= 0.0 && fc0 >= 0.0 && fr1 <= (double)(H - 1) && fc1 <= (double)(W - 1);
   const int r0 = (int)fmax(fr0, 0.0), c0 = ((int)fmax(fc0, 0.0)) & ~(align - 1);
-  const int rows = (int)fmin(fr1, (double)(H - 1)) - r0 + 1;
+  int rows = (int)fmin(fr1, (double)(H - 1)) - r0 + 1;
   const int cols = (int)fmin(fc1, (double)(W - 1)) - c0 + 1;
   if (rows <= 0 || cols <= 0) return;                       // window entirely off-frame
   const int pitch = min((cols + align - 1) & ~(align - 1), W - c0);   // W % align == 0
-  if (rows * pitch > cap) return;                           // too large: taps from global memory
+  if (rows * pitch > cap) {
+    // too large for the tile: stage the rows that fit; the taps below them come from global memory
+    // (bounds-checked path), which is still most of the traffic saved
+    rows = cap / pitch;
+    interior = false;
+    if (rows <= 0) return;
+  }
   x.box_lo = (uint32_t)r0 | ((uint32_t)c0 << 13) | (interior ? (1u << 26) : 0u) | (1u << 27);
   x.box_hi = (uint32_t)rows | ((uint32_t)pitch << 13);
 }

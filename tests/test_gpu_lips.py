@@ -251,7 +251,8 @@ def test_frame_kernel_edge_cases_in_one_batch():
                 assert d.max() <= 1 and (d != 0).mean() < 2e-3, kind
 
 
-@pytest.mark.parametrize("H,W,T", [(288, 352, 40), (120, 176, 33), (96, 128, 150), (240, 320, 149), (224, 224, 297)])
+@pytest.mark.parametrize("H,W,T", [(288, 352, 40), (120, 176, 33), (96, 128, 150), (240, 320, 149), (224, 224, 297),
+                                   (480, 640, 21)])      # 480 x 640: footprints larger than either kernel's tile
 def test_frame_kernel_equals_generic_path(H, W, T):
     """The frame-owner kernel (gray wanted) and the generic work-queue path (no gray) are two
     implementations of the same arithmetic: identical ROI bytes, crop origins and transforms on
