@@ -68,3 +68,27 @@ def test_batch_is_per_clip(golden):
     out = ON.add_noise_batch(np.concatenate(cl), co, np.concatenate(nz), no, [float(golden[f"{n}_snr"]) for n in names])
     for i, n in enumerate(names):
         np.testing.assert_array_equal(out[co[i]:co[i + 1]], golden[f"{n}_mixed"])
+
+
+def test_noise_plan_host_logic():
+    """The shim's bookkeeping (no GPU needed): SNR divisors as the reference's Python expression gives
+    them, offsets validation, the reference's ZeroDivisionError for an empty noise clip, workspace
+    sized by the library."""
+    import torch
+    from avsl_b200 import audio as AA
+    plan = AA.NoisePlan([0, 10, 10, 500000], [0, 4, 4, 9], [10, 0, -5.5], "cpu")
+    assert plan.B == 3 and plan.max_len == 499990 and plan.d_ratio.dtype == torch.float32
+    np.testing.assert_array_equal(plan.d_ratio.numpy(), np.array([ON.snr_ratio(10), ON.snr_ratio(0), ON.snr_ratio(-5.5)]))
+    assert AA.snr_ratio(20) == np.float32(10.0) and AA.snr_ratio(0) == np.float32(1.0)
+    assert plan.ws.numel() >= 3 * 2 * (2 << 13) * 4                      # depth 13 for ~31 s
+    assert AA.NoisePlan([0, 5], [0, 2], 3, "cpu").d_ratio.shape == (1,)     # scalar SNR is broadcast
+    with pytest.raises(ZeroDivisionError):
+        AA.NoisePlan([0, 10], [0, 0], 0, "cpu")
+    with pytest.raises(ValueError):
+        AA.NoisePlan([0, 10, 5], [0, 1, 2], 0, "cpu")
+    with pytest.raises(ValueError):
+        AA.NoisePlan([0, 10], [0, 1, 2], 0, "cpu")
+    with pytest.raises(ValueError):
+        AA.NoisePlan([0, 10], [0, 1], 0, "cpu", out_dtype=torch.float64)
+    with pytest.raises(ValueError):
+        AA.NoisePlan([0, 1 << 40], [0, 1], 0, "cpu")                     # longer than the library supports
