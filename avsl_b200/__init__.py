@@ -13,7 +13,7 @@ from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, Logfban
                     mel_filters, pad_or_trim, peak_normalize, process_audio_for_av_hubert, spec_augment,
                     spec_augment_bands)
 from .frontend import (AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, bind_to_gpu_numa_node,
-                       pack_utterances, shard)
+                       pack_utterances, shard, shard_balanced)
 from .fusion import (ModalityFusion, fuse_modalities, fuse_transpose_layernorm, modality_dropout_flags,
                      modality_dropout_mask)
 from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,

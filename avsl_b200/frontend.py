@@ -316,6 +316,25 @@ def shard(n_items: int, rank: int, world_size: int) -> np.ndarray:
     return np.arange(rank, n_items, world_size)
 
 
+def shard_balanced(durations, rank: int, world_size: int) -> np.ndarray:
+    """Length-balanced variant of ``shard`` (the cost of an utterance is proportional to its
+    duration: SURVEY 8(e)): longest-processing-time-first assignment of the utterances to the
+    ranks, computed identically by every rank from the duration list alone -- no communication.
+    Returns the sorted indices rank ``rank`` owns; the ranks' sets partition ``range(len(durations))``
+    and their total durations differ by at most the longest utterance."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank must be in [0, world_size)")
+    d = np.asarray(durations, dtype=np.float64).reshape(-1)
+    order = np.argsort(-d, kind="stable")                   # longest first, ties by index: deterministic
+    load = np.zeros(world_size, dtype=np.float64)
+    owner = np.empty(len(d), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(load))                            # first of the least-loaded ranks
+        owner[i] = r
+        load[r] += d[i]
+    return np.flatnonzero(owner == rank)
+
+
 def aggregate_rank_stats(elapsed_ms: float, audio_seconds: float, alg_bytes: float, launches: float = 0.0,
                          device="cpu"):
     """Job-level numbers from per-rank ones: time = MAX over ranks, work = SUM over ranks.

@@ -50,6 +50,24 @@ def test_shard_is_a_disjoint_cover():
         frontend.shard(10, 3, 3)
 
 
+def test_shard_balanced_partitions_and_balances():
+    durs = synth.ami_durations(10000, 3407)
+    for w in (1, 2, 8):
+        parts = [frontend.shard_balanced(durs, r, w) for r in range(w)]
+        np.testing.assert_array_equal(np.sort(np.concatenate(parts)), np.arange(len(durs)))
+        loads = np.array([durs[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= durs.max() + 1e-9
+        assert all((np.diff(p) > 0).all() for p in parts)
+        # strided shards of the same list are less even than the balanced ones
+        strided = np.array([durs[frontend.shard(len(durs), r, w)].sum() for r in range(w)])
+        assert loads.max() - loads.min() <= strided.max() - strided.min() + 1e-9
+    np.testing.assert_array_equal(frontend.shard_balanced([], 0, 2), np.zeros(0, dtype=np.int64))
+    np.testing.assert_array_equal(frontend.shard_balanced([5.0, 1.0, 1.0, 3.0], 0, 2), [0])       # 5 | 3 + 1 + 1
+    np.testing.assert_array_equal(frontend.shard_balanced([5.0, 1.0, 1.0, 3.0], 1, 2), [1, 2, 3])
+    with pytest.raises(ValueError):
+        frontend.shard_balanced([1.0], 2, 2)
+
+
 def test_modality_dropout_draws_match_reference_block():
     """Same RNG stream, same decisions as av_hubert_encoder.py:292-298 (two draws per forward,
     even in eval)."""

@@ -33,12 +33,19 @@ def _worker(rank, world, port, out):
         dist.all_gather_object(gathered, full.tolist())
         step_idx = [None] * world
         dist.all_gather_object(step_idx, idx.tolist())
+        # the length-balanced shards: every rank derives the same partition on its own
+        alld = synth.ami_durations(bench.N_SWEEP, bench.SEED)
+        bal = [None] * world
+        dist.all_gather_object(bal, frontend.shard_balanced(alld, rank, world).tolist())
+        bal_loads = [float(alld[np.asarray(x, dtype=np.int64)].sum()) for x in bal]
         # per-rank fake timing: rank r took (10 + r) ms for its own audio seconds
         t, a, b, l = frontend.aggregate_rank_stats(10.0 + rank, float(durs.sum()), 1000.0 * (rank + 1), 5.0)
         if rank == 0:
             out.put({"cover": sorted(sum(gathered, [])) == list(range(bench.N_SWEEP)),
                      "disjoint": len(set(step_idx[0]) & set(step_idx[1])) == 0,
                      "t": t, "audio": a, "bytes": b, "launches": l,
+                     "bal_cover": sorted(sum(bal, [])) == list(range(bench.N_SWEEP)),
+                     "bal_gap": abs(bal_loads[0] - bal_loads[1]), "max_dur": float(alld.max()),
                      "expect_audio": float(synth.ami_durations(bench.N_SWEEP, bench.SEED)[np.r_[0:64]].sum())})
     finally:
         dist.destroy_process_group()
@@ -58,6 +65,7 @@ def test_two_rank_sharding_and_reduction():
         p.join(timeout=30)
         assert p.exitcode == 0
     assert res["cover"] and res["disjoint"]
+    assert res["bal_cover"] and res["bal_gap"] <= res["max_dur"]
     assert res["t"] == 11.0                       # max over ranks
     assert res["bytes"] == 3000.0 and res["launches"] == 10.0
     # ranks 0 and 1 own utterances 0,2,..,62 and 1,3,..,63: together the first 64 of the sweep
