@@ -24,5 +24,11 @@ Every function restates the algorithm of one reference symbol (file:line into
 * fusion       : concat / add are the reference's two torch expressions
                  (``avsl/modules/av_hubert_encoder.py:315-326``); weighted-sum and
                  per-sample masks are build-defined (**parity unpinned**: the reference
-                 raises ``ValueError``).
+                 raises ``ValueError``).  fusion + transpose + LayerNorm: the reference's own
+                 torch ops (pinned).
+* SNR noise mixing: pinned bit-exact against the reference function itself
+                 (``preprocess/audio_process.py:110-150``, taken out of its module by name and
+                 run unmodified when the golden vectors were generated; ``oracle/noise.py``).
+* collation, logfbank, SpecAugment sampling: **parity unpinned** (upstream / third-party code
+                 absent from the snapshot and the image; see each file's header).
 """
