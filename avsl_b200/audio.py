@@ -308,8 +308,11 @@ def extract_logfbank_features(audio_data, sample_rate: int = 16000, stack_order:
 # ----------------------------------------------------------------------------- SNR noise mixing
 def snr_ratio(snr) -> np.float32:
     """``float32(10 ** (snr / 20))``: the divisor of preprocess/audio_process.py:135 as numpy 2
-    evaluates it next to a float32 scalar (the Python float takes the scalar's type)."""
-    return np.float32(10 ** (snr / 20))
+    evaluates it next to a float32 scalar (the Python float takes the scalar's type).  ``snr`` is
+    taken as a Python number, which is what the reference's call site passes (``noise_snr=0``,
+    :200); a numpy float64 scalar would make numpy carry the whole mix in float64 -- a different
+    (unpinned) result that this library does not reproduce."""
+    return np.float32(10 ** (float(snr) / 20))
 
 
 class NoisePlan:
