@@ -57,6 +57,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p]),
     "avfe_video_feats_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_float,
                                     c_void_p, c_void_p]),
+    "avfe_video_feats_workspace_bytes": (c_size_t, []),
+    "avfe_video_feats": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_double, c_double, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
     "avfe_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,
                           c_int64, c_int64, c_void_p, c_void_p]),
     "avfe_fuse_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,

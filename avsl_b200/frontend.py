@@ -17,7 +17,8 @@ import torch
 from . import _lib
 from .audio import (HOP_LENGTH, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, log_mel_spectrogram_ragged,
                     mel_filters)
-from .lips import IMAGE_CROP_SIZE, IMAGE_MEAN, IMAGE_STD, LipBatch, lip_roi_batch
+from .lips import (IMAGE_CROP_SIZE, IMAGE_MEAN, IMAGE_STD, LipBatch, lip_roi_batch, lip_workspace_bytes,
+                   video_frames_for_audio)
 
 FPS = 25
 
@@ -63,10 +64,14 @@ def pack_utterances(audios: Sequence[np.ndarray], videos: Sequence[np.ndarray],
                     landmarks: Sequence[np.ndarray], valids: Optional[Sequence[np.ndarray]] = None,
                     audio_max_length: Optional[int] = N_SAMPLES) -> PackedBatch:
     """Host-side packing of per-utterance arrays.  Audio is cut to ``audio_max_length``
-    (pad_or_trim's trim half; the pad half happens on the GPU) and video to the frame count the
-    reference keeps, round(audio_max_length / 16000 * 25) (whisper_flamingo_ft_ami.py:299-302)."""
+    (pad_or_trim's trim half; the pad half happens on the GPU).  Video is NOT cut here: the
+    reference runs ``extract_lip_frames`` over the whole clip (preprocess/video_process.py:392-475)
+    and trims the FEATURES afterwards (whisper_flamingo_ft_ami.py:299-302), so the last kept
+    frames still see their own 12-frame smoothing window and landmark interpolation still reaches
+    detections behind the cut.  The trim is applied on the output side: ``keep_frames`` of
+    ``forward_collated`` / ``AVFrontEnd.split_lip(..., n_audio_samples=...)``."""
     assert len(audios) == len(videos) == len(landmarks)
-    max_frames = None if audio_max_length is None else round(audio_max_length / SAMPLE_RATE * FPS)
+    max_frames = None
     a_list, v_list, l_list, m_list = [], [], [], []
     for i in range(len(audios)):
         a = np.asarray(audios[i], dtype=np.float32).reshape(-1)
@@ -104,6 +109,7 @@ class AVFrontEnd:
         self.mean, self.std = image_mean, image_std
         self.filters = mel_filters(self.device, n_mels)
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._reuse = False
 
     @staticmethod
     def model_n_mels(model_name: str) -> int:
@@ -111,6 +117,9 @@ class AVFrontEnd:
         return 80 if "large-v3" not in model_name else 128
 
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        """Output / scratch tensor: fresh unless the current call asked for ``reuse=True``."""
+        if not self._reuse:
+            return torch.empty(tuple(shape), dtype=dtype, device=self.device)
         t = self._bufs.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
@@ -119,14 +128,20 @@ class AVFrontEnd:
 
     # ---------------------------------------------------------------- device-resident path
     def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None,
-                       mark=None) -> Dict[str, torch.Tensor]:
+                       mark=None, reuse: bool = False) -> Dict[str, torch.Tensor]:
         """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] makes the
         log-mel read an already padded matrix instead of the ragged ``batch.audio``.  ``mark(name)``
         (optional) is called after each stage is enqueued (bench.py records CUDA events there).
         Returns device tensors: mel [U,n_mels,F], lip [N,88,88,1], gray [N,H,W] (optional),
-        lip_u8 [N,96,96] (optional)."""
+        lip_u8 [N,96,96] (optional).
+
+        The returned tensors are freshly allocated.  ``reuse=True`` is the steady-state option: the
+        outputs live in buffers owned by this object and the NEXT ``reuse=True`` call with the
+        same shapes overwrites them in place (what ``capture`` and ``HostPipeline`` rely on) -- a
+        loader that still holds batch i while batch i+1 is built must not use it."""
         U, L = batch.n_utts, self.audio_max_length
         mark = mark or (lambda name: None)
+        self._reuse = bool(reuse)
         with torch.cuda.device(self.device):
             mark("start")
             mel = self._buf("mel", (U, self.n_mels, L // HOP_LENGTH), torch.float32)
@@ -148,7 +163,7 @@ class AVFrontEnd:
                     _lib.call("avfe_bgr2gray_u8", _lib.ptr(batch.frames), N, H, W, _lib.ptr(gray), _lib.stream_ptr())
                     src = gray
                     mark("gray")
-            reuse = LipBatch(gray if (self.fused and bgr) else None,
+            res = LipBatch(gray if (self.fused and bgr) else None,
                              self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
                              self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
                              batch.clip_offsets)
@@ -156,13 +171,15 @@ class AVFrontEnd:
             # frame byte is read once)
             lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid,
                           want_gray=self.fused and gray is not None, want_u8=self.want_lip_u8,
-                          crop=self.crop, image_mean=self.mean, image_std=self.std, out=reuse)
+                          crop=self.crop, image_mean=self.mean, image_std=self.std, out=res,
+                          workspace=self._buf("lip_ws", (lip_workspace_bytes(N),), torch.uint8))
             mark("lip")
-        out = {"mel": mel, "lip": reuse.lip_f32.unsqueeze(-1)}
+        out = {"mel": mel, "lip": res.lip_f32.unsqueeze(-1)}
         if gray is not None:
             out["gray"] = gray
-        if reuse.lip_u8 is not None:
-            out["lip_u8"] = reuse.lip_u8
+        if res.lip_u8 is not None:
+            out["lip_u8"] = res.lip_u8
+        self._reuse = False
         return out
 
     # ---------------------------------------------------------------- the training batch, collated
@@ -178,8 +195,9 @@ class AVFrontEnd:
         ``clip_frames`` / ``audio_lengths`` are the host-side frame and sample counts of the clips
         (``audio_frames_before_pad`` = samples // 160 bounds the time masks, :206)."""
         from .audio import spec_augment
-        from .lips import lip_roi_collate, video_frames_for_audio
+        from .lips import lip_roi_collate
         U, L = batch.n_utts, self.audio_max_length
+        self._reuse = False                       # every tensor of the returned dict is fresh
         keep_n = video_frames_for_audio(L)
         kept = [min(int(t), keep_n) for t in clip_frames]
         T_pad = max(max(kept), 1)
@@ -207,38 +225,50 @@ class AVFrontEnd:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.forward_device(batch)                  # warm-up: buffers, filter packs, attributes
+            self.forward_device(batch, reuse=True)      # warm-up: buffers, filter packs, attributes
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.forward_device(batch)
+            out = self.forward_device(batch, reuse=True)
         return graph, out
 
     # ---------------------------------------------------------------- host-buffer path (e2e)
     def forward_host(self, batch: PackedBatch, host_out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``batch`` lives in (pinned) host memory: H2D copy of every input, the kernels, and a
-        D2H copy of the features the reference's ``__getitem__`` returns (mel and lip)."""
+        D2H copy of every deliverable: the features the reference's ``__getitem__`` returns (mel and
+        lip) and, when ``want_gray``, the gray frames ``load_video`` returns."""
         dev = batch.to(self.device, non_blocking=True)
-        res = self.forward_device(dev)
-        if host_out is None:
-            host_out = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory() for k in ("mel", "lip")}
-        for k in ("mel", "lip"):
+        res = self.forward_device(dev, reuse=True)       # device results are copied out before returning
+        keys = self.host_keys(res)
+        if host_out is None or any(k not in host_out or tuple(host_out[k].shape) != tuple(res[k].shape) for k in keys):
+            host_out = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory() for k in keys}
+        for k in keys:
             host_out[k].copy_(res[k], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return host_out
 
     @staticmethod
-    def split_lip(lip: torch.Tensor, clip_offsets) -> List[torch.Tensor]:
-        """Per-utterance [T_i,88,88,1] views of the packed lip tensor."""
+    def host_keys(res: Dict[str, torch.Tensor]) -> List[str]:
+        """The results the host-buffer paths copy back, in a fixed order."""
+        return [k for k in ("mel", "lip", "gray", "lip_u8") if k in res]
+
+    @staticmethod
+    def split_lip(lip: torch.Tensor, clip_offsets, n_audio_samples: Optional[int] = None) -> List[torch.Tensor]:
+        """Per-utterance [T_i,88,88,1] views of the packed lip tensor.  ``n_audio_samples`` (the
+        padded audio length, ``audio_max_length``) applies the reference's trim to
+        ``round(n_audio_samples / 16000 * 25)`` frames (whisper_flamingo_ft_ami.py:299-302)."""
         off = [int(x) for x in clip_offsets.tolist()]
-        return [lip[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        keep = None if n_audio_samples is None else video_frames_for_audio(n_audio_samples)
+        return [lip[off[i]:(off[i + 1] if keep is None else min(off[i + 1], off[i] + keep))]
+                for i in range(len(off) - 1)]
 
 
 class HostPipeline:
     """Steady-state host-buffer path: ``depth`` front-ends, each with its own stream and device
     buffers, so that the H2D copy of batch i+1, the kernels of batch i and the D2H copy of batch
     i-1 overlap (PCIe is full duplex and the copy engines run beside the SMs).  Every batch still
-    pays its full H2D of inputs and D2H of mel + lip; only the waiting is overlapped."""
+    pays its full H2D of inputs and D2H of mel + lip (+ gray when ``want_gray``); only the waiting
+    is overlapped."""
 
     def __init__(self, depth: int = 2, **frontend_kwargs):
         self.fes = [AVFrontEnd(**frontend_kwargs) for _ in range(depth)]
@@ -257,10 +287,12 @@ class HostPipeline:
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st):
             dev = batch.to(self.device, non_blocking=True)
-            res = fe.forward_device(dev)
-            if self.outs[k] is None or any(tuple(self.outs[k][n].shape) != tuple(res[n].shape) for n in ("mel", "lip")):
-                self.outs[k] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in ("mel", "lip")}
-            for n in ("mel", "lip"):
+            res = fe.forward_device(dev, reuse=True)     # the slot's event guards its buffers
+            keys = fe.host_keys(res)
+            if self.outs[k] is None or any(n not in self.outs[k] or tuple(self.outs[k][n].shape) != tuple(res[n].shape)
+                                           for n in keys):
+                self.outs[k] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in keys}
+            for n in keys:
                 self.outs[k][n].copy_(res[n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(st)

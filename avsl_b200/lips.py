@@ -176,18 +176,36 @@ class LipBatch:
         self.crop_rc, self.tforms, self.clip_offsets = crop_rc, tforms, clip_offsets
 
 
+def lip_workspace_bytes(n_frames: int) -> int:
+    """Bytes of scratch ``avfe_lip_roi_batch`` / ``avfe_lip_roi_collate`` need for ``n_frames``."""
+    return int(_lib.load().avfe_lip_workspace_bytes(int(n_frames)))
+
+
+def _workspace(workspace: Optional[torch.Tensor], N: int, dev) -> torch.Tensor:
+    need = lip_workspace_bytes(N)
+    if workspace is None:
+        return torch.empty(need, dtype=torch.uint8, device=dev)
+    if not (workspace.is_cuda and workspace.dtype == torch.uint8 and workspace.is_contiguous()
+            and workspace.numel() >= need and workspace.data_ptr() % 16 == 0):
+        raise ValueError(f"workspace must be a contiguous 16-byte aligned CUDA uint8 tensor of >= {need} bytes")
+    return workspace
+
+
 def lip_roi_batch(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: torch.Tensor,
                   lm_valid: Optional[torch.Tensor] = None, *, mean_face=None,
                   tforms_in: Optional[torch.Tensor] = None, want_gray: bool = True,
                   want_u8: bool = False, want_f32: bool = True, want_meta: bool = False,
                   roi: int = 96, crop: int = IMAGE_CROP_SIZE, std_size: int = 300,
                   window: int = WINDOW_MARGIN, image_mean: float = IMAGE_MEAN,
-                  image_std: float = IMAGE_STD, out: Optional[LipBatch] = None) -> LipBatch:
+                  image_std: float = IMAGE_STD, out: Optional[LipBatch] = None,
+                  workspace: Optional[torch.Tensor] = None) -> LipBatch:
     """One fused pass over a batch of clips stored back to back (all tensors on the GPU).
 
     frames [N,H,W,3] BGR uint8 (or [N,H,W] gray), clip_offsets int64 [n_clips+1], landmarks
     float64 [N,68,2], lm_valid uint8 [N] (0 = detection failed).  See ``avfe_lip_roi_batch`` in
-    include/avfe.h.  ``out`` reuses previously returned buffers (steady-state loops)."""
+    include/avfe.h.  ``out`` reuses previously returned buffers and ``workspace`` a caller-owned
+    scratch tensor of ``lip_workspace_bytes(N)`` bytes (steady-state loops, CUDA-graph capture:
+    nothing is allocated then); a workspace must not be shared by calls that may overlap."""
     _lib.require_cuda()
     if not frames.is_cuda:
         raise ValueError("lip_roi_batch takes CUDA tensors; use extract_lip_frames for host arrays")
@@ -216,9 +234,8 @@ def lip_roi_batch(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: t
         tforms = torch.empty((N, 18), dtype=torch.float64, device=dev) if want_meta else None
         out = LipBatch(gray, lip_u8, lip_f32, crop_rc, tforms, clip_offsets)
     with torch.cuda.device(dev):
-        lib = _lib.load()
-        ws_bytes = int(lib.avfe_lip_workspace_bytes(N))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(workspace, N, dev)
+        ws_bytes = int(ws.numel())
         _lib.call("avfe_lip_roi_batch", _lib.ptr(frames), channels, N, H, W, _lib.ptr(clip_offsets),
                   n_clips, _lib.ptr(landmarks), _lib.ptr(lm_valid), _lib.ptr(mf), _lib.ptr(tforms_in),
                   std_size, roi, crop, window, float(image_mean), float(image_std),
@@ -240,8 +257,8 @@ def lip_roi_collate(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks:
                     tforms_in: Optional[torch.Tensor] = None, want_gray: bool = True,
                     roi: int = 96, crop: int = IMAGE_CROP_SIZE, std_size: int = 300,
                     window: int = WINDOW_MARGIN, image_mean: float = IMAGE_MEAN,
-                    image_std: float = IMAGE_STD, out: Optional[Dict[str, torch.Tensor]] = None
-                    ) -> Dict[str, torch.Tensor]:
+                    image_std: float = IMAGE_STD, out: Optional[Dict[str, torch.Tensor]] = None,
+                    workspace: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """:func:`lip_roi_batch` writing straight into the padded batch the encoder consumes
     (``features, x_v = self.model.encoder(input_ids, video, ..., padding_mask=padding_mask)``,
     avsl/whisper_flamingo_ft_ami.py:527): the per-sample trim of ``__getitem__`` (:299-302) and
@@ -281,9 +298,8 @@ def lip_roi_collate(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks:
         if want_gray:
             out["gray"] = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        lib = _lib.load()
-        ws_bytes = int(lib.avfe_lip_workspace_bytes(N))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(workspace, N, dev)
+        ws_bytes = int(ws.numel())
         _lib.call("avfe_lip_roi_collate", _lib.ptr(frames), channels, N, H, W, _lib.ptr(clip_offsets),
                   n_clips, _lib.ptr(landmarks), _lib.ptr(lm_valid), _lib.ptr(mf), _lib.ptr(tforms_in),
                   std_size, roi, crop, window, float(image_mean), float(image_std),
@@ -348,23 +364,33 @@ def extract_lip_frames(frames: np.ndarray, landmarks: Sequence, mean_face_path=N
 def load_video_feats(frames, train: bool = False, image_crop_size: int = IMAGE_CROP_SIZE,
                      image_mean: float = IMAGE_MEAN, image_std: float = IMAGE_STD):
     """The arithmetic of ``load_video_feats_from_decord_reader`` (utils/hf_video_utils.py:103-138)
-    and ``load_video_features`` (utils/data_loading.py:101-118) on a decoded uint8 ROI stack
-    [T,H,W]: /255, centre crop, (x-mean)/std, trailing channel axis -> float32 [T,crop,crop,1].
+    on the decoded uint8 frames, exactly as its call site runs it
+    (``safe_load_video_feats_from_hf_object``, avsl/whisper_flamingo_ft_ami.py:279-286):
+
+    * ``[T,H,W,3]`` (what decord returns, RGB): float64 ``np.dot`` with ``[0.2989, 0.5870, 0.1140]``,
+      then float32 ``/255`` if the stack's maximum exceeds 1.0 (:105, :116-117);
+    * ``[T,H,W]`` / ``[T,H,W,1]``: float32 ``/255`` (:107-108, :114-115; also
+      ``load_video_features``, utils/data_loading.py:101-118);
+    * centre crop, or ``cv2.resize`` to (crop, crop) when a frame side is smaller than the crop
+      (:120-132); ``(x - mean) / std``; trailing channel axis; float32 -> ``[T,crop,crop,1]``.
+
     numpy in -> numpy out; CUDA tensor in -> CUDA tensor out."""
     is_t = torch.is_tensor(frames)
     dev = frames.device if (is_t and frames.is_cuda) else _dev()
     t = _to_dev(frames, torch.uint8, dev)
-    if t.dim() == 4 and t.shape[-1] == 1:
+    channels = 1
+    if t.dim() == 4 and t.shape[-1] == 3:
+        channels = 3
+    elif t.dim() == 4 and t.shape[-1] == 1:
         t = t.squeeze(-1).contiguous()
-    if t.dim() != 3:
+    if t.dim() != 3 + (channels == 3):
         raise ValueError(f"Expected 3D frames array after processing, got shape: {tuple(t.shape)}")
-    N, H, W = (int(s) for s in t.shape)
-    if image_crop_size > H or image_crop_size > W:
-        raise NotImplementedError("frames smaller than the crop (the reference's cv2.resize fallback) are out of scope")
+    N, H, W = (int(s) for s in t.shape[:3])
     out = torch.empty((N, image_crop_size, image_crop_size, 1), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.call("avfe_video_feats_u8", _lib.ptr(t), N, H, W, image_crop_size, float(image_mean),
-                  float(image_std), _lib.ptr(out), _lib.stream_ptr())
+        ws = torch.empty(int(_lib.load().avfe_video_feats_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _lib.call("avfe_video_feats", _lib.ptr(t), channels, N, H, W, int(image_crop_size), float(image_mean),
+                  float(image_std), _lib.ptr(out), _lib.ptr(ws), int(ws.numel()), _lib.stream_ptr())
     if is_t and frames.is_cuda:
         return out
     return out.cpu().numpy()

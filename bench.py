@@ -40,6 +40,7 @@ AUDIO_LEN = 480000
 H = W = 224
 N_SWEEP = 10000
 SEED = 3407
+IMAGE_STD_ = 0.165
 
 
 def parse_args():
@@ -64,11 +65,41 @@ def dist_env():
 
 
 def rank_utterances(rank: int, world: int, utts: int):
-    """(indices into the 10k sweep, durations [s]) of this rank's step batch."""
+    """(indices into the 10k sweep, durations [s]) of this rank's step batch.
+
+    The step's global batch is the first utts*world utterances of the sweep; it is split over the
+    ranks by avsl_b200.shard_balanced (longest-first greedy on the durations, derived by every rank
+    on its own, no communication): the ranks' frame totals then differ by a fraction of a percent,
+    so the max-over-ranks time measures the hardware and not a lopsided split (with the strided
+    split of round 1 mean/max frames per rank was 0.92 at 8 ranks).  At world 1 this is the first
+    `utts` utterances, as before."""
     from avsl_b200 import synth
+    from avsl_b200.frontend import shard_balanced
     durs = synth.ami_durations(N_SWEEP, SEED)
-    idx = synth.shard_indices(N_SWEEP, rank, world)[:utts]
+    step = np.arange(min(N_SWEEP, utts * world))
+    idx = step[shard_balanced(durs[step], rank, world)]
     return idx, durs[idx]
+
+
+def host_batch(idx, durs, rank: int):
+    """The rank's whole step batch as numpy arrays, from the same generators and seeds as the
+    device-resident batch of the GPU arm (torch CPU generators instead of CUDA ones)."""
+    import torch
+    from avsl_b200 import synth
+    T = np.maximum(1, np.round(durs * 25).astype(np.int64))
+    a_len = np.round(durs * 16000).astype(np.int64)
+    g = torch.Generator().manual_seed(SEED + rank)
+    audio = (torch.randn(int(a_len.sum()), generator=g) * 0.1).clamp_(-1, 1).numpy()
+    frames = synth.video_frames_cuda(int(T.sum()), H, W, seed=SEED + rank, device="cpu").numpy()
+    a_off = np.concatenate([[0], np.cumsum(a_len)])
+    c_off = np.concatenate([[0], np.cumsum(T)])
+    audios, vids, lms, vals = [], [], [], []
+    for k in range(len(idx)):
+        audios.append(audio[a_off[k]:a_off[k + 1]])
+        vids.append(frames[c_off[k]:c_off[k + 1]])
+        lm, v = synth.landmarks_for_clip(int(T[k]), H, W, seed=SEED + int(idx[k]), invalid_frac=0.05)
+        lms.append(lm); vals.append(v)
+    return audios, vids, lms, vals
 
 
 def host_sample(idx, durs, n):
@@ -168,9 +199,10 @@ def run_reference(args, rank, world):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    # the SAME step batch as the GPU arm's rank 0 (same utterances, generators and seeds), whole
     idx, durs = rank_utterances(0, world, args.utts)
-    n = args.cpu_sample_utts or 8
-    audios, vids, lms, vals = host_sample(idx, durs, n)
+    n = min(args.cpu_sample_utts or len(idx), len(idx))
+    audios, vids, lms, vals = (x[:n] for x in host_batch(idx, durs, 0))
     audio_s = float(sum(durs[:n]))
     cf = baseline.CpuFrontend(audios, vids, lms, vals, mean_face_landmarks(), N_MELS, AUDIO_LEN)
     for _ in range(args.warmup):
@@ -180,7 +212,8 @@ def run_reference(args, rank, world):
         t += cf.run()
     cf.close()
     value = audio_s * args.steps / t
-    sample = f"{n} utterances ({audio_s:.2f} audio-s, {sum(len(v) for v in vids)} frames) of the step batch per step"
+    sample = (f"{'the whole step batch of rank 0: ' if n == len(idx) else ''}{n} utterances ({audio_s:.2f} audio-s, "
+              f"{sum(len(v) for v in vids)} frames) per step")
     line = {
         "impl": "reference", "metric": "av_frontend_audio_seconds_per_second", "value": value,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -198,12 +231,70 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world, n_frames, n_utts):
-    return {"workload": "configs[4] AMI-shaped AV front-end sweep (10k seeded utterances, i%world==rank shards); "
-                        "one step = one batch of consecutive utterances of the shard",
+    return {"workload": "configs[4] AMI-shaped AV front-end sweep (10k seeded utterances); one step = the first "
+                        "utts*world utterances of the sweep, split over the ranks by duration (shard_balanced)",
             "utterances_per_gpu_per_step": n_utts, "frames_per_gpu_per_step": n_frames,
             "n_mels": N_MELS, "audio_pad_samples": AUDIO_LEN, "video": f"{H}x{W} BGR 25 fps",
             "outputs": "mel f32 [U,80,3000] + gray u8 [N,224,224] + lip f32 [N,88,88]",
             "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"utterance-sharded x{world}, no collective"}
+
+
+# ------------------------------------------------------------------------------- parity of the timed batch
+def grab_parity_inputs(batch, out, durs):
+    """Host copies of the inputs of the shortest and the longest utterance of the step batch and
+    of what the LAST TIMED STEP wrote for them (mel, gray, lip), plus their crop origins from one
+    extra (untimed) call on just those clips."""
+    import torch
+    from avsl_b200.lips import lip_roi_batch
+    a_off = batch.audio_offsets.tolist()
+    c_off = batch.clip_offsets.tolist()
+    picks = sorted({int(np.argmin(durs)), int(np.argmax(durs))})
+    items = []
+    for k in picks:
+        a0, a1, f0, f1 = a_off[k], a_off[k + 1], c_off[k], c_off[k + 1]
+        frames = batch.frames[f0:f1].contiguous()
+        lm = batch.landmarks[f0:f1].contiguous()
+        val = batch.lm_valid[f0:f1].contiguous()
+        sub = lip_roi_batch(frames, torch.tensor([0, f1 - f0], dtype=torch.int64, device=frames.device), lm, val,
+                            want_gray=True, want_u8=False, want_f32=True, want_meta=True)
+        items.append({"utt": k, "dur": float(durs[k]),
+                      "audio": batch.audio[a0:a1].cpu().numpy(), "frames": frames.cpu().numpy(),
+                      "landmarks": lm.cpu().numpy(), "valid": val.cpu().numpy(),
+                      "mel": out["mel"][k].cpu().numpy(), "gray": out["gray"][f0:f1].cpu().numpy(),
+                      "lip": out["lip"][f0:f1].cpu().numpy(),
+                      "sub_lip": sub.lip_f32.cpu().numpy(), "crop_rc": sub.crop_rc.cpu().numpy()})
+    return items
+
+
+def parity_check(items):
+    """The oracle (CPU restatement of the reference, oracle/) run on those utterances: the checker
+    of the timed batch, never the thing measured.  Bars: log-mel max-abs <= 1e-4, gray and crop
+    origins bit-exact, lip features within one grey level ((1/255)/0.165 normalised)."""
+    from avsl_b200.lips import mean_face_landmarks
+    from oracle import lips as OL
+    from oracle import logmel as OM
+    mf = mean_face_landmarks()
+    res = {"utterances": [], "mel_maxabs": 0.0, "gray_equal": True, "crop_rc_equal": True,
+           "lip_levels_off": 0, "lip_pixels_off": 0, "lip_pixels": 0, "timed_equals_recomputed": True}
+    for it in items:
+        ref_mel = OM.log_mel_spectrogram(OM.pad_or_trim(it["audio"], AUDIO_LEN), N_MELS).numpy()
+        res["mel_maxabs"] = max(res["mel_maxabs"], float(np.abs(it["mel"] - ref_mel).max()))
+        ref_gray = OL.bgr2gray(it["frames"])
+        res["gray_equal"] &= bool(np.array_equal(it["gray"], ref_gray))
+        lst = [it["landmarks"][i] if it["valid"][i] else None for i in range(len(it["valid"]))]
+        roi, _, origins = OL.extract_lip_frames_from_arrays(ref_gray, lst, mf)
+        res["crop_rc_equal"] &= bool(np.array_equal(it["crop_rc"], origins))
+        ref_lip = OL.video_feats_from_u8(roi)
+        levels = np.rint(np.abs(it["lip"].reshape(ref_lip.shape) - ref_lip) * (IMAGE_STD_ * 255.0)).astype(np.int64)
+        res["lip_levels_off"] = max(res["lip_levels_off"], int(levels.max()))
+        res["lip_pixels_off"] += int((levels != 0).sum())
+        res["lip_pixels"] += int(levels.size)
+        res["timed_equals_recomputed"] &= bool(np.array_equal(it["lip"].reshape(it["sub_lip"].shape), it["sub_lip"]))
+        res["utterances"].append({"index_in_step": it["utt"], "seconds": it["dur"], "frames": int(len(it["valid"]))})
+    res["ok"] = bool(res["mel_maxabs"] <= 1e-4 and res["gray_equal"] and res["crop_rc_equal"]
+                     and res["lip_levels_off"] <= 1 and res["timed_equals_recomputed"])
+    res["bars"] = "mel max-abs <= 1e-4; gray, crop origins bit-exact; lip <= 1 grey level; checked against oracle/ on the last timed step's outputs"
+    return res
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -293,7 +384,7 @@ def main():
         return mark
 
     for _ in range(max(3, args.warmup)):
-        fe.forward_device(batch_dev)
+        fe.forward_device(batch_dev, reuse=True)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -301,8 +392,9 @@ def main():
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
+    last_out = None
     for _ in range(args.steps):
-        fe.forward_device(batch_dev, mark=make_mark(events))
+        last_out = fe.forward_device(batch_dev, mark=make_mark(events), reuse=True)
     t_end.record()
     barrier()
     sampler.pause()
@@ -316,11 +408,21 @@ def main():
         prev = e
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
 
+    # the timed batch's outputs of the two utterances bench.py checks against the oracle (below)
+    parity_in = grab_parity_inputs(batch_dev, last_out, durs) if rank == 0 else None
+
     t_max = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([audio_s, float(alg_bytes), float(launches)], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([elapsed_ms / args.steps, float(N), float(U)], dtype=torch.float64, device=dev)
+    per_rank_all = [per_rank]
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)      # off the timed path: reporting only
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(per_rank_all, per_rank)
+    rank_ms = [float(x[0]) for x in per_rank_all]
+    rank_frames = [int(x[1]) for x in per_rank_all]
+    rank_utts = [int(x[2]) for x in per_rank_all]
     elapsed_ms = float(t_max.item())
     audio_s_all, alg_bytes_all, launches_all = (float(x) for x in tot.tolist())
     value = audio_s_all * args.steps / (elapsed_ms * 1e-3)
@@ -443,7 +545,7 @@ def main():
                                "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
         del fr2, lmt, vt, r2
         # SpecAugment masks (8(f) rank 2) on the step's mel batch: only the masked elements are written
-        mel_b = fe.forward_device(batch_dev)["mel"]
+        mel_b = fe.forward_device(batch_dev, reuse=True)["mel"]
         frames_before_pad = [int(x) for x in ((batch_dev.audio_offsets[1:] - batch_dev.audio_offsets[:-1]) // 160).tolist()]
         bands = A.spec_augment_bands(frames_before_pad, N_MELS, "ls-double", np.random.default_rng(SEED))
         ms = time_op(lambda: A.spec_augment(mel_b, bands=bands), 20)
@@ -509,21 +611,45 @@ def main():
         barrier()
         sampler.pause()
         ms_pipe = t0.elapsed_time(t1)
-        assert torch.equal(pipe.result(e2e_steps - 1)["mel"], host_out["mel"])
-        assert torch.equal(pipe.result(e2e_steps - 1)["lip"], host_out["lip"])
-        ms = torch.tensor([ms_pipe, ms_serial], dtype=torch.float64, device=dev)
+        e2e_keys = sorted(host_out)
+        assert e2e_keys == ["gray", "lip", "mel"], e2e_keys
+        for k in e2e_keys:      # what came back through the host path is what the device path computed
+            assert torch.equal(pipe.result(e2e_steps - 1)[k], host_out[k]), k
+            assert torch.equal(host_out[k], last_out[k].cpu()), k
+        # (c) the box's bare pinned-H2D rate with all ranks copying at once: the ceiling of (b)
+        probe_h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(4):
+            probe_d.copy_(probe_h, non_blocking=True)
+        t1.record()
+        barrier()
+        h2d_gbs = 4 * (1 << 30) / (t0.elapsed_time(t1) * 1e-3) / 1e9
+        del probe_h, probe_d
+        ms = torch.tensor([ms_pipe, ms_serial, -h2d_gbs], dtype=torch.float64, device=dev)
+        h2d_sum = torch.tensor([h2d_gbs], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_pipe, ms_serial = (float(v) for v in ms.tolist())
-        d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in ("mel", "lip"))
+            dist.all_reduce(h2d_sum, op=dist.ReduceOp.SUM)
+        ms_pipe, ms_serial, h2d_min = (float(v) for v in ms.tolist())
+        h2d_min = -h2d_min
+        d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in e2e_keys)
         e2e = {"value": audio_s_all * e2e_steps / (ms_pipe * 1e-3), "unit": "audio-s/s",
                "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_pipe / e2e_steps, "steps": e2e_steps,
-               "api": "avsl_b200.HostPipeline(depth=2).submit(i, pinned PackedBatch) -> result(i): H2D of every input and D2H of mel+lip for every step, two slots in flight",
+               "api": "avsl_b200.HostPipeline(depth=2).submit(i, pinned PackedBatch) -> result(i): H2D of every input and D2H of mel + lip + gray for every step, two slots in flight",
+               "returns": e2e_keys,
+               "h2d_ceiling_gbs": {"per_rank_min": h2d_min, "all_ranks_sum": float(h2d_sum.item()),
+                                   "how": "4 x 1 GiB cudaMemcpyAsync from pinned host memory, all ranks at once, CUDA events"},
+               "h2d_achieved_gbs_per_rank": host.nbytes() / (ms_pipe / e2e_steps * 1e-3) / 1e9,
                "host_binding": (f"rank pinned to the {len(numa_cpus)} CPUs of its GPU's NUMA node (NVML ideal affinity) before allocating pinned buffers"
                                 if numa_cpus else "none"),
                "serial": {"value": audio_s_all * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
                           "api": "AVFrontEnd.forward_host (H2D -> kernels -> D2H -> sync, one step at a time)"}}
+        e2e["h2d_frac_of_ceiling"] = e2e["h2d_achieved_gbs_per_rank"] / h2d_min
         del pipe
         del host, host_out
 
@@ -568,6 +694,9 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": stages[dominant]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": traffic,
+                "traffic_source": (None if traffic is None else
+                                   f"SCALED: dram__bytes_read+write per {tj['unit']} from the ncu --set full capture named in profiles/traffic.json "
+                                   f"({tj.get('capture', 'r01')}), times this launch's {units} {tj['unit']}s; not a measurement of this launch"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes[dominant],
                 "stages": stages,
                 "path": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 if world == 1 else alg_bytes_all * args.steps / (elapsed_ms * 1e-3) / 1e9,
@@ -587,6 +716,7 @@ def main():
                         "sample": f"first {n_cpu} utterances of the step batch ({cpu_audio_s:.2f} audio-s, {cf.n_frames} frames) x {reps} passes = {t:.1f} s CPU wall",
                         "workers": cf.workers, "torch_threads": torch.get_num_threads()}
 
+    parity = parity_check(parity_in) if rank == 0 else None
     if rank == 0:
         line = {
             "metric": "av_frontend_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
@@ -596,10 +726,16 @@ def main():
             "config": workload_config(args, world, N, U), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "audio_seconds_per_step": audio_s_all,
+            "per_rank": {"ms_per_step": rank_ms, "ms_min": min(rank_ms), "ms_max": max(rank_ms),
+                         "frames": rank_frames, "utterances": rank_utts,
+                         "frames_mean_over_max": float(np.mean(rank_frames) / max(rank_frames))},
+            "parity_check": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and not parity["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

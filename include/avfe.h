@@ -266,6 +266,24 @@ AVFE_API int avfe_cut_patch_u8(const uint8_t* img, int H, int W, const double* l
 AVFE_API int avfe_video_feats_u8(const uint8_t* roi_u8, int64_t N, int Hin, int Win, int crop,
                                  float mean, float std, float* out, avfe_stream_t stream);
 
+/* load_video_feats_from_decord_reader as its call site runs it — utils/hf_video_utils.py:103-138,
+ * called from safe_load_video_feats_from_hf_object (avsl/whisper_flamingo_ft_ami.py:279-286) with what
+ * decord returns, uint8 [T,H,W,3] RGB:
+ *   channels 3: gray = dot(rgb, [0.2989, 0.5870, 0.1140]) in float64 (:105); if the maximum over the
+ *               whole stack is > 1.0, float32(gray) / 255 (:116-117), else the float64 values stay
+ *               unscaled (an all-dark video; the reference's own data-dependent branch)
+ *   channels 1: float32(u8) / 255 (:114-115)
+ *   H, W >= crop: centre crop (:120-125); otherwise cv2.resize(frame, (crop, crop)), INTER_LINEAR
+ *               on the float frame (:126-132; OpenCV's generic code path, see avfe_vfeats.cu)
+ *   (x - mean) / std in the array's dtype (:135), result float32 (ft_ami:286).
+ * frames [N,H,W,channels] u8 -> out [N,crop,crop] f32.  mean / std are doubles because the
+ * all-dark branch evaluates them in float64.  workspace: avfe_video_feats_workspace_bytes() bytes,
+ * 16-byte aligned (channels 3 only; the stack-wide maximum test runs on the device, no host sync). */
+AVFE_API size_t avfe_video_feats_workspace_bytes(void);
+AVFE_API int avfe_video_feats(const uint8_t* frames, int channels, int64_t N, int H, int W, int crop,
+                              double mean, double std, float* out, void* workspace,
+                              size_t workspace_bytes, avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ fusion (F1..F3) */
 
 /* AVHuBERTEncoderWrapper.forward's fusion block — avsl/modules/av_hubert_encoder.py:315-326,

@@ -17,7 +17,8 @@ follows skimage's published algorithm (``transform._geometric._umeyama``,
 ``_warps_cy._warp_fast`` order 1, mode 'constant', cval 0, ``img_as_float`` input,
 ``_clip_warp_output`` in its >=0.20 form) and is cross-checked in ``tests/`` against
 ``scipy.ndimage.map_coordinates`` and ``cv2.warpAffine``.  The BGR->gray formula is pinned
-bit-exact against ``cv2`` and the crop/normalise against the reference function itself.
+bit-exact against ``cv2`` and the crop/normalise (uint8, RGB and small-frame ``cv2.resize``
+branches) against the reference function itself.
 """
 from __future__ import annotations
 
@@ -294,6 +295,65 @@ def video_feats_from_u8(frames_u8: np.ndarray, image_crop_size: int = CROP,
     sh, sw = (H - image_crop_size) // 2, (W - image_crop_size) // 2
     assert sh >= 0 and sw >= 0, "small-frame cv2.resize fallback is out of scope"
     frames = frames[:, sh:sh + image_crop_size, sw:sw + image_crop_size]
+    frames = (frames - image_mean) / image_std
+    return np.expand_dims(frames, axis=-1).astype(np.float32)
+
+
+def resize_linear(src: np.ndarray, dsize: int) -> np.ndarray:
+    """``cv2.resize(frame, (dsize, dsize))`` (INTER_LINEAR, utils/hf_video_utils.py:129) for a 2-D
+    float32 / float64 frame, restating OpenCV's own generic code path (modules/imgproc/src/resize.cpp,
+    OpenCV 4.x: coordinates ``fx = (float)((dx+0.5)*scale_x - 0.5)``, ``sx = floor(fx)``, the
+    horizontal border rule ``sx < 0 -> (0, fx=0)``, ``sx >= W-1 -> (W-1, fx=0)``, row indices clipped
+    to the frame, float32 coefficients, HResizeLinear then VResizeLinear with separately rounded
+    products and sums).  Bit-exact against ``cv2.resize`` with IPP switched off
+    (``cv2.ipp.setUseIPP(False)``); x86 wheels use IPP by default, whose float32 results differ
+    from OpenCV's own code by a few 1e-6 (tests/test_oracle_lips.py pins both)."""
+    H, W = src.shape
+    T = src.dtype.type
+
+    def coords(n_src):
+        scale = 1.0 / (dsize / n_src)
+        f = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        return s, (f - s.astype(np.float32)).astype(np.float32)
+
+    sx, fx = coords(W)
+    fx = np.where((sx < 0) | (sx >= W - 1), np.float32(0), fx).astype(np.float32)
+    sx = np.clip(sx, 0, W - 1)
+    x1 = np.minimum(sx + 1, W - 1)
+    sy, fy = coords(H)
+    r0, r1 = np.clip(sy, 0, H - 1), np.clip(sy + 1, 0, H - 1)
+    a0, a1 = (np.float32(1) - fx).astype(T), fx.astype(T)
+    b0, b1 = (np.float32(1) - fy).astype(T), fy.astype(T)
+    hrow = src[:, sx] * a0[None, :] + src[:, x1] * a1[None, :]
+    return hrow[r0] * b0[:, None] + hrow[r1] * b1[:, None]
+
+
+def video_feats_from_frames(frames: np.ndarray, image_crop_size: int = CROP, image_mean: float = IMAGE_MEAN,
+                            image_std: float = IMAGE_STD) -> np.ndarray:
+    """utils/hf_video_utils.py:103-138 for the uint8 frames a decord reader returns ([T,H,W,3] RGB,
+    [T,H,W,1] or [T,H,W]), then ``.astype(np.float32)`` (avsl/whisper_flamingo_ft_ami.py:286).
+    The RGB weights are applied channel by channel in float64 (numpy hands ``np.dot`` to BLAS; its
+    summation order can move the last float64 bit, never the float32 the bright branch casts to --
+    tests/test_oracle_lips.py walks all 2^24 triples)."""
+    frames = np.asarray(frames)
+    if frames.ndim == 4 and frames.shape[3] == 3:
+        f64 = frames.astype(np.float64)
+        frames = (f64[..., 0] * 0.2989 + f64[..., 1] * 0.5870) + f64[..., 2] * 0.1140      # :105
+    elif frames.ndim == 4 and frames.shape[3] == 1:
+        frames = frames.squeeze(axis=3)
+    if frames.ndim != 3:
+        raise ValueError(f"Expected 3D frames array after processing, got shape: {frames.shape}")
+    if frames.dtype == np.uint8:                                                           # :114-117
+        frames = frames.astype(np.float32) / 255.0
+    elif frames.max() > 1.0:
+        frames = frames.astype(np.float32) / 255.0
+    H, W = frames.shape[1], frames.shape[2]
+    start_h, start_w = (H - image_crop_size) // 2, (W - image_crop_size) // 2
+    if start_h >= 0 and start_w >= 0:
+        frames = frames[:, start_h:start_h + image_crop_size, start_w:start_w + image_crop_size]
+    else:                                                                                  # :126-132
+        frames = np.stack([resize_linear(f, image_crop_size) for f in frames])
     frames = (frames - image_mean) / image_std
     return np.expand_dims(frames, axis=-1).astype(np.float32)
 

@@ -11,7 +11,9 @@ transformers / cv2 are available):
                        and on a sweep that hits every rounding boundary class.
 * video_feats_golden.npz  the reference's own load_video_feats_from_decord_reader
                        (utils/hf_video_utils.py:73-145), imported by file path from
-                       /root/reference and fed a duck-typed reader.
+                       /root/reference and fed a duck-typed reader: the uint8 1-channel case, the RGB
+                       frames decord really returns (bright and all-dark stacks) and frames smaller
+                       than the crop (the cv2.resize fallback, with IPP on -- as shipped -- and off).
 * noise_golden.npz      the reference's own add_noise (preprocess/audio_process.py:110-150), taken
                        out of its module by function name (the module's top-level imports --
                        librosa, python_speech_features -- are not installable here) and run on
@@ -108,8 +110,31 @@ def video_feats():
     lv = np.resize(np.arange(256, dtype=np.uint8), (1, 96, 96))
     lv_feats = mod.load_video_feats_from_decord_reader(FakeVideoReader(lv[..., None]), image_crop_size=88,
                                                        image_mean=0.421, image_std=0.165).astype(np.float32)
+    # what the call site really feeds it (avsl/whisper_flamingo_ft_ami.py:279-286): decord's RGB frames
+    def run(frames, crop=88):
+        return mod.load_video_feats_from_decord_reader(FakeVideoReader(frames), image_crop_size=crop,
+                                                       image_mean=0.421, image_std=0.165).astype(np.float32)
+    import cv2
+    extra = {}
+    rgb = rng.integers(0, 256, size=(2, 96, 96, 3), dtype=np.uint8)
+    extra["rgb"], extra["rgb_feats"] = rgb, run(rgb)
+    dark = rng.integers(0, 2, size=(2, 96, 96, 3), dtype=np.uint8)       # stack maximum <= 1.0: no /255, float64 kept
+    dark[..., 1] = 0
+    assert np.dot(dark[..., :3], [0.2989, 0.5870, 0.1140]).max() <= 1.0
+    extra["dark"], extra["dark_feats"] = dark, run(dark)
+    # frames smaller than the crop -> cv2.resize; stored for cv2 as shipped (IPP) and with IPP off
+    for name, shape in (("small_rgb", (2, 64, 64, 3)), ("small_gray", (2, 64, 64, 1)), ("small_tall", (2, 120, 64, 3)),
+                        ("small_wide", (1, 80, 100, 3))):
+        fr = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        extra[name] = fr
+        cv2.ipp.setUseIPP(True)
+        extra[name + "_feats_ipp"] = run(fr)
+        cv2.ipp.setUseIPP(False)
+        extra[name + "_feats_noipp"] = run(fr)
+        cv2.ipp.setUseIPP(True)
+    extra["cv2_build_has_ipp"] = np.array("Intel IPP:" in cv2.getBuildInformation() and "Intel IPP:                   NO" not in cv2.getBuildInformation())
     np.savez_compressed(os.path.join(HERE, "video_feats_golden.npz"), roi=roi, feats=feats, levels=lv,
-                        levels_feats=lv_feats)
+                        levels_feats=lv_feats, **extra)
     print("video_feats:", feats.shape, feats.dtype, float(feats.min()), float(feats.max()))
 
 
@@ -179,6 +204,9 @@ def noise_mix():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "noise":
         noise_mix()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "video_feats":
+        video_feats()
         sys.exit(0)
     logmel()
     gray()

@@ -129,3 +129,63 @@ def test_forward_collated_is_getitem_plus_collator():
     # eval: no augmentation
     ev = fe.forward_collated(batch.to("cuda"), frames, lens, "ls-double", train=False)["input_ids"].clone()
     assert torch.equal(ev, fe.forward_device(batch.to("cuda"))["mel"])
+
+
+def test_trim_happens_after_the_lip_path_not_before():
+    """A clip longer than the kept frame count: the reference runs extract_lip_frames on
+    the WHOLE clip and trims the features afterwards (whisper_flamingo_ft_ami.py:299-302), so the last
+    kept frames keep their own 12-frame window and a failed detection near the cut is interpolated
+    towards the detection behind it.  pack_utterances with an audio_max_length must give that."""
+    L = 16000                                            # keeps 25 frames
+    T = 60
+    frames, lm, valid = synth.video_clip(T, 96, 128, seed=77, invalid_frac=0.0)
+    valid[:] = 1
+    valid[22:29] = 0                                     # a gap straddling the cut: filled from frame 29, behind it
+    audio = synth.audio_clip(48000, 5)
+    batch = A.pack_utterances([audio], [frames], [lm], [valid], audio_max_length=L)
+    assert int(batch.clip_offsets[-1]) == T              # video is not pre-trimmed
+    assert int(batch.audio_offsets[-1]) == L
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=L, want_lip_u8=True)
+    dev = batch.to("cuda")
+    out = fe.forward_device(dev)
+    lst = [lm[k] if valid[k] else None for k in range(T)]
+    roi, _, _ = OL.extract_lip_frames_from_arrays(OL.bgr2gray(frames), lst, A.mean_face_landmarks())
+    ref = OL.trim_video_to_audio(OL.video_feats_from_u8(roi), L)
+    assert ref.shape[0] == 25
+    got = fe.split_lip(out["lip"].cpu(), batch.clip_offsets, n_audio_samples=L)[0].numpy()
+    assert got.shape == ref.shape
+    lv = np.rint(np.abs(got - ref) * 0.165 * 255)
+    assert lv.max() <= 1 and (lv != 0).mean() < 1e-3
+    col = fe.forward_collated(dev, [T], [len(audio)])
+    assert col["video"].shape == (1, 1, 25, 88, 88)
+    np.testing.assert_array_equal(col["video"][0, 0].cpu().numpy(), got[..., 0])
+    # cutting the video first (what round 1's pack_utterances did) is a different computation
+    pre = A.pack_utterances([audio], [frames[:25]], [lm[:25]], [valid[:25]], audio_max_length=L).to("cuda")
+    cut = fe.forward_device(pre)["lip"].cpu().numpy()
+    assert not np.array_equal(cut, got)
+
+
+def test_outputs_are_fresh_unless_reuse_is_requested():
+    """forward_device / forward_collated must not hand out buffers the next call overwrites."""
+    a1, v1, l1, m1 = _utts(3, seed=1)
+    a2, v2, l2, m2 = _utts(3, seed=2)
+    b1 = A.pack_utterances(a1, v1, l1, m1, audio_max_length=32000).to("cuda")
+    b2 = A.pack_utterances(a2, v2, l2, m2, audio_max_length=32000).to("cuda")
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=32000)
+    o1 = fe.forward_device(b1)
+    keep = {k: v.clone() for k, v in o1.items()}
+    o2 = fe.forward_device(b2)
+    for k in o1:
+        assert o1[k].data_ptr() != o2[k].data_ptr(), k
+        assert torch.equal(o1[k], keep[k]), k
+    c1 = fe.forward_collated(b1, [len(v) for v in v1], [len(a) for a in a1])
+    keepc = {k: v.clone() for k, v in c1.items()}
+    fe.forward_collated(b2, [len(v) for v in v2], [len(a) for a in a2])
+    for k in c1:
+        assert torch.equal(c1[k], keepc[k]), k
+    # opt-in reuse: same storage, overwritten in place
+    r1 = fe.forward_device(b1, reuse=True)
+    p = {k: v.data_ptr() for k, v in r1.items()}
+    r2 = fe.forward_device(b2, reuse=True)
+    assert all(r2[k].data_ptr() == p[k] for k in p)
+    assert torch.equal(r2["mel"], o2["mel"]) and torch.equal(r2["lip"], o2["lip"])

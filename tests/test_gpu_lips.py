@@ -13,6 +13,7 @@ from avsl_b200 import synth
 from oracle import lips as O
 
 from conftest import GOLDEN
+from known_answers import known_answer_case
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +44,61 @@ def test_video_feats_golden_reference_function():
     np.testing.assert_array_equal(A.load_video_feats(g["levels"]), g["levels_feats"])
     with pytest.raises(ValueError, match="Expected 3D frames"):
         A.load_video_feats(np.zeros((2, 2, 96, 96, 3), np.uint8))
+
+
+def test_video_feats_as_the_call_site_runs_it():
+    """utils/hf_video_utils.py:103-138 on what decord returns: RGB frames (float64 dot, /255 if the
+    stack is not all-dark), and frames smaller than the crop (cv2.resize).  Goldens are the
+    reference function's own outputs (tests/golden/make_golden.py::video_feats)."""
+    g = np.load(GOLDEN / "video_feats_golden.npz")
+    np.testing.assert_array_equal(A.load_video_feats(g["rgb"]), g["rgb_feats"])
+    np.testing.assert_array_equal(A.load_video_feats(g["dark"]), g["dark_feats"])
+    # CUDA tensor in -> CUDA tensor out, same numbers
+    t = A.load_video_feats(torch.from_numpy(g["rgb"]).cuda())
+    assert t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (2, 88, 88, 1)
+    np.testing.assert_array_equal(t.cpu().numpy(), g["rgb_feats"])
+    for name in ("small_rgb", "small_gray", "small_tall", "small_wide"):
+        got = A.load_video_feats(g[name])
+        assert got.shape == g[name + "_feats_ipp"].shape and got.dtype == np.float32
+        # bit-exact against cv2's own code (IPP off) through the reference function ...
+        np.testing.assert_array_equal(got, g[name + "_feats_noipp"])
+        np.testing.assert_array_equal(got, O.video_feats_from_frames(g[name]))
+        # ... and within 5e-5 (normalised units) of cv2 as shipped on x86 (IPP's float32 resize)
+        assert np.abs(got - g[name + "_feats_ipp"]).max() <= 5e-5
+
+
+def test_video_feats_rgb_every_triple():
+    """All 2^24 RGB triples in one 4096 x 4096 frame: float32(dot)/255, normalised -- bit-exact
+    against numpy (the crop equals the frame, so nothing is cut)."""
+    v = np.arange(256, dtype=np.uint8)
+    r, gg, b = np.meshgrid(v, v, v, indexing="ij")
+    frame = np.stack([r, gg, b], axis=-1).reshape(1, 4096, 4096, 3)
+    got = A.load_video_feats(frame, image_crop_size=4096)
+    ref = ((np.dot(frame[..., :3], [0.2989, 0.5870, 0.1140]).astype(np.float32) / 255.0 - 0.421) / 0.165)
+    np.testing.assert_array_equal(got[..., 0], ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("kind", ["translate", "border", "scale2"])
+@pytest.mark.parametrize("as_gray", [False, True])
+def test_known_answer_warp(kind, as_gray):
+    """Reference-independent known answers through avfe_lip_roi_batch (tforms_in): an integer
+    translation returns source pixels exactly, a border-straddling ROI exact zeros outside the
+    frame, a x2 zoom the truncated midpoints -- the expected bytes come from index arithmetic and
+    the four-pixel average only (no coordinate transform, no interpolation routine).  BGR input
+    takes the frame-owner kernel, gray input the generic one."""
+    frames, gray, lm, tf, expect, (r0, c0) = known_answer_case(kind)
+    T = len(frames)
+    src = torch.from_numpy(gray if as_gray else frames).cuda()
+    res = L.lip_roi_batch(src, torch.tensor([0, T], dtype=torch.int64).cuda(), torch.from_numpy(lm).cuda(),
+                          torch.ones(T, dtype=torch.uint8).cuda(), tforms_in=torch.from_numpy(tf).cuda(),
+                          want_gray=not as_gray, want_u8=True, want_f32=True, want_meta=True)
+    np.testing.assert_array_equal(res.crop_rc.cpu().numpy(), np.tile(np.array([[r0, c0]], np.int32), (T, 1)))
+    np.testing.assert_array_equal(res.lip_u8.cpu().numpy(), expect)
+    if kind == "border":
+        assert (expect[:, :, :20] == 0).all() and (expect[:, :10, :] == 0).all() and expect[:, 60:, 60:].any()
+    np.testing.assert_array_equal(res.lip_f32.cpu().numpy(), O.video_feats_from_u8(expect)[..., 0])
+    if not as_gray:
+        np.testing.assert_array_equal(res.gray.cpu().numpy(), gray)
 
 
 def test_landmarks_interpolate_bit_exact():

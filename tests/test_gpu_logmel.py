@@ -60,15 +60,19 @@ def test_chirp_silence_against_f64_truth():
     assert np.abs(out - f32).max() <= TOL
 
 
-def test_config3_batch64_per_clip_max():
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_config3_batch64_every_clip(n_mels):
+    """BASELINE configs[2] at full size: 64 x 30 s, every clip of the batch against the oracle
+    (per-clip maxima differ by construction of the batch), both filterbanks."""
     b = synth.audio_batch(64, 480000, 3407)
-    out = A.log_mel_spectrogram(b.cuda(), n_mels=80)
-    assert out.is_cuda and out.shape == (64, 80, 3000)
+    out = A.log_mel_spectrogram(b.cuda(), n_mels=n_mels)
+    assert out.is_cuda and out.shape == (64, n_mels, 3000)
     out = out.cpu()
-    for i in (0, 17, 63):
-        assert (out[i] - O.log_mel_spectrogram(b[i], 80)).abs().max().item() <= TOL
-    out128 = A.log_mel_spectrogram(b[:4].cuda(), n_mels=128).cpu()
-    assert (out128 - O.log_mel_spectrogram(b[:4], 128)).abs().max().item() <= TOL
+    worst = 0.0
+    for i in range(0, 64, 8):                      # the oracle runs 8 clips at a time (memory)
+        ref = torch.stack([O.log_mel_spectrogram(b[k], n_mels) for k in range(i, i + 8)])
+        worst = max(worst, (out[i:i + 8] - ref).abs().max().item())
+    assert worst <= TOL
 
 
 def test_padding_argument_and_leading_dims():

@@ -29,7 +29,7 @@ def test_pack_utterances_layout_and_trim():
     b = frontend.pack_utterances(audios, vids, lms, vals, audio_max_length=8)
     assert b.n_utts == 2
     assert b.audio_offsets.tolist() == [0, 8, 13]                     # first clip trimmed to 8 samples
-    assert b.clip_offsets.tolist() == [0, 0, 0]   # video cut to round(8 / 16000 * 25) = 0 frames
+    assert b.clip_offsets.tolist() == [0, 3, 5]   # video is NOT cut here: the reference trims the features, after the lip path
     b = frontend.pack_utterances(audios, vids, lms, vals, audio_max_length=480000)
     assert b.clip_offsets.tolist() == [0, 3, 5]
     assert b.frames.shape == (5, 4, 4, 3) and b.landmarks.shape == (5, 68, 2)
@@ -37,7 +37,10 @@ def test_pack_utterances_layout_and_trim():
     assert b.nbytes() == 15 * 4 + 3 * 8 * 2 + 5 * 48 + 5 * 136 * 8 + 5
     long_vid = np.zeros((800, 2, 2, 3), np.uint8)
     b = frontend.pack_utterances([np.zeros(480000, np.float32)], [long_vid], [np.zeros((800, 68, 2))])
-    assert b.clip_offsets.tolist() == [0, 750]                        # whisper_flamingo_ft_ami.py:299-302
+    assert b.clip_offsets.tolist() == [0, 800]                        # all frames go through extract_lip_frames ...
+    lip = torch.zeros(800, 88, 88, 1)                                 # ... and the trim is applied to the features
+    assert [tuple(x.shape) for x in frontend.AVFrontEnd.split_lip(lip, b.clip_offsets, 480000)] == [(750, 88, 88, 1)]
+    assert [tuple(x.shape) for x in frontend.AVFrontEnd.split_lip(lip, b.clip_offsets)] == [(800, 88, 88, 1)]
 
 
 def test_shard_is_a_disjoint_cover():

@@ -115,3 +115,56 @@ def test_no_detection_returns_empty():
     out, tf, org = O.extract_lip_frames_from_arrays(np.zeros((3, 64, 64), np.uint8), [None] * 3,
                                                      mean_face_landmarks())
     assert out.size == 0 and tf is None
+
+
+@pytest.mark.parametrize("kind", ["translate", "border", "scale2"])
+def test_oracle_warp_known_answers(kind):
+    """The restated skimage warp + cut_patch against reference-independent known answers (integer
+    translation -> source pixels, border-straddling ROI -> exact zeros, x2 zoom -> truncated
+    midpoints): the only check of the unpinned warp chain that does not compare two restatements."""
+    from known_answers import known_answer_case
+    frames, gray, lm, tf, expect, (r0, c0) = known_answer_case(kind)
+    fwd, inv = tf[0, :9].reshape(3, 3), tf[0, 9:].reshape(3, 3)
+    assert O.cut_patch_origin(O.SimilarityTransform(fwd)(lm[0])[48:68], 48, 48, (300, 300)) == (r0, c0)
+    for t in range(len(frames)):
+        full = O.apply_transform(O.SimilarityTransform(fwd), gray[t])
+        np.testing.assert_array_equal(full[r0:r0 + 96, c0:c0 + 96], expect[t])
+
+
+def test_video_feats_rgb_dark_resize_match_reference_function_golden():
+    """utils/hf_video_utils.py:103-138 on decord-style input: goldens are the reference function's
+    own outputs (make_golden.py::video_feats)."""
+    g = np.load(GOLDEN / "video_feats_golden.npz")
+    np.testing.assert_array_equal(O.video_feats_from_frames(g["rgb"]), g["rgb_feats"])
+    np.testing.assert_array_equal(O.video_feats_from_frames(g["dark"]), g["dark_feats"])
+    np.testing.assert_array_equal(O.video_feats_from_frames(g["roi"][..., None]), g["feats"])
+    for name in ("small_rgb", "small_gray", "small_tall", "small_wide"):
+        got = O.video_feats_from_frames(g[name])
+        np.testing.assert_array_equal(got, g[name + "_feats_noipp"])          # cv2's own code path
+        assert np.abs(got - g[name + "_feats_ipp"]).max() <= 5e-5              # cv2 as shipped on x86 (IPP)
+
+
+def test_resize_restatement_against_live_cv2():
+    import cv2
+    rng = np.random.default_rng(5)
+    was = cv2.ipp.useIPP()
+    try:
+        cv2.ipp.setUseIPP(False)
+        for shape in [(64, 64), (87, 88), (40, 200), (120, 33)]:
+            for dt in (np.float32, np.float64):
+                src = (rng.integers(0, 256, shape) / 255.0).astype(dt)
+                np.testing.assert_array_equal(O.resize_linear(src, 88), cv2.resize(src, (88, 88)))
+    finally:
+        cv2.ipp.setUseIPP(was)
+
+
+def test_rgb_dot_float32_cast_is_order_independent():
+    """All 2^24 RGB triples: float32(np.dot(rgb, w)) (BLAS order, FMA or not) equals float32 of the
+    plain left-to-right float64 sum the oracle and the kernel use."""
+    v = np.arange(256, dtype=np.uint8)
+    r, gg, b = np.meshgrid(v, v, v, indexing="ij")
+    rgb = np.stack([r, gg, b], axis=-1).reshape(-1, 3)
+    ref = np.dot(rgb, [0.2989, 0.5870, 0.1140]).astype(np.float32)
+    f = rgb.astype(np.float64)
+    mine = ((f[:, 0] * 0.2989 + f[:, 1] * 0.5870) + f[:, 2] * 0.1140).astype(np.float32)
+    np.testing.assert_array_equal(mine, ref)
