@@ -551,13 +551,15 @@ using namespace avfe;
 
 template <bool STREAM, int SPAN>
 static int launch_fused(const LipJob& j, cudaStream_t s) {
-  const int smem = STREAM ? (int)sizeof(FusedSmem) : (int)offsetof(FusedSmem, ring);
+  // without stream warps the ring space holds footprint slots 2..5
+  const int smem = STREAM ? (int)sizeof(FusedSmem)
+                          : (int)(offsetof(FusedSmem, raw) + sizeof(uint4) * kQueueSlots * (kTilePx * 3 / 16));
   if (cudaFuncSetAttribute(lip_fused_kernel<STREAM, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            smem) != cudaSuccess) {
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  const int threads = STREAM ? 1024 : Roles<SPAN>::kHandoverThreads;
+  const int threads = STREAM ? 1024 : Roles<SPAN, kQueueSlots>::kHandoverThreads;
   const int64_t ctas = j.N < kNumSMs ? j.N : kNumSMs;                  // one persistent CTA per SM
   lip_fused_kernel<STREAM, SPAN><<<(unsigned)(STREAM ? kNumSMs : ctas), threads, smem, s>>>(j);
   return AVFE_OK;

@@ -4,9 +4,11 @@
 //   blend warps    (22 for an 88-px window, 24 for 96) float64 bilinear blend of one frame's ROI
 //                  in skimage's operation order, u8 ROI + normalised f32 centre crop; thread =
 //                  (column, row phase), rows fully unrolled; issue / FP64-pipe bound
-//   producer warps (2) pull frames from an atomic work queue and stage them one to two items
-//                  ahead in double-buffered slots: frame descriptor + source footprint fetched
-//                  with 16-byte cp.async.  The blend warps turn the raw BGR footprint into gray
+//   producer warps (NSLOT: 2 beside the stream warps, 6 without them) pull frames from an atomic
+//                  work queue and stage them ahead, one slot per producer warp: frame descriptor
+//                  + source footprint fetched with 16-byte cp.async.  Six footprints in flight per
+//                  SM are what keeps PCIe busy when `frames` is mapped pinned HOST memory (the
+//                  zero-copy e2e mode: only the footprints cross the link).  The blend warps turn the raw BGR footprint into gray
 //                  in shared memory themselves (704 threads, two quads each - so there is no
 //                  dependency on the stream warps) and release the slot right after that
 //   stream warps   (the remaining 8 / 6) BGR->gray over the flat pixel stream in 1024-px chunks,
@@ -20,23 +22,29 @@
 
 namespace avfe {
 
-constexpr int kProducerWarps = 2;
-constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kStreamSlots = 2;             // footprint slots when the stream warps use the ring space
+constexpr int kQueueSlots = 6;              // ... and when they do not (the ring space holds 4 more slots)
+constexpr int kMaxSlots = 6;
 constexpr int kRingStages = 4;              // 3 chunks (9 KB) per stream warp in flight
 constexpr int kChunkVec = 192;              // one stream chunk = 2 groups = 1024 px = 192 uint4 in
 constexpr int kMaxStreamWarps = 8;
 constexpr unsigned kItemDone = 0xffffffffu;
 
-// warp roles for a compile-time window side (0 = run-time side, laid out like 88)
-template <int SPAN>
+// warp roles for a compile-time window side (0 = run-time side, laid out like 88) and slot count
+template <int SPAN, int NSLOT = kStreamSlots>
 struct Roles {
   static constexpr int kSide = SPAN ? SPAN : 88;
+  static constexpr int kSlots = NSLOT;
+  static constexpr int kProducerWarps = NSLOT;                        // one producer warp per slot
+  static constexpr int kProducerThreads = kProducerWarps * 32;
   static constexpr int kBlendWarps = 8 * kSide / 32;                  // 22 or 24
   static constexpr int kBlendThreads = kBlendWarps * 32;
-  static constexpr int kStreamWarps = 32 - kBlendWarps - kProducerWarps;   // 8 or 6
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kProducerWarps;   // 8 or 6 (NSLOT == 2 only)
   static constexpr int kHandoverThreads = kBlendThreads + kProducerThreads;   // blend + producer threads
   static constexpr int kSlotThreads = kBlendThreads + 32;   // a slot's barriers: blend warps + its producer warp
 };
+// named barriers: FULL[slot] = 2 + slot, EMPTY[slot] = 8 + slot, 14 = blend warps only
+constexpr int kBarFull = 2, kBarEmpty = 8, kBarBlend = 14;
 
 struct LipJob {
   const uint8_t* frames;   // [N,H,W,channels]
@@ -71,15 +79,18 @@ struct FusedSmem {
   // pairs whatever their k: the tap lookups are bank-conflict free.
   double lut255[256 * 16];
   float lutn[256];                    // ((k/255) - mean) / std in float32
-  unsigned next_item[2];              // producer-internal hand-off of queue indices
-  unsigned pad[2];
-  ItemDesc desc[2];                   // slot s: written by the producers, read by the blend warps
+  unsigned pad[4];
+  ItemDesc desc[kMaxSlots];           // slot s: written by its producer, read by the blend warps
   BlendBuf buf[2];
-  uint4 raw[2][kTilePx * 3 / 16];     // slot s: cp.async landing zone, footprint bytes as in the frame
-  uint4 ring[kMaxStreamWarps][kRingStages][kChunkVec];   // stream warps (absent when not streaming)
+  // slot s: cp.async landing zone, footprint bytes as in the frame.  raw[0..1] are followed by the
+  // stream warps' ring; without stream warps that space is slots 2..5 (raw_slot()).
+  uint4 raw[kStreamSlots][kTilePx * 3 / 16];
+  uint4 ring[kMaxStreamWarps][kRingStages][kChunkVec];
 };
+static_assert(sizeof(uint4) * kMaxStreamWarps * kRingStages * kChunkVec >=
+              sizeof(uint4) * (kQueueSlots - kStreamSlots) * (kTilePx * 3 / 16), "ring space holds the extra slots");
+__device__ __forceinline__ uint4* raw_slot(FusedSmem& sm, int s) { return &sm.raw[0][0] + (size_t)s * (kTilePx * 3 / 16); }
 
-// named barriers: 1 = producers only, 2/3 = FULL[slot], 4/5 = EMPTY[slot], 6 = blend warps only
 __device__ __forceinline__ void bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -242,9 +253,9 @@ __device__ __forceinline__ void convert_footprint(const LipJob& j, const Footpri
 // other: draw a frame from the queue, fetch its descriptor, wait until the blend warps have
 // released the slot, copy the footprint, publish.  While the blend warps work on one slot the
 // other warp's copy is in flight.
-template <int SPAN>
+template <int SPAN, int NSLOT>
 __device__ __forceinline__ void producer_run(const LipJob& j, FusedSmem& sm, int tid) {
-  using R = Roles<SPAN>;
+  using R = Roles<SPAN, NSLOT>;
   const unsigned total = (unsigned)j.N;
   const int lane = tid & 31, s = tid >> 5;              // slot == producer warp index
   for (unsigned n = 0;; ++n) {
@@ -253,18 +264,18 @@ __device__ __forceinline__ void producer_run(const LipJob& j, FusedSmem& sm, int
     t = __shfl_sync(0xffffffffu, t, 0);
     FrameXform x;
     if (t < total) x = j.xf[t];
-    if (n >= 1) bar_sync(4 + s, R::kSlotThreads);       // blend warps are done with this slot's previous item
+    if (n >= 1) bar_sync(kBarEmpty + s, R::kSlotThreads);   // blend warps are done with this slot's previous item
     if (t >= total) {
       if (lane == 0) sm.desc[s].item = kItemDone;
       __syncwarp();
-      bar_arrive(2 + s, R::kSlotThreads);
+      bar_arrive(kBarFull + s, R::kSlotThreads);
       break;
     }
-    prefetch_footprint(j, (int64_t)t, unpack_footprint(x), sm.raw[s], lane);
+    prefetch_footprint(j, (int64_t)t, unpack_footprint(x), raw_slot(sm, s), lane);
     if (lane == 0) { sm.desc[s].x = x; sm.desc[s].item = t; }
     cp_async_wait_group<0>();
     __syncwarp();
-    bar_arrive(2 + s, R::kSlotThreads);                 // slot FULL
+    bar_arrive(kBarFull + s, R::kSlotThreads);          // slot FULL
   }
 }
 
@@ -296,11 +307,11 @@ __device__ __forceinline__ uint32_t bilinear_interior(double r, double c, const 
   return (uint32_t)(int)f64mul(v, 255.0);
 }
 
-template <int SPAN>
+template <int SPAN, int NSLOT>
 __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const FrameXform& x,
                                            const Footprint& fp, const BlendBuf& slot,
                                            const FusedSmem& sm, int tid) {
-  using R = Roles<SPAN>;
+  using R = Roles<SPAN, NSLOT>;
   const double* lut = sm.lut255 + (tid & 15);           // this lane's copy of the k/255 table
   const int off = (j.roi - j.crop) / 2;
   const int lo = j.lip_u8 ? 0 : off;
@@ -366,9 +377,9 @@ __device__ __forceinline__ void blend_item(const LipJob& j, int64_t f, const Fra
   }
 }
 
-template <int SPAN>
+template <int SPAN, int NSLOT>
 __device__ __forceinline__ void blend_run(const LipJob& j, FusedSmem& sm, int tid) {
-  using R = Roles<SPAN>;
+  using R = Roles<SPAN, NSLOT>;
   for (int k = tid; k < 256; k += R::kBlendThreads) {
     const double q = f64div((double)k, 255.0);
 #pragma unroll
@@ -378,20 +389,21 @@ __device__ __forceinline__ void blend_run(const LipJob& j, FusedSmem& sm, int ti
   const int off = (j.roi - j.crop) / 2;
   const int lo = j.lip_u8 ? 0 : off;
   const int span = SPAN ? SPAN : (j.lip_u8 ? j.roi : j.crop);
-  bool alive0 = true, alive1 = true;                    // a slot's producer publishes kItemDone once
-  for (unsigned k = 0; alive0 || alive1; ++k) {
-    const int s = (int)(k & 1u);
-    if (!(s ? alive1 : alive0)) continue;
-    bar_sync(2 + s, R::kSlotThreads);                   // slot FULL: descriptor + raw footprint landed
+  unsigned alive = (1u << NSLOT) - 1u;                  // a slot's producer publishes kItemDone once
+  unsigned nb = 0;                                      // items blended so far: picks the BlendBuf
+  for (int s = 0; alive != 0u; s = (s + 1 == NSLOT) ? 0 : s + 1) {
+    if (!((alive >> s) & 1u)) continue;
+    bar_sync(kBarFull + s, R::kSlotThreads);            // slot FULL: descriptor + raw footprint landed
     const unsigned item = sm.desc[s].item;
     if (item == kItemDone) {
-      if (s) alive1 = false; else alive0 = false;
+      alive &= ~(1u << s);
       continue;
     }
     const FrameXform x = sm.desc[s].x;
     const Footprint fp = unpack_footprint(x);
-    BlendBuf& buf = sm.buf[s];
-    convert_footprint(j, fp, sm.raw[s], buf.tile, tid, R::kBlendThreads);
+    BlendBuf& buf = sm.buf[nb & 1u];
+    ++nb;
+    convert_footprint(j, fp, raw_slot(sm, s), buf.tile, tid, R::kBlendThreads);
     if (x.r0 >= 0) {
       // hoisted products: x_ = (M0*c + M1*r) + M2 is evaluated as (colx[c] + rowx[r]) + M2 with
       // the same two roundings per product as skimage's _transform_affine
@@ -405,24 +417,25 @@ __device__ __forceinline__ void blend_run(const LipJob& j, FusedSmem& sm, int ti
         buf.rowy[tid - 128] = f64mul(x.inv[4], tr);
       }
     }
-    bar_sync(6, R::kBlendThreads);                      // tile + tables ready; raw/desc no longer read
-    bar_arrive(4 + s, R::kSlotThreads);                 // slot EMPTY: its producer may refill it
-    blend_item<SPAN>(j, (int64_t)item, x, fp, buf, sm, tid);
+    bar_sync(kBarBlend, R::kBlendThreads);              // tile + tables ready; raw/desc no longer read
+    bar_arrive(kBarEmpty + s, R::kSlotThreads);         // slot EMPTY: its producer may refill it
+    blend_item<SPAN, NSLOT>(j, (int64_t)item, x, fp, buf, sm, tid);
   }
 }
 
-// STREAM: blend + producer + stream warps (1024 threads); otherwise blend + producer warps only.
+// STREAM: blend + 2 producer + stream warps (1024 threads); otherwise blend + 6 producer warps.
 template <bool STREAM, int SPAN>
-__global__ void __launch_bounds__(STREAM ? 1024 : Roles<SPAN>::kHandoverThreads, 1)
+__global__ void __launch_bounds__(STREAM ? 1024 : Roles<SPAN, kQueueSlots>::kHandoverThreads, 1)
 lip_fused_kernel(const LipJob j) {
-  using R = Roles<SPAN>;
+  constexpr int NSLOT = STREAM ? kStreamSlots : kQueueSlots;
+  using R = Roles<SPAN, NSLOT>;
   extern __shared__ __align__(16) unsigned char fused_smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
   const int tid = threadIdx.x;
   if (tid < R::kBlendThreads) {
-    blend_run<SPAN>(j, sm, tid);
+    blend_run<SPAN, NSLOT>(j, sm, tid);
   } else if (tid < R::kHandoverThreads) {
-    producer_run<SPAN>(j, sm, tid - R::kBlendThreads);
+    producer_run<SPAN, NSLOT>(j, sm, tid - R::kBlendThreads);
   } else if (STREAM) {
     stream_run(j, sm, tid - R::kHandoverThreads, R::kStreamWarps);
   }

@@ -55,8 +55,12 @@ class PackedBatch:
         return PackedBatch(*[None if getattr(self, f) is None else getattr(self, f).cpu().contiguous().pin_memory()
                              for f in self.FIELDS])
 
-    def to(self, device, non_blocking: bool = True) -> "PackedBatch":
-        return PackedBatch(*[None if getattr(self, f) is None else getattr(self, f).to(device, non_blocking=non_blocking)
+    def to(self, device, non_blocking: bool = True, frames_stay_on_host: bool = False) -> "PackedBatch":
+        """Copy to ``device``.  ``frames_stay_on_host`` leaves the (pinned) frames where they are:
+        the zero-copy mode of the lip kernel reads them through the mapped host pointer."""
+        return PackedBatch(*[None if getattr(self, f) is None else
+                             (getattr(self, f) if (frames_stay_on_host and f == "frames") else
+                              getattr(self, f).to(device, non_blocking=non_blocking))
                              for f in self.FIELDS])
 
 
@@ -233,11 +237,19 @@ class AVFrontEnd:
         return graph, out
 
     # ---------------------------------------------------------------- host-buffer path (e2e)
+    def zero_copy(self, batch: PackedBatch) -> bool:
+        """Whether the host-buffer paths leave the frames in pinned host memory and let the lip
+        kernel pull only each frame's ROI footprint across PCIe (about a seventh of the frame
+        bytes): possible when no gray frames are wanted, which need every pixel on the device."""
+        return (not self.want_gray) and (not batch.frames.is_cuda) and batch.frames.is_pinned()
+
     def forward_host(self, batch: PackedBatch, host_out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``batch`` lives in (pinned) host memory: H2D copy of every input, the kernels, and a
         D2H copy of every deliverable: the features the reference's ``__getitem__`` returns (mel and
-        lip) and, when ``want_gray``, the gray frames ``load_video`` returns."""
-        dev = batch.to(self.device, non_blocking=True)
+        lip) and, when ``want_gray``, the gray frames ``load_video`` returns.
+        With ``want_gray=False`` the frames are not copied: see :meth:`zero_copy` (the batch must
+        stay untouched until this call returns, as with any asynchronous copy)."""
+        dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=self.zero_copy(batch))
         res = self.forward_device(dev, reuse=True)       # device results are copied out before returning
         keys = self.host_keys(res)
         if host_out is None or any(k not in host_out or tuple(host_out[k].shape) != tuple(res[k].shape) for k in keys):
@@ -268,7 +280,9 @@ class HostPipeline:
     buffers, so that the H2D copy of batch i+1, the kernels of batch i and the D2H copy of batch
     i-1 overlap (PCIe is full duplex and the copy engines run beside the SMs).  Every batch still
     pays its full H2D of inputs and D2H of mel + lip (+ gray when ``want_gray``); only the waiting
-    is overlapped."""
+    is overlapped.  With ``want_gray=False`` the frames stay in pinned host memory and the lip
+    kernel reads just the ROI footprints through the mapped pointer (``AVFrontEnd.zero_copy``);
+    a submitted batch must not be modified before ``result(i)`` returns."""
 
     def __init__(self, depth: int = 2, **frontend_kwargs):
         self.fes = [AVFrontEnd(**frontend_kwargs) for _ in range(depth)]
@@ -286,7 +300,7 @@ class HostPipeline:
         fe, st = self.fes[k], self.streams[k]
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st):
-            dev = batch.to(self.device, non_blocking=True)
+            dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=fe.zero_copy(batch))
             res = fe.forward_device(dev, reuse=True)     # the slot's event guards its buffers
             keys = fe.host_keys(res)
             if self.outs[k] is None or any(n not in self.outs[k] or tuple(self.outs[k][n].shape) != tuple(res[n].shape)

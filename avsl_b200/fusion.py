@@ -51,11 +51,19 @@ def modality_dropout_mask(batch_size: int, training: bool, modality_dropout: flo
 
 
 def _mask_tensor(mask, B: int, device) -> Optional[torch.Tensor]:
-    """[B,2] keep-mask as a uint8 device tensor (None stays None); a sample with both modalities
-    dropped raises like the reference (``av_hubert_encoder.py:301-302``)."""
+    """[B,2] keep-mask as a uint8 device tensor (None stays None).  A host mask (numpy / CPU
+    tensor) with a sample that drops both modalities raises like the reference
+    (``av_hubert_encoder.py:301-302``).  A CUDA mask is used as it is, without a device-to-host
+    copy -- the call stays asynchronous -- so that check is the caller's; the kernels zero-fill a
+    sample whose two flags are both 0."""
     if mask is None:
         return None
-    m = torch.as_tensor(np.asarray(mask.cpu() if torch.is_tensor(mask) else mask) != 0).to(torch.uint8)
+    if torch.is_tensor(mask) and mask.is_cuda:
+        if tuple(mask.shape) != (B, 2):
+            raise ValueError("mask must be [B, 2]")
+        m = mask if mask.dtype == torch.uint8 else (mask != 0).to(torch.uint8)
+        return m.contiguous().to(device)
+    m = torch.as_tensor(np.asarray(mask) != 0).to(torch.uint8)
     if tuple(m.shape) != (B, 2):
         raise ValueError("mask must be [B, 2]")
     if not bool((m.sum(dim=1) > 0).all()):
@@ -63,12 +71,87 @@ def _mask_tensor(mask, B: int, device) -> Optional[torch.Tensor]:
     return m.contiguous().to(device, non_blocking=True)
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _FuseFn(torch.autograd.Function):
+    """avfe_fuse with its backward kernel (avfe_fuse_backward): the reference's fusion runs in the
+    training forward, so gradients must reach both feature extractors."""
+
+    @staticmethod
+    def forward(ctx, fa, fv, m, mode, wa, wv):
+        B, C, T = (int(s) for s in fa.shape)
+        out = torch.empty((B, 2 * C, T) if mode == _lib.FUSE_CONCAT else (B, C, T), dtype=fa.dtype, device=fa.device)
+        with torch.cuda.device(fa.device):
+            _lib.call("avfe_fuse", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, wa, wv, _DTYPES[fa.dtype],
+                      B, C, T, _lib.ptr(out), _lib.stream_ptr())
+        ctx.mask = m
+        ctx.meta = (mode, wa, wv, B, C, T)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        mode, wa, wv, B, C, T = ctx.meta
+        g = grad_out.contiguous()
+        gfa = torch.empty((B, C, T), dtype=g.dtype, device=g.device)
+        gfv = torch.empty_like(gfa)
+        with torch.cuda.device(g.device):
+            _lib.call("avfe_fuse_backward", _lib.ptr(g), _lib.ptr(ctx.mask), mode, wa, wv, _DTYPES[g.dtype],
+                      B, C, T, _lib.ptr(gfa), _lib.ptr(gfv), _lib.stream_ptr())
+        return (gfa if ctx.needs_input_grad[0] else None, gfv if ctx.needs_input_grad[1] else None,
+                None, None, None, None)
+
+
+class _FuseLayerNormFn(torch.autograd.Function):
+    """avfe_fuse_layernorm with its backward kernel (avfe_fuse_layernorm_backward): gradients for
+    both feature maps and for layer_norm.weight / .bias; the moments are recomputed in the backward
+    pass, so only the inputs are kept."""
+
+    @staticmethod
+    def forward(ctx, fa, fv, weight, bias, m, mode, wa, wv, eps):
+        B, C, T = (int(s) for s in fa.shape)
+        Cout = 2 * C if mode == _lib.FUSE_CONCAT else C
+        out = torch.empty((B, T, Cout), dtype=fa.dtype, device=fa.device)
+        with torch.cuda.device(fa.device):
+            _lib.call("avfe_fuse_layernorm", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, wa, wv,
+                      _DTYPES[fa.dtype], B, C, T, _lib.ptr(weight), _lib.ptr(bias), eps, _lib.ptr(out),
+                      _lib.stream_ptr())
+        ctx.save_for_backward(fa, fv, weight)
+        ctx.mask = m
+        ctx.meta = (mode, wa, wv, eps, B, C, T, Cout, bias is not None)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        fa, fv, weight = ctx.saved_tensors
+        mode, wa, wv, eps, B, C, T, Cout, has_bias = ctx.meta
+        g = grad_out.contiguous()
+        gfa, gfv = torch.empty_like(fa), torch.empty_like(fv)
+        want_w = weight is not None and ctx.needs_input_grad[2]
+        want_b = has_bias and ctx.needs_input_grad[3]
+        gw = torch.empty(Cout, dtype=torch.float32, device=g.device) if want_w else None
+        gb = torch.empty(Cout, dtype=torch.float32, device=g.device) if want_b else None
+        with torch.cuda.device(g.device):
+            lib = _lib.load()
+            ws_bytes = int(lib.avfe_fuse_layernorm_backward_workspace_bytes(B, C, T, mode))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+            _lib.call("avfe_fuse_layernorm_backward", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(ctx.mask), mode, wa, wv,
+                      _DTYPES[fa.dtype], B, C, T, _lib.ptr(weight), eps, _lib.ptr(g), _lib.ptr(gfa), _lib.ptr(gfv),
+                      _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        return (gfa if ctx.needs_input_grad[0] else None, gfv if ctx.needs_input_grad[1] else None, gw, gb,
+                None, None, None, None, None)
+
+
 def fuse_modalities(features_audio: torch.Tensor, features_video: torch.Tensor,
                     mask=None, fusion_type: str = "concat", weights: Tuple[float, float] = (0.5, 0.5),
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """features_audio, features_video: [B, C, T] CUDA tensors of one dtype (fp32/fp16/bf16).
     mask: [B,2] (numpy / tensor; nonzero = present) or None.  Returns [B,2C,T] for "concat",
-    [B,C,T] for "add" / "weighted_sum"."""
+    [B,C,T] for "add" / "weighted_sum".  Differentiable: when an input requires grad the result
+    carries a ``grad_fn`` whose backward is a libavfe kernel (``out=`` cannot be combined with that)."""
     if fusion_type not in _MODES:
         raise ValueError(f"Unsupported fusion type: {fusion_type}")
     _lib.require_cuda()
@@ -82,12 +165,16 @@ def fuse_modalities(features_audio: torch.Tensor, features_video: torch.Tensor,
     fa, fv = fa.contiguous(), fv.contiguous()
     B, C, T = (int(s) for s in fa.shape)
     mode = _MODES[fusion_type]
+    m = _mask_tensor(mask, B, fa.device)
+    if _needs_grad(fa, fv):
+        if out is not None:
+            raise ValueError("out= cannot be used when gradients are required")
+        return _FuseFn.apply(fa, fv, m, mode, float(weights[0]), float(weights[1]))
     shape = (B, 2 * C, T) if mode == _lib.FUSE_CONCAT else (B, C, T)
     if out is None:
         out = torch.empty(shape, dtype=fa.dtype, device=fa.device)
     elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == shape):
         raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {shape}")
-    m = _mask_tensor(mask, B, fa.device)
     with torch.cuda.device(fa.device):
         _lib.call("avfe_fuse", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
                   float(weights[1]), _DTYPES[fa.dtype], B, C, T, _lib.ptr(out), _lib.stream_ptr())
@@ -103,7 +190,8 @@ def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch
     (``av_hubert_encoder.py:329-330``): ``features.transpose(1, 2)`` and ``self.layer_norm``
     (``LayerNorm`` of ``av_hubert_layers.py:438-440``: float32 arithmetic, result cast back), in
     one kernel.  [B,C,T] x 2 -> [B,T,C'] (C' = 2C for "concat").  ``weight`` / ``bias`` are the
-    LayerNorm parameters (float32 [C'])."""
+    LayerNorm parameters (float32 [C']).  Differentiable with respect to both feature maps,
+    ``weight`` and ``bias`` (one backward kernel; ``out=`` cannot be combined with that)."""
     if fusion_type not in _MODES:
         raise ValueError(f"Unsupported fusion type: {fusion_type}")
     _lib.require_cuda()
@@ -122,11 +210,15 @@ def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch
         if prm is not None and not (prm.is_cuda and prm.dtype == torch.float32 and prm.is_contiguous()
                                     and tuple(prm.shape) == (Cout,)):
             raise ValueError(f"{name} must be a contiguous float32 CUDA tensor of shape ({Cout},)")
+    m = _mask_tensor(mask, B, fa.device)
+    if _needs_grad(fa, fv, weight, bias):
+        if out is not None:
+            raise ValueError("out= cannot be used when gradients are required")
+        return _FuseLayerNormFn.apply(fa, fv, weight, bias, m, mode, float(weights[0]), float(weights[1]), float(eps))
     if out is None:
         out = torch.empty((B, T, Cout), dtype=fa.dtype, device=fa.device)
     elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == (B, T, Cout)):
         raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {(B, T, Cout)}")
-    m = _mask_tensor(mask, B, fa.device)
     with torch.cuda.device(fa.device):
         _lib.call("avfe_fuse_layernorm", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
                   float(weights[1]), _DTYPES[fa.dtype], B, C, T, _lib.ptr(weight), _lib.ptr(bias),

@@ -207,8 +207,15 @@ def lip_roi_batch(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: t
     scratch tensor of ``lip_workspace_bytes(N)`` bytes (steady-state loops, CUDA-graph capture:
     nothing is allocated then); a workspace must not be shared by calls that may overlap."""
     _lib.require_cuda()
-    if not frames.is_cuda:
-        raise ValueError("lip_roi_batch takes CUDA tensors; use extract_lip_frames for host arrays")
+    host_frames = not frames.is_cuda
+    if host_frames:
+        # Zero-copy: page-locked host memory is mapped into the device's address space (unified
+        # addressing), so the kernel can pull just the ROI footprints across PCIe instead of the
+        # whole frames being copied first.  Only without gray output (that needs every pixel).
+        if not frames.is_pinned():
+            raise ValueError("lip_roi_batch takes CUDA tensors or PINNED host frames; use extract_lip_frames for host arrays")
+        if want_gray:
+            raise ValueError("host-resident (zero-copy) frames cannot be combined with want_gray=True")
     if frames.dtype != torch.uint8 or not frames.is_contiguous():
         raise ValueError("frames must be contiguous uint8")
     if frames.dim() == 4 and frames.shape[-1] == 3:
@@ -218,7 +225,7 @@ def lip_roi_batch(frames: torch.Tensor, clip_offsets: torch.Tensor, landmarks: t
     else:
         raise ValueError("frames must be [N,H,W,3] (BGR) or [N,H,W] (gray)")
     N, H, W = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
-    dev = frames.device
+    dev = clip_offsets.device if host_frames else frames.device
     n_clips = int(clip_offsets.numel()) - 1
     if clip_offsets.dtype != torch.int64 or not clip_offsets.is_cuda:
         raise ValueError("clip_offsets must be a CUDA int64 tensor")

@@ -10,7 +10,11 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer (cudaMalloc'd on the current device), row-major,
- *    caller-allocated and caller-owned; inputs are const and never written;
+ *    caller-allocated and caller-owned; inputs are const and never written.  One documented
+ *    exception: `frames` of avfe_lip_roi_batch / avfe_lip_roi_collate may point to page-locked
+ *    HOST memory (cudaHostAlloc / cudaHostRegister: mapped into the device's address space under
+ *    unified addressing) when gray_out is NULL -- the kernel then pulls only each frame's ROI
+ *    footprint across PCIe ("zero-copy"), about a seventh of the frame bytes;
  *  - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
  *    stream); no call synchronises the host, allocates device memory or keeps state, so
  *    calls are re-entrant and may be issued concurrently from several host threads;
@@ -306,6 +310,30 @@ AVFE_API int avfe_fuse_layernorm(const void* fa, const void* fv, const uint8_t* 
                                  float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
                                  const float* gamma, const float* beta, float eps, void* out,
                                  avfe_stream_t stream);
+
+/* ------------------------------------------------------------------ fusion, backward
+ * The reference's fusion block runs inside the TRAINING forward (modality dropout under
+ * self.training, avsl/modules/av_hubert_encoder.py:292-330), so a drop-in has to pass gradients to
+ * the feature extractors and to layer_norm.weight / .bias.  The Python shim wraps these in
+ * torch.autograd.Function (avsl_b200/fusion.py). */
+
+/* d(avfe_fuse)/d(fa, fv): grad_out [B, 2C, T] (CONCAT) or [B, C, T] -> grad_fa, grad_fv [B, C, T].
+ * The gradient of a masked-out (zero-filled) modality is zero; WSUM scales by w_a / w_v. */
+AVFE_API int avfe_fuse_backward(const void* grad_out, const uint8_t* mask, int mode, float w_a, float w_v,
+                                int dtype, int64_t B, int64_t C, int64_t T, void* grad_fa, void* grad_fv,
+                                avfe_stream_t stream);
+
+/* Backward of avfe_fuse_layernorm in one pass: fa, fv, mask, mode, weights, gamma, eps as in the
+ * forward call (the moments are recomputed, nothing has to be saved); grad_out [B, T, C'] of `dtype`.
+ *   grad_fa, grad_fv [B, C, T] of `dtype`; grad_gamma, grad_beta [C'] float32 (nullable)
+ *   workspace avfe_fuse_layernorm_backward_workspace_bytes(...) bytes, 16-byte aligned (per-CTA
+ *   partial sums of grad_gamma / grad_beta, added in a fixed order: the result is deterministic). */
+AVFE_API size_t avfe_fuse_layernorm_backward_workspace_bytes(int64_t B, int64_t C, int64_t T, int mode);
+AVFE_API int avfe_fuse_layernorm_backward(const void* fa, const void* fv, const uint8_t* mask, int mode,
+                                          float w_a, float w_v, int dtype, int64_t B, int64_t C, int64_t T,
+                                          const float* gamma, float eps, const void* grad_out, void* grad_fa,
+                                          void* grad_fv, float* grad_gamma, float* grad_beta, void* workspace,
+                                          size_t workspace_bytes, avfe_stream_t stream);
 
 #ifdef __cplusplus
 }

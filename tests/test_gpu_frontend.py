@@ -189,3 +189,31 @@ def test_outputs_are_fresh_unless_reuse_is_requested():
     r2 = fe.forward_device(b2, reuse=True)
     assert all(r2[k].data_ptr() == p[k] for k in p)
     assert torch.equal(r2["mel"], o2["mel"]) and torch.equal(r2["lip"], o2["lip"])
+
+
+def test_zero_copy_frames_give_the_same_features():
+    """want_gray=False host path: the frames stay in pinned host memory and the lip kernel reads the
+    ROI footprints through the mapped pointer -- same bytes as the device-resident path, for
+    interior ROIs, ROIs hanging over the frame border (global taps) and a clip without detections."""
+    audios, vids, lms, vals = _utts(4, seed=5)
+    lms[1] = lms[1] + np.array([40.0, 30.0])            # mouth near the frame edge: footprint not interior
+    vals[2][:] = 0                                      # no detection at all: zero ROI
+    batch = A.pack_utterances(audios, vids, lms, vals, audio_max_length=32000).pin()
+    ref = A.AVFrontEnd(n_mels=80, audio_max_length=32000, want_gray=True).forward_host(batch)
+    fe = A.AVFrontEnd(n_mels=80, audio_max_length=32000, want_gray=False)
+    assert fe.zero_copy(batch)
+    out = fe.forward_host(batch)
+    assert sorted(out) == ["lip", "mel"]
+    assert torch.equal(out["lip"], ref["lip"]) and torch.equal(out["mel"], ref["mel"])
+    pipe = A.HostPipeline(depth=2, n_mels=80, audio_max_length=32000, want_gray=False)
+    for i in range(3):
+        pipe.submit(i, batch)
+    assert torch.equal(pipe.result(2)["lip"], ref["lip"])
+    pipe.drain()
+    # the C ABI contract: host frames only without gray output
+    dev = batch.to("cuda", frames_stay_on_host=True)
+    with pytest.raises(ValueError, match="want_gray"):
+        A.lip_roi_batch(dev.frames, dev.clip_offsets, dev.landmarks, dev.lm_valid, want_gray=True)
+    with pytest.raises(ValueError, match="PINNED"):
+        A.lip_roi_batch(torch.zeros((2, 8, 8, 3), dtype=torch.uint8), dev.clip_offsets, dev.landmarks, dev.lm_valid,
+                        want_gray=False)

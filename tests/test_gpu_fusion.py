@@ -129,3 +129,96 @@ def test_fuse_transpose_layernorm_config4_properties():
     ref = torch.nn.functional.layer_norm((A.fuse_modalities(fa.half(), fv.half(), mask, "add")).transpose(1, 2).float(),
                                          (1024,), None, None, 1e-5).half()
     assert (add.float() - ref.float()).abs().max().item() <= 2.5e-3 * ref.float().abs().max().item()
+
+
+# ------------------------------------------------------------------ gradients
+def _ref_fuse(fa, fv, mask, mode, wa=0.5, wv=0.5):
+    """The reference's fusion expressions (av_hubert_encoder.py:315-326) with zero-filled missing
+    modalities, in torch ops autograd can differentiate."""
+    m = torch.as_tensor(np.asarray(mask), device=fa.device).to(fa.dtype)
+    a = fa * m[:, 0].view(-1, 1, 1)
+    v = fv * m[:, 1].view(-1, 1, 1)
+    if mode == "concat":
+        return torch.cat([a, v], dim=1)
+    if mode == "add":
+        return a + v
+    return wa * a + wv * v
+
+
+@pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_fuse_backward_matches_torch_autograd(mode, dtype):
+    fa, fv, mask = synth.fusion_inputs(5, 24, 37, seed=11, dtype=dtype)
+    fa, fv = fa.cuda().requires_grad_(), fv.cuda().requires_grad_()
+    out = A.fuse_modalities(fa, fv, mask, mode, weights=(0.25, 0.75))
+    assert out.grad_fn is not None
+    g = torch.randn_like(out)
+    out.backward(g)
+    ra, rv = fa.detach().clone().requires_grad_(), fv.detach().clone().requires_grad_()
+    _ref_fuse(ra, rv, mask, mode, 0.25, 0.75).backward(g)
+    assert torch.equal(fa.grad, ra.grad) and torch.equal(fv.grad, rv.grad)      # exact: copies / one product
+
+
+@pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("shape", [(3, 40, 75), (2, 256, 33), (1, 520, 100)])
+def test_fuse_layernorm_backward_matches_torch_autograd(mode, dtype, tol, shape):
+    """Gradients of fusion + transpose + LayerNorm w.r.t. both feature maps and the LayerNorm
+    parameters against torch autograd over the reference's own ops (av_hubert_encoder.py:315-330)."""
+    B, C, T = shape
+    fa, fv, mask = synth.fusion_inputs(B, C, T, seed=13, dtype=dtype)
+    Cout = 2 * C if mode == "concat" else C
+    gen = torch.Generator().manual_seed(3)
+    w0 = (torch.rand(Cout, generator=gen) + 0.5).cuda()
+    b0 = torch.randn(Cout, generator=gen).cuda()
+    fa, fv = fa.cuda().requires_grad_(), fv.cuda().requires_grad_()
+    w, b = w0.clone().requires_grad_(), b0.clone().requires_grad_()
+    out = A.fuse_transpose_layernorm(fa, fv, mask, mode, w, b, weights=(0.4, 0.6))
+    assert out.grad_fn is not None and out.shape == (B, T, Cout)
+    g = torch.randn(out.shape, generator=gen).to(dtype).cuda()
+    out.backward(g)
+    # reference in float32 from the same (rounded) inputs
+    ra, rv = fa.detach().float().requires_grad_(), fv.detach().float().requires_grad_()
+    rw, rb = w0.clone().requires_grad_(), b0.clone().requires_grad_()
+    fused = _ref_fuse(ra, rv, mask, mode, 0.4, 0.6)
+    if dtype != torch.float32:
+        fused = fused + (fused.to(dtype).float() - fused).detach()      # the forward rounds the fused value to dtype
+    ref = torch.nn.functional.layer_norm(fused.transpose(1, 2), (Cout,), rw, rb, 1e-5)
+    ref.backward(g.float())
+    scale = max(1.0, ra.grad.abs().max().item())
+    assert (fa.grad.float() - ra.grad).abs().max().item() <= tol * scale
+    assert (fv.grad.float() - rv.grad).abs().max().item() <= tol * scale
+    n_red = B * T
+    assert (w.grad - rw.grad).abs().max().item() <= 2e-5 * n_red ** 0.5 * max(1.0, rw.grad.abs().max().item())
+    assert (b.grad - rb.grad).abs().max().item() <= 2e-5 * n_red ** 0.5 * max(1.0, rb.grad.abs().max().item())
+    # a masked-out modality receives an exactly zero gradient
+    m = np.asarray(mask)
+    for k in range(B):
+        if not m[k, 0]:
+            assert not fa.grad[k].any()
+        if not m[k, 1]:
+            assert not fv.grad[k].any()
+    # deterministic: a second backward gives the same bits
+    fa2, fv2 = fa.detach().clone().requires_grad_(), fv.detach().clone().requires_grad_()
+    w2, b2 = w0.clone().requires_grad_(), b0.clone().requires_grad_()
+    A.fuse_transpose_layernorm(fa2, fv2, mask, mode, w2, b2, weights=(0.4, 0.6)).backward(g)
+    assert torch.equal(fa2.grad, fa.grad) and torch.equal(w2.grad, w.grad) and torch.equal(b2.grad, b.grad)
+
+
+def test_modality_fusion_module_trains_and_no_grad_path_is_unchanged():
+    fa, fv, mask = synth.fusion_inputs(4, 16, 20, seed=2)
+    fa, fv = fa.cuda(), fv.cuda()
+    plain = A.fuse_modalities(fa, fv, mask, "concat")
+    assert plain.grad_fn is None
+    fa_g = fa.clone().requires_grad_()
+    with torch.no_grad():
+        assert A.fuse_modalities(fa_g, fv, mask, "concat").grad_fn is None
+    with pytest.raises(ValueError, match="out="):
+        A.fuse_modalities(fa_g, fv, mask, "concat", out=torch.empty_like(plain))
+    mod = A.ModalityFusion("add", modality_dropout=0.0).cuda().train()
+    out = mod(fa_g, fv)
+    out.sum().backward()
+    assert torch.equal(fa_g.grad, torch.ones_like(fa_g))
+    # a CUDA mask is taken without a host round trip
+    cm = torch.as_tensor(np.asarray(mask)).cuda()
+    assert torch.equal(A.fuse_modalities(fa, fv, cm, "concat"), plain)
