@@ -625,6 +625,14 @@ static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, i
   if (!frames || !clip_offsets || !landmarks || !mean_face) return AVFE_ERR_INVALID_ARG;
   if (gray_out && channels != 3) return AVFE_ERR_INVALID_ARG;
   if (N > 0x0fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  // the one pointer that may be mapped pinned host memory (zero-copy mode, avfe.h "Conventions")
+  bool frames_on_host = false;
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, frames) == cudaSuccess) frames_on_host = (pa.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+  }
+  if (frames_on_host && gray_out) return AVFE_ERR_INVALID_ARG;     // gray needs every pixel on the device
   if (!workspace || workspace_bytes < avfe_lip_workspace_bytes(N) || !aligned16(workspace))
     return AVFE_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -659,7 +667,7 @@ static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, i
     j.frames = frames; j.channels = channels; j.H = H; j.W = W; j.N = N; j.xf = nullptr; j.dst_slot = nullptr;
     j.roi = roi; j.crop = crop; j.mean = mean; j.stdv = std;
     j.gray_out = gray_out; j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = nullptr;
-    j.ngroups = 0; j.stage_align = fp_align;
+    j.ngroups = 0; j.stage_align = fp_align; j.host_frames = 0;
     fj.tf = ta;
     fj.tf.fp_cap = kFrameTilePx;                            // u8 tiles: twice the generic kernel's capacity
     fj.groups_per_frame = (int)((int64_t)H * W / 16);
@@ -693,6 +701,7 @@ static int lip_roi_impl(const uint8_t* frames, int channels, int64_t N, int H, i
     j.lip_u8 = lip_u8; j.lip_f32 = lip_f32; j.counter = counter;
     j.ngroups = (N * npx) / 512;
     j.stage_align = fp_align;
+    j.host_frames = frames_on_host ? 1 : 0;
     int rc = AVFE_OK;
     if (fuse_gray) {
       if (span_sel == 96) rc = launch_fused<true, 96>(j, s);

@@ -60,6 +60,7 @@ struct LipJob {
   unsigned* counter;       // work queue of the producers (zeroed by tform_kernel)
   int64_t ngroups;         // full 512-px groups in the flat pixel stream
   int stage_align;         // cp.async width for footprints (16 or 4); 0 = footprints not staged
+  int host_frames;         // `frames` is mapped pinned HOST memory: footprints are pulled across PCIe
 };
 
 struct ItemDesc {
@@ -203,7 +204,32 @@ __device__ __forceinline__ void prefetch_footprint(const LipJob& j, int64_t f, c
     const int64_t row_bytes = (int64_t)j.W * C;
     const uint8_t* base = j.frames + (f * (int64_t)j.H * j.W + (int64_t)fp.r0 * j.W + fp.c0) * C;
     const int lane = tid & 31;                           // one producer warp copies one footprint
-    if (j.stage_align == 16) {
+    if (j.stage_align == 16 && j.host_frames) {
+      // Host-resident frames: 128-bit loads through registers, eight per lane in flight (4 KB per
+      // warp, 24 KB per SM).  Measured on the benchmark batch (16,441 frames): 7.2 ms against
+      // 14.4 ms with the cp.async loop below, which puts a whole footprint's ~36 requests per lane
+      // in flight at once; 7.2 ms is the link's rate for 240..288-byte row pieces
+      // (profiles/r02/pcie_probe.txt: 46.5 GB/s against 55.6 GB/s for the copy engine).
+      const int vpr = fp.pitch * C / 16;
+      const int total = fp.rows * vpr;
+      const unsigned magic = (0xFFFFFFFFu / (unsigned)vpr) + 1u;
+      for (int b0 = 0; b0 < total; b0 += 256) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = b0 + 32 * u + lane;
+          if (idx < total) {
+            const int r = (int)__umulhi((unsigned)idx, magic), w = idx - r * vpr;
+            v[u] = ldg_stream(reinterpret_cast<const uint4*>(base + r * row_bytes + 16 * w));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = b0 + 32 * u + lane;
+          if (idx < total) raw[idx] = v[u];
+        }
+      }
+    } else if (j.stage_align == 16) {
       const int vpr = fp.pitch * C / 16;                 // 16-byte chunks per footprint row
       const int total = fp.rows * vpr;
       const unsigned magic = (0xFFFFFFFFu / (unsigned)vpr) + 1u;       // exact idx / vpr (idx < 2^16)

@@ -132,7 +132,7 @@ class AVFrontEnd:
 
     # ---------------------------------------------------------------- device-resident path
     def forward_device(self, batch: PackedBatch, padded_audio: Optional[torch.Tensor] = None,
-                       mark=None, reuse: bool = False) -> Dict[str, torch.Tensor]:
+                       mark=None, reuse: bool = False, lip_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """All inputs already on ``self.device``.  ``padded_audio`` [U, audio_max_length] makes the
         log-mel read an already padded matrix instead of the ragged ``batch.audio``.  ``mark(name)``
         (optional) is called after each stage is enqueued (bench.py records CUDA events there).
@@ -142,7 +142,10 @@ class AVFrontEnd:
         The returned tensors are freshly allocated.  ``reuse=True`` is the steady-state option: the
         outputs live in buffers owned by this object and the NEXT ``reuse=True`` call with the
         same shapes overwrites them in place (what ``capture`` and ``HostPipeline`` rely on) -- a
-        loader that still holds batch i while batch i+1 is built must not use it."""
+        loader that still holds batch i while batch i+1 is built must not use it.
+        ``lip_out`` (float32 [N,crop,crop], a CUDA tensor or a PINNED host tensor) receives the lip
+        features instead of a device buffer; with a pinned tensor the blend warps store across
+        PCIe themselves, which overlaps with the footprint reads of the zero-copy mode."""
         U, L = batch.n_utts, self.audio_max_length
         mark = mark or (lambda name: None)
         self._reuse = bool(reuse)
@@ -157,6 +160,10 @@ class AVFrontEnd:
                 log_mel_spectrogram(padded_audio, self.n_mels, filters=self.filters, out=mel)
             mark("logmel")
             N, H, W = (int(s) for s in batch.frames.shape[:3])
+            if lip_out is not None and not (lip_out.dtype == torch.float32 and lip_out.is_contiguous()
+                                            and tuple(lip_out.shape) == (N, self.crop, self.crop)
+                                            and (lip_out.is_cuda or lip_out.is_pinned())):
+                raise ValueError(f"lip_out must be a contiguous float32 CUDA or pinned tensor of shape {(N, self.crop, self.crop)}")
             src = batch.frames
             gray = None
             bgr = batch.frames.dim() == 4
@@ -169,8 +176,8 @@ class AVFrontEnd:
                     mark("gray")
             res = LipBatch(gray if (self.fused and bgr) else None,
                              self._buf("lip_u8", (N, 96, 96), torch.uint8) if self.want_lip_u8 else None,
-                             self._buf("lip", (N, self.crop, self.crop), torch.float32), None, None,
-                             batch.clip_offsets)
+                             lip_out if lip_out is not None else self._buf("lip", (N, self.crop, self.crop), torch.float32),
+                             None, None, batch.clip_offsets)
             # fused: one launch does the transform fits, the gray frames and the ROI warp (every
             # frame byte is read once)
             lip_roi_batch(src, batch.clip_offsets, batch.landmarks, batch.lm_valid,
@@ -249,15 +256,29 @@ class AVFrontEnd:
         lip) and, when ``want_gray``, the gray frames ``load_video`` returns.
         With ``want_gray=False`` the frames are not copied: see :meth:`zero_copy` (the batch must
         stay untouched until this call returns, as with any asynchronous copy)."""
-        dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=self.zero_copy(batch))
-        res = self.forward_device(dev, reuse=True)       # device results are copied out before returning
-        keys = self.host_keys(res)
-        if host_out is None or any(k not in host_out or tuple(host_out[k].shape) != tuple(res[k].shape) for k in keys):
-            host_out = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory() for k in keys}
-        for k in keys:
-            host_out[k].copy_(res[k], non_blocking=True)
+        host_out = dict(host_out or {})
+        res = self._run_host(batch, host_out)
         torch.cuda.current_stream(self.device).synchronize()
-        return host_out
+        return {k: host_out[k] for k in self.host_keys(res)}
+
+    def _run_host(self, batch: PackedBatch, host_out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Enqueue one host-buffer step on the current stream; ``host_out`` (pinned tensors, reused
+        when their shapes fit, created otherwise) receives the results.  No synchronisation."""
+        def pinned(name, shape, dtype):
+            t = host_out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = host_out[name] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            return t
+        zc = self.zero_copy(batch)
+        dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=zc)
+        lip_out = None
+        if zc:      # the blend warps store the lip features across PCIe themselves: no device buffer, no D2H copy
+            lip_out = pinned("lip", (int(batch.frames.shape[0]), self.crop, self.crop, 1), torch.float32).squeeze(-1)
+        res = self.forward_device(dev, reuse=True, lip_out=lip_out)   # device results are copied out before the buffers are reused
+        for k in self.host_keys(res):
+            if res[k].is_cuda:
+                pinned(k, res[k].shape, res[k].dtype).copy_(res[k], non_blocking=True)
+        return res
 
     @staticmethod
     def host_keys(res: Dict[str, torch.Tensor]) -> List[str]:
@@ -300,14 +321,9 @@ class HostPipeline:
         fe, st = self.fes[k], self.streams[k]
         st.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(st):
-            dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=fe.zero_copy(batch))
-            res = fe.forward_device(dev, reuse=True)     # the slot's event guards its buffers
-            keys = fe.host_keys(res)
-            if self.outs[k] is None or any(n not in self.outs[k] or tuple(self.outs[k][n].shape) != tuple(res[n].shape)
-                                           for n in keys):
-                self.outs[k] = {n: torch.empty(res[n].shape, dtype=res[n].dtype).pin_memory() for n in keys}
-            for n in keys:
-                self.outs[k][n].copy_(res[n], non_blocking=True)
+            if self.outs[k] is None:
+                self.outs[k] = {}
+            fe._run_host(batch, self.outs[k])            # the slot's event guards its buffers
             ev = torch.cuda.Event()
             ev.record(st)
             self.events[k] = ev

@@ -13,8 +13,10 @@ The 10k sweep itself does not fit one GPU (169 GB of BGR frames), so a step is t
 that is kept resident; per-GPU work is fixed as N grows (weak scaling), no collective on the path.
 
 `value`  : device-resident (inputs in HBM before the timed region), CUDA events, max over ranks.
-`e2e`    : same batch through AVFrontEnd.forward_host: pinned host buffers -> H2D -> kernels ->
-           D2H of the features the reference's __getitem__ returns (mel + lip), every step.
+`e2e`    : same batch from pinned host buffers through avsl_b200.HostPipeline to pinned host results,
+           every step: the features the reference's __getitem__ returns (mel + lip; the frames are
+           read zero-copy, footprints only); `e2e.with_gray` also copies in every frame and returns
+           the gray frames.
 `roofline`: the dominant kernel's algorithmic bytes / its own CUDA-event time inside the timed steps.
 `cpu_baseline` (N=1, rank 0): the oracle restatement of the reference CPU path on a bounded sample.
 `--impl reference`: that CPU path alone, on rank 0, all host cores.
@@ -238,6 +240,35 @@ def workload_config(args, world, n_frames, n_utts):
             "n_mels": N_MELS, "audio_pad_samples": AUDIO_LEN, "video": f"{H}x{W} BGR 25 fps",
             "outputs": "mel f32 [U,80,3000] + gray u8 [N,224,224] + lip f32 [N,88,88]",
             "l2": "inputs larger than L2 (no flush needed)", "pre_warmup_steps": PRE_WARMUP, "parallelism": f"utterance-sharded x{world}, no collective"}
+
+
+def zero_copy_read_bytes(batch):
+    """Bytes lip_fused_kernel pulls from pinned host memory in the zero-copy mode: per frame the
+    ROI's source footprint (rows x 16-pixel-aligned pitch x 3), recomputed from the transforms the
+    kernel reports (same box arithmetic as pack_footprint in avfe_lip.cu)."""
+    from avsl_b200.lips import lip_roi_batch
+    meta = lip_roi_batch(batch.frames, batch.clip_offsets, batch.landmarks, batch.lm_valid, want_gray=False,
+                         want_f32=True, want_meta=True)
+    tf, rc = meta.tforms.cpu().numpy(), meta.crop_rc.cpu().numpy().astype(np.float64)
+    Hh, Ww = int(batch.frames.shape[1]), int(batch.frames.shape[2])
+    m = tf[:, 9:15]
+    lo, span = 4, 88
+    sr, sc = [], []
+    for dr in (0, span - 1):
+        for dc in (0, span - 1):
+            tr, tc = rc[:, 0] + lo + dr, rc[:, 1] + lo + dc
+            sc.append(m[:, 0] * tc + m[:, 1] * tr + m[:, 2])
+            sr.append(m[:, 3] * tc + m[:, 4] * tr + m[:, 5])
+    sr, sc = np.stack(sr), np.stack(sc)
+    r_lo = np.maximum(np.floor(sr.min(0)) - 1, 0)
+    r_hi = np.minimum(np.ceil(sr.max(0)) + 1, Hh - 1)
+    c_lo = (np.maximum(np.floor(sc.min(0)) - 1, 0).astype(np.int64)) & ~15
+    c_hi = np.minimum(np.ceil(sc.max(0)) + 1, Ww - 1)
+    rows = np.maximum(r_hi - r_lo + 1, 0)
+    cols = np.maximum(c_hi - c_lo + 1, 0).astype(np.int64)
+    pitch = np.minimum((cols + 15) & ~15, Ww - c_lo)
+    ok = (rc[:, 0] >= 0) & (rows > 0) & (cols > 0)
+    return int((rows * pitch * 3)[ok].sum())
 
 
 # ------------------------------------------------------------------------------- parity of the timed batch
@@ -664,26 +695,35 @@ def main():
         ms_pipe, ms_serial, h2d_min, ms_feat = (float(v) for v in ms.tolist())
         h2d_min = -h2d_min
         d2h = sum(host_out[k].numel() * host_out[k].element_size() for k in e2e_keys)
-        e2e = {"value": audio_s_all * e2e_steps / (ms_pipe * 1e-3), "unit": "audio-s/s",
-               "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms_pipe / e2e_steps, "steps": e2e_steps,
-               "api": "avsl_b200.HostPipeline(depth=2).submit(i, pinned PackedBatch) -> result(i): H2D of every input and D2H of mel + lip + gray for every step, two slots in flight",
-               "returns": e2e_keys,
+        zc_read = zero_copy_read_bytes(batch_dev)             # footprint bytes the kernel pulls from pinned memory
+        # Headline: what the reference's public API returns (AmiVideoHFDataset.__getitem__ -> mel + lip
+        # features).  The mode that also returns the full gray frames (SURVEY 8(d)'s extra
+        # deliverable) is measured with the same hygiene and reported under "with_gray".
+        e2e = {"value": audio_s_all * e2e_steps / (ms_feat * 1e-3), "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(feat_h2d + zc_read), "d2h_bytes_per_step": int(feat_d2h),
+               "ms_per_step": ms_feat / e2e_steps, "steps": e2e_steps, "returns": ["lip", "mel"],
+               "h2d_copied_bytes_per_step": int(feat_h2d), "h2d_zero_copy_read_bytes_per_step": int(zc_read),
+               "host_frame_bytes_per_step": int(host.frames.numel()),
+               "mode": "features_only: mel [U,80,3000] + lip [N,88,88,1] in pinned host memory, every step, from pinned host inputs",
+               "api": "avsl_b200.HostPipeline(depth=2, want_gray=False).submit(i, pinned PackedBatch) -> result(i): audio, landmarks and "
+                      "offsets are copied H2D; the frames stay in pinned host memory and lip_fused_kernel reads only each frame's ROI footprint "
+                      "through the mapped pointer (6 footprints in flight per SM) and stores the lip features straight into the pinned result "
+                      "(PCIe reads and writes overlap inside the one kernel); mel is copied D2H; two slots in flight",
+               "pcie_gbs_both_directions": (feat_h2d + zc_read + feat_d2h) / (ms_feat / e2e_steps * 1e-3) / 1e9,
                "h2d_ceiling_gbs": {"per_rank_min": h2d_min, "all_ranks_sum": float(h2d_sum.item()),
                                    "how": "4 x 1 GiB cudaMemcpyAsync from pinned host memory, all ranks at once, CUDA events"},
-               "h2d_achieved_gbs_per_rank": host.nbytes() / (ms_pipe / e2e_steps * 1e-3) / 1e9,
                "host_binding": (f"rank pinned to the {len(numa_cpus)} CPUs of its GPU's NUMA node (NVML ideal affinity) before allocating pinned buffers"
                                 if numa_cpus else "none"),
-               "serial": {"value": audio_s_all * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
-                          "api": "AVFrontEnd.forward_host (H2D -> kernels -> D2H -> sync, one step at a time)"}}
-        e2e["h2d_frac_of_ceiling"] = e2e["h2d_achieved_gbs_per_rank"] / h2d_min
-        e2e["features_only"] = {
-            "value": audio_s_all * e2e_steps / (ms_feat * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_feat / e2e_steps,
-            "returns": ["lip", "mel"], "h2d_bytes_per_step": int(feat_h2d), "d2h_bytes_per_step": int(feat_d2h),
-            "zero_copy_frame_bytes_available": int(host.frames.numel()),
-            "api": "avsl_b200.HostPipeline(depth=2, want_gray=False): what AmiVideoHFDataset.__getitem__ returns (mel + lip); audio, "
-                   "landmarks and offsets are copied H2D, the frames stay in pinned host memory and lip_fused_kernel reads only the ROI "
-                   "footprints through the mapped pointer (6 footprints in flight per SM); D2H of mel + lip every step"}
+               "with_gray": {
+                   "value": audio_s_all * e2e_steps / (ms_pipe * 1e-3), "unit": "audio-s/s",
+                   "h2d_bytes_per_step": host.nbytes(), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_pipe / e2e_steps,
+                   "returns": e2e_keys,
+                   "api": "avsl_b200.HostPipeline(depth=2, want_gray=True): H2D of every input (frames included) and D2H of mel + lip + gray "
+                          "frames for every step, two slots in flight",
+                   "h2d_achieved_gbs_per_rank": host.nbytes() / (ms_pipe / e2e_steps * 1e-3) / 1e9,
+                   "h2d_frac_of_ceiling": host.nbytes() / (ms_pipe / e2e_steps * 1e-3) / 1e9 / h2d_min,
+                   "serial": {"value": audio_s_all * e2e_steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / e2e_steps,
+                              "api": "AVFrontEnd.forward_host (H2D -> kernels -> D2H -> sync, one step at a time)"}}}
         del pipe
         del host, host_out
 

@@ -30,6 +30,55 @@ __global__ void ldg_seg_kernel(const uint8_t* __restrict__ src, int64_t nseg, in
   if (acc == 0x12345678u) *sink = acc;
 }
 
+// the same segments fetched with 16-byte cp.async (LDGSTS) into shared memory, a footprint per warp
+__global__ void ldgsts_seg_kernel(const uint8_t* __restrict__ src, int64_t nitems, int seg, int stride, int nrow, unsigned* sink) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint8_t* mine = smem + (size_t)wid * seg * nrow;
+  const int vps = seg / 16, total = vps * nrow;
+  unsigned acc = 0;
+  for (int64_t it = (int64_t)blockIdx.x * nw + wid; it < nitems; it += (int64_t)gridDim.x * nw) {
+    const uint8_t* p = src + it * (int64_t)stride * nrow;
+    for (int idx = lane; idx < total; idx += 32) {
+      const int r = idx / vps, v = idx - r * vps;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(mine + 16 * idx);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p + (int64_t)r * stride + 16 * v) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    acc ^= *reinterpret_cast<volatile unsigned*>(mine + 16 * lane);
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+// coalesced 128-bit stores to mapped host memory (posted PCIe writes)
+__global__ void stg_kernel(uint4* __restrict__ dst, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = make_uint4((unsigned)i, 1u, 2u, 3u);
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+}
+// one kernel reading rd_vec vectors from host and writing wr_vec vectors to host, interleaved by CTA parity
+__global__ void duplex_kernel(const uint4* __restrict__ src, int64_t rd_vec, uint4* __restrict__ dst, int64_t wr_vec, unsigned* sink) {
+  const int half = gridDim.x / 2;
+  if (blockIdx.x & 1) {
+    const int b = blockIdx.x / 2;
+    for (int64_t i = (int64_t)b * blockDim.x + threadIdx.x; i < wr_vec; i += (int64_t)half * blockDim.x) {
+      asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "r"((unsigned)i), "r"(1u), "r"(2u), "r"(3u) : "memory");
+    }
+  } else {
+    const int b = blockIdx.x / 2;
+    unsigned acc = 0;
+    for (int64_t i = (int64_t)b * blockDim.x + threadIdx.x; i < rd_vec; i += (int64_t)half * blockDim.x) {
+      uint4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = acc;
+  }
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(n)); }
 __device__ __forceinline__ void mbar_expect(uint64_t* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned phase) {
@@ -94,6 +143,13 @@ int main() {
     ldg_seg_kernel<<<148 * 4, 256>>>(h, nseg, seg, stride, sink); CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(a)); ldg_seg_kernel<<<148 * 4, 256>>>(h, nseg, seg, stride, sink); report(nm, (double)nseg * seg);
   }
+  for (int nw : {2, 6, 8}) {
+    const int seg = 288, stride = 672, nrow = 64; const int64_t nitems = (int64_t)(bytes / ((int64_t)stride * nrow)) - 1;
+    char nm[128]; snprintf(nm, 128, "LDGSTS.128 rows %d B / stride %d x %d rows, %d warps/SM", seg, stride, nrow, nw);
+    CK(cudaFuncSetAttribute(ldgsts_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ldgsts_seg_kernel<<<148, nw * 32, nw * seg * nrow>>>(h, nitems, seg, stride, nrow, sink); CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a)); ldgsts_seg_kernel<<<148, nw * 32, nw * seg * nrow>>>(h, nitems, seg, stride, nrow, sink); report(nm, (double)nitems * seg * nrow);
+  }
   // bulk copies: contiguous chunks
   for (int chunk : {512, 2048, 8192, 32768}) {
     const int64_t nitems = bytes / chunk;
@@ -114,6 +170,45 @@ int main() {
     CK(cudaFuncSetAttribute(bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     bulk_kernel<4><<<148 * cps, 32, 4 * seg * nrow>>>(h, nitems, seg, stride, nrow, sink); CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(a)); bulk_kernel<4><<<148 * cps, 32, 4 * seg * nrow>>>(h, nitems, seg, stride, nrow, sink); report(nm, (double)nitems * seg * nrow);
+  }
+  // ---- the other direction and both at once
+  uint8_t* h2; CK(cudaHostAlloc(&h2, bytes, cudaHostAllocDefault));
+  cudaStream_t s2, s3; CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+  CK(cudaMemcpy(h2, d, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaEventRecord(a)); CK(cudaMemcpyAsync(h2, d, bytes, cudaMemcpyDeviceToHost)); report("copy engine D2H 1 GiB", (double)bytes);
+  for (int cps : {1, 4}) {
+    char nm[128]; snprintf(nm, 128, "STG.128 coalesced to host, 256 thr x %d CTA/SM", cps);
+    stg_kernel<<<148 * cps, 256>>>((uint4*)h2, bytes / 16); CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a)); stg_kernel<<<148 * cps, 256>>>((uint4*)h2, bytes / 16); report(nm, (double)bytes);
+  }
+  {
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a));
+    CK(cudaMemcpyAsync(h2, d, bytes, cudaMemcpyDeviceToHost, s2));
+    CK(cudaMemcpyAsync(d, h, bytes / 2, cudaMemcpyHostToDevice, s3));
+    CK(cudaStreamSynchronize(s2)); CK(cudaStreamSynchronize(s3));
+    report("copy engines: D2H 1 GiB || H2D 0.5 GiB (bytes = 1.5 GiB)", 1.5 * bytes);
+  }
+  {
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a));
+    CK(cudaMemcpyAsync(h2, d, bytes, cudaMemcpyDeviceToHost, s2));
+    ldg_kernel<<<148 * 2, 256, 0, s3>>>((const uint4*)h, bytes / 32, sink);
+    CK(cudaStreamSynchronize(s2)); CK(cudaStreamSynchronize(s3));
+    report("copy engine D2H 1 GiB || LDG.128 zero-copy read 0.5 GiB", 1.5 * bytes);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a));
+    CK(cudaMemcpyAsync(h2, d, bytes, cudaMemcpyDeviceToHost, s2));
+    ldg_seg_kernel<<<148 * 4, 256, 0, s3>>>(h, (int64_t)(bytes / 672) - 1, 288, 672, sink);
+    CK(cudaStreamSynchronize(s2)); CK(cudaStreamSynchronize(s3));
+    report("copy engine D2H 1 GiB || LDG.128 288 B segments (0.43 GiB)", bytes + ((double)(bytes / 672) - 1) * 288);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a)); ldg_kernel<<<148 * 2, 256>>>((const uint4*)h, bytes / 32, sink); report("  (LDG.128 zero-copy read 0.5 GiB alone)", 0.5 * bytes);
+  }
+  for (int cps : {2, 4}) {
+    char nm[128]; snprintf(nm, 128, "one kernel: LDG 0.5 GiB from host + STG 1 GiB to host, %d CTA/SM", cps);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a)); duplex_kernel<<<148 * cps, 256>>>((const uint4*)h, bytes / 32, (uint4*)h2, bytes / 16, sink); report(nm, 1.5 * bytes);
   }
   return 0;
 }

@@ -29,3 +29,21 @@ print("device frames, no gray  : %.3f ms" % timeit(lambda: LP.lip_roi_batch(fram
 print("pinned host frames      : %.3f ms" % timeit(lambda: LP.lip_roi_batch(host, off, lm, val, want_gray=False, want_f32=True)))
 dbuf = torch.empty_like(frames)
 print("H2D copy of all frames  : %.3f ms (%.1f GB/s)" % ((t := timeit(lambda: dbuf.copy_(host, non_blocking=True))), host.numel() / t / 1e6))
+# outputs written straight to pinned host memory by the blend warps (no D2H copy afterwards)
+lip_host = torch.empty((N, 88, 88), dtype=torch.float32).pin_memory()
+res_h = LP.LipBatch(None, None, lip_host, None, None, off)
+def zc_both():
+    LP.lip_roi_batch(host, off, lm, val, want_gray=False, want_f32=True, out=res_h)
+zc_both(); torch.cuda.synchronize()
+print("zero-copy in AND out equals reference:", torch.equal(lip_host, ref.lip_f32.cpu()))
+print("pinned frames in, pinned lip out : %.3f ms" % timeit(zc_both))
+lip_dev = torch.empty((N, 88, 88), dtype=torch.float32, device=dev)
+res_d = LP.LipBatch(None, None, lip_dev, None, None, off)
+def zc_then_copy():
+    LP.lip_roi_batch(host, off, lm, val, want_gray=False, want_f32=True, out=res_d)
+    lip_host.copy_(lip_dev, non_blocking=True)
+print("pinned frames in, device lip + D2H copy (serial) : %.3f ms" % timeit(zc_then_copy))
+def dev_out_host():
+    LP.lip_roi_batch(frames, off, lm, val, want_gray=False, want_f32=True, out=res_h)
+print("device frames in, pinned lip out : %.3f ms" % timeit(dev_out_host))
+print("D2H copy of lip alone : %.3f ms" % timeit(lambda: lip_host.copy_(lip_dev, non_blocking=True)))
