@@ -226,6 +226,76 @@ def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch
     return out
 
 
+# --------------------------------------------------------------------------- post_extract_proj
+def alloc_features(B: int, C: int, T: int, dtype=torch.float16, device=None) -> torch.Tensor:
+    """A ``[B, C, T]`` feature map whose time rows start on 16-byte boundaries (row pitch = T rounded
+    up to a multiple of 8): what :func:`fuse_layernorm_project` needs for its TMA loads.  Let the
+    feature extractor write into it (``out=`` / ``copy_``); the padding is never read."""
+    pitch = (T + 7) // 8 * 8
+    return torch.empty((B, C, pitch), dtype=dtype, device=device)[:, :, :T]
+
+
+class FoldedProjection:
+    """``post_extract_proj`` (``nn.Linear(2C, D)``) with the preceding LayerNorm's affine folded into
+    it once (``avfe_proj_fold``): ``W' = gamma * W``, ``s = sum_k W'``, ``c = W beta + bias``."""
+
+    def __init__(self, proj_weight: torch.Tensor, proj_bias: Optional[torch.Tensor], ln_weight: Optional[torch.Tensor],
+                 ln_bias: Optional[torch.Tensor], dtype=torch.float16):
+        _lib.require_cuda()
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("the tensor-core projection runs in float16 or bfloat16")
+        if proj_weight.dim() != 2 or not proj_weight.is_cuda:
+            raise ValueError("proj_weight must be a CUDA tensor [D, 2C]")
+        W = proj_weight.detach().contiguous()
+        if W.dtype not in (torch.float32, dtype):
+            W = W.float()
+        self.D, self.K = int(W.shape[0]), int(W.shape[1])
+        self.dtype = dtype
+        f32 = lambda t: None if t is None else t.detach().float().contiguous()
+        g, b, bias = f32(ln_weight), f32(ln_bias), f32(proj_bias)
+        lib = _lib.load()
+        self.buffer = torch.empty(int(lib.avfe_proj_fold_bytes(self.D, self.K)), dtype=torch.uint8, device=W.device)
+        with torch.cuda.device(W.device):
+            _lib.call("avfe_proj_fold", _lib.ptr(W), _DTYPES[W.dtype], _lib.ptr(g), _lib.ptr(b), _lib.ptr(bias),
+                      self.D, self.K, _DTYPES[dtype], _lib.ptr(self.buffer), _lib.stream_ptr())
+
+
+def fuse_layernorm_project(features_audio: torch.Tensor, features_video: torch.Tensor, mask, folded: FoldedProjection,
+                           eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``post_extract_proj(layer_norm(cat([fa, fv], 1).transpose(1, 2)))`` (av_hubert_encoder.py:315-334)
+    in one pass on the tensor cores: ``[B,C,T] x 2 -> [B,T,D]`` (float16 / bfloat16).  The feature maps
+    must have unit stride in time and a row pitch that is a multiple of 8 elements (``alloc_features``);
+    inference only (no backward kernel for the projection yet)."""
+    _lib.require_cuda()
+    fa, fv = features_audio, features_video
+    if _needs_grad(fa, fv):
+        raise RuntimeError("fuse_layernorm_project has no backward; use fuse_transpose_layernorm + nn.Linear when training")
+    if not (fa.is_cuda and fv.is_cuda) or fa.shape != fv.shape or fa.dim() != 3 or fa.dtype != fv.dtype:
+        raise ValueError("features_audio and features_video must both be CUDA [B, C, T] of one dtype")
+    if fa.dtype != folded.dtype:
+        raise ValueError(f"features are {fa.dtype} but the projection was folded for {folded.dtype}")
+    B, C, T = (int(s) for s in fa.shape)
+    if 2 * C != folded.K:
+        raise ValueError(f"projection expects {folded.K} fused channels, got 2 x {C}")
+    for t in (fa, fv):
+        if t.stride(2) != 1 or t.stride(1) % 8 != 0 or t.stride(0) != C * t.stride(1) or t.stride(1) != fa.stride(1):
+            raise ValueError("feature maps need unit time stride and a row pitch that is a multiple of 8 elements "
+                             "(allocate them with avsl_b200.alloc_features): tensor-map TMA loads 16-byte aligned rows")
+    m = _mask_tensor(mask, B, fa.device)
+    if out is None:
+        out = torch.empty((B, T, folded.D), dtype=fa.dtype, device=fa.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == (B, T, folded.D)):
+        raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {(B, T, folded.D)}")
+    with torch.cuda.device(fa.device):
+        lib = _lib.load()
+        ws_bytes = int(lib.avfe_fuse_ln_proj_workspace_bytes(B, T))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fa.device)
+        _lib.call("avfe_fuse_ln_proj", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), _DTYPES[fa.dtype], B, C, T,
+                  int(fa.stride(1)), _lib.ptr(folded.buffer), folded.D, float(eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                  _lib.stream_ptr())
+    return out
+
+
 class ModalityFusion(torch.nn.Module):
     """The modality-select / dropout / fuse block of ``AVHuBERTEncoderWrapper.forward`` as a
     module: same flags (``use_audio``, ``use_visual``, ``modality_override``), same dropout draw,

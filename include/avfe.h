@@ -311,6 +311,31 @@ AVFE_API int avfe_fuse_layernorm(const void* fa, const void* fv, const uint8_t* 
                                  const float* gamma, const float* beta, float eps, void* out,
                                  avfe_stream_t stream);
 
+/* post_extract_proj fused behind concat + transpose + LayerNorm -- avsl/modules/av_hubert_encoder.py:315-334:
+ *     features = self.post_extract_proj(self.layer_norm(cat([fa, fv], 1).transpose(1, 2)))
+ * (nn.Linear(2C -> D) where self.embed != encoder_embed_dim, :160-166; fp16 / bf16 under `precision: 16`).
+ * The contraction runs on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands
+ * staged by tensor-map TMA); LayerNorm is folded around it (avfe_pep.cu), so the fused, transposed and
+ * normalised tensors are never materialised.
+ *
+ * avfe_proj_fold, once per set of weights: W [D, 2C] (w_dtype: AVFE_F32 master weights, or the GEMM
+ * dtype), gamma / beta [2C] float32 (LayerNorm weight / bias, NULL = 1 / 0), bias [D] float32 (NULL = 0)
+ * -> `folded` (avfe_proj_fold_bytes(D, 2C) bytes, 16-byte aligned): W' = gamma * W in `dtype`,
+ * s = sum_k W', c = W beta + bias.
+ *
+ * avfe_fuse_ln_proj: fa, fv [B, C, T] of `dtype` (AVFE_F16 / AVFE_BF16) whose rows are `t_pitch`
+ * elements apart (t_pitch >= T, a multiple of 8: TMA needs 16-byte aligned rows -- T = 750 lives in a
+ * [B, C, 752] allocation); C a multiple of 64, D a multiple of 256; mask [B,2] u8 or NULL as for avfe_fuse
+ * (the K blocks of a missing modality are skipped).  out [B, T, D] of `dtype`.
+ * workspace: avfe_fuse_ln_proj_workspace_bytes(B, T) bytes (the LayerNorm moments). */
+AVFE_API size_t avfe_proj_fold_bytes(int64_t D, int64_t K);
+AVFE_API int avfe_proj_fold(const void* W, int w_dtype, const float* gamma, const float* beta, const float* bias,
+                            int64_t D, int64_t K, int dtype, void* folded, avfe_stream_t stream);
+AVFE_API size_t avfe_fuse_ln_proj_workspace_bytes(int64_t B, int64_t T);
+AVFE_API int avfe_fuse_ln_proj(const void* fa, const void* fv, const uint8_t* mask, int dtype, int64_t B, int64_t C,
+                               int64_t T, int64_t t_pitch, const void* folded, int64_t D, float eps, void* out,
+                               void* workspace, size_t workspace_bytes, avfe_stream_t stream);
+
 /* ------------------------------------------------------------------ fusion, backward
  * The reference's fusion block runs inside the TRAINING forward (modality dropout under
  * self.training, avsl/modules/av_hubert_encoder.py:292-330), so a drop-in has to pass gradients to
