@@ -24,6 +24,7 @@
 // 4..7 = epilogue (tcgen05.ld 32x32b, LayerNorm fold, cast, store).  K blocks of a masked-out
 // modality are skipped by producer and issuer alike (zero-fill contributes nothing).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -108,6 +109,7 @@ struct GemmArgs {
   int B, C, T, D;
   int tiles_per_sample, n_tiles_n, n_tiles;
   int bf16;
+  int experiment;
 };
 
 struct Smem {
@@ -263,6 +265,208 @@ pep_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
+
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs of one cluster (same TPC) share a 256 x 256 tile: CTA r stages the A rows of its own 128
+// time steps and HALF of the W' rows (128 of the 256 output channels); one tcgen05.mma.cta_group::2
+// (M 256, N 256, K 16), issued by the leader CTA, reads both CTAs' shared memory and accumulates
+// into both CTAs' TMEM.  Per CTA and K block 32 KB are staged instead of 48 KB: the single-CTA
+// kernel pulls 14 TB/s out of L2, which is what bounds it.
+constexpr int kStages2 = 6;
+constexpr int kB2Bytes = (kBN / 2) * kBK * 2;       // 16 KB: this CTA's 128 W' rows
+constexpr int kStage2Bytes = kABytes + kB2Bytes;    // 32 KB
+
+struct Smem2 {
+  uint64_t full[kStages2], empty[kStages2], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data into this CTA's shared memory, completion on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc2_commit_both(uint64_t* bar) {      // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(int ab_format) {      // M 256 across the pair
+  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | (1u << 15) | (0u << 16) |
+         ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+}
+
+// g.tiles_per_sample here counts PAIR tiles (256 time steps) per sample; map_w's box is 64 x 128.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pep_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v,
+                 const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t pep_smem[];
+  uint8_t* tiles = pep_smem + ((1024u - (smem_u32(pep_smem) & 1023u)) & 1023u);   // same offset in both CTAs
+  float* sc = reinterpret_cast<float*>(tiles + kStages2 * kStage2Bytes);
+  Smem2& sm = *reinterpret_cast<Smem2*>(tiles + kStages2 * kStage2Bytes + 2 * (size_t)g.D * sizeof(float));
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  for (int i = threadIdx.x; i < g.D; i += kThreads) { sc[i] = g.s[i]; sc[g.D + i] = g.c[i]; }
+  if (wid == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (wid == 1 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tmem_full[a], 1); mbar_init(&sm.tmem_empty[a], 8); }   // 4 warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const int kb_per_mod = g.C / kBK;
+
+  if (wid == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < g.n_tiles; tile += n_pairs) {
+        const int nt = tile % g.n_tiles_n, mb = tile / g.n_tiles_n;
+        const int b = mb / g.tiles_per_sample, t0 = (mb % g.tiles_per_sample) * (2 * kBM) + (int)rank * kBM;
+        const unsigned m = sample_mask(g.mask, b);
+        for (int kb = 0; kb < 2 * kb_per_mod; ++kb) {
+          const int mod = kb / kb_per_mod;
+          if (!((m >> mod) & 1u)) continue;
+          mbar_wait(&sm.empty[stage], phase ^ 1u);      // the pair's MMAs have retired this stage (both CTAs are told)
+          uint8_t* a_dst = tiles + stage * kStage2Bytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          const uint32_t bar = map_to_rank(&sm.full[stage], 0);
+          if (leader) mbar_expect_tx(&sm.full[stage], 2 * kStage2Bytes);     // both CTAs' bytes land on the leader's barrier
+          const CUtensorMap* map = mod ? &map_v : &map_a;
+          const int c0 = (kb - mod * kb_per_mod) * kBK;
+          tma2_load_3d(a_dst, map, bar, t0, c0, b);
+          tma2_load_3d(a_dst + kABytes / 2, map, bar, t0 + 64, c0, b);
+          tma2_load_2d(b_dst, &map_w, bar, kb * kBK, nt * kBN + (int)rank * (kBN / 2));
+          if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (wid == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc2(g.bf16) & ~((uint32_t)g.experiment << 15);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < g.n_tiles; tile += n_pairs) {
+        const int mb = tile / g.n_tiles_n;
+        const int b = mb / g.tiles_per_sample;
+        const unsigned m = sample_mask(g.mask, b);
+        mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1u);          // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < 2 * kb_per_mod; ++kb) {
+          if (!((m >> (kb / kb_per_mod)) & 1u)) continue;
+          mbar_wait(&sm.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(tiles + stage * kStage2Bytes), b_base = a_base + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = make_desc(a_base + k * 2048, kABytes / 2, 1024);
+            const uint64_t bdesc = make_desc(b_base + k * 32, 0, 1024);
+            tc2_mma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+          tc2_commit_both(&sm.empty[stage]);
+          if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+        }
+        tc2_commit_both(&sm.tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (wid >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = wid - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < g.n_tiles; tile += n_pairs) {
+      const int nt = tile % g.n_tiles_n, mb = tile / g.n_tiles_n;
+      const int b = mb / g.tiles_per_sample, t0 = (mb % g.tiles_per_sample) * (2 * kBM) + (int)rank * kBM;
+      const int t = t0 + ew * 32 + lane;
+      const bool ok = t < g.T;
+      float2 st = make_float2(0.f, 0.f);
+      if (ok) st = g.stats[(int64_t)b * g.T + t];
+      mbar_wait(&sm.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBN);
+      uint16_t* orow = static_cast<uint16_t*>(g.out) + ((int64_t)b * g.T + t) * g.D + nt * kBN;
+      for (int ch = 0; ch < kBN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (ok) {
+          const float* s = sc + nt * kBN + ch * 32;
+          const float* c = s + g.D;
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float y0 = fmaf(st.y, __uint_as_float(v[2 * j]) - st.x * s[2 * j], c[2 * j]);
+            const float y1 = fmaf(st.y, __uint_as_float(v[2 * j + 1]) - st.x * s[2 * j + 1], c[2 * j + 1]);
+            if (g.bf16) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+              packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+            } else {
+              const __half2 h = __floats2half2_rn(y0, y1);
+              packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_rank(&sm.tmem_empty[acc], 0));   // the issuer lives in the leader CTA
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody leaves (or frees TMEM) while the peer may still signal it
+  if (wid == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm moments per (b, t)
 // [B, C, T] x 2 (row pitch `pitch` elements) -> (mean, rstd) over the 2C fused channels.  A CTA owns
 // 64 consecutive time steps of one sample; a warp reads 4 channel rows x 128 bytes per instruction
@@ -301,15 +505,30 @@ pep_stats_kernel(const T* __restrict__ fa, const T* __restrict__ fv, const uint8
   // the shift: channel 0 of the fused tensor (audio channel 0, or 0 when audio is masked out)
   if (m & 1u) load8(fa, 0, K);
   for (int mod = 0; mod < 2; ++mod) {
-    const bool present = (m >> mod) & 1u;
-    const T* base = mod ? fv : fa;
-    for (int c = wid * 4 + rsub; c < C; c += 32) {
-      float x[8];
-      if (present) load8(base, c, x);
-      else {
+    if (!((m >> mod) & 1u)) {                           // zero-filled modality: C zeros per time step
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const float n = (float)((C - (wid * 4 + rsub) + 31) / 32);   // channels this lane would have visited
+        sum[j] -= n * K[j]; sq[j] += n * K[j] * K[j];
       }
+      continue;
+    }
+    const T* base = mod ? fv : fa;
+    // eight independent 16-byte loads per lane in flight (the loop is latency-bound otherwise)
+    int c = wid * 4 + rsub;
+    for (; c + 7 * 32 < C; c += 8 * 32) {
+      float x[8][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) load8(base, c + 32 * u, x[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = x[u][j] - K[j]; sum[j] += d; sq[j] += d * d; }
+      }
+    }
+    for (; c < C; c += 32) {
+      float x[8];
+      load8(base, c, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float d = x[j] - K[j]; sum[j] += d; sq[j] += d * d; }
     }
@@ -456,10 +675,12 @@ extern "C" int avfe_fuse_ln_proj(const void* fa, const void* fv, const uint8_t* 
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return AVFE_ERR_CUDA;
   }
+  // CTA pairs (cta_group::2) unless AVFE_PEP_SINGLE_CTA is set (kept for A/B measurements)
+  static const bool single_cta = (getenv("AVFE_PEP_SINGLE_CTA") != nullptr);
   {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)D};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)pep::kBK, (cuuint32_t)pep::kBN};
+    const cuuint32_t box[2] = {(cuuint32_t)pep::kBK, (cuuint32_t)(single_cta ? pep::kBN : pep::kBN / 2)};
     const cuuint32_t estr[2] = {1, 1};
     if (enc(&map_w, dt, 2, const_cast<void*>(folded), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -482,17 +703,30 @@ extern "C" int avfe_fuse_ln_proj(const void* fa, const void* fv, const uint8_t* 
   g.s = reinterpret_cast<const float*>(static_cast<const char*>(folded) + (size_t)D * K * 2);
   g.c = g.s + D;
   g.mask = mask; g.out = out; g.B = (int)B; g.C = (int)C; g.T = (int)T; g.D = (int)D;
-  g.tiles_per_sample = (int)((T + pep::kBM - 1) / pep::kBM);
   g.n_tiles_n = (int)(D / pep::kBN);
-  g.n_tiles = (int)B * g.tiles_per_sample * g.n_tiles_n;
   g.bf16 = (dtype == AVFE_BF16) ? 1 : 0;
-  const size_t smem = (size_t)pep::kStages * pep::kStageBytes + 2 * (size_t)D * sizeof(float) + sizeof(pep::Smem) + 1024;
-  if (cudaFuncSetAttribute(pep::pep_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError();
-    return AVFE_ERR_CUDA;
+  g.experiment = getenv("AVFE_PEP_EXPERIMENT") ? 1 : 0;
+  if (single_cta) {
+    g.tiles_per_sample = (int)((T + pep::kBM - 1) / pep::kBM);
+    g.n_tiles = (int)B * g.tiles_per_sample * g.n_tiles_n;
+    const size_t smem = (size_t)pep::kStages * pep::kStageBytes + 2 * (size_t)D * sizeof(float) + sizeof(pep::Smem) + 1024;
+    if (cudaFuncSetAttribute(pep::pep_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+    const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+    pep::pep_gemm_kernel<<<grid, pep::kThreads, smem, st>>>(map_a, map_v, map_w, g);
+  } else {
+    g.tiles_per_sample = (int)((T + 2 * pep::kBM - 1) / (2 * pep::kBM));          // pair tiles: 256 time steps
+    g.n_tiles = (int)B * g.tiles_per_sample * g.n_tiles_n;
+    const size_t smem = (size_t)pep::kStages2 * pep::kStage2Bytes + 2 * (size_t)D * sizeof(float) + sizeof(pep::Smem2) + 1024;
+    if (cudaFuncSetAttribute(pep::pep_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+    const int pairs = g.n_tiles < kNumSMs / 2 ? g.n_tiles : kNumSMs / 2;
+    pep::pep_gemm2_kernel<<<2 * pairs, pep::kThreads, smem, st>>>(map_a, map_v, map_w, g);   // __cluster_dims__(2,1,1)
   }
-  const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-  pep::pep_gemm_kernel<<<grid, pep::kThreads, smem, st>>>(map_a, map_v, map_w, g);
   count_launch();
   return check_launch();
 }

@@ -544,7 +544,56 @@ def main():
                 "kernel": "fuse_ln_kernel (fusion + transpose + LayerNorm, av_hubert_encoder.py:315-330; masked)",
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
             del xa, xv, lout
-        del fa, fv
+        # post_extract_proj fused behind concat + transpose + LayerNorm on the tensor cores
+        # (av_hubert_encoder.py:315-334): B 64 x T 750, 2 x 1024 -> 1024, fp16 / bf16,
+        # against the unfused pair fuse_ln_kernel + cuBLAS (torch F.linear) on the same box
+        import torch.nn.functional as F
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ms_flush = time_op(lambda: flush.zero_(), 10)
+        gproj = torch.Generator(device=dev).manual_seed(SEED)
+        Wp = torch.randn(1024, 2048, generator=gproj, device=dev) / 2048 ** 0.5
+        bp = torch.randn(1024, generator=gproj, device=dev) * 0.1
+        gam = torch.rand(2048, generator=gproj, device=dev) + 0.5
+        bet = torch.randn(2048, generator=gproj, device=dev) * 0.2
+        for dt, tag, pmask in ((torch.float16, "f16", None), (torch.bfloat16, "bf16", None), (torch.float16, "f16_masked", fmask)):
+            xa, xv = A.alloc_features(64, 1024, 750, dt, dev), A.alloc_features(64, 1024, 750, dt, dev)   # row pitch 752
+            xa.copy_(fa.to(dt)); xv.copy_(fv.to(dt))
+            folded = A.FoldedProjection(Wp, bp, gam, bet, dt)
+            pout = torch.empty((64, 750, 1024), dtype=dt, device=dev)
+
+            def run_proj():
+                flush.zero_()
+                A.fuse_layernorm_project(xa, xv, pmask, folded, out=pout)
+            xac, xvc, Wl, bl = xa.contiguous(), xv.contiguous(), Wp.to(dt), bp.to(dt)
+            ln_tmp = torch.empty((64, 750, 2048), dtype=dt, device=dev)
+
+            def run_unfused():
+                flush.zero_()
+                A.fuse_transpose_layernorm(xac, xvc, pmask, "concat", gam, bet, out=ln_tmp)
+                F.linear(ln_tmp, Wl, bl)
+            ms = time_op(run_proj, 20) - ms_flush
+            ms_ref = time_op(run_unfused, 20) - ms_flush
+            # masked-out modalities contribute nothing and their K blocks are skipped: count the executed FLOPs
+            n_present = present if pmask is not None else 128
+            flops = 2.0 * 750 * 1024 * 1024 * n_present
+            pm = torch.as_tensor(pmask if pmask is not None else np.ones((64, 2), np.uint8), device=dev).float()
+            ref = F.linear(F.layer_norm(torch.cat([xac[:4].float() * pm[:4, :1].view(-1, 1, 1),
+                                                   xvc[:4].float() * pm[:4, 1:].view(-1, 1, 1)], 1).transpose(1, 2),
+                                        (2048,), gam, bet), Wp, bp)
+            err = (pout[:4].float() - ref).abs().max().item() / ref.abs().max().item()
+            side[f"fuse_ln_proj_{tag}"] = {
+                "kernel": "pep_stats_kernel + pep_gemm2_kernel (tcgen05.mma cta_group::2, TMEM accumulators, tensor-map TMA; LayerNorm folded around the GEMM)"
+                          + ("; masked: the K blocks of a missing modality are skipped, FLOPs counted are the executed ones" if pmask is not None else "; all modalities present"),
+                "ms": ms, "flops_executed": flops, "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+                "frac_of_bf16_sustained_peak": flops / (ms * 1e-3) / 1e12 / tf_peak, "peak_tflops": tf_peak,
+                "unfused_fuse_ln_plus_cublas_ms": ms_ref, "speedup_vs_unfused": ms_ref / ms,
+                "max_rel_err_vs_f32_reference_ops": err,
+                "algorithmic_bytes": int(n_present * 1024 * 750 * 2 + pout.numel() * 2),
+                "achieved_gbs": (n_present * 1024 * 750 * 2 + pout.numel() * 2) / (ms * 1e-3) / 1e9}
+            del xa, xv, xac, xvc, ln_tmp, pout, folded
+        del flush, fa, fv
         # the lip stage with the 96x96 u8 ROI (what extract_lip_frames returns) as a third output
         from avsl_b200.lips import lip_roi_batch
         r96 = None
