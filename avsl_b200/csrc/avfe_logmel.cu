@@ -8,7 +8,7 @@
 //                           staged once in shared memory, Hann window, 16 complex 400-point
 //                           shared-memory FFTs (two real frames each), power, sparse mel
 //                           projection, log10, raw store + per-clip atomic max
-//   logmel_finalize_kernel  max(x, clip_max - 8), (x + 4) / 4 in place (output still in L2)
+//   logmel_finalize_tiles_kernel  the clamp max(x, clip_max - 8), only for the tiles that need it
 //
 // Frames, spectra and powers never touch HBM: traffic is the audio read plus the output.
 #include <limits.h>
@@ -42,15 +42,27 @@ struct MelPack {
   float wts[kMaxPacked];
 };
 
+// 65.9 KB per CTA: three CTAs (30 warps) per SM.  The Z storage is used three times per tile: first
+// as the landing zone of the reflect-padded audio span (5,700 skewed floats), then -- once every
+// thread holds its windowed samples in registers -- as the 20x20 exchange, finally for the 32 power
+// rows (first 26 KB) and the staged outputs (behind them).
+constexpr int kStageOutOffset = ((kTileFrames * kPStride + 3) / 4) * 4;      // floats; 16-byte aligned
+static_assert(kTileFloats * 4 <= kPairs * kZPair * 8, "audio span fits the Z storage");
+// staged outputs [n_mels][kSoStride]: lanes that hold DIFFERENT filters write the same frame column,
+// so the row stride must be odd (with 32 they all hit one bank: 5.0 M of the 13.3 M excess
+// shared-memory wavefronts of a 64 x 30 s launch, profiles/r02/logmel_r2a_*).
+constexpr int kSoStride = kTileFrames + 1;
+static_assert((kStageOutOffset + kMaxMels * kSoStride) * 4 <= kPairs * kZPair * 8, "power rows + staged outputs fit the Z storage");
+static_assert(kTileFloats <= kStageOutOffset, "the next tile's audio never lands on outputs that are still being written");
 struct Smem {
-  float2 Z[kPairs * kZPair];            // 53,760 B  20x20 exchange / spectra, then the 32 power rows
-  float audio[2][kTileFloats];          // 45,600 B  double-buffered reflect-padded audio span (skewed)
+  float2 Z[kPairs * kZPair];            // 53,760 B  audio span / 20x20 exchange / power rows + staged outputs
   float2 tw[kNfft];                     //  3,200 B
   float hann[kNfft];                    //  1,600 B
   __align__(16) float wts[kMaxPacked];  //  4,096 B  zero-padded to quads
   int4 rec[kMaxMels];                   //  2,048 B
   unsigned assign[kThreads];            //  1,280 B
-  int red[16];
+  unsigned long long bar;               // completion of the bulk copies of the audio span
+  int red[14];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -60,6 +72,25 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+// mbarrier + 1-D bulk copy (TMA, UBLKCP): the aligned interior tiles' audio span is fetched as 17
+// contiguous pieces of 320 samples, each landing at its skewed position -- no per-thread copy
+// instructions and none of the bank conflicts the 16-byte cp.async form has on the skewed span
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(n));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nLM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra LM_WAIT;\n}" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -182,7 +213,7 @@ __global__ void __launch_bounds__(256)
 logmel_live_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets, int64_t B,
                    int64_t L, int64_t Lp, int tiles_per_clip, int* __restrict__ clip_max,
                    uint8_t* __restrict__ silent, int* __restrict__ live_count,
-                   int2* __restrict__ live_list) {
+                   int2* __restrict__ live_list, int* __restrict__ tile_min) {
   const int lane = threadIdx.x & 31;
   const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -201,7 +232,10 @@ logmel_live_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
     const int tt = t0 + lane;
     const bool live = tt < tiles_per_clip && classify_tile(clip, len, Lp, tt) != kSilent;
     const unsigned m = __ballot_sync(0xffffffffu, live);
-    if (tt < tiles_per_clip) silent[b * tiles_per_clip + tt] = live ? 0 : 1;
+    if (tt < tiles_per_clip) {
+      silent[b * tiles_per_clip + tt] = live ? 0 : 1;
+      tile_min[b * tiles_per_clip + tt] = 0x7f7fffff;          // key of FLT_MAX: the tile kernel lowers it
+    }
     if (live) live_list[base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)b, tt);
     base += __popc(m);
   }
@@ -209,12 +243,15 @@ logmel_live_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   if (lane == 0) clip_max[b] = (n_live < tiles_per_clip) ? float_key(log10_floor(0.0f)) : (int)0x80808080;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ float normalised(float x);
+
+__global__ void __launch_bounds__(kThreads, 3)
 logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets, int64_t B,
                    int64_t L, int64_t Lp, int64_t n_frames, int n_mels, const float* __restrict__ fb,
                    const MelPack* __restrict__ pack, float* __restrict__ out,
                    int* __restrict__ clip_max, uint8_t* __restrict__ silent,
-                   const int* __restrict__ live_count, const int2* __restrict__ live_list) {
+                   const int* __restrict__ live_count, const int2* __restrict__ live_list,
+                   int* __restrict__ tile_min, int tiles_per_clip) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -233,74 +270,88 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   const bool mel_fast = packed && pack->balanced != 0;
   const int n_live = *live_count;                        // tiles to compute (logmel_live_kernel)
 
-  // (clip, tile) records are read from the live list two tiles ahead so that the list load's
-  // latency never sits in front of a cp.async issue
+  // (clip, tile) records are read from the live list one tile ahead
   const int2 none = make_int2(-1, 0);
-  // this thread's 16-byte chunks of a tile: span samples 4*tid + 1280*k (k = 0..4); 1280 samples
-  // are four skew blocks, so the skewed position advances by 1280 + 4*kTileSkew per step
-  const int chunk0 = tile_pos(4 * tid);
-  constexpr int kChunkStep = 4 * kThreads + 4 * kTileSkew;
-  constexpr int kChunks = (kTileSamples / 4 + kThreads - 1) / kThreads;   // 5, the last one partial
+  const int stride = (int)gridDim.x;
+  auto list_at = [&](int item) -> int2 { return item < n_live ? live_list[item] : none; };
+  float* au = reinterpret_cast<float*>(sm.Z);            // the audio span shares the Z storage
+  float* P = reinterpret_cast<float*>(sm.Z);             // so do the power rows ...
+  float* stage_out = P + kStageOutOffset;                // ... and the staged outputs [n_mels][32]
+
+  // (clip, tile) record, clip pointer / length and tile class are looked up ONE TILE AHEAD, so that
+  // their dependent global loads overlap the previous tile's arithmetic and the span's copy can be
+  // issued the moment a tile starts
   struct TileRef { const float* clip; int64_t len; int cls; };
-  auto locate = [&](int2 it) -> TileRef {
+  auto locate = [&](int2 rec) -> TileRef {
     TileRef r{nullptr, 0, kSilent};
-    if (it.x >= 0) {
-      r.clip = clip_of(audio, offsets, it.x, L, Lp, r.len);
-      r.cls = classify_tile(r.clip, r.len, Lp, it.y);
+    if (rec.x >= 0) {
+      r.clip = clip_of(audio, offsets, rec.x, L, Lp, r.len);
+      r.cls = classify_tile(r.clip, r.len, Lp, rec.y);
     }
     return r;
   };
-  auto prefetch = [&](int2 it, const TileRef& r, int buf) {
-    if (it.x >= 0) {
-      const float* src = r.clip + ((int64_t)it.y * (kTileFrames * kHop) - kNfft / 2);
-      if (r.cls == kFast16) {
-        float* dst = &sm.audio[buf][chunk0];
-        const float* s4 = src + 4 * tid;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k)
-          if (k < kChunks - 1 || tid < kTileSamples / 4 - (kChunks - 1) * kThreads)
-            cp_async16(dst + k * kChunkStep, s4 + k * (4 * kThreads));   // skew is a multiple of 4 floats
-      } else if (r.cls == kFast4) {
-        for (int i = tid; i < kTileSamples; i += kThreads) cp_async4(&sm.audio[buf][tile_pos(i)], src + i);
-      }
-    }
-    cp_async_commit();
-  };
-  const int stride = (int)gridDim.x;
-  auto list_at = [&](int item) -> int2 { return item < n_live ? live_list[item] : none; };
-
-  int cur = 0;
-  int2 it = list_at((int)blockIdx.x), it_next = list_at((int)blockIdx.x + stride);
+  int2 it = list_at((int)blockIdx.x);
   TileRef ref = locate(it);
-  prefetch(it, ref, 0);
-  for (int item = (int)blockIdx.x; item < n_live; item += stride, cur ^= 1) {
-    const int2 it_after = list_at(item + 2 * stride);
-    const TileRef ref_next = locate(it_next);
-    cp_async_wait<0>();                                  // this tile's copies have landed
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned bar_phase = 0;
+  __syncthreads();                                       // tables and barrier visible
+  for (int item = (int)blockIdx.x; item < n_live; item += stride) {
     const int64_t b = it.x;
     const int tt = it.y;
     const int64_t t0 = (int64_t)tt * kTileFrames;
-    float* au = sm.audio[cur];
-    if (ref.cls == kEdge) {                              // clip edges: reflection / zero padding, sample by sample
-      const int64_t p0 = t0 * kHop;
-      for (int i = tid; i < kTileSamples; i += kThreads) au[tile_pos(i)] = padded_sample(ref.clip, ref.len, Lp, p0 + i);
+    // ---- the tile's audio span.  No barrier is needed in front of it: what it overwrites (the
+    // power rows) was last read before the barrier that follows the mel projection, and the
+    // staged outputs the slower warps may still be writing out lie behind the span. ----
+    {
+      const float* src = ref.clip + ((int64_t)tt * (kTileFrames * kHop) - kNfft / 2);
+      if (ref.cls == kFast16) {
+        if (wid == 0) {
+          // the span overwrites power rows written through the generic proxy: order the two proxies
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (lane == 0) mbar_expect_tx(&sm.bar, kTileSamples * 4);
+          __syncwarp();
+          constexpr int kPieces = (kTileSamples + 319) / 320;              // 17: sixteen of 320 samples + one of 240
+          if (lane < kPieces)
+            bulk_g2s(au + lane * (320 + kTileSkew), src + 320 * lane,
+                     (unsigned)(4 * (lane < kPieces - 1 ? 320 : kTileSamples - 320 * (kPieces - 1))), &sm.bar);
+          mbar_wait(&sm.bar, bar_phase);                 // one warp polls; the CTA barrier below releases the rest
+        }
+        bar_phase ^= 1u;
+      } else if (ref.cls == kFast4) {
+        for (int i = tid; i < kTileSamples; i += kThreads) cp_async4(&au[tile_pos(i)], src + i);
+      } else {                                           // clip edges: reflection / zero padding, sample by sample
+        const int64_t p0 = t0 * kHop;
+        for (int i = tid; i < kTileSamples; i += kThreads) au[tile_pos(i)] = padded_sample(ref.clip, ref.len, Lp, p0 + i);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
     }
-    // barrier: tile visible to all; every warp has left the previous tile (its power rows and its
-    // staged outputs, which sit in the buffer the next prefetch is about to overwrite)
-    __syncthreads();
-    prefetch(it_next, ref_next, cur ^ 1);                // next tile of this CTA goes in flight
-    float vmax = -INFINITY;
+    const int2 it_next = list_at(item + stride);         // next tile's lookups ride under this tile's work
+    const TileRef ref_next = locate(it_next);
+    __syncthreads();                                     // span visible to all
+    float vmax = -INFINITY, vmin = INFINITY;
     {
       // ---- 16 complex FFT-400: columns, twiddle, rows ----
-      stage1(g, j, au, sm.hann, sm.tw, sm.Z);
+      {
+        float2 x[20];
+        stage1_load(g, j, au, sm.hann, x);
+        __syncthreads();                                 // every thread holds its samples: Z may overwrite the span
+        stage1_dft(g, j, x, sm.tw, sm.Z);
+      }
       __syncthreads();
-      stage2(g, j, sm.Z);
-      __syncthreads();
-      // ---- untangle the two real frames of each FFT; power rows overwrite the Z storage ----
+      // ---- rows; untangle the two real frames of each FFT straight from the registers (the
+      // partner's half comes through shared memory); power rows then overwrite the Z storage ----
       float pa[kBinsPerThread], pb[kBinsPerThread];
-      split_load(g, j, sm.Z, pa, pb);
+      {
+        float2 x[20];
+        stage2_keep(g, j, sm.Z, x);
+        __syncthreads();
+        split_from_regs(g, j, sm.Z, x, pa, pb);
+      }
       __syncthreads();
-      float* P = reinterpret_cast<float*>(sm.Z);
       split_store(g, j, P, pa, pb);
       __syncthreads();
       // ---- sparse mel projection + log10 ----
@@ -309,7 +360,6 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
         // <= 16 quad-padded weights sit in registers, so a (filter, frame) pair costs 4 LDS + 4
         // FFMA per quad.  Results are staged in the (now free) audio buffer and written out row
         // by row so that the global stores are coalesced.
-        float* stage_out = au;                           // [n_mels][32]
         const unsigned a = sm.assign[tid];
         const int nf = (int)(a >> 16);
         if (nf > 0) {
@@ -320,7 +370,7 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
           const float4 w0 = rc.w > 0 ? wq[0] : z4, w1 = rc.w > 1 ? wq[1] : z4;
           const float4 w2 = rc.w > 2 ? wq[2] : z4, w3 = rc.w > 3 ? wq[3] : z4;
           const float* prow = P + prow_offset(f0) + rc.x;
-          float* so = stage_out + m * kTileFrames + f0;
+          float* so = stage_out + m * kSoStride + f0;
           // one loop per support length (uniform within a warp: threads are sorted by quads),
           // two frames per trip so that the second frame's loads overlap the first frame's FMAs
           auto dot = [&](const float* pr, int quads) -> float {
@@ -363,9 +413,10 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
         if (t < n_frames) {
           float* orow = out + (b * n_mels + wid) * n_frames + t;
           for (int m = wid; m < n_mels; m += kThreads / 32, orow += (int64_t)(kThreads / 32) * n_frames) {
-            const float v = stage_out[m * kTileFrames + lane];
-            *orow = v;
+            const float v = stage_out[m * kSoStride + lane];
+            *orow = normalised(v);
             vmax = fmaxf(vmax, v);
+            vmin = fminf(vmin, v);
           }
         }
       } else {
@@ -379,74 +430,69 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
           const float v = packed ? mel_log10_quads(prow + rc.x, reinterpret_cast<const float4*>(sm.wts + rc.z), rc.w)
                                  : mel_log10(prow + rc.x, fb + (size_t)m * kBins + rc.x, rc.y);
           if (live) {
-            *orow = v;
+            *orow = normalised(v);
             vmax = fmaxf(vmax, v);
+            vmin = fminf(vmin, v);
           }
         }
+        __syncthreads();                                 // the power rows are read to the end of this path
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) atomicMax(clip_max + b, float_key(vmax));
+    for (int o = 16; o > 0; o >>= 1) {
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    }
+    if (lane == 0) {
+      atomicMax(clip_max + b, float_key(vmax));
+      atomicMin(tile_min + b * tiles_per_clip + tt, float_key(vmin));
+    }
     it = it_next;
-    it_next = it_after;
     ref = ref_next;
   }
-  cp_async_wait<0>();
 }
 
-// max(x, clip_max - 8), (x + 4) / 4.  Silent tiles (flagged by logmel_live_kernel) were never
-// written: their raw value is the constant log10(1e-10), so they are stored without a read.
-// Row form (frame count a multiple of 4, 16-byte aligned output): one CTA per (clip, mel) row,
-// no per-element index arithmetic, every thread's float4s issued before any is used.
-__global__ void __launch_bounds__(256)
-logmel_finalize_rows_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
-                            const uint8_t* __restrict__ silent, int64_t n_frames, int n_mels) {
-  const int64_t row = blockIdx.x, b = row / n_mels;
-  const int tiles_per_clip = (int)((n_frames + kTileFrames - 1) / kTileFrames);
-  const uint8_t* flags = silent + b * tiles_per_clip;
+// The tile kernel stores y = (x + 4) / 4 right away; what is left is the clamp max(x, clip_max - 8),
+// known only when the whole clip has been seen.  Rounding is monotonic, so
+// (max(x, f) + 4) / 4 == max(y, (f + 4) / 4) bit for bit: the clamp is an elementwise maximum with a
+// per-clip constant, and a tile whose smallest raw value is >= f (tile_min, kept by the tile kernel)
+// needs no work at all -- it is neither read nor written again (a 64 x 30 s batch of noise: every
+// tile).  Silent tiles (flagged by logmel_live_kernel) were never written: their raw value is the
+// constant log10(1e-10), stored here without a read.
+// One CTA per tile: a tile that needs nothing costs one flag load and an exit.
+__device__ __forceinline__ float normalised(float x) { return __fmul_rn(__fadd_rn(x, 4.0f), 0.25f); }
+
+__global__ void __launch_bounds__(128)
+logmel_finalize_tiles_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
+                             const uint8_t* __restrict__ silent, const int* __restrict__ tile_min,
+                             int64_t n_frames, int n_mels, int tiles_per_clip, int vec_ok) {
+  const int64_t tile = blockIdx.x, b = tile / tiles_per_clip;
+  const int tt = (int)(tile - b * tiles_per_clip);
   const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
-  const float raw_silent = log10_floor(0.0f);
-  float4* o4 = reinterpret_cast<float4*>(out + row * n_frames);
-  const int n4 = (int)(n_frames >> 2);
-  constexpr int U = 4;
-  for (int i0 = threadIdx.x; i0 < n4; i0 += 256 * U) {
-    float4 x[U];
-    bool sil[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 256;
-      sil[u] = i < n4 ? flags[(4 * i) / kTileFrames] != 0 : true;   // a float4 never straddles a 32-frame tile
-      x[u] = sil[u] ? make_float4(raw_silent, raw_silent, raw_silent, raw_silent) : o4[i];
+  const bool sil = silent[tile] != 0;
+  if (!sil && !(key_float(tile_min[tile]) < floor_v)) return;      // the common case: nothing to clamp
+  const float floor_y = normalised(floor_v);
+  const float sil_y = normalised(fmaxf(log10_floor(0.0f), floor_v));
+  const int64_t t0 = (int64_t)tt * kTileFrames;
+  const int nt = (int)min((int64_t)kTileFrames, n_frames - t0);
+  float* base = out + b * n_mels * n_frames + t0;
+  if (vec_ok && nt == kTileFrames) {
+    for (int idx = threadIdx.x; idx < n_mels * (kTileFrames / 4); idx += blockDim.x) {
+      float4* p = reinterpret_cast<float4*>(base + (int64_t)(idx >> 3) * n_frames) + (idx & 7);
+      if (sil) *p = make_float4(sil_y, sil_y, sil_y, sil_y);
+      else {
+        float4 v = *p;
+        v.x = fmaxf(v.x, floor_y); v.y = fmaxf(v.y, floor_y); v.z = fmaxf(v.z, floor_y); v.w = fmaxf(v.w, floor_y);
+        *p = v;
+      }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 256;
-      if (i >= n4) break;
-      float4 v = x[u];
-      v.x = __fmul_rn(__fadd_rn(fmaxf(v.x, floor_v), 4.0f), 0.25f);
-      v.y = __fmul_rn(__fadd_rn(fmaxf(v.y, floor_v), 4.0f), 0.25f);
-      v.z = __fmul_rn(__fadd_rn(fmaxf(v.z, floor_v), 4.0f), 0.25f);
-      v.w = __fmul_rn(__fadd_rn(fmaxf(v.w, floor_v), 4.0f), 0.25f);
-      o4[i] = v;
+  } else {
+    for (int idx = threadIdx.x; idx < n_mels * kTileFrames; idx += blockDim.x) {
+      const int f = idx & (kTileFrames - 1);
+      if (f >= nt) continue;
+      float* p = base + (int64_t)(idx / kTileFrames) * n_frames + f;
+      *p = sil ? sil_y : fmaxf(*p, floor_y);
     }
-  }
-}
-
-// generic form (any frame count / alignment)
-__global__ void __launch_bounds__(256)
-logmel_finalize_kernel(float* __restrict__ out, const int* __restrict__ clip_max,
-                       const uint8_t* __restrict__ silent, int64_t n_frames, int n_mels,
-                       int64_t total) {
-  const int64_t per_clip = (int64_t)n_mels * n_frames;
-  const int64_t tiles_per_clip = (n_frames + kTileFrames - 1) / kTileFrames;
-  const float raw_silent = log10_floor(0.0f);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / per_clip, t = (i - b * per_clip) % n_frames;
-    const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
-    const float x = fmaxf(silent[b * tiles_per_clip + t / kTileFrames] ? raw_silent : out[i], floor_v);
-    out[i] = __fmul_rn(__fadd_rn(x, 4.0f), 0.25f);
   }
 }
 
@@ -523,9 +569,9 @@ extern "C" size_t avfe_logmel_workspace_bytes(int64_t B, int64_t L, int64_t padd
   (void)n_mels;
   if (L < 0 || padding < 0) return 0;
   const size_t tiles = (size_t)B * (size_t)(((L + padding) / lm::kHop + lm::kTileFrames - 1) / lm::kTileFrames);
-  // clip maxima | MelPack | silent flags | live-tile count | live-tile list
+  // clip maxima | MelPack | silent flags | live-tile count | live-tile list | per-tile minima
   return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + sizeof(lm::MelPack) + ((tiles + 15) & ~(size_t)15) + 16 +
-         tiles * sizeof(int2) + 64;
+         tiles * sizeof(int2) + tiles * sizeof(int) + 64;
 }
 
 extern "C" size_t avfe_logmel_pack_bytes(void) { return sizeof(lm::MelPack); }
@@ -553,12 +599,13 @@ static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int
   // live-tile count and list follow the silent flags in the workspace
   int* live_count = reinterpret_cast<int*>(silent + (((size_t)n_tiles + 15) & ~(size_t)15));
   int2* live_list = reinterpret_cast<int2*>(live_count + 4);
+  int* tile_min = reinterpret_cast<int*>(live_list + n_tiles);
   if (cudaMemsetAsync(live_count, 0, 16, s) != cudaSuccess) {
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
   lm::logmel_live_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>(
-      audio, offsets, B, L, Lp, (int)tiles_per_clip, clip_max, silent, live_count, live_list);
+      audio, offsets, B, L, Lp, (int)tiles_per_clip, clip_max, silent, live_count, live_list, tile_min);
   count_launch();
   // per-device attribute: set on every call (cheap) so multi-device processes stay correct
   if (cudaFuncSetAttribute(lm::logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -566,19 +613,14 @@ static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  int64_t ctas = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;   // 2 resident CTAs per SM
+  int64_t ctas = n_tiles < 3 * kNumSMs ? n_tiles : 3 * kNumSMs;   // 3 resident CTAs per SM
   lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
       audio, offsets, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent,
-      live_count, live_list);
+      live_count, live_list, tile_min, (int)tiles_per_clip);
   count_launch();
-  const int64_t total = B * (int64_t)n_mels * n_frames;
-  if ((n_frames & 3) == 0 && aligned16(out) && B * n_mels <= 0x7fffffffLL) {
-    lm::logmel_finalize_rows_kernel<<<(unsigned)(B * n_mels), 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels);
-  } else {
-    int64_t fin = (total + 255) / 256;
-    if (fin > (int64_t)kNumSMs * 16) fin = (int64_t)kNumSMs * 16;
-    lm::logmel_finalize_kernel<<<(unsigned)fin, 256, 0, s>>>(out, clip_max, silent, n_frames, n_mels, total);
-  }
+  const int vec_ok = ((n_frames & 3) == 0 && aligned16(out)) ? 1 : 0;
+  lm::logmel_finalize_tiles_kernel<<<(unsigned)n_tiles, 128, 0, s>>>(out, clip_max, silent, tile_min, n_frames, n_mels,
+                                                                      (int)tiles_per_clip, vec_ok);
   count_launch();
   return check_launch();
 }

@@ -118,9 +118,10 @@ AVFE_HD float padded_sample(const float* clip, int64_t L, int64_t Lp, int64_t p)
 // physical position of span sample s in the skewed tile
 AVFE_HD int tile_pos(int s) { return s + kTileSkew * (s / 320); }
 
-AVFE_HD void stage1(int g, int j, const float* tile, const float* hann, const float2* tw,
-                    float2* Z) {
-  float2 x[20];
+// Stage 1 comes in two halves so that the audio span can share its storage with Z (which is what
+// lets three CTAs fit on an SM): stage1_load puts the thread's 2 x 20 windowed samples in registers;
+// after a CTA barrier (every thread has its samples) stage1_dft transforms and overwrites the span.
+AVFE_HD void stage1_load(int g, int j, const float* tile, const float* hann, float2 (&x)[20]) {
   // frame 2g starts at span sample 320g, frame 2g+1 160 later; within the thread's 20 reads the
   // skew block index is g plus one or two carries that depend on (j + 20m) only
   const float* base = tile + 320 * g + kTileSkew * g + j;
@@ -132,11 +133,21 @@ AVFE_HD void stage1(int g, int j, const float* tile, const float* hann, const fl
     const int cb = (ob + j >= 320) ? kTileSkew : 0;      // ob + j <= 559
     x[m] = make_float2(w * base[oa + ca], w * base[ob + cb]);
   }
+}
+
+AVFE_HD void stage1_dft(int g, int j, float2 (&x)[20], const float2* tw, float2* Z) {
   dft20(x);
   float2* z = Z + g * kZPair + j;
   z[0] = x[0];
 #pragma unroll
   for (int k1 = 1; k1 < 20; ++k1) z[k1 * kZRow] = cmul(x[k1], tw[k1 * 20 + j]);
+}
+
+AVFE_HD void stage1(int g, int j, const float* tile, const float* hann, const float2* tw,
+                    float2* Z) {
+  float2 x[20];
+  stage1_load(g, j, tile, hann, x);
+  stage1_dft(g, j, x, tw, Z);
 }
 
 // Stage 2, thread (g, k1): 20-point DFT over j of row k1, in place:
@@ -149,6 +160,39 @@ AVFE_HD void stage2(int g, int k1, float2* Z) {
   dft20(x);
 #pragma unroll
   for (int k2 = 0; k2 < 20; ++k2) z[k2] = x[k2];
+}
+
+// Stage 2 that keeps its result in registers: after the DFT thread (g, k1) holds bins k1 + 20*k2 in
+// x[k2].  The untangling of bin k needs bin 400-k, which is x[19-k2] of thread (g, 20-k1): only the
+// upper half x[10..19] is ever read by a partner, so only that half goes back to shared memory (into
+// the thread's own row: nobody else touches it during this stage, hence no barrier in front).
+AVFE_HD void stage2_keep(int g, int k1, float2* Z, float2 (&x)[20]) {
+  float2* z = Z + g * kZPair + k1 * kZRow;
+#pragma unroll
+  for (int j = 0; j < 20; ++j) x[j] = z[j];
+  dft20(x);
+#pragma unroll
+  for (int k2 = 10; k2 < 20; ++k2) z[k2] = x[k2];
+}
+
+// Untangle from registers (after a barrier behind stage2_keep): own bins k = j + 20*m from x[m], the
+// mirrors from the partner's row; thread j = 0 (bins 20*m) is its own partner.  Same arithmetic as
+// split_load.
+AVFE_HD void split_from_regs(int g, int j, const float2* Z, const float2 (&x)[20], float (&pa)[kBinsPerThread],
+                             float (&pb)[kBinsPerThread]) {
+  const float2* zp = Z + g * kZPair + (20 - j) * kZRow;      // partner row (j > 0)
+#pragma unroll
+  for (int m = 0; m < kBinsPerThread; ++m) {
+    if (m == 10 && j != 0) { pa[m] = 0.0f; pb[m] = 0.0f; continue; }
+    const float2 u = x[m];
+    float2 v;
+    if (j == 0) v = (m == 0) ? x[0] : x[20 - m];
+    else v = zp[19 - m];
+    const float ar = u.x + v.x, ai = u.y - v.y;
+    const float br = u.y + v.y, bi = v.x - u.x;
+    pa[m] = 0.25f * (ar * ar + ai * ai);
+    pb[m] = 0.25f * (br * br + bi * bi);
+  }
 }
 
 // Float offset of the power row of tile frame f (0..31) inside the Z storage.

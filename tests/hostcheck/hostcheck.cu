@@ -36,11 +36,15 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
   std::vector<float> pa(kThreads * kBinsPerThread), pb(kThreads * kBinsPerThread);
   for (int i = 0; i < kTileSamples; ++i) buf[tile_pos(i)] = padded_sample(clip, L, Lp, t0 * kHop + i);
   for (int tid = 0; tid < kThreads; ++tid) stage1(tid / 20, tid % 20, buf.data(), hann.data(), tw.data(), Z.data());
-  for (int tid = 0; tid < kThreads; ++tid) stage2(tid / 20, tid % 20, Z.data());
-  // phase A (all threads), barrier, phase B (all threads): power rows overwrite the Z slab
+  // stage 2 keeps its bins in "registers" (one array per thread) and stores only the upper half;
+  // barrier; untangle from registers + the partner's row; barrier; power rows overwrite the Z slab
+  std::vector<float2> regs(kThreads * 20);
   for (int tid = 0; tid < kThreads; ++tid)
-    split_load(tid / 20, tid % 20, Z.data(), *reinterpret_cast<float(*)[kBinsPerThread]>(&pa[tid * kBinsPerThread]),
-               *reinterpret_cast<float(*)[kBinsPerThread]>(&pb[tid * kBinsPerThread]));
+    stage2_keep(tid / 20, tid % 20, Z.data(), *reinterpret_cast<float2(*)[20]>(&regs[tid * 20]));
+  for (int tid = 0; tid < kThreads; ++tid)
+    split_from_regs(tid / 20, tid % 20, Z.data(), *reinterpret_cast<const float2(*)[20]>(&regs[tid * 20]),
+                    *reinterpret_cast<float(*)[kBinsPerThread]>(&pa[tid * kBinsPerThread]),
+                    *reinterpret_cast<float(*)[kBinsPerThread]>(&pb[tid * kBinsPerThread]));
   float* P = reinterpret_cast<float*>(Z.data());
   for (int tid = 0; tid < kThreads; ++tid)
     split_store(tid / 20, tid % 20, P, *reinterpret_cast<float(*)[kBinsPerThread]>(&pa[tid * kBinsPerThread]),
