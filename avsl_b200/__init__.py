@@ -8,7 +8,8 @@ function raises if the library has not been built or no CUDA device is present.
 """
 from . import _lib  # noqa: F401
 from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, LogfbankPlan, NoisePlan, add_noise, add_noise_batch,
-                    extract_logfbank_features,
+                    align_audio_video_features, aligned_lengths, extract_logfbank_features, process_audio_dual_encoder,
+                    spec_augment_warp_points, spec_time_warp,
                     log_mel_spectrogram, log_mel_spectrogram_ragged, logfbank_batch, logfbank_num_frames,
                     mel_filters, pad_or_trim, peak_normalize, process_audio_for_av_hubert, spec_augment,
                     spec_augment_bands)

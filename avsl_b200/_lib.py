@@ -31,6 +31,7 @@ _SIGNATURES = {
     "avfe_logmel_ragged_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "avfe_spec_mask_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_float, c_void_p]),
+    "avfe_spec_time_warp_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "avfe_add_noise_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "avfe_add_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -455,6 +455,82 @@ def spec_augment_bands(audio_frames, n_mels: int = 80, policy: str = "ls-double"
     return bands
 
 
+def spec_augment_warp_points(audio_frames, W: int = 80, rng=None) -> np.ndarray:
+    """Draw SpecAugment's time-warp points for a batch on the host: int32 ``[B, 3]`` rows
+    ``(tau, center, warped)`` with ``center ~ U{W..tau-W-1}`` and ``warped = center + w``,
+    ``w ~ U{-W..W}`` (the paper's W = 80 for the LibriSpeech policies); clips with ``tau <= 2 W`` are
+    left alone (``center = 0``).  Drawn per clip BEFORE the clip's masks when combined with
+    :func:`spec_augment_bands` on one generator (the paper's order: warp, frequency masks, time masks)."""
+    rng = rng if rng is not None else np.random.default_rng()
+    frames = np.atleast_1d(np.asarray(audio_frames, dtype=np.int64))
+    pts = np.zeros((len(frames), 3), dtype=np.int32)
+    for b, tau in enumerate(frames):
+        pts[b, 0] = tau
+        if tau - W > W:
+            c = int(rng.integers(W, tau - W))
+            pts[b, 1] = c
+            pts[b, 2] = c + int(rng.integers(-W, W + 1))
+    return pts
+
+
+def spec_time_warp(mel: torch.Tensor, warp_points: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SpecAugment time warping of ``mel`` float32 CUDA ``[B, n_mels, n_frames]`` with given warp points
+    (``spec_augment_warp_points``); returns a new tensor (the warp cannot run in place)."""
+    _lib.require_cuda()
+    if not (mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous() and mel.dim() == 3):
+        raise ValueError("mel must be a contiguous float32 CUDA tensor [B, n_mels, n_frames]")
+    B, n_mels, n_frames = (int(s) for s in mel.shape)
+    pts = np.ascontiguousarray(warp_points, dtype=np.int32)
+    if pts.shape != (B, 3):
+        raise ValueError("warp_points must be [B, 3]")
+    if out is None:
+        out = torch.empty_like(mel)
+    elif out.data_ptr() == mel.data_ptr() or out.shape != mel.shape or out.dtype != mel.dtype or not out.is_contiguous():
+        raise ValueError("out must be a separate contiguous tensor of mel's shape")
+    d_pts = torch.from_numpy(pts).to(mel.device)
+    with torch.cuda.device(mel.device):
+        _lib.call("avfe_spec_time_warp_f32", _lib.ptr(mel), B, n_mels, n_frames, _lib.ptr(d_pts), _lib.ptr(out),
+                  _lib.stream_ptr())
+    return out
+
+
+def align_audio_video_features(audio_features, video_features):
+    """``align_audio_video_features`` (preprocess/audio_process.py:238-264): truncate the longer of the
+    two feature sequences to the length of the shorter (first axis); ``None`` passes through.  Works on
+    numpy arrays and (CUDA) tensors alike and returns views -- nothing is copied."""
+    if audio_features is None or video_features is None:
+        return audio_features, video_features
+    audio_len, video_len = len(audio_features), len(video_features)
+    if audio_len > video_len:
+        audio_features = audio_features[:video_len]
+    elif audio_len < video_len:
+        video_features = video_features[:audio_len]
+    return audio_features, video_features
+
+
+def aligned_lengths(audio_rows, video_frames) -> np.ndarray:
+    """Per-clip common length ``min(audio_rows[i], video_frames[i])`` for a packed batch: the
+    ``keep_frames`` of :func:`avsl_b200.lips.lip_roi_collate` and the row count to keep of each clip's
+    logfbank features, i.e. :func:`align_audio_video_features` for every clip at once."""
+    return np.minimum(np.asarray(audio_rows, dtype=np.int64), np.asarray(video_frames, dtype=np.int64))
+
+
+def process_audio_dual_encoder(audio, stack_order: int = 1, normalize: bool = True, sample_rate: int = SAMPLE_RATE):
+    """``process_audio_dual_encoder`` (preprocess/audio_process.py:267-299) from the loaded 16 kHz
+    waveform on (the reference's ``librosa.load`` is the caller's): one upload, two kernels --
+    logfbank features for AV-HuBERT (stacked, normalised; :284-285) and the peak-normalised float32
+    waveform for Whisper (:289-293).  numpy in -> numpy out; a CUDA tensor in -> CUDA tensors out."""
+    _lib.require_cuda()
+    is_dev = torch.is_tensor(audio) and audio.is_cuda
+    a = audio if is_dev else torch.from_numpy(np.ascontiguousarray(np.asarray(audio).astype(np.float32).reshape(-1))).cuda()
+    a = a.to(torch.float32).reshape(-1).contiguous()
+    feats, _ = logfbank_batch(a, [0, a.numel()], stack_order, normalize)
+    wave = peak_normalize(a)
+    if not is_dev:
+        feats, wave = feats.cpu().numpy(), wave.cpu().numpy()
+    return {"waveform": wave, "sample_rate": sample_rate, "av_hubert_features": feats}
+
+
 def spec_augment(mel: torch.Tensor, audio_frames=None, policy: str = "ls-double", rng=None,
                  bands: Optional[np.ndarray] = None, fill: float = 0.0) -> torch.Tensor:
     """Apply SpecAugment masks in place to ``mel`` float32 CUDA ``[B, n_mels, n_frames]`` (or

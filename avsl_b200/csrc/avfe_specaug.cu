@@ -34,7 +34,60 @@ spec_mask_kernel(float* __restrict__ mel, int n_mels, int64_t n_frames, const in
   }
 }
 
+// SpecAugment's first step, time warping (Park et al. 2019, sec. 2): a point `center` on the time
+// axis of a clip's [n_mels, tau] spectrogram is moved to `warped`; the two sides are stretched /
+// squeezed linearly.  Output frame t takes its value from source position
+//     s(t) = t * center / warped                                   (t <  warped)
+//          = center + (t - warped) * (tau - center) / (tau - warped)   (t >= warped)
+// by linear interpolation between the neighbouring source frames (float32, products rounded
+// separately).  Frames at and beyond tau (the padding) are copied.  The upstream sampler /
+// interpolant is un-vendored: this definition is the build's, the warp points are an input.
+__global__ void __launch_bounds__(256)
+spec_time_warp_kernel(const float* __restrict__ in, int n_mels, int64_t n_frames, const int32_t* __restrict__ warp,
+                      float* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const int tau = min(max(warp[3 * b], 0), (int)min(n_frames, (int64_t)0x7fffffff));
+  const int center = warp[3 * b + 1], warped = warp[3 * b + 2];
+  const bool active = tau >= 2 && center > 0 && center < tau && warped > 0 && warped < tau;
+  const float a0 = active ? __fdiv_rn((float)center, (float)warped) : 1.0f;
+  const float a1 = active ? __fdiv_rn((float)(tau - center), (float)(tau - warped)) : 1.0f;
+  const int64_t total = (int64_t)n_mels * n_frames;
+  const float* src = in + b * total;
+  float* dst = out + b * total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / n_frames;
+    const int t = (int)(i - f * n_frames);
+    float v;
+    if (!active || t >= tau) v = src[i];
+    else {
+      const float s = (t < warped) ? __fmul_rn((float)t, a0) : __fadd_rn((float)center, __fmul_rn((float)(t - warped), a1));
+      int s0 = (int)floorf(s);
+      s0 = min(max(s0, 0), tau - 1);
+      const int s1 = min(s0 + 1, tau - 1);
+      const float w = fminf(fmaxf(__fsub_rn(s, (float)s0), 0.0f), 1.0f);
+      const float* row = src + f * n_frames;
+      v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, w), row[s0]), __fmul_rn(w, row[s1]));
+    }
+    dst[i] = v;
+  }
+}
+
 }  // namespace avfe
+
+extern "C" int avfe_spec_time_warp_f32(const float* mel, int64_t B, int n_mels, int64_t n_frames, const int32_t* warp,
+                                       float* out, avfe_stream_t stream) {
+  using namespace avfe;
+  if (B < 0 || n_mels < 0 || n_frames < 0) return AVFE_ERR_INVALID_ARG;
+  if (B == 0 || n_mels == 0 || n_frames == 0) return AVFE_OK;
+  if (!mel || !warp || !out || mel == out) return AVFE_ERR_INVALID_ARG;
+  if (B > 65535 || n_frames > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  int64_t gx = ((int64_t)n_mels * n_frames + 255) / 256;
+  if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
+  dim3 grid((unsigned)gx, (unsigned)B);
+  spec_time_warp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, n_mels, n_frames, warp, out);
+  count_launch();
+  return check_launch();
+}
 
 extern "C" int avfe_spec_mask_f32(float* mel, int64_t B, int n_mels, int64_t n_frames, const int32_t* bands,
                                   int n_bands, float fill, avfe_stream_t stream) {

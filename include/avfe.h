@@ -122,6 +122,17 @@ AVFE_API int avfe_logmel_ragged_f32(const float* audio, const int64_t* offsets, 
 AVFE_API int avfe_spec_mask_f32(float* mel, int64_t B, int n_mels, int64_t n_frames, const int32_t* bands,
                                 int n_bands, float fill, avfe_stream_t stream);
 
+/* SpecAugment's time-warping step (Park et al. 2019) for the same call site.  RNG contract of both
+ * SpecAugment entry points: the library draws NOTHING -- mask rectangles and warp points are INPUTS
+ * (drawn on the host by avsl_b200.audio.spec_augment_bands / spec_augment_warp_points, whose sampling
+ * follows the paper; the upstream sampler is un-vendored, so its random stream is not reproduced).
+ *   warp [B, 3] int32 = (tau, center, warped): the first tau frames of clip b are warped so that source
+ *   frame `center` lands on frame `warped`, both sides resampled linearly (definition in
+ *   avfe_specaug.cu); rows outside 0 < center, warped < tau copy the clip unchanged.
+ *   mel -> out, both [B, n_mels, n_frames] float32, out != mel. */
+AVFE_API int avfe_spec_time_warp_f32(const float* mel, int64_t B, int n_mels, int64_t n_frames, const int32_t* warp,
+                                     float* out, avfe_stream_t stream);
+
 /* AV-HuBERT audio features — extract_logfbank_features + audio_to_tensor,
  * preprocess/audio_process.py:152-197 (and utils/data_loading.py:181-201):
  * python_speech_features.logfbank(audio, samplerate=16000) = pre-emphasis 0.97, 400-sample frames

@@ -19,3 +19,25 @@ def apply_bands(mel: np.ndarray, bands: np.ndarray, fill: float = 0.0) -> np.nda
             if f1 > f0 and t1 > t0:
                 out[b, f0:f1, t0:t1] = fill
     return out
+
+
+def time_warp(mel: np.ndarray, warp: np.ndarray) -> np.ndarray:
+    """SpecAugment time warping as avfe_spec_time_warp_f32 defines it (PARITY UNPINNED: build-defined,
+    see the kernel's header): mel [B, n_mels, n_frames] float32, warp [B, 3] = (tau, center, warped)."""
+    out = mel.copy()
+    B, n_mels, n_frames = mel.shape
+    f32 = np.float32
+    for b in range(B):
+        tau, center, warped = (int(v) for v in warp[b])
+        tau = min(max(tau, 0), n_frames)
+        if not (tau >= 2 and 0 < center < tau and 0 < warped < tau):
+            continue
+        a0 = f32(center) / f32(warped)
+        a1 = f32(tau - center) / f32(tau - warped)
+        t = np.arange(tau)
+        s = np.where(t < warped, t.astype(f32) * a0, f32(center) + (t - warped).astype(f32) * a1).astype(f32)
+        s0 = np.clip(np.floor(s).astype(np.int64), 0, tau - 1)
+        s1 = np.minimum(s0 + 1, tau - 1)
+        w = np.clip((s - s0.astype(f32)).astype(f32), f32(0), f32(1))
+        out[b, :, :tau] = ((f32(1) - w) * mel[b][:, s0]).astype(f32) + (w * mel[b][:, s1]).astype(f32)
+    return out

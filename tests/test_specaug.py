@@ -1,6 +1,7 @@
 """SpecAugment masks: host-side band sampling (CPU tier) and the in-place GPU application."""
 import numpy as np
 import pytest
+import torch
 
 from avsl_b200.audio import SPEC_AUGMENT_POLICIES, spec_augment_bands
 from oracle import specaug as OS
@@ -49,3 +50,71 @@ def test_gpu_masks_bit_exact(n_mels):
     A.spec_augment(one, audio_frames=[3000], policy="ls-basic", rng=np.random.default_rng(2), fill=-0.5)
     ref = OS.apply_bands(mel[:1], A.spec_augment_bands([3000], n_mels, "ls-basic", np.random.default_rng(2)), -0.5)
     np.testing.assert_array_equal(one.cpu().numpy(), ref[0])
+
+
+# ------------------------------------------------------------------ time warping + the dual-encoder mirrors
+def test_warp_points_sampling_contract():
+    import avsl_b200 as A
+    rng = np.random.default_rng(5)
+    pts = A.spec_augment_warp_points([3000, 500, 160, 100, 161], W=80, rng=rng)
+    assert pts.shape == (5, 3) and pts.dtype == np.int32
+    for tau, c, w in pts[[0, 1, 4]]:
+        assert 80 <= c < tau - 80 and abs(int(w) - int(c)) <= 80 and 0 < w < tau
+    assert pts[2, 1] == 0 and pts[3, 1] == 0            # tau <= 2 W: no warp
+
+
+def test_oracle_time_warp_properties():
+    from oracle import specaug as OS
+    rng = np.random.default_rng(1)
+    mel = rng.standard_normal((2, 6, 300)).astype(np.float32)
+    ident = OS.time_warp(mel, np.array([[300, 120, 120], [300, 0, 0]], np.int32))
+    np.testing.assert_array_equal(ident, mel)           # center == warped: s(t) = t exactly
+    ramp = np.tile(np.arange(300, dtype=np.float32), (1, 4, 1))
+    out = OS.time_warp(ramp, np.array([[200, 100, 150]], np.int32))
+    np.testing.assert_array_equal(out[0, :, 200:], ramp[0, :, 200:])          # padding untouched
+    assert out[0, 0, 0] == 0 and abs(out[0, 0, 150] - 100) < 1e-4 and abs(out[0, 0, 199] - 198.0) < 1.1
+    assert (np.diff(out[0, 0, :200]) > 0).all()         # monotone: a warp, not a shuffle
+
+
+def test_align_mirrors_reference_semantics():
+    import avsl_b200 as A
+    a, v = np.zeros((10, 104)), np.zeros((8, 88, 88, 1))
+    a2, v2 = A.align_audio_video_features(a, v)
+    assert a2.shape[0] == 8 and v2.shape[0] == 8 and a2.base is a
+    a3, v3 = A.align_audio_video_features(a[:5], v)
+    assert a3.shape[0] == 5 and v3.shape[0] == 5
+    assert A.align_audio_video_features(None, v) == (None, v)
+    np.testing.assert_array_equal(A.aligned_lengths([10, 5, 7], [8, 8, 7]), [8, 5, 7])
+
+
+@pytest.mark.gpu
+def test_gpu_time_warp_matches_oracle_bit_for_bit():
+    import avsl_b200 as A
+    from oracle import specaug as OS
+    rng = np.random.default_rng(2)
+    mel = rng.standard_normal((5, 80, 3000)).astype(np.float32)
+    pts = A.spec_augment_warp_points([3000, 1234, 700, 150, 2999], W=80, rng=rng)
+    pts[4] = (2999, 500, 420)
+    got = A.spec_time_warp(torch.from_numpy(mel).cuda(), pts).cpu().numpy()
+    np.testing.assert_array_equal(got, OS.time_warp(mel, pts))
+    assert not np.array_equal(got[0], mel[0]) and np.array_equal(got[3], mel[3])
+    with pytest.raises(ValueError):
+        x = torch.from_numpy(mel).cuda()
+        A.spec_time_warp(x, pts, out=x)
+
+
+@pytest.mark.gpu
+def test_gpu_process_audio_dual_encoder():
+    import avsl_b200 as A
+    from avsl_b200 import synth
+    from oracle import logfbank as OL
+    from oracle import logmel as OM
+    a = synth.audio_clip(24000, 3) * 4.0                 # some samples beyond [-1, 1]: the waveform gets peak-normalised
+    d = A.process_audio_dual_encoder(a, stack_order=4, normalize=True)
+    assert d["sample_rate"] == 16000 and d["waveform"].dtype == np.float32
+    np.testing.assert_array_equal(d["waveform"], OM.peak_normalize(a))
+    ref = OL.audio_to_tensor(OL.extract_logfbank_features(a, stack_order=4), normalize=True)
+    assert d["av_hubert_features"].shape == ref.shape
+    assert np.abs(d["av_hubert_features"] - ref).max() <= 2e-3
+    dev = A.process_audio_dual_encoder(torch.from_numpy(a).cuda(), stack_order=4)
+    assert dev["waveform"].is_cuda and dev["av_hubert_features"].is_cuda
