@@ -65,6 +65,9 @@ _SIGNATURES = {
                           c_int64, c_int64, c_void_p, c_void_p]),
     "avfe_fuse_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,
                                     c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "avfe_fuse_layernorm_tma_ok": (c_int, [c_int, c_int64, c_int64, c_int64]),
+    "avfe_fuse_layernorm_pitched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int64,
+                                            c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "avfe_proj_fold_bytes": (c_size_t, [c_int64, c_int64]),
     "avfe_proj_fold": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "avfe_fuse_ln_proj_workspace_bytes": (c_size_t, [c_int64, c_int64]),

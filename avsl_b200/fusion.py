@@ -202,10 +202,17 @@ def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch
         raise ValueError("features_audio and features_video must both be [B, C, T] of one dtype")
     if fa.dtype not in _DTYPES:
         raise ValueError(f"unsupported dtype {fa.dtype}")
-    fa, fv = fa.contiguous(), fv.contiguous()
     B, C, T = (int(s) for s in fa.shape)
     mode = _MODES[fusion_type]
     Cout = 2 * C if mode == _lib.FUSE_CONCAT else C
+
+    def pitched(t):             # unit time stride, rows `pitch` apart, samples C * pitch apart
+        return t.stride(2) == 1 and t.stride(0) == C * t.stride(1) and t.stride(1) >= T
+    pitch = T
+    if pitched(fa) and pitched(fv) and fa.stride(1) == fv.stride(1) and fa.stride(1) != T and not _needs_grad(fa, fv, weight, bias):
+        pitch = int(fa.stride(1))       # a padded allocation (alloc_features): TMA-addressable rows
+    else:
+        fa, fv = fa.contiguous(), fv.contiguous()
     for name, prm in (("weight", weight), ("bias", bias)):
         if prm is not None and not (prm.is_cuda and prm.dtype == torch.float32 and prm.is_contiguous()
                                     and tuple(prm.shape) == (Cout,)):
@@ -220,8 +227,8 @@ def fuse_transpose_layernorm(features_audio: torch.Tensor, features_video: torch
     elif not (out.is_cuda and out.is_contiguous() and out.dtype == fa.dtype and tuple(out.shape) == (B, T, Cout)):
         raise ValueError(f"out must be a contiguous {fa.dtype} CUDA tensor of shape {(B, T, Cout)}")
     with torch.cuda.device(fa.device):
-        _lib.call("avfe_fuse_layernorm", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
-                  float(weights[1]), _DTYPES[fa.dtype], B, C, T, _lib.ptr(weight), _lib.ptr(bias),
+        _lib.call("avfe_fuse_layernorm_pitched", _lib.ptr(fa), _lib.ptr(fv), _lib.ptr(m), mode, float(weights[0]),
+                  float(weights[1]), _DTYPES[fa.dtype], B, C, T, pitch, _lib.ptr(weight), _lib.ptr(bias),
                   float(eps), _lib.ptr(out), _lib.stream_ptr())
     return out
 

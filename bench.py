@@ -543,7 +543,16 @@ def main():
             side[f"fuse_ln_{mode}_{'f32' if esz == 4 else 'f16'}"] = {
                 "kernel": "fuse_ln_kernel (fusion + transpose + LayerNorm, av_hubert_encoder.py:315-330; masked)",
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
-            del xa, xv, lout
+            # the same with the feature maps in a padded allocation (row pitch 752: 16-byte aligned rows),
+            # which lets tensor-map TMA fill the tile (avfe_fuse_ln_tma.cu)
+            pa_, pv_ = A.alloc_features(64, 1024, 750, dt, dev), A.alloc_features(64, 1024, 750, dt, dev)
+            pa_.copy_(xa); pv_.copy_(xv)
+            ms_t = time_op(lambda: A.fuse_transpose_layernorm(pa_, pv_, fmask, mode, w, bz, out=lout), 20)
+            assert (lout.float() - A.fuse_transpose_layernorm(xa, xv, fmask, mode, w, bz).float()).abs().max().item() < (1e-4 if esz == 4 else 2e-2)
+            side[f"fuse_ln_tma_{mode}_{'f32' if esz == 4 else 'f16'}"] = {
+                "kernel": "fuse_ln_tma_kernel (same op; [B,C,752]-pitched inputs, tile filled by tensor-map TMA, SWIZZLE_32B; masked)",
+                "ms": ms_t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms_t * 1e-3) / 1e9}
+            del xa, xv, lout, pa_, pv_
         # post_extract_proj fused behind concat + transpose + LayerNorm on the tensor cores
         # (av_hubert_encoder.py:315-334): B 64 x T 750, 2 x 1024 -> 1024, fp16 / bf16,
         # against the unfused pair fuse_ln_kernel + cuBLAS (torch F.linear) on the same box

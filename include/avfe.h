@@ -322,6 +322,18 @@ AVFE_API int avfe_fuse_layernorm(const void* fa, const void* fv, const uint8_t* 
                                  const float* gamma, const float* beta, float eps, void* out,
                                  avfe_stream_t stream);
 
+/* avfe_fuse_layernorm for feature maps whose time rows are `t_pitch` elements apart (t_pitch >= T).
+ * When the rows keep 16-byte alignment (t_pitch * sizeof(dtype) % 16 == 0 -- T = 750 in a [B, C, 752]
+ * allocation) and C is a multiple of 256, the tile fill is done by tensor-map TMA (avfe_fuse_ln_tma.cu:
+ * the kernel is no longer bound by the SM's load/store pipe); avfe_fuse_layernorm_tma_ok tells.  A
+ * contiguous layout that does not qualify falls through to avfe_fuse_layernorm; a padded one that
+ * does not returns AVFE_ERR_UNSUPPORTED. */
+AVFE_API int avfe_fuse_layernorm_tma_ok(int dtype, int64_t C, int64_t T, int64_t t_pitch);
+AVFE_API int avfe_fuse_layernorm_pitched(const void* fa, const void* fv, const uint8_t* mask, int mode, float w_a,
+                                         float w_v, int dtype, int64_t B, int64_t C, int64_t T, int64_t t_pitch,
+                                         const float* gamma, const float* beta, float eps, void* out,
+                                         avfe_stream_t stream);
+
 /* post_extract_proj fused behind concat + transpose + LayerNorm -- avsl/modules/av_hubert_encoder.py:315-334:
  *     features = self.post_extract_proj(self.layer_norm(cat([fa, fv], 1).transpose(1, 2)))
  * (nn.Linear(2C -> D) where self.embed != encoder_embed_dim, :160-166; fp16 / bf16 under `precision: 16`).

@@ -222,3 +222,29 @@ def test_modality_fusion_module_trains_and_no_grad_path_is_unchanged():
     # a CUDA mask is taken without a host round trip
     cm = torch.as_tensor(np.asarray(mask)).cuda()
     assert torch.equal(A.fuse_modalities(fa, fv, cm, "concat"), plain)
+
+
+# ------------------------------------------------------------------ TMA-filled fused LayerNorm (padded rows)
+@pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,C,T", [(3, 256, 37), (2, 1024, 750), (2, 512, 8)])
+def test_fuse_layernorm_tma_path_matches_oracle(mode, dtype, tol, B, C, T):
+    """Feature maps in a padded allocation (row pitch a multiple of 16 bytes) take the tensor-map TMA
+    kernel; same numbers as the oracle (the reference's torch ops) and as the LSU kernel."""
+    from avsl_b200 import _lib
+    fa0, fv0, mask = synth.fusion_inputs(B, C, T, seed=21, dtype=dtype)
+    fa, fv = A.alloc_features(B, C, T, dtype, "cuda"), A.alloc_features(B, C, T, dtype, "cuda")
+    fa.copy_(fa0); fv.copy_(fv0)
+    assert fa.stride(1) % (16 // fa.element_size()) == 0
+    assert _lib.load().avfe_fuse_layernorm_tma_ok(A.fusion._DTYPES[dtype], C, T, fa.stride(1)) == 1
+    Cout = 2 * C if mode == "concat" else C
+    gen = torch.Generator().manual_seed(1)
+    w = (torch.rand(Cout, generator=gen) + 0.5).cuda()
+    bz = torch.randn(Cout, generator=gen).cuda()
+    got = A.fuse_transpose_layernorm(fa, fv, mask, mode, w, bz, weights=(0.3, 0.7))
+    assert got.shape == (B, T, Cout) and got.dtype == dtype
+    from oracle import fusion as OFU
+    ref = OFU.fuse_transpose_layernorm(fa0, fv0, mask, mode, w.cpu(), bz.cpu(), w_a=0.3, w_v=0.7)
+    assert (got.cpu().float() - ref.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
+    lsu = A.fuse_transpose_layernorm(fa0.cuda(), fv0.cuda(), mask, mode, w, bz, weights=(0.3, 0.7))   # contiguous: LSU kernel
+    assert (got.float() - lsu.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
