@@ -4,10 +4,13 @@
 // (same code in utils/data_loading.py:181-201); called from process_audio_for_av_hubert (:199-236)
 // and process_audio_dual_encoder (:267-299).
 //
-//   logfbank_kernel   one CTA = 8 consecutive frames of one clip: pre-emphasis (float32, as numpy
-//                     evaluates it) while staging the audio span, four complex 512-point FFTs (two
-//                     real frames each, 8 x 8 x 8, 64 threads per FFT), power spectrum / 512,
-//                     26 triangular filters, log, stack `stack` frames per row, (x - mean) / (std + 1e-5)
+//   logfbank_kernel   one CTA pass = 16 consecutive frames of one clip: pre-emphasis (float32, as
+//                     numpy evaluates it) while staging the audio span; every warp transforms one
+//                     pair of frames (complex 512-point FFT = 16 x 32, register-resident 16-point
+//                     codelets, one shared-memory exchange, avfe_logfbank_core.cuh) and leaves the
+//                     pair's power rows in its own exchange slot; filters are dealt to the warps by
+//                     weight (prep kernel), a warp's lanes = 16 frames x the two halves of a filter's
+//                     support; log, stack `stack` frames per row, (x - mean) / (std + 1e-5)
 //
 // Frames, spectra and filterbank energies never touch HBM: traffic is the audio read plus the
 // [rows, 26 * stack] output.
@@ -19,32 +22,32 @@ namespace fbk {
 
 #include "avfe_logfbank_tables.inc"   // kTw512Re / kTw512Im: exp(-2 pi i j / 512), float64 -> float32
 
-constexpr int kTileFrames = 8;
-constexpr int kFfts = kTileFrames / 2;
-constexpr int kThreads = kFfts * kFftThreads;                 // 256
-constexpr int kSpan = (kTileFrames - 1) * kHop + kFrame;       // 1520 samples per tile
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;                          // 256
+constexpr int kTileFrames = 2 * kWarps;                        // 16: one pair of frames per warp
+constexpr int kSpan = (kTileFrames - 1) * kHop + kFrame;       // 2800 samples per tile
 constexpr int kMaxFilt = 40;             // filters per bank (python_speech_features: 26; fbank-40 fits)
-
-constexpr int kMaxTaps = 640;             // packed nonzero filter weights (26 HTK filters: 2 x 257 at most)
-
-constexpr int kPRow = 268;            // floats between the power rows of consecutive tile frames (= 12 banks)
+constexpr int kMaxTaps = 640;            // packed nonzero filter weights (26 HTK filters: 459)
 
 struct Smem {
-  float2 tw[kNfft];
-  float2 S[kFfts][kSFloat2];            // exchange storage; the power rows overwrite it
-  float2 C[kFfts][kNfft];               // spectra; the tile's pre-emphasised samples (kSpan floats, zero past
-                                        // the clip) live here until step 1 has consumed them
-  float feat[kTileFrames * kMaxFilt];   // log energies [frame][nfilt] packed = the stacked row layout
-  float wts[kMaxTaps];                  // filter weights, supports back to back
+  float slots[kWarps * kSlotFloats];     // per warp: S exchange, then U (tail) and the pair's power rows (head)
+  float y[kSpan];                        // the tile's pre-emphasised samples, zero past the clip
+  float2 tw1[16 * 32];                   // W512^(l r), lane-contiguous rows
+  float2 tw2[2 * 16];                    // W32^(m q)
+  float feat[kTileFrames * kMaxFilt];    // log energies [frame][nfilt] packed = the stacked row layout
+  float wts[kMaxTaps];                   // filter weights, supports back to back
   int lo[kMaxFilt], hi[kMaxFilt], woff[kMaxFilt];   // filter supports and weight offsets
-  float stat[kTileFrames][2];
+  unsigned char wf[kWarps][kMaxFilt];    // the filters of each warp ...
+  int wf_cnt[kWarps];                    // ... and how many
 };
 
-// workspace: supports [kMaxFilt][2], weight offsets [kMaxFilt], total, packed weights [kMaxTaps]
+// workspace: supports, weight offsets, the warps' filter lists, packed weights
 struct FilterPack {
   int support[kMaxFilt][2];
   int woff[kMaxFilt];
   int total, pad[3];
+  int wf_cnt[kWarps];
+  unsigned char wf[kWarps][kMaxFilt];
   float wts[kMaxTaps];
 };
 
@@ -54,7 +57,8 @@ __host__ __device__ inline int64_t num_frames(int64_t len) {
 }
 
 // filter supports [first, last + 1) of the nonzero weights and the weights packed back to back,
-// once per call: one warp per filter, then a serial prefix over <= 64 lengths
+// once per call: one warp per filter, then a serial prefix over <= 40 lengths and the deal of the
+// filters to the tile kernel's warps (longest support first, always to the least loaded warp)
 __global__ void __launch_bounds__(256)
 logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __restrict__ pack) {
   __shared__ int s_lo[kMaxFilt], s_hi[kMaxFilt], s_off[kMaxFilt + 1];
@@ -76,6 +80,21 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
     for (int m = 0; m < nfilt; ++m) { s_off[m] = acc; acc += s_hi[m] - s_lo[m]; }
     s_off[nfilt] = acc;
     pack->total = acc;
+    // longest-processing-time deal: cost of a filter = half its support (two half-warps share it) + a constant
+    int load[kWarps], cnt[kWarps];
+    unsigned long long done = 0ull;
+    for (int w = 0; w < kWarps; ++w) { load[w] = 0; cnt[w] = 0; }
+    for (int i = 0; i < nfilt; ++i) {
+      int best = -1, best_len = -1;
+      for (int m = 0; m < nfilt; ++m)
+        if (!((done >> m) & 1ull) && s_hi[m] - s_lo[m] > best_len) { best = m; best_len = s_hi[m] - s_lo[m]; }
+      done |= 1ull << best;
+      int w = 0;
+      for (int v = 1; v < kWarps; ++v) if (load[v] < load[w]) w = v;
+      pack->wf[w][cnt[w]++] = (unsigned char)best;
+      load[w] += (best_len + 1) / 2 + 6;
+    }
+    for (int w = 0; w < kWarps; ++w) pack->wf_cnt[w] = cnt[w];
   }
   __syncthreads();
   const bool fits = s_off[nfilt] <= kMaxTaps;
@@ -86,141 +105,150 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
   }
 }
 
-// One wave of CTAs; the tiles of the whole (ragged) batch form one list that the CTAs stride over,
-// so that the twiddle table and the filter supports are set up once per CTA and a long clip does not
-// leave the CTAs of the short ones idle.  The list is virtual: clip b's tiles start at unit
-// V_b = row_offsets[b] / rows_per_tile + b (monotone, and V_{b+1} - V_b >= the clip's tile count), a
-// unit that falls into the slack between two clips is skipped; the clip of a unit is found by a
-// binary search over row_offsets.
-__global__ void __launch_bounds__(kThreads)
+// One resident wave of CTAs; the tiles of the whole (ragged) batch form one list, of which every CTA
+// takes a contiguous run (consecutive tiles of a clip overlap by 240 samples, and the clip of the
+// next tile is the same or one of the next few).  The list is virtual: clip b's tiles start at unit
+// V_b = row_offsets[b] / rows_per_tile + b (monotone, and V_{b+1} - V_b >= the clip's tile count); a
+// unit that falls into the slack between two clips is skipped.
+__global__ void __launch_bounds__(kThreads, 3)
 logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets,
                 const int64_t* __restrict__ row_offsets, int64_t B, const float* __restrict__ fb, int nfilt,
                 const FilterPack* __restrict__ pack, int stack, int normalize, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char fbk_smem[];
   Smem& sm = *reinterpret_cast<Smem*>(fbk_smem);
-  const int tid = threadIdx.x;
-  for (int i = tid; i < kNfft; i += kThreads) sm.tw[i] = make_float2(kTw512Re[i], kTw512Im[i]);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 16 * 32; i += kThreads) {
+    const int e = tw1_index(i >> 5, i & 31);
+    sm.tw1[i] = make_float2(kTw512Re[e], kTw512Im[e]);
+  }
+  if (tid < 32) {
+    const int e = tw2_index(tid >> 4, tid & 15);
+    sm.tw2[tid] = make_float2(kTw512Re[e], kTw512Im[e]);
+  }
   if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.woff[tid] = pack->woff[tid]; }
+  if (tid < kWarps) sm.wf_cnt[tid] = pack->wf_cnt[tid];
+  for (int i = tid; i < kWarps * kMaxFilt; i += kThreads) sm.wf[i / kMaxFilt][i % kMaxFilt] = pack->wf[i / kMaxFilt][i % kMaxFilt];
   const bool packed = pack->total <= kMaxTaps;
   if (packed)
     for (int i = tid; i < pack->total; i += kThreads) sm.wts[i] = pack->wts[i];
-  // tile-invariant work split of the filterbank stage: item = (frame, filter)
-  constexpr int kItems = (kTileFrames * kMaxFilt + kThreads - 1) / kThreads;   // 2
-  int it_f[kItems], it_m[kItems];
-#pragma unroll
-  for (int q = 0; q < kItems; ++q) {
-    const int i = tid + q * kThreads;
-    // the 8 frames of one filter sit in adjacent lanes: a warp holds 4 neighbouring filters, whose
-    // supports have similar lengths (a warp runs as long as its widest filter), and the 8 power rows
-    // are kPRow = 268 floats apart, i.e. 12 banks: same-bin reads of the 8 frames do not collide
-    it_f[q] = (i < kTileFrames * nfilt) ? i % kTileFrames : -1;
-    it_m[q] = (i < kTileFrames * nfilt) ? i / kTileFrames : 0;
-  }
+
   const int rows_here = kTileFrames / stack, width = stack * nfilt;
-  float* tile_y = reinterpret_cast<float*>(sm.C);               // dead between power_rows and the next step 3
-  static_assert(kSpan * sizeof(float) <= sizeof(sm.C), "the tile's samples must fit in the spectrum storage");
-
-  const int rpt_shift = 31 - __clz(rows_here);                   // rows per tile is 1, 2, 4 or 8 (8 % stack == 0)
-  const int stack_shift = 31 - __clz(stack);                     // ... and so is stack: shifts, not 64-bit divisions per tile
+  const int rpt_shift = 31 - __clz(rows_here);                   // rows per tile and stack are powers of two:
+  const int stack_shift = 31 - __clz(stack);                     // shifts, not 64-bit divisions per tile
   const int64_t units = (row_offsets[B] >> rpt_shift) + B;
-  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+  const int64_t per = (units + gridDim.x - 1) / gridDim.x;
+  const int64_t u_begin = (int64_t)blockIdx.x * per, u_end = min(units, u_begin + per);
+  auto first_unit = [&](int64_t c) -> int64_t { return (row_offsets[c] >> rpt_shift) + c; };
   int64_t b = 0;
-  for (int64_t hi = B - 1; b < hi;) {                           // largest b with V_b <= u (CTA-uniform)
+  for (int64_t hi = B - 1; b < hi;) {                           // largest b with V_b <= u_begin, once per CTA
     const int64_t mid = (b + hi + 1) >> 1;
-    if ((row_offsets[mid] >> rpt_shift) + mid <= u) b = mid; else hi = mid - 1;
+    if (first_unit(mid) <= u_begin) b = mid; else hi = mid - 1;
   }
-  const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
-  const int64_t nfr = num_frames(len);
-  const int64_t rows = (nfr + stack - 1) >> stack_shift;        // stacked rows (zero-padded tail)
-  const int64_t f0 = (u - ((row_offsets[b] >> rpt_shift) + b)) * kTileFrames;
-  if (len <= 0 || f0 < 0 || f0 >= (rows << stack_shift)) continue;   // slack unit
-  const float* clip = audio + beg;
-  // raw samples of the span (one coalesced load each, plus the sample before the span), then the
-  // pre-emphasis y[n] = x[n] - 0.97 x[n-1] from registers; beyond the clip: framesig's zeros
-  {
-    const int64_t s0 = f0 * kHop;
-    constexpr int kPer = (kSpan + kThreads - 1) / kThreads;       // 6
-    float cur[kPer], prev[kPer];
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int64_t n = s0 + tid + q * kThreads;
-      cur[q] = (n < len) ? clip[n] : 0.0f;
-      prev[q] = (n >= 1 && n < len) ? clip[n - 1] : 0.0f;       // a neighbouring lane's line: L1 hit
-    }
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int i = tid + q * kThreads;
-      const int64_t n = s0 + i;
-      if (i < kSpan) tile_y[i] = (n == 0 || n >= len) ? cur[q] : __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));
-    }
-  }
+  float* slot = sm.slots + wid * kSlotFloats;                    // this warp's exchange slot
   __syncthreads();
 
-  const int g = tid / kFftThreads, t = tid % kFftThreads;       // FFT g: tile frames 2g, 2g + 1
-  float2* S = sm.S[g];
-  float2* C = sm.C[g];
-  step1(t, tile_y + (2 * g) * kHop, tile_y + (2 * g + 1) * kHop, sm.tw, S);
-  __syncthreads();
-  float2 x[8];
-  step2_load(t, S, x);
-  __syncthreads();
-  step2_store(t, sm.tw, x, S);
-  __syncthreads();
-  step3(t, S, C);
-  __syncthreads();
-  float* Pall = reinterpret_cast<float*>(sm.S);                 // the tile's power rows overwrite the exchange storage
-  power_rows(t, C, Pall + (2 * g) * kPRow, Pall + (2 * g + 1) * kPRow);
-  __syncthreads();
-
-  // log filterbank energies: item = (frame, filter); frames past the clip's last one are the
-  // zero rows extract_logfbank_features appends before stacking
+  for (int64_t u = u_begin; u < u_end; ++u) {
+    while (b + 1 < B && first_unit(b + 1) <= u) ++b;             // CTA-uniform; the run is contiguous: a step or two
+    const int64_t beg = offsets[b], len = offsets[b + 1] - beg;
+    const int64_t nfr = num_frames(len);
+    const int64_t rows = (nfr + stack - 1) >> stack_shift;      // stacked rows (zero-padded tail)
+    const int64_t f0 = (u - first_unit(b)) * kTileFrames;
+    if (len <= 0 || f0 >= (rows << stack_shift)) continue;       // slack unit
+    const float* clip = audio + beg;
+    // raw samples of the span (one coalesced load each, plus the sample before), then the
+    // pre-emphasis y[n] = x[n] - 0.97 x[n-1] from registers; beyond the clip: framesig's zeros
+    {
+      const int64_t s0 = f0 * kHop;
+      const int64_t left = len - s0;                             // samples of the clip from the span's start on
+      const float* src = clip + s0;
+      constexpr int kPer = (kSpan + kThreads - 1) / kThreads;    // 11
+      float cur[kPer], prev[kPer];
 #pragma unroll
-  for (int q = 0; q < kItems; ++q) {
-    const int f = it_f[q], m = it_m[q];
-    if (f < 0) continue;
-    const float* Pf = Pall + f * kPRow;
-    float v = 0.0f;
-    if (f0 + f < nfr) {
-      const int lo = sm.lo[m], hi = sm.hi[m];
-      v = packed ? log_fbank(Pf + lo, sm.wts + sm.woff[m], 0, hi - lo) : log_fbank(Pf, fb + (size_t)m * kBins, lo, hi);
-    }
-    sm.feat[f * nfilt + m] = v;
-  }
-  __syncthreads();
-
-  // rows of `stack` consecutive frames (contiguous in feat); audio_to_tensor:
-  // (x - mean) / (std + 1e-5), population std
-  if (normalize) {
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int r = wid; r < rows_here; r += kThreads / 32) {
-      const float* row = sm.feat + r * width;
-      float sum = 0.0f;
-      for (int i = lane; i < width; i += 32) sum += row[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum / (float)width;
-      float v = 0.0f;
-      for (int i = lane; i < width; i += 32) {
-        const float d = row[i] - mean;
-        v = fmaf(d, d, v);
+      for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * kThreads;
+        const bool in = i < left;                                // also false for every i when left <= 0
+        cur[q] = in ? src[i] : 0.0f;
+        prev[q] = (in && (i > 0 || s0 > 0)) ? src[i - 1] : 0.0f; // a neighbouring lane's line: L1 hit
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) { sm.stat[r][0] = mean; sm.stat[r][1] = sqrtf(v / (float)width) + 1e-5f; }
+      for (int q = 0; q < kPer; ++q) {
+        const int i = tid + q * kThreads;
+        if (i < kSpan) sm.y[i] = __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));   // clip[0] - 0.97 * 0 = clip[0]; 0 - 0 past the end
+      }
     }
-    __syncthreads();
-  }
-  const int64_t row0 = f0 >> stack_shift;
-  float* o = out + (row_offsets[b] + row0) * width;
-  for (int r = 0; r < rows_here; ++r) {
-    if (row0 + r >= rows) break;
-    const float mean = normalize ? sm.stat[r][0] : 0.0f, sd = normalize ? sm.stat[r][1] : 1.0f;
-    for (int c = tid; c < width; c += kThreads) {
-      const float v = sm.feat[r * width + c];
-      o[r * width + c] = normalize ? __fdiv_rn(v - mean, sd) : v;
+    __syncthreads();                                             // span visible (and the previous tile's rows are out)
+
+    // ---- this warp's pair of frames: FFT, untangle, power rows into the head of its own slot ----
+    {
+      float2* S = reinterpret_cast<float2*>(slot);
+      float2* U = reinterpret_cast<float2*>(slot + kUOffset);
+      fft_stage1(lane, sm.y + (2 * wid) * kHop, sm.y + (2 * wid + 1) * kHop, sm.tw1, S);
+      __syncwarp();
+      float2 x[16];
+      fft_stage2(lane, S, sm.tw2, x);
+      __syncwarp();                                              // every lane has read S: U may overwrite its tail
+      fft_upper_store(lane, x, U);
+      __syncwarp();
+      fft_power(lane, x, U, slot, slot + kPRow);                 // rows and U do not overlap
     }
-  }
-  __syncthreads();                                              // staging buffers are reused
+    __syncthreads();                                             // all 16 power rows written; the span is dead
+
+    // ---- log filterbank energies: warp = some filters (dealt by weight), lane = (frame, half of the
+    // support); frames past the clip's last one are the zero rows extract_logfbank_features appends ----
+    {
+      const int f = lane & 15, h = lane >> 4;
+      const float* Pf = sm.slots + (f >> 1) * kSlotFloats + (f & 1) * kPRow;
+      const bool live = f0 + f < nfr;
+      const int cnt = sm.wf_cnt[wid];
+      for (int i = 0; i < cnt; ++i) {
+        const int m = sm.wf[wid][i];
+        const int lo = sm.lo[m], n = sm.hi[m] - lo, n0 = (n + 1) >> 1;
+        const int k0 = h ? n0 : 0, k1 = h ? n : n0;              // this half-warp's taps
+        const float* w = packed ? sm.wts + sm.woff[m] : fb + (size_t)m * kBins + lo;
+        const float* p = Pf + lo;
+        float a0 = 0.0f, a1 = 0.0f;
+        int k = k0;
+        for (; k + 2 <= k1; k += 2) {
+          a0 = fmaf(w[k], p[k], a0);
+          a1 = fmaf(w[k + 1], p[k + 1], a1);
+        }
+        if (k < k1) a0 = fmaf(w[k], p[k], a0);
+        float acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (h == 0) sm.feat[f * nfilt + m] = live ? log_energy(acc) : 0.0f;
+      }
+    }
+    __syncthreads();                                             // feat complete; the power rows are dead
+
+    // ---- rows of `stack` consecutive frames (contiguous in feat); audio_to_tensor:
+    // (x - mean) / (std + 1e-5), population std; one warp per row, which also writes it out ----
+    {
+      const int64_t row0 = f0 >> stack_shift;
+      float* o = out + (row_offsets[b] + row0) * width;
+      for (int r = wid; r < rows_here; r += kWarps) {
+        if (row0 + r >= rows) break;
+        const float* row = sm.feat + r * width;
+        float mean = 0.0f, sd = 1.0f;
+        if (normalize) {
+          float sum = 0.0f;
+          for (int i = lane; i < width; i += 32) sum += row[i];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+          mean = sum / (float)width;
+          float v = 0.0f;
+          for (int i = lane; i < width; i += 32) {
+            const float d = row[i] - mean;
+            v = fmaf(d, d, v);
+          }
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          sd = sqrtf(v / (float)width) + 1e-5f;
+        }
+        for (int c = lane; c < width; c += 32) o[r * width + c] = normalize ? __fdiv_rn(row[c] - mean, sd) : row[c];
+      }
+    }
+    // no barrier here: the next tile's span store touches only y (dead since the second barrier), and
+    // its first barrier orders this tile's feat reads before the next filter stage's writes
   }
 }
 
@@ -240,7 +268,7 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
                                  int stack, int normalize, float* out, void* workspace,
                                  size_t workspace_bytes, avfe_stream_t stream) {
   if (B < 0 || nfilt <= 0 || stack <= 0 || max_samples < 0) return AVFE_ERR_INVALID_ARG;
-  if (nfilt > fbk::kMaxFilt || (fbk::kTileFrames % stack) != 0) return AVFE_ERR_UNSUPPORTED;
+  if (nfilt > fbk::kMaxFilt || (fbk::kTileFrames % stack) != 0 || (stack & (stack - 1)) != 0) return AVFE_ERR_UNSUPPORTED;
   if (B == 0) return AVFE_OK;
   if (!audio || !offsets || !row_offsets || !fbank || !out) return AVFE_ERR_INVALID_ARG;
   if (!workspace || workspace_bytes < avfe_logfbank_workspace_bytes()) return AVFE_ERR_WORKSPACE;
@@ -258,7 +286,7 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  // one resident wave (5 CTAs per SM: shared memory), each CTA striding over the batch's tile list
+  // one resident wave (3 CTAs per SM: registers), each CTA taking a contiguous run of the batch's tile list
   int resident = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fbk::logfbank_kernel, fbk::kThreads, sizeof(fbk::Smem)) !=
           cudaSuccess || resident < 1) {

@@ -65,41 +65,46 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
   }
 }
 
-// raw log filterbank energies of frames fa, fb (two frames of one clip) -> out[2][nfilt]
+// raw log filterbank energies of frames fa, fb (two frames of one clip) -> out[2][nfilt]: the warp's
+// 16 x 32 transform stepped lane by lane
 void hc_logfbank_pair(const float* clip, int64_t len, int64_t fa, int64_t fb, int nfilt, const float* fbank,
                       float* out) {
   using namespace fbk;
-  std::vector<float2> tw(kNfft);
-  for (int j = 0; j < kNfft; ++j)
-    tw[j] = make_float2((float)cos(-2.0 * M_PI * j / kNfft), (float)sin(-2.0 * M_PI * j / kNfft));
+  std::vector<float2> tw1(16 * 32), tw2(2 * 16);
+  auto w512 = [](int e) { return make_float2((float)cos(-2.0 * M_PI * e / kNfft), (float)sin(-2.0 * M_PI * e / kNfft)); };
+  for (int r = 0; r < 16; ++r)
+    for (int l = 0; l < 32; ++l) tw1[r * 32 + l] = w512(tw1_index(r, l));
+  for (int q = 0; q < 2; ++q)
+    for (int m = 0; m < 16; ++m) tw2[q * 16 + m] = w512(tw2_index(q, m));
   std::vector<float> ya(kFrame), yb(kFrame);
   for (int n = 0; n < kFrame; ++n) {
     ya[n] = preemph_sample(clip, len, fa * kHop + n);
     yb[n] = preemph_sample(clip, len, fb * kHop + n);
   }
-  std::vector<float2> S(kSFloat2), C(kNfft);
-  std::vector<float> P(2 * kPStride);
-  for (int t = 0; t < kFftThreads; ++t) step1(t, ya.data(), yb.data(), tw.data(), S.data());
-  std::vector<float2> regs(kFftThreads * 8);
-  for (int t = 0; t < kFftThreads; ++t) step2_load(t, S.data(), *reinterpret_cast<float2(*)[8]>(&regs[t * 8]));
-  for (int t = 0; t < kFftThreads; ++t) step2_store(t, tw.data(), *reinterpret_cast<float2(*)[8]>(&regs[t * 8]), S.data());
-  for (int t = 0; t < kFftThreads; ++t) step3(t, S.data(), C.data());
-  for (int t = 0; t < kFftThreads; ++t) power_rows(t, C.data(), P.data(), P.data() + kPStride);
+  std::vector<float> slot(kSlotFloats);
+  float2* S = reinterpret_cast<float2*>(slot.data());
+  float2* U = reinterpret_cast<float2*>(slot.data() + kUOffset);
+  for (int l = 0; l < 32; ++l) fft_stage1(l, ya.data(), yb.data(), tw1.data(), S);
+  std::vector<float2> regs(32 * 16);
+  for (int l = 0; l < 32; ++l) fft_stage2(l, S, tw2.data(), *reinterpret_cast<float2(*)[16]>(&regs[l * 16]));
+  for (int l = 0; l < 32; ++l) fft_upper_store(l, *reinterpret_cast<float2(*)[16]>(&regs[l * 16]), U);
+  for (int l = 0; l < 32; ++l)
+    fft_power(l, *reinterpret_cast<float2(*)[16]>(&regs[l * 16]), U, slot.data(), slot.data() + kPRow);
   for (int f = 0; f < 2; ++f)
     for (int m = 0; m < nfilt; ++m) {
       int lo = kBins, hi = 0;
       for (int k = 0; k < kBins; ++k)
         if (fbank[m * kBins + k] != 0.0f) { lo = lo < k ? lo : k; hi = k + 1; }
       if (lo >= hi) { lo = 0; hi = 0; }
-      out[f * nfilt + m] = log_fbank(P.data() + f * kPStride, fbank + m * kBins, lo, hi);
+      out[f * nfilt + m] = log_fbank(slot.data() + f * kPRow, fbank + m * kBins, lo, hi);
     }
 }
 
-void hc_dft8(const float* in_ri, float* out_ri) {
-  float2 x[8];
-  for (int i = 0; i < 8; ++i) x[i] = make_float2(in_ri[2 * i], in_ri[2 * i + 1]);
-  fbk::dft8(x);
-  for (int i = 0; i < 8; ++i) { out_ri[2 * i] = x[i].x; out_ri[2 * i + 1] = x[i].y; }
+void hc_dft16(const float* in_ri, float* out_ri) {
+  float2 x[16];
+  for (int i = 0; i < 16; ++i) x[i] = make_float2(in_ri[2 * i], in_ri[2 * i + 1]);
+  fbk::dft16(x);
+  for (int i = 0; i < 16; ++i) { out_ri[2 * i] = x[i].x; out_ri[2 * i + 1] = x[i].y; }
 }
 
 void hc_dft20(const float* in_ri, float* out_ri) {

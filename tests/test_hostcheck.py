@@ -49,14 +49,14 @@ def test_logmel_tile_codelets(hostcheck, n_mels, L, pad):
         assert np.abs(out[:, :nv] - ref).max() < 2e-5
 
 
-def test_dft8_and_logfbank_codelets(hostcheck):
-    """The 8 x 8 x 8 two-frames-per-FFT 512-point transform, pre-emphasis and the filterbank
-    against the oracle's restatement of python_speech_features.logfbank."""
+def test_dft16_and_logfbank_codelets(hostcheck):
+    """The warp-per-FFT 16 x 32 two-frames-per-FFT 512-point transform, pre-emphasis and the
+    filterbank against the oracle's restatement of python_speech_features.logfbank."""
     from oracle import logfbank as OF
     rng = np.random.default_rng(1)
-    x = (rng.normal(size=8) + 1j * rng.normal(size=8)).astype(np.complex64)
-    o = np.zeros(8, np.complex64)
-    hostcheck.hc_dft8(vp(x), vp(o))
+    x = (rng.normal(size=16) + 1j * rng.normal(size=16)).astype(np.complex64)
+    o = np.zeros(16, np.complex64)
+    hostcheck.hc_dft16(vp(x), vp(o))
     assert np.abs(o - np.fft.fft(x.astype(np.complex128))).max() < 2e-6
     fb = np.ascontiguousarray(OF.get_filterbanks().astype(np.float32))
     for L in (16000, 5000, 401, 400, 37):
