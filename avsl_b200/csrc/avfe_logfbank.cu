@@ -27,7 +27,7 @@ constexpr int kThreads = kWarps * 32;                          // 256
 constexpr int kTileFrames = 2 * kWarps;                        // 16: one pair of frames per warp
 constexpr int kSpan = (kTileFrames - 1) * kHop + kFrame;       // 2800 samples per tile
 constexpr int kMaxFilt = 40;             // filters per bank (python_speech_features: 26; fbank-40 fits)
-constexpr int kMaxTaps = 640;            // packed nonzero filter weights (26 HTK filters: 459)
+constexpr int kMaxTaps = 768;            // packed filter weights, each half-support zero-padded to quads (26 HTK filters: 572)
 
 struct Smem {
   float slots[kWarps * kSlotFloats];     // per warp: S exchange, then U (tail) and the pair's power rows (head)
@@ -35,8 +35,9 @@ struct Smem {
   float2 tw1[16 * 32];                   // W512^(l r), lane-contiguous rows
   float2 tw2[2 * 16];                    // W32^(m q)
   float feat[kTileFrames * kMaxFilt];    // log energies [frame][nfilt] packed = the stacked row layout
-  float wts[kMaxTaps];                   // filter weights, supports back to back
-  int lo[kMaxFilt], hi[kMaxFilt], woff[kMaxFilt];   // filter supports and weight offsets
+  __align__(16) float wts[kMaxTaps];     // filter weights: per filter the two half-supports, each zero-padded to quads
+  int4 rec[kMaxFilt];                    // first bin, weight offset, quads of the first / second half
+  int lo[kMaxFilt], hi[kMaxFilt];        // filter supports (dense filterbanks: weights stay in global memory)
   unsigned char wf[kWarps][kMaxFilt];    // the filters of each warp ...
   int wf_cnt[kWarps];                    // ... and how many
 };
@@ -44,8 +45,8 @@ struct Smem {
 // workspace: supports, weight offsets, the warps' filter lists, packed weights
 struct FilterPack {
   int support[kMaxFilt][2];
-  int woff[kMaxFilt];
-  int total, pad[3];
+  int4 rec[kMaxFilt];                    // first bin, weight offset, quads of the first / second half
+  int total, pad[3];                     // total = padded weights; > kMaxTaps: not packed
   int wf_cnt[kWarps];
   unsigned char wf[kWarps][kMaxFilt];
   float wts[kMaxTaps];
@@ -75,12 +76,15 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
     if (lane == 0) { s_lo[m] = lo < hi ? lo : 0; s_hi[m] = lo < hi ? hi : 0; }
   }
   __syncthreads();
+  // half-supports in quads: the first half takes ceil(n / 2) taps rounded up to a quad
+  auto q0_of = [](int n) { return ((n + 1) / 2 + 3) >> 2; };
+  auto q1_of = [&](int n) { const int rest = n - 4 * q0_of(n); return rest > 0 ? (rest + 3) >> 2 : 0; };
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int m = 0; m < nfilt; ++m) { s_off[m] = acc; acc += s_hi[m] - s_lo[m]; }
+    for (int m = 0; m < nfilt; ++m) { const int n = s_hi[m] - s_lo[m]; s_off[m] = acc; acc += 4 * (q0_of(n) + q1_of(n)); }
     s_off[nfilt] = acc;
     pack->total = acc;
-    // longest-processing-time deal: cost of a filter = half its support (two half-warps share it) + a constant
+    // longest-processing-time deal: cost of a filter = the quads of its longer half + a constant
     int load[kWarps], cnt[kWarps];
     unsigned long long done = 0ull;
     for (int w = 0; w < kWarps; ++w) { load[w] = 0; cnt[w] = 0; }
@@ -92,16 +96,21 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
       int w = 0;
       for (int v = 1; v < kWarps; ++v) if (load[v] < load[w]) w = v;
       pack->wf[w][cnt[w]++] = (unsigned char)best;
-      load[w] += (best_len + 1) / 2 + 6;
+      load[w] += 9 * q0_of(best_len) + 12;
     }
     for (int w = 0; w < kWarps; ++w) pack->wf_cnt[w] = cnt[w];
   }
   __syncthreads();
   const bool fits = s_off[nfilt] <= kMaxTaps;
   for (int m = threadIdx.x >> 5; m < nfilt; m += blockDim.x >> 5) {
-    if (lane == 0) { pack->support[m][0] = s_lo[m]; pack->support[m][1] = s_hi[m]; pack->woff[m] = s_off[m]; }
+    const int n = s_hi[m] - s_lo[m], q0 = q0_of(n), q1 = q1_of(n);
+    if (lane == 0) {
+      pack->support[m][0] = s_lo[m];
+      pack->support[m][1] = s_hi[m];
+      pack->rec[m] = make_int4(s_lo[m], s_off[m], q0, q1);
+    }
     if (fits)
-      for (int k = s_lo[m] + lane; k < s_hi[m]; k += 32) pack->wts[s_off[m] + k - s_lo[m]] = fb[(size_t)m * kBins + k];
+      for (int k = lane; k < 4 * (q0 + q1); k += 32) pack->wts[s_off[m] + k] = (k < n) ? fb[(size_t)m * kBins + s_lo[m] + k] : 0.0f;
   }
 }
 
@@ -110,7 +119,7 @@ logfbank_prep_kernel(const float* __restrict__ fb, int nfilt, FilterPack* __rest
 // next tile is the same or one of the next few).  The list is virtual: clip b's tiles start at unit
 // V_b = row_offsets[b] / rows_per_tile + b (monotone, and V_{b+1} - V_b >= the clip's tile count); a
 // unit that falls into the slack between two clips is skipped.
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ offsets,
                 const int64_t* __restrict__ row_offsets, int64_t B, const float* __restrict__ fb, int nfilt,
                 const FilterPack* __restrict__ pack, int stack, int normalize, float* __restrict__ out) {
@@ -125,7 +134,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     const int e = tw2_index(tid >> 4, tid & 15);
     sm.tw2[tid] = make_float2(kTw512Re[e], kTw512Im[e]);
   }
-  if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.woff[tid] = pack->woff[tid]; }
+  if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.rec[tid] = pack->rec[tid]; }
   if (tid < kWarps) sm.wf_cnt[tid] = pack->wf_cnt[tid];
   for (int i = tid; i < kWarps * kMaxFilt; i += kThreads) sm.wf[i / kMaxFilt][i % kMaxFilt] = pack->wf[i / kMaxFilt][i % kMaxFilt];
   const bool packed = pack->total <= kMaxTaps;
@@ -200,22 +209,39 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
       const float* Pf = sm.slots + (f >> 1) * kSlotFloats + (f & 1) * kPRow;
       const bool live = f0 + f < nfr;
       const int cnt = sm.wf_cnt[wid];
-      for (int i = 0; i < cnt; ++i) {
-        const int m = sm.wf[wid][i];
-        const int lo = sm.lo[m], n = sm.hi[m] - lo, n0 = (n + 1) >> 1;
-        const int k0 = h ? n0 : 0, k1 = h ? n : n0;              // this half-warp's taps
-        const float* w = packed ? sm.wts + sm.woff[m] : fb + (size_t)m * kBins + lo;
-        const float* p = Pf + lo;
-        float a0 = 0.0f, a1 = 0.0f;
-        int k = k0;
-        for (; k + 2 <= k1; k += 2) {
-          a0 = fmaf(w[k], p[k], a0);
-          a1 = fmaf(w[k + 1], p[k + 1], a1);
+      if (packed) {
+        // per filter: one record, then quads of (LDS.128 weights, 4 LDS powers, 4 FFMA); the padded
+        // taps carry zero weights and read finite slots (bins 257..260 of a row are zeroed)
+        for (int i = 0; i < cnt; ++i) {
+          const int m = sm.wf[wid][i];
+          const int4 rc = sm.rec[m];                             // first bin, weight offset, quads of either half
+          const int skip = h ? 4 * rc.z : 0, quads = h ? rc.w : rc.z;
+          const float4* w4 = reinterpret_cast<const float4*>(sm.wts + rc.y + skip);
+          const float* p = Pf + rc.x + skip;
+          float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 2
+          for (int q = 0; q < quads; ++q) {
+            const float4 c = w4[q];
+            a0 = fmaf(c.x, p[4 * q], a0);
+            a1 = fmaf(c.y, p[4 * q + 1], a1);
+            a0 = fmaf(c.z, p[4 * q + 2], a0);
+            a1 = fmaf(c.w, p[4 * q + 3], a1);
+          }
+          float acc = a0 + a1;
+          acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+          if (h == 0) sm.feat[f * nfilt + m] = live ? log_energy(acc) : 0.0f;
         }
-        if (k < k1) a0 = fmaf(w[k], p[k], a0);
-        float acc = a0 + a1;
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (h == 0) sm.feat[f * nfilt + m] = live ? log_energy(acc) : 0.0f;
+      } else {                                                   // dense filterbank: weights from global memory
+        for (int i = 0; i < cnt; ++i) {
+          const int m = sm.wf[wid][i];
+          const int lo = sm.lo[m], n = sm.hi[m] - lo, n0 = (n + 1) >> 1;
+          const float* w = fb + (size_t)m * kBins + lo;
+          const float* p = Pf + lo;
+          float acc = 0.0f;
+          for (int k = h ? n0 : 0; k < (h ? n : n0); ++k) acc = fmaf(__ldg(w + k), p[k], acc);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+          if (h == 0) sm.feat[f * nfilt + m] = live ? log_energy(acc) : 0.0f;
+        }
       }
     }
     __syncthreads();                                             // feat complete; the power rows are dead
@@ -286,7 +312,7 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
     cudaGetLastError();
     return AVFE_ERR_CUDA;
   }
-  // one resident wave (3 CTAs per SM: registers), each CTA taking a contiguous run of the batch's tile list
+  // one resident wave (4 CTAs per SM), each CTA taking a contiguous run of the batch's tile list
   int resident = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fbk::logfbank_kernel, fbk::kThreads, sizeof(fbk::Smem)) !=
           cudaSuccess || resident < 1) {

@@ -159,13 +159,20 @@ AVFE_HD void fft_power(int l, const float2 (&x)[16], const float2* U, float* Pa,
     const float ar = x[8].x + x[8].x, br = x[8].y + x[8].y;
     Pa[kNfft / 2] = scale * (ar * ar);
     Pb[kNfft / 2] = scale * (br * br);
+  } else if (l < 5) {                                                // slots the quad-padded filter taps may read (zero weights)
+    Pa[kNfft / 2 + l] = 0.0f;
+    Pb[kNfft / 2 + l] = 0.0f;
   }
 }
 
 // feat = fb_row . pspec over [lo, hi); zero -> float64 eps (numpy.finfo(float).eps); natural log
 AVFE_HD float log_energy(float acc) {
   if (acc == 0.0f) acc = 2.220446049250313e-16f;
+#if defined(__CUDA_ARCH__)
+  return __log2f(acc) * 0.69314718055994531f;   // MUFU.LG2: abs error ~2e-6 over the range of the energies
+#else
   return logf(acc);
+#endif
 }
 AVFE_HD float log_fbank(const float* P, const float* w, int lo, int hi) {
   float acc = 0.0f;
