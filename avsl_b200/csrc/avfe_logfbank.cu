@@ -33,7 +33,6 @@ struct Smem {
   float slots[kWarps * kSlotFloats];     // per warp: S exchange, then U (tail) and the pair's power rows (head)
   float y[kSpan];                        // the tile's pre-emphasised samples, zero past the clip
   float2 tw1[16 * 32];                   // W512^(l r), lane-contiguous rows
-  float2 tw2[2 * 16];                    // W32^(m q)
   float feat[kTileFrames * kMaxFilt];    // log energies [frame][nfilt] packed = the stacked row layout
   __align__(16) float wts[kMaxTaps];     // filter weights: per filter the two half-supports, each zero-padded to quads
   int4 rec[kMaxFilt];                    // first bin, weight offset, quads of the first / second half
@@ -130,10 +129,6 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
     const int e = tw1_index(i >> 5, i & 31);
     sm.tw1[i] = make_float2(kTw512Re[e], kTw512Im[e]);
   }
-  if (tid < 32) {
-    const int e = tw2_index(tid >> 4, tid & 15);
-    sm.tw2[tid] = make_float2(kTw512Re[e], kTw512Im[e]);
-  }
   if (tid < nfilt) { sm.lo[tid] = pack->support[tid][0]; sm.hi[tid] = pack->support[tid][1]; sm.rec[tid] = pack->rec[tid]; }
   if (tid < kWarps) sm.wf_cnt[tid] = pack->wf_cnt[tid];
   for (int i = tid; i < kWarps * kMaxFilt; i += kThreads) sm.wf[i / kMaxFilt][i % kMaxFilt] = pack->wf[i / kMaxFilt][i % kMaxFilt];
@@ -171,18 +166,30 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
       const int64_t left = len - s0;                             // samples of the clip from the span's start on
       const float* src = clip + s0;
       constexpr int kPer = (kSpan + kThreads - 1) / kThreads;    // 11
-      float cur[kPer], prev[kPer];
+      if (s0 > 0 && left >= kSpan) {                             // interior tile (CTA-uniform): nothing to test per sample
+        const float* mine = src + tid;
 #pragma unroll
-      for (int q = 0; q < kPer; ++q) {
-        const int i = tid + q * kThreads;
-        const bool in = i < left;                                // also false for every i when left <= 0
-        cur[q] = in ? src[i] : 0.0f;
-        prev[q] = (in && (i > 0 || s0 > 0)) ? src[i - 1] : 0.0f; // a neighbouring lane's line: L1 hit
-      }
+        for (int q0 = 0; q0 < kPer; q0 += 4) {                   // four samples per thread in flight
+          float cur[4], prev[4];
 #pragma unroll
-      for (int q = 0; q < kPer; ++q) {
-        const int i = tid + q * kThreads;
-        if (i < kSpan) sm.y[i] = __fsub_rn(cur[q], __fmul_rn(kPreemph, prev[q]));   // clip[0] - 0.97 * 0 = clip[0]; 0 - 0 past the end
+          for (int q = q0; q < q0 + 4 && q < kPer; ++q)
+            if (q < kPer - 1 || tid + q * kThreads < kSpan) {
+              cur[q - q0] = mine[q * kThreads];
+              prev[q - q0] = mine[q * kThreads - 1];             // a neighbouring lane's line: L1 hit
+            }
+#pragma unroll
+          for (int q = q0; q < q0 + 4 && q < kPer; ++q)
+            if (q < kPer - 1 || tid + q * kThreads < kSpan)
+              sm.y[tid + q * kThreads] = __fsub_rn(cur[q - q0], __fmul_rn(kPreemph, prev[q - q0]));
+        }
+      } else {
+#pragma unroll 1
+        for (int i = tid; i < kSpan; i += kThreads) {
+          const bool in = i < left;                              // also false for every i when left <= 0
+          const float cur = in ? src[i] : 0.0f;
+          const float prev = (in && (i > 0 || s0 > 0)) ? src[i - 1] : 0.0f;
+          sm.y[i] = __fsub_rn(cur, __fmul_rn(kPreemph, prev));   // clip[0] - 0.97 * 0 = clip[0]; 0 - 0 past the end
+        }
       }
     }
     __syncthreads();                                             // span visible (and the previous tile's rows are out)
@@ -194,7 +201,7 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
       fft_stage1(lane, sm.y + (2 * wid) * kHop, sm.y + (2 * wid + 1) * kHop, sm.tw1, S);
       __syncwarp();
       float2 x[16];
-      fft_stage2(lane, S, sm.tw2, x);
+      fft_stage2(lane, S, x);
       __syncwarp();                                              // every lane has read S: U may overwrite its tail
       fft_upper_store(lane, x, U);
       __syncwarp();
@@ -268,9 +275,9 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
           }
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-          sd = sqrtf(v / (float)width) + 1e-5f;
+          sd = __frcp_rn(sqrtf(v / (float)width) + 1e-5f);      // one reciprocal per row: 1 ulp from the division, bar 1e-3
         }
-        for (int c = lane; c < width; c += 32) o[r * width + c] = normalize ? __fdiv_rn(row[c] - mean, sd) : row[c];
+        for (int c = lane; c < width; c += 32) o[r * width + c] = normalize ? (row[c] - mean) * sd : row[c];
       }
     }
     // no barrier here: the next tile's span store touches only y (dead since the second barrier), and

@@ -108,9 +108,8 @@ AVFE_HD float preemph_sample(const float* clip, int64_t len, int64_t n) {
 #endif
 }
 
-// twiddle tables: tw1[r * 32 + l] = W512^(l r) (r = 0..15), tw2[q * 16 + m] = W32^(m q)
+// twiddle table: tw1[r * 32 + l] = W512^(l r) (r = 0..15)
 AVFE_HD int tw1_index(int r, int l) { return (l * r) & (kNfft - 1); }        // exponent of W512
-AVFE_HD int tw2_index(int q, int m) { return (16 * m * q) & (kNfft - 1); }   // W32^m = W512^(16 m)
 
 // stage 1, lane l.  ya / yb: the two frames' 400 pre-emphasised samples
 AVFE_HD void fft_stage1(int l, const float* ya, const float* yb, const float2* tw1, float2* S) {
@@ -125,14 +124,27 @@ AVFE_HD void fft_stage1(int l, const float* ya, const float* yb, const float2* t
   for (int r = 1; r < 16; ++r) S[r * kSRow + l] = cmul(x[r], tw1[r * 32 + l]);
 }
 
-// stage 2, lane l = r + 16 q: afterwards x[s] = X[l + 32 s]
-AVFE_HD void fft_stage2(int l, const float2* S, const float2* tw2, float2 (&x)[16]) {
+// stage 2, lane l = r + 16 q: afterwards x[s] = X[l + 32 s].  The twiddles W32^(m q) are selected
+// immediates applied under a predicate (q = 0: none) instead of a table: no shared-memory traffic.
+AVFE_HD void fft_stage2(int l, const float2* S, float2 (&x)[16]) {
+  // W32^m = exp(-2 pi i m / 32), m = 1..15
+  constexpr float kC[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                            0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f,
+                            0.0f, -0.19509032201612825f, -0.38268343236508977f, -0.55557023301960218f,
+                            -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+  constexpr float kS[16] = {0.0f, -0.19509032201612825f, -0.38268343236508977f, -0.55557023301960218f,
+                            -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f,
+                            -1.0f, -0.98078528040323043f, -0.92387953251128674f, -0.83146961230254524f,
+                            -0.70710678118654752f, -0.55557023301960218f, -0.38268343236508977f, -0.19509032201612825f};
   const int r = l & 15, q = l >> 4;
   const float2* row = S + r * kSRow;
   const float sgn = q ? -1.0f : 1.0f;
-  x[0] = caxpy(sgn, row[16], row[0]);
 #pragma unroll
-  for (int m = 1; m < 16; ++m) x[m] = cmul(caxpy(sgn, row[m + 16], row[m]), tw2[q * 16 + m]);
+  for (int m = 0; m < 16; ++m) x[m] = caxpy(sgn, row[m + 16], row[m]);
+  if (q) {                                                           // predicated multiplies by immediates
+#pragma unroll
+    for (int m = 1; m < 16; ++m) x[m] = cmul(x[m], make_float2(kC[m], kS[m]));
+  }
   dft16(x);
 }
 

@@ -86,15 +86,26 @@ __device__ __forceinline__ void piece_loads(const float* __restrict__ src, uint3
                                             int j, float (&v)[kLeafMax / 8], float& tail) {
   const uint32_t body = len & ~7u;
   const float* __restrict__ mine = src + start + j;        // one address per lane, constant offsets from it
+  if (!WRAP && len >= 64u) {                                // every piece of a tree deeper than its root has >= 64 elements
 #pragma unroll
-  for (int t = 0; t < kLeafMax / 8; ++t) {
-    v[t] = 0.f;
-    if ((uint32_t)(8 * t) < body) v[t] = WRAP ? src[(start + (uint32_t)(8 * t + j)) % period] : mine[8 * t];
+    for (int t = 0; t < 8; ++t) v[t] = mine[8 * t];
+#pragma unroll
+    for (int t = 8; t < kLeafMax / 8; ++t) {
+      v[t] = 0.f;
+      if ((uint32_t)(8 * t) < body) v[t] = mine[8 * t];
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < kLeafMax / 8; ++t) {
+      v[t] = 0.f;
+      if ((uint32_t)(8 * t) < body) v[t] = WRAP ? src[(start + (uint32_t)(8 * t + j)) % period] : mine[8 * t];
+    }
   }
   tail = 0.f;
   if (body + (uint32_t)j < len) tail = WRAP ? src[(start + body + (uint32_t)j) % period] : mine[body];
 }
 
+template <bool TAIL = true>
 __device__ __forceinline__ float piece_sum(const float (&v)[kLeafMax / 8], float tail) {
   float r = __fmul_rn(v[0], v[0]);
 #pragma unroll
@@ -102,9 +113,11 @@ __device__ __forceinline__ float piece_sum(const float (&v)[kLeafMax / 8], float
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
   r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-  tail = __fmul_rn(tail, tail);
+  if (TAIL) {                                                // leftover (< 8) elements, added one by one
+    tail = __fmul_rn(tail, tail);
 #pragma unroll
-  for (int u = 0; u < 7; ++u) r = __fadd_rn(r, __shfl_sync(0xffffffffu, tail, u, 8));
+    for (int u = 0; u < 7; ++u) r = __fadd_rn(r, __shfl_sync(0xffffffffu, tail, u, 8));
+  }
   return r;
 }
 
@@ -427,6 +440,350 @@ noise_mix_kernel(MixArgs m) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same pipeline in ONE launch per batch: a thread-block cluster owns a clip, so that the clip's
+// two waveforms cross HBM once (the mix re-reads them from L2 a few microseconds after the sums).
+//
+// CTA `rank` of a CS-CTA cluster owns the subtree under heap node CS + rank of numpy's pairwise
+// tree (depth log2 CS), i.e. one contiguous CS-th of the clip:
+//   1. leaf sums of its pieces straight into a LOCAL heap in shared memory (same walk as
+//      noise_leaf_kernel, started at the subtree's root),
+//   2. the subtree is added up in shared memory (node lengths top-down, children bottom-up),
+//   3. the CS pairs of partial sums are exchanged through distributed shared memory (every CTA stores
+//      its pair into every CTA's table), one cluster barrier, and every CTA adds the top log2 CS
+//      levels in numpy's order and derives the gain -- redundantly, with the same roundings,
+//   4. the CTA mixes its own stretch (still in L2), provisional int16 / float output, per-clip max / min
+//      through the same order-preserving atomics; the rescale pass stays noise_mix_kernel<true>.
+// A clip too short to have CS * 256 samples is handled by CTA 0 alone from the root (its tree may
+// end above depth log2 CS).  The exchange table is double-buffered: a CTA that is two clips ahead
+// has passed a barrier every other CTA has arrived at, hence nobody still reads the older entry.
+constexpr int kClusterThreads = 512;                       // two CTAs per SM (of different clips: their phases overlap)
+constexpr int kClusterMaxLocalDepth = 12;                    // 8192 slots per signal: 80 KB of shared memory
+
+struct ClusterSmem {
+  float2 xch[2][8];                                          // partial sums (clean, noise) of every rank
+  float gain;
+  uint32_t pad[3];
+  float heap[1];                                             // [2][slots] sums, then [slots / 2] node lengths
+};
+
+// the leaf piece under (off, len) that holds element pos: local heap index (root = 1), offset, length
+__device__ __forceinline__ uint32_t locate_piece_from(uint32_t pos, uint32_t& off, uint32_t& len) {
+  uint32_t k = 1;
+  while (len > (uint32_t)kLeafMax) {
+    const uint32_t half = (len >> 1) & ~7u;
+    if (pos < off + half) {
+      len = half;
+      k = 2 * k;
+    } else {
+      off += half;
+      len -= half;
+      k = 2 * k + 1;
+    }
+  }
+  return k;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(kClusterThreads, 2)
+noise_cluster_kernel(MixArgs m, int local_depth) {
+  extern __shared__ __align__(16) unsigned char cl_raw[];
+  ClusterSmem& sm = *reinterpret_cast<ClusterSmem*>(cl_raw);
+  const NoiseArgs& a = m.n;
+  const uint32_t slots = 2u << local_depth;
+  float* hc = sm.heap;
+  float* hz = sm.heap + slots;
+  uint32_t* len_s = reinterpret_cast<uint32_t*>(sm.heap + 2 * slots);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned rank = 0;
+  if (CS > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    // "I am running": waited for just before the first remote store (a CTA's shared memory must not be
+    // written before the CTA has started)
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  }
+  const int64_t b = blockIdx.x / CS;
+  const int64_t c0 = a.clean_offsets[b];
+  const uint32_t n = (uint32_t)(a.clean_offsets[b + 1] - c0);
+  const int64_t z0 = a.noise_offsets[b];
+  const uint32_t period = (uint32_t)(a.noise_offsets[b + 1] - z0);
+  const float* __restrict__ clean = a.clean + c0;
+  const float* __restrict__ noise = a.noise + z0;
+
+  // this CTA's subtree: node CS + rank when the tree is full down to that depth, else the root for rank 0
+  const bool split = CS > 1 && n >= (uint32_t)(256 * CS);
+  uint32_t off_r = 0, len_r = (split || rank == 0) ? n : 0u;
+  if (split) {
+#pragma unroll
+    for (int d = 0; (1 << d) < CS; ++d) {                    // walk the bits of `rank` from the top
+      const uint32_t half = (len_r >> 1) & ~7u;
+      constexpr int kLog = (CS == 8) ? 3 : (CS == 4) ? 2 : 1;
+      if ((rank >> (kLog - 1 - d)) & 1u) { off_r += half; len_r -= half; } else { len_r = half; }
+    }
+  }
+  if (rank == 0 && tid == 0) {                               // armed before the barrier: every CTA's atomics come after it
+    a.clips[b].max_key = 0u;
+    a.clips[b].min_key = 0xffffffffu;
+  }
+
+  // ---- 0. ask L2 for the whole stretch at once (bulk prefetch, 16 KB per instruction): the leaf rounds
+  // below are a chain of dependent round trips per warp, which then go to L2 instead of HBM ----
+  if (len_r > 0) {
+    auto prefetch_range = [&](const float* first, const float* last, int shift) {
+      const uintptr_t a0 = (reinterpret_cast<uintptr_t>(first) + 15u) & ~(uintptr_t)15u;
+      const uintptr_t a1 = reinterpret_cast<uintptr_t>(last) & ~(uintptr_t)15u;
+      constexpr uintptr_t kChunk = 16384;
+      if (a1 <= a0) return;
+      const uint32_t nch = (uint32_t)((a1 - a0 + kChunk - 1) / kChunk);
+      for (uint32_t c = (uint32_t)((tid + kClusterThreads - shift) % kClusterThreads); c < nch; c += kClusterThreads) {
+        const uintptr_t at = a0 + (uintptr_t)c * kChunk;
+        const uint32_t bytes = (uint32_t)min((uintptr_t)kChunk, a1 - at);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(at), "r"(bytes) : "memory");
+      }
+    };
+    prefetch_range(clean + off_r, clean + off_r + len_r, 0);
+    if (period > 0) {
+      const uint32_t q0 = off_r % period;
+      const uint32_t e1 = min(q0 + len_r, period);                       // [q0, e1), then the wrapped part [0, e2)
+      prefetch_range(noise + q0, noise + e1, 32);
+      if (q0 + len_r > period) prefetch_range(noise, noise + min(q0 + len_r - period, q0), 64);
+    }
+  }
+
+  // ---- 1. leaf sums of the pieces of [off_r, off_r + len_r) ----
+  if (len_r > 0) {
+    const int j = lane & 7, grp = lane >> 3;
+    const uint32_t first = (off_r + 63u) >> 6, end = off_r + len_r;     // multiples of 64 inside the stretch
+    const uint32_t count = ((end - 1u) >> 6) >= first ? ((end - 1u) >> 6) - first + 1u : 0u;
+    for (uint32_t blk = (uint32_t)wid; blk * 32u < count; blk += kClusterThreads / 32) {
+      const uint32_t idx = blk * 32u + (uint32_t)lane;
+      const uint32_t pos = (first + idx) << 6;
+      uint32_t k = 0, off = off_r, len = len_r, p0 = 0;
+      if (idx < count) {
+        k = locate_piece_from(pos, off, len);
+        if (pos - off >= 64u) k = 0;                         // the piece belongs to the lane before
+        if (period > 0) p0 = off % period;
+      }
+      uint32_t owners = __ballot_sync(0xffffffffu, k != 0);
+      // pieces whose length is not a multiple of 8 exist only on the right edge of the tree: the
+      // seven-shuffle tail is skipped for the rounds (almost all) that have none
+      const uint32_t tails = __ballot_sync(0xffffffffu, k != 0 && (len & 7u) != 0);
+#pragma unroll 1
+      while (owners != 0u) {
+        // the four lowest owners, one per 8-lane group
+        uint32_t mleft = owners;
+        int cand = lane;
+        bool has = false;
+#pragma unroll
+        for (int gsel = 0; gsel < 4; ++gsel) {
+          const int pos = __ffs((int)mleft) - 1;             // -1 when the set is exhausted
+          if (gsel == grp) { has = pos >= 0; cand = has ? pos : lane; }
+          mleft &= mleft - 1u;
+        }
+        const uint32_t round_set = owners & ~mleft;
+        owners = mleft;
+        const uint32_t k_any = __shfl_sync(0xffffffffu, k, cand);
+        const uint32_t kk = has ? k_any : 0u;
+        const uint32_t o = __shfl_sync(0xffffffffu, off, cand);
+        const uint32_t l_any = __shfl_sync(0xffffffffu, len, cand);
+        const uint32_t l = kk ? l_any : 0u;
+        const uint32_t q = __shfl_sync(0xffffffffu, p0, cand);
+        float vc[kLeafMax / 8], vz[kLeafMax / 8], tc, tz;
+        piece_loads<false>(clean, o, l, 0u, j, vc, tc);
+        const uint32_t lz = period > 0 ? l : 0u;
+        if (q + lz <= period) {
+          piece_loads<false>(noise, q, lz, period, j, vz, tz);
+        } else {
+          piece_loads<true>(noise, q, lz, period, j, vz, tz);
+        }
+        float sc, sz;
+        if (round_set & tails) {                             // warp-uniform
+          sc = piece_sum<true>(vc, tc);
+          sz = piece_sum<true>(vz, tz);
+        } else {
+          sc = piece_sum<false>(vc, tc);
+          sz = piece_sum<false>(vz, tz);
+        }
+        if (kk != 0 && kk < slots && j < 2) (j ? hz : hc)[kk] = j ? sz : sc;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. the subtree, in shared memory ----
+  if (len_r > (uint32_t)kLeafMax) {
+    if (tid == 0) len_s[1] = len_r;
+    __syncthreads();
+    for (int d = 0; d + 1 < local_depth; ++d) {
+      for (uint32_t k = (1u << d) + tid; k < (2u << d); k += kClusterThreads) {
+        const uint32_t len = len_s[k];
+        const uint32_t half = len > (uint32_t)kLeafMax ? (len >> 1) & ~7u : 0u;
+        len_s[2 * k] = half;
+        len_s[2 * k + 1] = len > (uint32_t)kLeafMax ? len - half : 0u;
+      }
+      __syncthreads();
+    }
+    for (int d = local_depth - 1; d >= 0; --d) {
+      for (uint32_t k = (1u << d) + tid; k < (2u << d); k += kClusterThreads)
+        if (len_s[k] > (uint32_t)kLeafMax) {
+          hc[k] = __fadd_rn(hc[2 * k], hc[2 * k + 1]);
+          hz[k] = __fadd_rn(hz[2 * k], hz[2 * k + 1]);
+        }
+      __syncthreads();
+    }
+  }
+
+  // ---- 3. exchange, top levels, gain ----
+  const int par = (int)(b & 1);       // one clip per cluster and launch: the table is written once; parity kept for striding callers
+  if (CS > 1) {
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");      // every CTA of the cluster has started
+    if (tid < CS) {
+      const float2 mine = make_float2(len_r > 0 ? hc[1] : 0.f, len_r > 0 ? hz[1] : 0.f);
+      const unsigned local = (unsigned)__cvta_generic_to_shared(&sm.xch[par][rank]);
+      unsigned remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((unsigned)tid));
+      asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(mine.x), "f"(mine.y) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    if (tid == 0) sm.xch[par][0] = make_float2(hc[1], hz[1]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float sc, sz;
+    if (split) {
+      float pc[8], pz[8];
+#pragma unroll
+      for (int r = 0; r < CS; ++r) { pc[r] = sm.xch[par][r].x; pz[r] = sm.xch[par][r].y; }
+#pragma unroll
+      for (int w = CS; w > 1; w >>= 1)
+#pragma unroll
+        for (int r = 0; r < w / 2; ++r) {
+          pc[r] = __fadd_rn(pc[2 * r], pc[2 * r + 1]);
+          pz[r] = __fadd_rn(pz[2 * r], pz[2 * r + 1]);
+        }
+      sc = pc[0];
+      sz = pz[0];
+    } else {
+      sc = sm.xch[par][0].x;
+      sz = sm.xch[par][0].y;
+    }
+    float gain = 0.f;
+    if (n > 0 && period > 0) {
+      const float clean_ms = __double2float_rn(__ddiv_rn((double)sc, (double)n));
+      const float noise_ms = __double2float_rn(__ddiv_rn((double)sz, (double)n));
+      const float clean_rms = __fsqrt_rn(clean_ms), noise_rms = __fsqrt_rn(noise_ms);
+      gain = __fdiv_rn(__fdiv_rn(clean_rms, a.snr_ratio[b]), noise_rms);
+    }
+    sm.gain = gain;
+    if (rank == 0) a.clips[b].gain = gain;
+  }
+  __syncthreads();
+  if (len_r == 0) return;
+  const float gain = sm.gain;
+
+  // ---- 4. the mix of [off_r, off_r + len_r): full groups of four samples on absolute 16-byte boundaries
+  // (32-bit indices from the first group, nothing to test per sample), the <= 3 samples in front of
+  // and behind them one thread each ----
+  const int64_t lo = c0 + off_r, hi = lo + len_r;            // absolute sample range in the packed buffer
+  const int64_t a_lo = min((lo + 3) & ~(int64_t)3, hi), a_hi = max(hi & ~(int64_t)3, a_lo);
+  const uint32_t nb = (uint32_t)((a_hi - a_lo) >> 2);         // full groups
+  const bool noise_vec = ((reinterpret_cast<uintptr_t>(noise) & 15u) == 0);
+  const uint32_t per = period ? period : 1u;
+  float vmax = -INFINITY, vmin = INFINITY;
+  auto mix1 = [&](float x, float z) -> float { return period > 0 ? __fadd_rn(x, __fmul_rn(z, gain)) : x; };
+  {                                                           // edges: samples [lo, a_lo) and [a_hi, hi)
+    const int64_t s = tid < 3 ? lo + tid : a_hi + (tid - 32);
+    const bool mine = tid < 3 ? s < a_lo : (tid >= 32 && tid < 35 && s < hi);
+    if (mine) {
+      const float v = mix1(a.clean[s], period > 0 ? noise[(uint32_t)(s - c0) % per] : 0.f);
+      vmax = v;
+      vmin = v;
+      const int16_t q = to_i16(v);
+      if (m.out_i16) m.out_i16[s] = q;
+      if (m.out_f32) m.out_f32[s] = (float)q;
+    }
+  }
+  const float4* __restrict__ xb = reinterpret_cast<const float4*>(a.clean + a_lo);
+  const uint32_t step = (uint32_t)((4u * kClusterThreads) % per);
+  uint32_t p = (uint32_t)((uint64_t)(a_lo - c0 + 4 * (int64_t)tid) % per);   // noise position of this thread's group
+  constexpr int kU = 4;                                       // groups in flight per thread
+  for (uint32_t g0 = (uint32_t)tid; g0 < nb; g0 += kU * kClusterThreads) {
+    float4 x[kU], z[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint32_t g = g0 + u * kClusterThreads;
+      x[u] = z[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < nb) {
+        x[u] = xb[g];
+        if (period > 0) {
+          if (noise_vec && (p & 3u) == 0 && p + 4 <= period) {
+            z[u] = *reinterpret_cast<const float4*>(noise + p);
+          } else if (p + 4 <= period) {
+            z[u] = make_float4(noise[p], noise[p + 1], noise[p + 2], noise[p + 3]);
+          } else {
+            z[u] = make_float4(noise[p], noise[(p + 1) % period], noise[(p + 2) % period], noise[(p + 3) % period]);
+          }
+        }
+      }
+      p += step;
+      if (p >= per) p -= per;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint32_t g = g0 + u * kClusterThreads;
+      if (g >= nb) break;
+      const float v0 = mix1(x[u].x, z[u].x), v1 = mix1(x[u].y, z[u].y), v2 = mix1(x[u].z, z[u].z), v3 = mix1(x[u].w, z[u].w);
+      vmax = fmaxf(fmaxf(vmax, fmaxf(v0, v1)), fmaxf(v2, v3));
+      vmin = fminf(fminf(vmin, fminf(v0, v1)), fminf(v2, v3));
+      const int16_t q0 = to_i16(v0), q1 = to_i16(v1), q2 = to_i16(v2), q3 = to_i16(v3);
+      const int64_t s = a_lo + 4 * (int64_t)g;
+      if (m.out_i16) {
+        const uint32_t w0 = (uint16_t)q0 | ((uint32_t)(uint16_t)q1 << 16);
+        const uint32_t w1 = (uint16_t)q2 | ((uint32_t)(uint16_t)q3 << 16);
+        *reinterpret_cast<uint2*>(m.out_i16 + s) = make_uint2(w0, w1);
+      }
+      if (m.out_f32) *reinterpret_cast<float4*>(m.out_f32 + s) = make_float4((float)q0, (float)q1, (float)q2, (float)q3);
+    }
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, sft));
+  }
+  if (lane == 0 && vmax >= vmin) {
+    atomicMax(&a.clips[b].max_key, float_key(vmax));
+    atomicMin(&a.clips[b].min_key, float_key(vmin));
+  }
+}
+
+template <int CS>
+static int launch_noise_cluster(const MixArgs& m, int64_t B, int local_depth, cudaStream_t s) {
+  const size_t slots = (size_t)2 << local_depth;
+  const size_t smem = offsetof(ClusterSmem, heap) + (2 * slots + slots / 2) * sizeof(float);
+  if (cudaFuncSetAttribute(noise_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CS));
+  cfg.blockDim = dim3(kClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, noise_cluster_kernel<CS>, m, local_depth) != cudaSuccess) {
+    cudaGetLastError();
+    return AVFE_ERR_CUDA;
+  }
+  return AVFE_OK;
+}
+
 inline size_t noise_heap_bytes(int64_t B, int depth) {
   return (size_t)B * 2 * ((size_t)2 << depth) * sizeof(float);
 }
@@ -471,6 +828,28 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
   m.n.depth = depth;
   m.out_i16 = out_i16;
   m.out_f32 = out_f32;
+  const unsigned chunks_rs = (unsigned)((max_len + 3 + kMixChunk - 1) / kMixChunk);
+  // one launch per batch, a cluster per clip (the waveforms cross HBM once); cluster width by clip length
+  {
+    const int cs = max_len >= 131072 ? 8 : max_len >= 32768 ? 4 : max_len >= 8192 ? 2 : 1;
+    const int log_cs = cs == 8 ? 3 : cs == 4 ? 2 : cs == 2 ? 1 : 0;
+    // local heap depth: the subtree of a split clip, or a whole clip shorter than 256 * cs samples
+    int local_depth = depth - log_cs;
+    const int short_depth = tree_depth((int64_t)256 * cs);
+    if (local_depth < short_depth) local_depth = short_depth;
+    if (local_depth < 1) local_depth = 1;
+    if (local_depth <= kClusterMaxLocalDepth && B * cs <= 0x7fffffffLL) {
+      int rc = cs == 8 ? launch_noise_cluster<8>(m, B, local_depth, s)
+             : cs == 4 ? launch_noise_cluster<4>(m, B, local_depth, s)
+             : cs == 2 ? launch_noise_cluster<2>(m, B, local_depth, s)
+                       : launch_noise_cluster<1>(m, B, local_depth, s);
+      if (rc != AVFE_OK) return rc;
+      noise_mix_kernel<true><<<dim3(chunks_rs < 16u ? chunks_rs : 16u, (unsigned)B), 256, 0, s>>>(m);
+      count_launch(2);
+      return check_launch();
+    }
+  }
+  // clips too long for the cluster kernel's shared-memory heap: leaf sums, combine, mix as separate launches
   // small CTAs (4 warps = 8192 samples) scheduled by the hardware: 39 us on 64 x 30 s, against 43.5 us
   // with 8-warp CTAs (3.2 waves) and 49-61 us with one resident wave of striding CTAs (the warps' rounds
   // are serial, so static striding leaves the tail uneven)

@@ -70,12 +70,10 @@ void hc_logmel_tile(const float* clip, int64_t L, int64_t Lp, int64_t t0, int n_
 void hc_logfbank_pair(const float* clip, int64_t len, int64_t fa, int64_t fb, int nfilt, const float* fbank,
                       float* out) {
   using namespace fbk;
-  std::vector<float2> tw1(16 * 32), tw2(2 * 16);
+  std::vector<float2> tw1(16 * 32);
   auto w512 = [](int e) { return make_float2((float)cos(-2.0 * M_PI * e / kNfft), (float)sin(-2.0 * M_PI * e / kNfft)); };
   for (int r = 0; r < 16; ++r)
     for (int l = 0; l < 32; ++l) tw1[r * 32 + l] = w512(tw1_index(r, l));
-  for (int q = 0; q < 2; ++q)
-    for (int m = 0; m < 16; ++m) tw2[q * 16 + m] = w512(tw2_index(q, m));
   std::vector<float> ya(kFrame), yb(kFrame);
   for (int n = 0; n < kFrame; ++n) {
     ya[n] = preemph_sample(clip, len, fa * kHop + n);
@@ -86,7 +84,7 @@ void hc_logfbank_pair(const float* clip, int64_t len, int64_t fa, int64_t fb, in
   float2* U = reinterpret_cast<float2*>(slot.data() + kUOffset);
   for (int l = 0; l < 32; ++l) fft_stage1(l, ya.data(), yb.data(), tw1.data(), S);
   std::vector<float2> regs(32 * 16);
-  for (int l = 0; l < 32; ++l) fft_stage2(l, S, tw2.data(), *reinterpret_cast<float2(*)[16]>(&regs[l * 16]));
+  for (int l = 0; l < 32; ++l) fft_stage2(l, S, *reinterpret_cast<float2(*)[16]>(&regs[l * 16]));
   for (int l = 0; l < 32; ++l) fft_upper_store(l, *reinterpret_cast<float2(*)[16]>(&regs[l * 16]), U);
   for (int l = 0; l < 32; ++l)
     fft_power(l, *reinterpret_cast<float2(*)[16]>(&regs[l * 16]), U, slot.data(), slot.data() + kPRow);

@@ -165,16 +165,39 @@ def test_full_size_batch_two_clips_checked():
     np.testing.assert_array_equal(got[5], want5)
 
 
-def test_clip_longer_than_the_shared_memory_heap():
-    """A 70 s clip needs a depth-14 tree: its heaps no longer fit in shared memory and the combine
-    kernel takes the global-memory path; a second, short clip in the same batch shares the launch."""
+@pytest.mark.parametrize("seconds", [70, 231])
+def test_long_clips(seconds):
+    """70 s: a depth-14 tree, the deepest local heaps of the cluster kernel (one launch per batch; a
+    second, short clip in the same batch is handled by CTA 0 of its cluster alone).  231 s: depth 16
+    exceeds the cluster kernel's shared-memory heap, the library falls back to separate leaf /
+    combine (global-memory path) / mix launches."""
     import torch
     import avsl_b200 as A
     rng = np.random.default_rng(11)
-    L = 70 * 16000 + 13
+    L = seconds * 16000 + 13
     clean = rng.integers(-8000, 8001, size=L + 4000).astype(np.float32)
     noise = rng.integers(-2000, 2001, size=50001 + 977).astype(np.float32)
     co, no = [0, L, L + 4000], [0, 50001, 50001 + 977]
     want = ON.add_noise_batch(clean, co, noise, no, [3.0, -2.0])
     got = A.add_noise_batch(torch.from_numpy(clean).cuda(), co, torch.from_numpy(noise).cuda(), no, [3.0, -2.0]).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("max_len", [300, 9000, 40000, 140000])
+def test_every_cluster_width(max_len):
+    """The cluster width follows the longest clip (1, 2, 4, 8 CTAs per clip); every width sees clips
+    from one sample up to the longest, unaligned starts, short and long noise."""
+    import torch
+    import avsl_b200 as A
+    rng = np.random.default_rng(max_len)
+    lens = [max_len, 1, 7, 129, 255, 256 * 2, 256 * 4 - 1, 256 * 8 + 3, max_len // 2 + 5, max_len - 1]
+    lens = [min(n, max_len) for n in lens]
+    nlens = [int(rng.integers(1, 3 * n + 2)) for n in lens]
+    co = np.concatenate([[0], np.cumsum(lens)])
+    no = np.concatenate([[0], np.cumsum(nlens)])
+    clean = rng.integers(-9000, 9001, size=co[-1]).astype(np.float32)
+    noise = rng.integers(-3000, 3001, size=no[-1]).astype(np.float32)
+    snr = [float(v) for v in rng.integers(-15, 20, size=len(lens))]
+    want = ON.add_noise_batch(clean, co, noise, no, snr)
+    got = A.add_noise_batch(torch.from_numpy(clean).cuda(), co, torch.from_numpy(noise).cuda(), no, snr).cpu().numpy()
     np.testing.assert_array_equal(got, want)
