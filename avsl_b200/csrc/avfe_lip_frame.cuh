@@ -95,6 +95,25 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       "r"(parity), "r"(0x989680u)                       // suspend-time hint (ns); the wait is re-armed if it expires
       : "memory");
 }
+// the same for a warp that is far ahead of its consumers (the tform warps): one probe, then sleep --
+// a polling warp costs the stream warps issue slots (10 % of the kernel's instructions were SYNCS /
+// BRA / NANOSLEEP of such loops, profiles/r01/lip_frame_kernel_final4_by_line.txt)
+__device__ __forceinline__ void mbar_wait_idle(void* bar, unsigned parity, unsigned sleep_ns) {
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(sleep_ns);
+  }
+}
 // global -> shared bulk copy (TMA, 1-D); completion is signalled on `bar` as transaction bytes
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar,
                                           unsigned long long policy) {
@@ -129,7 +148,7 @@ __device__ __forceinline__ void frame_tform_run(const FrameJob& j, FrameSmem<SPA
     int64_t dst;
     const FrameXform x = tform_frame(j.tf, f, lane, dst);
     const int slot = k % kDescRing, use = k / kDescRing;
-    if (use > 0) mbar_wait(&sm.desc_empty[slot], (unsigned)(use - 1) & 1u);   // every reader is done with it
+    if (use > 0) mbar_wait_idle(&sm.desc_empty[slot], (unsigned)(use - 1) & 1u, 1000u);   // every reader is done with it; a frame takes ~6 us
     if (lane == 0) {
       sm.desc[slot] = x;
       sm.dst[slot] = dst;
