@@ -272,7 +272,7 @@ class AVFrontEnd:
         zc = self.zero_copy(batch)
         dev = batch.to(self.device, non_blocking=True, frames_stay_on_host=zc)
         lip_out = None
-        if zc:      # the blend warps store the lip features across PCIe themselves: no device buffer, no D2H copy
+        if zc and getattr(self, "lip_direct", True):      # the blend warps store the lip features across PCIe themselves: no device buffer, no D2H copy
             lip_out = pinned("lip", (int(batch.frames.shape[0]), self.crop, self.crop, 1), torch.float32).squeeze(-1)
         res = self.forward_device(dev, reuse=True, lip_out=lip_out)   # device results are copied out before the buffers are reused
         for k in self.host_keys(res):
