@@ -80,9 +80,36 @@ def run_fuse_ln(iters):
     torch.cuda.synchronize()
 
 
+def run_fuse_ln_tma(iters):
+    """the padded-pitch layout ([B, C, 752] allocation): tensor-map TMA tile fill"""
+    for dtype in (torch.float32, torch.float16):
+        fa0, fv0, mask = synth.fusion_inputs(64, 1024, 750, device="cuda")
+        fa, fv = A.alloc_features(64, 1024, 750, dtype, "cuda"), A.alloc_features(64, 1024, 750, dtype, "cuda")
+        fa.copy_(fa0.to(dtype)); fv.copy_(fv0.to(dtype))
+        w, b = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
+        out = None
+        for _ in range(iters):
+            out = A.fuse_transpose_layernorm(fa, fv, mask, "concat", w, b, out=out)
+    torch.cuda.synchronize()
+
+
+def run_proj(iters):
+    """post_extract_proj behind the folded LayerNorm: pep_stats_kernel + pep_gemm2_kernel (tcgen05)"""
+    B, C, T, D = 64, 1024, 750, 1024
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fa, fv = A.alloc_features(B, C, T, torch.float16, "cuda"), A.alloc_features(B, C, T, torch.float16, "cuda")
+    fa.copy_(torch.randn(B, C, T, generator=g, device="cuda").half()); fv.copy_(torch.randn(B, C, T, generator=g, device="cuda").half())
+    W = torch.randn(D, 2 * C, generator=g, device="cuda") / (2 * C) ** 0.5
+    folded = A.FoldedProjection(W, torch.zeros(D, device="cuda"), torch.ones(2 * C, device="cuda"), torch.zeros(2 * C, device="cuda"), torch.float16)
+    out = torch.empty((B, T, D), dtype=torch.float16, device="cuda")
+    for _ in range(iters):
+        A.fuse_layernorm_project(fa, fv, None, folded, out=out)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "logfbank", "noise", "all"])
+    ap.add_argument("which", choices=["logmel", "lip", "fuse", "fuse_ln", "fuse_ln_tma", "proj", "logfbank", "noise", "all"])
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     if a.which in ("logmel", "all"):
@@ -97,4 +124,8 @@ if __name__ == "__main__":
         run_noise(a.iters)
     if a.which in ("fuse_ln", "all"):
         run_fuse_ln(a.iters)
+    if a.which in ("fuse_ln_tma", "all"):
+        run_fuse_ln_tma(a.iters)
+    if a.which in ("proj", "all"):
+        run_proj(a.iters)
     print("done", a.which)

@@ -77,7 +77,7 @@ def main():
     lc = os.path.join(src, f"{rnd}_launches_{tag}.csv")
     if os.path.exists(lc):
         launches(lc, dst, tag)
-    for key in ("lip", "logmel", "fuse", "fuseln", "noise", "logfbank"):
+    for key in ("lip", "logmel", "fuse", "fuseln", "fuselntma", "proj", "noise", "logfbank"):
         rep = os.path.join(src, f"{rnd}_{key}_{tag}.ncu-rep")
         if os.path.exists(rep):
             full(rep, key, dst, tag, lib)
