@@ -477,7 +477,7 @@ template <> __device__ __forceinline__ float cvt<__half>(__half v) { return __ha
 template <> __device__ __forceinline__ float cvt<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 pep_stats_kernel(const T* __restrict__ fa, const T* __restrict__ fv, const uint8_t* __restrict__ mask, int C, int Tn,
                  int64_t pitch, float eps, float2* __restrict__ stats) {
   __shared__ float red[8][2][64];
@@ -517,13 +517,24 @@ pep_stats_kernel(const T* __restrict__ fa, const T* __restrict__ fv, const uint8
     // eight independent 16-byte loads per lane in flight (the loop is latency-bound otherwise)
     int c = wid * 4 + rsub;
     for (; c + 7 * 32 < C; c += 8 * 32) {
-      float x[8][8];
+      if (full) {                                        // the loads stay packed (32 registers instead of 64) until they are used
+        uint4 q[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) load8(base, c + 32 * u, x[u]);
+        for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const uint4*>(base + ((int64_t)b * C + c + 32 * u) * pitch + t0 + tl);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 8; ++u) {
+          const T* e = reinterpret_cast<const T*>(&q[u]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = x[u][j] - K[j]; sum[j] += d; sq[j] += d * d; }
+          for (int j = 0; j < 8; ++j) { const float d = cvt<T>(e[j]) - K[j]; sum[j] += d; sq[j] += d * d; }
+        }
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+          float x[8];
+          load8(base, c + 32 * u, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = x[j] - K[j]; sum[j] += d; sq[j] += d * d; }
+        }
       }
     }
     for (; c < C; c += 32) {
