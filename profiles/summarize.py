@@ -81,14 +81,8 @@ def main():
         rep = os.path.join(src, f"{rnd}_{key}_{tag}.ncu-rep")
         if os.path.exists(rep):
             full(rep, key, dst, tag, lib)
-    for name in ("bench_n1_default.json", "bench_n1_reference.json", "bench_n2.json", "bench_n2_ref.json",
-                 "bench_n4.json", "bench_n8.json"):
-        p = os.path.join(src, name)
-        if os.path.exists(p):
-            # keep the JSON line only (torchrun / NCCL banners may precede it)
-            lines = [l for l in open(p) if l.startswith("{")]
-            if lines:
-                open(os.path.join(dst, name.replace(".json", f"_{tag}.json")), "w").write(lines[-1])
+    # bench lines are copied by hand from the run they belong to (gpurun_out/ keeps files of earlier
+    # rounds under the same names)
 
 
 if __name__ == "__main__":
