@@ -526,30 +526,6 @@ noise_cluster_kernel(MixArgs m, int local_depth) {
     a.clips[b].min_key = 0xffffffffu;
   }
 
-  // ---- 0. ask L2 for the whole stretch at once (bulk prefetch, 16 KB per instruction): the leaf rounds
-  // below are a chain of dependent round trips per warp, which then go to L2 instead of HBM ----
-  if (len_r > 0) {
-    auto prefetch_range = [&](const float* first, const float* last, int shift) {
-      const uintptr_t a0 = (reinterpret_cast<uintptr_t>(first) + 15u) & ~(uintptr_t)15u;
-      const uintptr_t a1 = reinterpret_cast<uintptr_t>(last) & ~(uintptr_t)15u;
-      constexpr uintptr_t kChunk = 16384;
-      if (a1 <= a0) return;
-      const uint32_t nch = (uint32_t)((a1 - a0 + kChunk - 1) / kChunk);
-      for (uint32_t c = (uint32_t)((tid + kClusterThreads - shift) % kClusterThreads); c < nch; c += kClusterThreads) {
-        const uintptr_t at = a0 + (uintptr_t)c * kChunk;
-        const uint32_t bytes = (uint32_t)min((uintptr_t)kChunk, a1 - at);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(at), "r"(bytes) : "memory");
-      }
-    };
-    prefetch_range(clean + off_r, clean + off_r + len_r, 0);
-    if (period > 0) {
-      const uint32_t q0 = off_r % period;
-      const uint32_t e1 = min(q0 + len_r, period);                       // [q0, e1), then the wrapped part [0, e2)
-      prefetch_range(noise + q0, noise + e1, 32);
-      if (q0 + len_r > period) prefetch_range(noise, noise + min(q0 + len_r - period, q0), 64);
-    }
-  }
-
   // ---- 1. leaf sums of the pieces of [off_r, off_r + len_r) ----
   if (len_r > 0) {
     const int j = lane & 7, grp = lane >> 3;
