@@ -80,11 +80,12 @@ __device__ __forceinline__ void fused_row(const uint8_t* tile_a, const uint8_t* 
   }
 }
 
-// CPL = channels per lane: 1 for float (a warp stores 32 floats = one line), 2 for the 16-bit types
-// (a lane stores a pair = 4 bytes)
+// The 16-bit types: one tile per CTA, four CTAs per SM (their tiles carry half the bytes for the same
+// arithmetic: they need the warps more than a second stage -- 59 % of the HBM peak like this, 48 % with the
+// two-stage ring below at three CTAs per SM).  CPL = channels per lane: 2 (a lane stores a pair = 4 bytes).
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
-fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Args a) {
+fuse_ln_tma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Args a) {
   constexpr int TT = kRowBytes / (int)sizeof(T);
   constexpr int CPL = (sizeof(T) == 4) ? 1 : 2;
   extern __shared__ __align__(1024) uint8_t flt_smem[];
@@ -231,6 +232,185 @@ fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+// CPL = channels per lane: 1 for float (a warp stores 32 floats = one line), 2 for the 16-bit types
+// (a lane stores a pair = 4 bytes).
+// Persistent CTAs with a two-deep tile ring: the TMA boxes of tile i+1 are requested before tile i is
+// touched, so a CTA hides its own TMA latency (before: one tile per CTA, latency hidden only by the
+// co-resident CTAs), and the barriers, the LayerNorm weights (32 registers) and the launch of 6,000-12,000
+// CTAs are paid once per CTA instead of once per 32 KB tile.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads, 3)
+fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Args a,
+                   const int n_tiles) {
+  constexpr int TT = kRowBytes / (int)sizeof(T);
+  constexpr int CPL = (sizeof(T) == 4) ? 1 : 2;
+  extern __shared__ __align__(1024) uint8_t flt_smem[];
+  uint8_t* tiles = flt_smem + ((1024u - (smem_u32(flt_smem) & 1023u)) & 1023u);
+  const size_t stage_bytes = 2 * (size_t)a.C * kRowBytes;                         // fa tile | fv tile
+  float* red = reinterpret_cast<float*>(tiles + 2 * stage_bytes);                 // [8 warps][2 TT], mean[TT], rstd[TT], K[TT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * 2 * TT + 3 * TT + (TT & 1));   // [2 stages][16]: one per 256 fused channels
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_blocks = a.Cout / kBoxRows;
+
+  auto sample_flags = [&](int64_t b) -> unsigned {
+    return a.mask == nullptr ? 3u : ((a.mask[2 * b] ? 1u : 0u) | (a.mask[2 * b + 1] ? 2u : 0u));
+  };
+  // One barrier per block of 256 fused channels, so that the moments pass can start on the first
+  // boxes while the later ones are still in flight.  concat: block q is one box (of fa or fv);
+  // add / weighted sum: block q is box q of both maps.
+  auto issue = [&](int tile, int st) {                  // thread 0 only
+    const int64_t b = tile / a.tiles_per_sample;
+    const int t0 = (tile % a.tiles_per_sample) * TT;
+    const unsigned m = sample_flags(b);
+    const bool has_a = (m & 1u) != 0, has_v = (m & 2u) != 0;
+    uint8_t* tile_a = tiles + st * stage_bytes;
+    uint8_t* tile_v = tile_a + (size_t)a.C * kRowBytes;
+    // the stage was read through the generic proxy one iteration ago: order those reads before the async writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int q = 0; q < n_blocks; ++q) {
+      const bool is_v = (MODE == AVFE_FUSE_CONCAT) && q * kBoxRows >= a.C;
+      const int c0 = is_v ? q * kBoxRows - a.C : q * kBoxRows;
+      const bool ld_a = (MODE == AVFE_FUSE_CONCAT) ? (!is_v && has_a) : has_a;
+      const bool ld_v = (MODE == AVFE_FUSE_CONCAT) ? (is_v && has_v) : has_v;
+      const unsigned bytes = (unsigned)((ld_a ? 1 : 0) + (ld_v ? 1 : 0)) * kBoxRows * kRowBytes;
+      uint64_t* bq = bar + st * 16 + q;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bq)), "r"(bytes) : "memory");
+      if (ld_a)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(tile_a + (size_t)c0 * kRowBytes)), "l"(&map_a), "r"(smem_u32(bq)), "r"(t0), "r"(c0), "r"((int)b) : "memory");
+      if (ld_v)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(smem_u32(tile_v + (size_t)c0 * kRowBytes)), "l"(&map_v), "r"(smem_u32(bq)), "r"(t0), "r"(c0), "r"((int)b) : "memory");
+    }
+  };
+  if (tid == 0) {
+    for (int q = 0; q < 2 * 16; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar + q)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < n_tiles) issue((int)blockIdx.x, 0);
+  }
+  // LayerNorm weight / bias of this thread's channels: fetched once, while the first tile is in flight
+  constexpr int kIter = 8;                              // channel groups per thread (C' <= 2048 * CPL)
+  float g[kIter][CPL], be[kIter][CPL];
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const int c = (tid + k * kThreads) * CPL;
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      g[k][u] = (a.gamma && c + u < a.Cout) ? a.gamma[c + u] : 1.0f;
+      be[k][u] = (a.beta && c + u < a.Cout) ? a.beta[c + u] : 0.0f;
+    }
+  }
+  __syncthreads();                                      // barriers initialised before anybody polls them
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const int st = it & 1;
+  const unsigned parity = (unsigned)(it >> 1) & 1u;
+  if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + (int)gridDim.x, st ^ 1);   // the other stage was drained one iteration ago
+  uint8_t* tile_a = tiles + st * stage_bytes;
+  uint8_t* tile_v = tile_a + (size_t)a.C * kRowBytes;
+  const int64_t b = tile / a.tiles_per_sample;
+  const int t0 = (tile % a.tiles_per_sample) * TT;
+  const int nt = min(TT, a.T - t0);
+  const unsigned m = sample_flags(b);
+  const bool has_a = (m & 1u) != 0, has_v = (m & 2u) != 0;
+  auto wait_block = [&](int q) {
+    asm volatile(
+        "{\n.reg .pred p;\nFLT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra FLT_WAIT;\n}" ::"r"(smem_u32(bar + st * 16 + q)), "r"(parity) : "memory");
+  };
+
+  // ---- pass 1: shifted moments per time step (K = fused channel 0), this thread's channels
+  float K[TT], s1[TT], s2[TT];
+  wait_block(0);
+  fused_row<T, MODE, TT>(tile_a, tile_v, 0, a.C, has_a, has_v, a.wa, a.wv, K);
+#pragma unroll
+  for (int i = 0; i < TT; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+  for (int c = tid * CPL; c < a.Cout; c += kThreads * CPL) {
+    // this round's channels are blocks [c0, c0 + CPL) for every thread of the CTA
+    const int q0 = (c - tid * CPL) / kBoxRows;
+#pragma unroll
+    for (int u = 0; u < CPL; ++u)
+      if (q0 + u < n_blocks) wait_block(q0 + u);
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      float x[TT];
+      fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x);
+#pragma unroll
+      for (int i = 0; i < TT; ++i) { const float d = x[i] - K[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+    }
+  }
+  // warp reduction by halving: after step k a lane keeps 2 TT / 2^k of the (s1 | s2) vector
+  float v[2 * TT];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) { v[i] = s1[i]; v[TT + i] = s2[i]; }
+  int idx = 0;                                          // first element index this lane still owns
+  constexpr int kFold = 32 / (2 * TT);                  // lanes that end up with the same element
+#pragma unroll
+  for (int half = TT, o = 16; half >= 1; half >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;                 // upper lanes keep the upper half of the vector
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[half + i];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+      v[i] = (upper ? v[half + i] : v[i]) + recv;
+    }
+    idx += upper ? half : 0;
+  }
+#pragma unroll
+  for (int o = kFold / 2; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  if ((lane & (kFold - 1)) == 0) red[wid * 2 * TT + idx] = v[0];
+  float* mean_s = red + 8 * 2 * TT;
+  float* rstd_s = mean_s + TT;
+  float* kref_s = rstd_s + TT;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < TT; ++i) kref_s[i] = K[i];
+  }
+  __syncthreads();
+  if (tid < TT) {
+    float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t1 += red[w * 2 * TT + tid]; t2 += red[w * 2 * TT + TT + tid]; }
+    const float n = (float)a.Cout;
+    const float md = t1 / n;
+    mean_s[tid] = kref_s[tid] + md;
+    rstd_s[tid] = rsqrtf(fmaxf((t2 - t1 * md) / n, 0.0f) + a.eps);
+  }
+  __syncthreads();
+
+  // ---- pass 2: normalise and store; a warp writes 32 * CPL consecutive channels of one time step
+  float mu[TT], rs[TT];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) { mu[i] = mean_s[i]; rs[i] = rstd_s[i]; }
+  T* out = static_cast<T*>(a.out) + (b * (int64_t)a.T + t0) * a.Cout;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const int c = (tid + k * kThreads) * CPL;
+    if (c >= a.Cout) break;
+    float x[CPL][TT];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x[u]);
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      if (i < nt) {
+        T* o = out + (int64_t)i * a.Cout + c;
+        if (CPL == 1) {
+          o[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
+        } else {
+          T pair[2];
+          pair[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
+          pair[1] = from_f32<T>(fmaf((x[CPL - 1][i] - mu[i]) * rs[i], g[k][CPL - 1], be[k][CPL - 1]));
+          *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(pair);
+        }
+      }
+    }
+  }
+  __syncthreads();                                      // the stage (and red / mean / rstd) may be reused
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -251,14 +431,31 @@ static EncodeTiledFn encode_fn() {
 template <typename T, int MODE>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mv, const Args& a, int64_t B, cudaStream_t s) {
   constexpr int TT = kRowBytes / (int)sizeof(T);
-  const size_t smem = 2 * (size_t)a.C * kRowBytes + (8 * 2 * TT + 3 * TT + 2) * sizeof(float) + 16 * 8 + 16 + 1024;
-  if (cudaFuncSetAttribute(fuse_ln_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError();
-    return AVFE_ERR_CUDA;
+  constexpr bool kRing = sizeof(T) == 4;                 // float: persistent CTAs with a two-stage ring
+  const size_t tile_bytes = 2 * (size_t)a.C * kRowBytes;
+  const size_t smem = (kRing ? 2 : 1) * tile_bytes + (8 * 2 * TT + 3 * TT + 2) * sizeof(float) + 2 * 16 * 8 + 16 + 1024;
+  const int64_t n_tiles = B * a.tiles_per_sample;
+  if (n_tiles > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
+  if constexpr (kRing) {
+    if (cudaFuncSetAttribute(fuse_ln_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+    int resident = 0;                                    // one resident wave of CTAs striding over the tiles
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fuse_ln_tma_kernel<T, MODE>, kThreads, smem) != cudaSuccess || resident < 1) {
+      cudaGetLastError();
+      resident = 1;
+    }
+    int64_t ctas = (int64_t)resident * kNumSMs;
+    if (ctas > n_tiles) ctas = n_tiles;
+    fuse_ln_tma_kernel<T, MODE><<<(unsigned)ctas, kThreads, smem, s>>>(ma, mv, a, (int)n_tiles);
+  } else {
+    if (cudaFuncSetAttribute(fuse_ln_tma_tile_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+    fuse_ln_tma_tile_kernel<T, MODE><<<(unsigned)n_tiles, kThreads, smem, s>>>(ma, mv, a);
   }
-  const int64_t ctas = B * a.tiles_per_sample;
-  if (ctas > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
-  fuse_ln_tma_kernel<T, MODE><<<(unsigned)ctas, kThreads, smem, s>>>(ma, mv, a);
   count_launch();
   return check_launch();
 }
