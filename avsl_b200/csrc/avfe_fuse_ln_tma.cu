@@ -161,7 +161,12 @@ fuse_ln_tma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       float x[TT];
       fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x);
 #pragma unroll
-      for (int i = 0; i < TT; ++i) { const float d = x[i] - K[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+      for (int i = 0; i < TT; i += 2) {                 // packed fp32x2 (FADD2 / FFMA2), the scalar roundings
+        const float2 d = __fadd2_rn(make_float2(x[i], x[i + 1]), make_float2(-K[i], -K[i + 1]));
+        const float2 t1 = __fadd2_rn(make_float2(s1[i], s1[i + 1]), d);
+        const float2 t2 = __ffma2_rn(d, d, make_float2(s2[i], s2[i + 1]));
+        s1[i] = t1.x; s1[i + 1] = t1.y; s2[i] = t2.x; s2[i + 1] = t2.y;
+      }
     }
   }
   // warp reduction by halving: after step k a lane keeps 2 TT / 2^k of the (s1 | s2) vector
@@ -215,16 +220,26 @@ fuse_ln_tma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     float x[CPL][TT];
 #pragma unroll
     for (int u = 0; u < CPL; ++u) fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x[u]);
+    // (x - mean) * rstd as packed fp32x2 over pairs of time steps, then the affine per channel
+#pragma unroll
+    for (int u = 0; u < CPL; ++u)
+#pragma unroll
+      for (int i = 0; i < TT; i += 2) {
+        const float2 h = __fmul2_rn(__fadd2_rn(make_float2(x[u][i], x[u][i + 1]), make_float2(-mu[i], -mu[i + 1])),
+                                    make_float2(rs[i], rs[i + 1]));
+        x[u][i] = fmaf(h.x, g[k][u], be[k][u]);
+        x[u][i + 1] = fmaf(h.y, g[k][u], be[k][u]);
+      }
 #pragma unroll
     for (int i = 0; i < TT; ++i) {
       if (i < nt) {
         T* o = out + (int64_t)i * a.Cout + c;
         if (CPL == 1) {
-          o[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
+          o[0] = from_f32<T>(x[0][i]);
         } else {
           T pair[2];
-          pair[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
-          pair[1] = from_f32<T>(fmaf((x[CPL - 1][i] - mu[i]) * rs[i], g[k][CPL - 1], be[k][CPL - 1]));
+          pair[0] = from_f32<T>(x[0][i]);
+          pair[1] = from_f32<T>(x[CPL - 1][i]);
           *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(pair);
         }
       }
@@ -338,7 +353,12 @@ fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       float x[TT];
       fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x);
 #pragma unroll
-      for (int i = 0; i < TT; ++i) { const float d = x[i] - K[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+      for (int i = 0; i < TT; i += 2) {                 // packed fp32x2 (FADD2 / FFMA2), the scalar roundings
+        const float2 d = __fadd2_rn(make_float2(x[i], x[i + 1]), make_float2(-K[i], -K[i + 1]));
+        const float2 t1 = __fadd2_rn(make_float2(s1[i], s1[i + 1]), d);
+        const float2 t2 = __ffma2_rn(d, d, make_float2(s2[i], s2[i + 1]));
+        s1[i] = t1.x; s1[i + 1] = t1.y; s2[i] = t2.x; s2[i + 1] = t2.y;
+      }
     }
   }
   // warp reduction by halving: after step k a lane keeps 2 TT / 2^k of the (s1 | s2) vector
@@ -392,16 +412,26 @@ fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     float x[CPL][TT];
 #pragma unroll
     for (int u = 0; u < CPL; ++u) fused_row<T, MODE, TT>(tile_a, tile_v, c + u, a.C, has_a, has_v, a.wa, a.wv, x[u]);
+    // (x - mean) * rstd as packed fp32x2 over pairs of time steps, then the affine per channel
+#pragma unroll
+    for (int u = 0; u < CPL; ++u)
+#pragma unroll
+      for (int i = 0; i < TT; i += 2) {
+        const float2 h = __fmul2_rn(__fadd2_rn(make_float2(x[u][i], x[u][i + 1]), make_float2(-mu[i], -mu[i + 1])),
+                                    make_float2(rs[i], rs[i + 1]));
+        x[u][i] = fmaf(h.x, g[k][u], be[k][u]);
+        x[u][i + 1] = fmaf(h.y, g[k][u], be[k][u]);
+      }
 #pragma unroll
     for (int i = 0; i < TT; ++i) {
       if (i < nt) {
         T* o = out + (int64_t)i * a.Cout + c;
         if (CPL == 1) {
-          o[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
+          o[0] = from_f32<T>(x[0][i]);
         } else {
           T pair[2];
-          pair[0] = from_f32<T>(fmaf((x[0][i] - mu[i]) * rs[i], g[k][0], be[k][0]));
-          pair[1] = from_f32<T>(fmaf((x[CPL - 1][i] - mu[i]) * rs[i], g[k][CPL - 1], be[k][CPL - 1]));
+          pair[0] = from_f32<T>(x[0][i]);
+          pair[1] = from_f32<T>(x[CPL - 1][i]);
           *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(pair);
         }
       }
