@@ -225,16 +225,14 @@ logfbank_kernel(const float* __restrict__ audio, const int64_t* __restrict__ off
           const int skip = h ? 4 * rc.z : 0, quads = h ? rc.w : rc.z;
           const float4* w4 = reinterpret_cast<const float4*>(sm.wts + rc.y + skip);
           const float* p = Pf + rc.x + skip;
-          float a0 = 0.0f, a1 = 0.0f;
+          float2 a01 = make_float2(0.0f, 0.0f);              // two accumulator chains as one packed fp32x2 chain (FFMA2)
 #pragma unroll 2
           for (int q = 0; q < quads; ++q) {
             const float4 c = w4[q];
-            a0 = fmaf(c.x, p[4 * q], a0);
-            a1 = fmaf(c.y, p[4 * q + 1], a1);
-            a0 = fmaf(c.z, p[4 * q + 2], a0);
-            a1 = fmaf(c.w, p[4 * q + 3], a1);
+            a01 = __ffma2_rn(make_float2(c.x, c.y), make_float2(p[4 * q], p[4 * q + 1]), a01);
+            a01 = __ffma2_rn(make_float2(c.z, c.w), make_float2(p[4 * q + 2], p[4 * q + 3]), a01);
           }
-          float acc = a0 + a1;
+          float acc = a01.x + a01.y;
           acc += __shfl_xor_sync(0xffffffffu, acc, 16);
           if (h == 0) sm.feat[f * nfilt + m] = live ? log_energy(acc) : 0.0f;
         }

@@ -525,7 +525,12 @@ pep_stats_kernel(const T* __restrict__ fa, const T* __restrict__ fv, const uint8
         for (int u = 0; u < 8; ++u) {
           const T* e = reinterpret_cast<const T*>(&q[u]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float d = cvt<T>(e[j]) - K[j]; sum[j] += d; sq[j] += d * d; }
+          for (int j = 0; j < 8; j += 2) {               // packed fp32x2 (FADD2 / FFMA2), the scalar roundings
+            const float2 d = __fadd2_rn(make_float2(cvt<T>(e[j]), cvt<T>(e[j + 1])), make_float2(-K[j], -K[j + 1]));
+            const float2 t1 = __fadd2_rn(make_float2(sum[j], sum[j + 1]), d);
+            const float2 t2 = __ffma2_rn(d, d, make_float2(sq[j], sq[j + 1]));
+            sum[j] = t1.x; sum[j + 1] = t1.y; sq[j] = t2.x; sq[j + 1] = t2.y;
+          }
         }
       } else {
 #pragma unroll 1
