@@ -830,6 +830,7 @@ def main():
                                    f"SCALED: dram__bytes_read+write per {tj['unit']} from the ncu --set full capture named in profiles/traffic.json "
                                    f"({tj.get('capture', 'r01')}), times this launch's {units} {tj['unit']}s; not a measurement of this launch"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kernel_bytes[dominant],
+                "frac_of_spec_sheet_8000_gbs": stages[dominant]["achieved_gbs"] / 8000.0,     # also quoted against the 8 TB/s spec sheet
                 "stages": stages,
                 "path": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 if world == 1 else alg_bytes_all * args.steps / (elapsed_ms * 1e-3) / 1e9,
                          "frac_of_peak_per_gpu": (alg_bytes_all / world) * args.steps / (elapsed_ms * 1e-3) / 1e9 / peak}}
