@@ -32,9 +32,12 @@
 //                         otherwise recomputes the mix, applies the reduction rate and rewrites
 //                         the clip.
 //
-// Algorithmic bytes per sample: 4 (clean) + 4 (noise, at most Ln of them) + 2 (int16 out); the
-// design reads both waveforms twice (sum of squares, then the mix), each pass touching every byte
-// once, which bounds it near half of the HBM roofline (measured: 33 %).
+// Algorithmic bytes per sample: 4 (clean) + 4 (noise, at most Ln of them) + 2 (int16 out).  The four
+// kernels above read both waveforms twice (sum of squares, then the mix); they are the fallback for
+// clips whose tree is too deep for a shared-memory heap.  The default path is noise_cluster_kernel
+// (further down): one launch per batch, a thread-block cluster per clip, partial sums exchanged
+// through distributed shared memory, the mix re-reading its stretch from L2 -- the waveforms cross HBM
+// once.
 #include "avfe_common.cuh"
 #include "avfe_noise_core.cuh"
 
