@@ -227,7 +227,7 @@ def test_modality_fusion_module_trains_and_no_grad_path_is_unchanged():
 # ------------------------------------------------------------------ TMA-filled fused LayerNorm (padded rows)
 @pytest.mark.parametrize("mode", ["concat", "add", "weighted_sum"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
-@pytest.mark.parametrize("B,C,T", [(3, 256, 37), (2, 1024, 750), (2, 512, 8)])
+@pytest.mark.parametrize("B,C,T", [(3, 256, 37), (2, 1024, 750), (2, 512, 8), (24, 256, 750)])   # the last: more tiles than resident CTAs
 def test_fuse_layernorm_tma_path_matches_oracle(mode, dtype, tol, B, C, T):
     """Feature maps in a padded allocation (row pitch a multiple of 16 bytes) take the tensor-map TMA
     kernel; same numbers as the oracle (the reference's torch ops) and as the LSU kernel."""
@@ -248,3 +248,21 @@ def test_fuse_layernorm_tma_path_matches_oracle(mode, dtype, tol, B, C, T):
     assert (got.cpu().float() - ref.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
     lsu = A.fuse_transpose_layernorm(fa0.cuda(), fv0.cuda(), mask, mode, w, bz, weights=(0.3, 0.7))   # contiguous: LSU kernel
     assert (got.float() - lsu.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 2e-3)])
+def test_fuse_layernorm_tma_full_size_equals_lsu_kernel(dtype, tol):
+    """configs[3] size (B 64, C 1024, T 750, masked): the persistent TMA kernel walks ~27 tiles per CTA
+    through its two-stage ring; same numbers as the LSU kernel on the contiguous tensors, and rows are
+    normalised (zero mean / unit variance with unit weight, zero bias)."""
+    B, C, T = 64, 1024, 750
+    fa0, fv0, mask = synth.fusion_inputs(B, C, T, seed=5, dtype=dtype, device="cuda")
+    fa, fv = A.alloc_features(B, C, T, dtype, "cuda"), A.alloc_features(B, C, T, dtype, "cuda")
+    fa.copy_(fa0); fv.copy_(fv0)
+    w, bz = torch.ones(2 * C, device="cuda"), torch.zeros(2 * C, device="cuda")
+    got = A.fuse_transpose_layernorm(fa, fv, mask, "concat", w, bz)
+    lsu = A.fuse_transpose_layernorm(fa0, fv0, mask, "concat", w, bz)
+    assert (got.float() - lsu.float()).abs().max().item() <= tol * max(1.0, lsu.float().abs().max().item())
+    g = got.float()
+    assert g.mean(dim=-1).abs().max().item() < (1e-4 if dtype == torch.float32 else 2e-3)
+    assert (g.var(dim=-1, unbiased=False) - 1.0).abs().max().item() < (1e-3 if dtype == torch.float32 else 1e-2)
