@@ -92,3 +92,27 @@ def test_noise_plan_host_logic():
         AA.NoisePlan([0, 10], [0, 1], 0, "cpu", out_dtype=torch.float64)
     with pytest.raises(ValueError):
         AA.NoisePlan([0, 1 << 40], [0, 1], 0, "cpu")                     # longer than the library supports
+
+
+@pytest.mark.parametrize("cs", [2, 4, 8])
+@pytest.mark.parametrize("n", [2048, 2049, 4099, 32768, 131072 + 13, 480000, 1120013])
+def test_cluster_split_of_the_pairwise_tree(cs, n):
+    """What noise_cluster_kernel relies on: CTA `rank` of a cs-wide cluster owns the subtree under heap
+    node cs + rank of numpy's pairwise tree -- a contiguous stretch whose bounds come from halving at
+    (len >> 1) & ~7 -- and adding the cs subtree sums pairwise, level by level, reproduces
+    np.add.reduce bit for bit (n >= 256 * cs: every node above that depth is an inner node)."""
+    if n < 256 * cs:
+        pytest.skip("short clips are summed by one CTA from the root")
+    sq = np.square((np.random.default_rng(n + cs).standard_normal(n) * 3000).astype(np.float32))
+    parts = [(0, n)]
+    while len(parts) < cs:
+        nxt = []
+        for off, ln in parts:
+            assert ln > 128
+            half = (ln >> 1) & ~7
+            nxt += [(off, half), (off + half, ln - half)]
+        parts = nxt
+    sums = [np.sum(sq[off:off + ln]) for off, ln in parts]      # each subtree is itself numpy's tree of its stretch
+    while len(sums) > 1:
+        sums = [np.float32(sums[i] + sums[i + 1]) for i in range(0, len(sums), 2)]
+    assert sums[0] == np.sum(sq)
