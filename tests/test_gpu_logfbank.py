@@ -62,3 +62,47 @@ def test_full_size_properties():
     raw, _ = A.logfbank_batch(audio, off, 1, False)
     raw2, _ = A.logfbank_batch(audio * 0.5, off, 1, False)
     assert (raw2 - raw - 2.0 * np.log(0.5)).abs().max().item() < 1e-3
+
+
+def _oracle_logfbank(a, fb):
+    """oracle/logfbank.py's pipeline with an arbitrary filterbank (float64)."""
+    sig = np.append(a[0], a[1:] - 0.97 * a[:-1]).astype(np.float64)
+    nfr = OF.num_frames(len(a))
+    sig = np.concatenate([sig, np.zeros((nfr - 1) * 160 + 400 - len(sig))])
+    idx = np.arange(400)[None, :] + 160 * np.arange(nfr)[:, None]
+    P = np.abs(np.fft.rfft(sig[idx], 512)) ** 2 / 512.0
+    e = P @ fb.astype(np.float64).T
+    return np.log(np.where(e == 0, np.finfo(float).eps, e))
+
+
+@pytest.mark.parametrize("stack", [1, 2, 8, 16])
+def test_forty_filters_and_other_stack_orders(stack):
+    """nfilt = 40 (the filter table's capacity: five filters per warp) and every stack order a
+    16-frame tile divides by, on a ragged batch whose clips start at odd offsets."""
+    lens = [16000 + 3, 4801, 399, 33333]
+    clips = [synth.audio_clip(n, 40 + i) * 1.5 for i, n in enumerate(lens)]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    fb = OF.get_filterbanks(40).astype(np.float32)
+    feats, row_off = A.logfbank_batch(torch.from_numpy(np.concatenate(clips)).cuda(), off, stack, False, nfilt=40)
+    feats = feats.cpu().numpy()
+    for i, c in enumerate(clips):
+        raw = _oracle_logfbank(c, fb)
+        pad = (-len(raw)) % stack
+        ref = np.concatenate([raw, np.zeros((pad, 40))]).reshape(-1, 40 * stack)
+        assert row_off[i + 1] - row_off[i] == len(ref)
+        assert np.abs(feats[row_off[i]:row_off[i + 1]] - ref).max() < 2e-4, (i, stack)
+
+
+def test_dense_filterbank_takes_the_unpacked_path():
+    """A filterbank without zeros (26 x 257 weights do not fit the packed table): weights are read
+    from global memory, supports are the whole spectrum."""
+    from avsl_b200 import _lib
+    rng = np.random.default_rng(9)
+    fb = (rng.random((26, 257)) * 0.01 + 1e-4).astype(np.float32)
+    a = synth.audio_clip(16000 + 77, 3) * 2.0
+    plan = A.LogfbankPlan([0, len(a)], 1, 26, torch.device("cuda"))
+    d_a, d_fb = torch.from_numpy(a).cuda(), torch.from_numpy(fb).cuda()
+    _lib.call("avfe_logfbank_f32", _lib.ptr(d_a), _lib.ptr(plan.d_off), _lib.ptr(plan.d_row), 1, plan.max_len,
+              _lib.ptr(d_fb), 26, 1, 0, _lib.ptr(plan.out), _lib.ptr(plan.ws), plan.ws.numel(), _lib.stream_ptr())
+    got = plan.out.cpu().numpy()
+    assert np.abs(got - _oracle_logfbank(a, fb)).max() < 2e-4
