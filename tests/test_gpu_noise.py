@@ -201,3 +201,20 @@ def test_every_cluster_width(max_len):
     want = ON.add_noise_batch(clean, co, noise, no, snr)
     got = A.add_noise_batch(torch.from_numpy(clean).cuda(), co, torch.from_numpy(noise).cuda(), no, snr).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+def test_empty_and_tiny_clips_beside_a_long_one():
+    """An 8-wide cluster per clip (the longest clip decides): an empty clip, a 5-sample clip and a
+    2047-sample clip (each summed by CTA 0 alone) share the launch with a 140,000-sample one."""
+    import torch
+    import avsl_b200 as A
+    rng = np.random.default_rng(77)
+    lens, nlens = [140000, 0, 5, 2047], [9000, 0, 3, 5000]
+    co, no = np.concatenate([[0], np.cumsum(lens)]), np.concatenate([[0], np.cumsum(nlens)])
+    clean = rng.integers(-9000, 9001, size=co[-1]).astype(np.float32)
+    noise = rng.integers(-3000, 3001, size=no[-1]).astype(np.float32)
+    snr = [5.0, 0.0, -3.0, 12.0]
+    want = ON.add_noise_batch(clean, co, noise, no, snr)
+    for dt in (torch.int16, torch.float32):
+        got = A.add_noise_batch(torch.from_numpy(clean).cuda(), co, torch.from_numpy(noise).cuda(), no, snr, out_dtype=dt)
+        np.testing.assert_array_equal(got.cpu().numpy().astype(np.int16), want)
