@@ -75,7 +75,6 @@ def pack_utterances(audios: Sequence[np.ndarray], videos: Sequence[np.ndarray],
     detections behind the cut.  The trim is applied on the output side: ``keep_frames`` of
     ``forward_collated`` / ``AVFrontEnd.split_lip(..., n_audio_samples=...)``."""
     assert len(audios) == len(videos) == len(landmarks)
-    max_frames = None
     a_list, v_list, l_list, m_list = [], [], [], []
     for i in range(len(audios)):
         a = np.asarray(audios[i], dtype=np.float32).reshape(-1)
@@ -84,8 +83,6 @@ def pack_utterances(audios: Sequence[np.ndarray], videos: Sequence[np.ndarray],
         v = np.asarray(videos[i], dtype=np.uint8)
         lm = np.asarray(landmarks[i], dtype=np.float64)
         ok = np.ones(len(v), dtype=np.uint8) if valids is None else np.asarray(valids[i], dtype=np.uint8)
-        if max_frames is not None:
-            v, lm, ok = v[:max_frames], lm[:max_frames], ok[:max_frames]
         a_list.append(a); v_list.append(v); l_list.append(lm); m_list.append(ok)
     a_off = np.concatenate([[0], np.cumsum([len(a) for a in a_list])]).astype(np.int64)
     c_off = np.concatenate([[0], np.cumsum([len(v) for v in v_list])]).astype(np.int64)
