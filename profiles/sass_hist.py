@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "avsl_b200", "lib", "libavfe.so")
 HOT = ["lip_frame_kernel", "lip_fused_kernel", "logmel_tile_kernel", "logmel_finalize_tiles_kernel", "pep_gemm2_kernel",
        "pep_gemm_kernel", "pep_stats_kernel", "fuse_vec_kernel", "fuse_ln_kernel", "fuse_ln_bwd_kernel", "logfbank_kernel",
-       "noise_leaf_kernel", "noise_mix_kernel", "gray_vec_kernel", "vfeats_kernel", "spec_time_warp_kernel"]
+       "noise_leaf_kernel", "noise_mix_kernel", "noise_cluster_kernel", "fuse_ln_tma_kernel", "fuse_ln_tma_tile_kernel", "gray_vec_kernel", "vfeats_kernel", "spec_time_warp_kernel"]
 MARK = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "IDP", "LDGSTS", "DFMA", "DMUL", "DADD", "HMMA"]
 
 
