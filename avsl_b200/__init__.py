@@ -15,7 +15,7 @@ from .audio import (HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, Logfban
                     spec_augment_bands)
 from .frontend import (AVFrontEnd, HostPipeline, PackedBatch, algorithmic_bytes, bind_to_gpu_numa_node,
                        pack_utterances, shard, shard_balanced)
-from .fusion import (FoldedProjection, ModalityFusion, alloc_features, fuse_layernorm_project, fuse_modalities,
+from .fusion import (FoldedProjection, FusedProjection, ModalityFusion, alloc_features, fuse_layernorm_project, fuse_modalities,
                      fuse_transpose_layernorm, modality_dropout_flags, modality_dropout_mask)
 from .lips import (SimilarityTransform, apply_transform, bgr2gray, cut_patch, extract_lip_frames,
                    landmarks_interpolate, lip_roi_batch, lip_roi_collate, load_video_feats, mean_face_landmarks,

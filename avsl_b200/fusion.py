@@ -271,12 +271,13 @@ def fuse_layernorm_project(features_audio: torch.Tensor, features_video: torch.T
                            eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``post_extract_proj(layer_norm(cat([fa, fv], 1).transpose(1, 2)))`` (av_hubert_encoder.py:315-334)
     in one pass on the tensor cores: ``[B,C,T] x 2 -> [B,T,D]`` (float16 / bfloat16).  The feature maps
-    must have unit stride in time and a row pitch that is a multiple of 8 elements (``alloc_features``);
-    inference only (no backward kernel for the projection yet)."""
+    must have unit stride in time and a row pitch that is a multiple of 8 elements (``alloc_features``).
+    This entry point is the inference form (weights folded once); :class:`FusedProjection` is the module
+    that also trains (its backward recomputes the normalised features and reuses the LayerNorm backward kernel)."""
     _lib.require_cuda()
     fa, fv = features_audio, features_video
     if _needs_grad(fa, fv):
-        raise RuntimeError("fuse_layernorm_project has no backward; use fuse_transpose_layernorm + nn.Linear when training")
+        raise RuntimeError("fuse_layernorm_project has no backward of its own; use avsl_b200.FusedProjection when training")
     if not (fa.is_cuda and fv.is_cuda) or fa.shape != fv.shape or fa.dim() != 3 or fa.dtype != fv.dtype:
         raise ValueError("features_audio and features_video must both be CUDA [B, C, T] of one dtype")
     if fa.dtype != folded.dtype:
@@ -301,6 +302,94 @@ def fuse_layernorm_project(features_audio: torch.Tensor, features_video: torch.T
                   int(fa.stride(1)), _lib.ptr(folded.buffer), folded.D, float(eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
                   _lib.stream_ptr())
     return out
+
+
+def _padded(t: torch.Tensor) -> torch.Tensor:
+    """``t`` itself when its rows are TMA-addressable, else a copy in an ``alloc_features`` buffer."""
+    B, C, T = (int(s) for s in t.shape)
+    if t.stride(2) == 1 and t.stride(1) % 8 == 0 and t.stride(0) == C * t.stride(1):
+        return t
+    p = alloc_features(B, C, T, t.dtype, t.device)
+    p.copy_(t)
+    return p
+
+
+class _FuseLayerNormProjectFn(torch.autograd.Function):
+    """Training form of :func:`fuse_layernorm_project`.  Forward: the LayerNorm affine is folded into the
+    current projection weights (``avfe_proj_fold``, microseconds) and the tcgen05 kernel runs as in
+    inference.  Backward (activation recomputation, nothing but the inputs is kept): the normalised
+    features are rebuilt by the fused LayerNorm kernel, ``dLN = dY W`` and ``dW = dY^T LN`` are two
+    library GEMMs, and ``avfe_fuse_layernorm_backward`` carries ``dLN`` back to both feature maps and
+    to ``layer_norm.weight / .bias``."""
+
+    @staticmethod
+    def forward(ctx, fa, fv, ln_w, ln_b, W, pb, m, eps):
+        folded = FoldedProjection(W, pb, ln_w, ln_b, fa.dtype)
+        out = fuse_layernorm_project(_padded(fa), _padded(fv), m, folded, eps)
+        ctx.save_for_backward(fa, fv, ln_w, ln_b, W)
+        ctx.mask, ctx.eps, ctx.has_pb = m, eps, pb is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        fa, fv, ln_w, ln_b, W = ctx.saved_tensors
+        B, C, T = (int(s) for s in fa.shape)
+        D = int(W.shape[0])
+        dt = fa.dtype
+        fa_c, fv_c = fa.contiguous(), fv.contiguous()
+        g2 = grad_out.contiguous().reshape(B * T, D)
+        ln = fuse_transpose_layernorm(fa_c, fv_c, ctx.mask, "concat", ln_w, ln_b, ctx.eps)       # [B, T, 2C], recomputed
+        d_ln = (g2 @ W.to(dt)).view(B, T, 2 * C)
+        gW = (g2.t() @ ln.reshape(B * T, 2 * C)).to(W.dtype) if ctx.needs_input_grad[4] else None
+        gpb = g2.float().sum(dim=0) if (ctx.has_pb and ctx.needs_input_grad[5]) else None
+        del ln
+        gfa, gfv = torch.empty_like(fa_c), torch.empty_like(fv_c)
+        want_w = ln_w is not None and ctx.needs_input_grad[2]
+        want_b = ln_b is not None and ctx.needs_input_grad[3]
+        gw = torch.empty(2 * C, dtype=torch.float32, device=fa.device) if want_w else None
+        gb = torch.empty(2 * C, dtype=torch.float32, device=fa.device) if want_b else None
+        with torch.cuda.device(fa.device):
+            lib = _lib.load()
+            ws_bytes = int(lib.avfe_fuse_layernorm_backward_workspace_bytes(B, C, T, _lib.FUSE_CONCAT))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fa.device)
+            _lib.call("avfe_fuse_layernorm_backward", _lib.ptr(fa_c), _lib.ptr(fv_c), _lib.ptr(ctx.mask), _lib.FUSE_CONCAT,
+                      0.5, 0.5, _DTYPES[dt], B, C, T, _lib.ptr(ln_w), ctx.eps, _lib.ptr(d_ln.contiguous()), _lib.ptr(gfa),
+                      _lib.ptr(gfv), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        return (gfa if ctx.needs_input_grad[0] else None, gfv if ctx.needs_input_grad[1] else None, gw, gb, gW,
+                None if gpb is None else gpb.to(W.dtype), None, None)
+
+
+class FusedProjection(torch.nn.Module):
+    """``cat`` + ``transpose(1, 2)`` + ``self.layer_norm`` + ``self.post_extract_proj`` of
+    ``AVHuBERTEncoderWrapper.forward`` (av_hubert_encoder.py:315-334) as one module holding the same
+    parameters (``layer_norm.weight / .bias`` float32 ``[2C]``, ``post_extract_proj.weight [D, 2C]`` /
+    ``.bias [D]``).  Inference: the folded projection is cached and reused until a parameter changes.
+    Training: every output carries a ``grad_fn`` (:class:`_FuseLayerNormProjectFn`), so gradients reach
+    the feature extractors and all four parameters.  Features are float16 / bfloat16 ``[B, C, T]``."""
+
+    def __init__(self, channels: int, out_dim: int, eps: float = 1e-5, dtype=torch.float16, device=None):
+        super().__init__()
+        self.layer_norm = torch.nn.LayerNorm(2 * channels, eps=eps, device=device)
+        self.post_extract_proj = torch.nn.Linear(2 * channels, out_dim, device=device)
+        self.dtype = dtype
+        self._folded = None
+        self._folded_key = None
+
+    def _params(self):
+        return (self.layer_norm.weight, self.layer_norm.bias, self.post_extract_proj.weight, self.post_extract_proj.bias)
+
+    def forward(self, features_audio: torch.Tensor, features_video: torch.Tensor, mask=None) -> torch.Tensor:
+        ln_w, ln_b, W, pb = self._params()
+        fa, fv = features_audio, features_video
+        if _needs_grad(fa, fv, ln_w, ln_b, W, pb):
+            m = _mask_tensor(mask, int(fa.shape[0]), fa.device)
+            return _FuseLayerNormProjectFn.apply(fa, fv, ln_w.float(), ln_b.float(), W, pb, m, float(self.layer_norm.eps))
+        key = tuple((p.data_ptr(), p._version) for p in self._params()) + (fa.dtype,)
+        if self._folded is None or self._folded_key != key:
+            self._folded = FoldedProjection(W, pb, ln_w, ln_b, fa.dtype)
+            self._folded_key = key
+        return fuse_layernorm_project(_padded(fa), _padded(fv), mask, self._folded, float(self.layer_norm.eps))
 
 
 class ModalityFusion(torch.nn.Module):

@@ -69,3 +69,57 @@ def test_contract_errors():
     # T a multiple of 8: a plain contiguous tensor qualifies
     x = torch.randn(2, 64, 104, device="cuda").half()
     assert A.fuse_layernorm_project(x, x, None, folded).shape == (2, 104, 256)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-2), (torch.bfloat16, 6e-2)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fused_projection_module_trains(dtype, tol, masked):
+    """FusedProjection in the reference's TRAINING forward (av_hubert_encoder.py:292-334): the output
+    equals the inference path, and the gradients of both feature maps, layer_norm.weight / .bias and
+    post_extract_proj.weight / .bias agree with torch autograd through the reference's own ops
+    (LayerNorm in float32, Linear in `dtype`)."""
+    B, C, T, D = 3, 128, 50, 256
+    g = torch.Generator().manual_seed(4)
+    fa = (torch.randn(B, C, T, generator=g) + 0.5).to(dtype).cuda().requires_grad_()
+    fv = (torch.randn(B, C, T, generator=g) - 0.25).to(dtype).cuda().requires_grad_()
+    mod = A.FusedProjection(C, D, dtype=dtype, device="cuda")
+    with torch.no_grad():
+        mod.layer_norm.weight.copy_(torch.rand(2 * C, generator=g) + 0.5)
+        mod.layer_norm.bias.copy_(torch.randn(2 * C, generator=g) * 0.2)
+    mask = None
+    if masked:
+        mask = np.ones((B, 2), np.uint8)
+        mask[0, 1] = 0
+        mask[1, 0] = 0
+    R = torch.randn(B, T, D, generator=g).cuda()
+    out = mod(fa, fv, mask)
+    assert out.grad_fn is not None and out.shape == (B, T, D) and out.dtype == dtype
+    (out.float() * R).sum().backward()
+    got = [fa.grad, fv.grad, mod.layer_norm.weight.grad, mod.layer_norm.bias.grad,
+           mod.post_extract_proj.weight.grad, mod.post_extract_proj.bias.grad]
+    # the reference's ops under torch autograd
+    fa2, fv2 = fa.detach().clone().requires_grad_(), fv.detach().clone().requires_grad_()
+    lw, lb = mod.layer_norm.weight.detach().clone().requires_grad_(), mod.layer_norm.bias.detach().clone().requires_grad_()
+    W, pb = mod.post_extract_proj.weight.detach().clone().requires_grad_(), mod.post_extract_proj.bias.detach().clone().requires_grad_()
+    m = torch.ones(B, 2) if mask is None else torch.as_tensor(mask).float()
+    m = m.cuda()
+    x = torch.cat([fa2.float() * m[:, 0].view(-1, 1, 1), fv2.float() * m[:, 1].view(-1, 1, 1)], dim=1).transpose(1, 2)
+    ref = F.linear(F.layer_norm(x, (2 * C,), lw, lb, mod.layer_norm.eps).to(dtype), W.to(dtype), pb.to(dtype))
+    (ref.float() * R).sum().backward()
+    want = [fa2.grad, fv2.grad, lw.grad, lb.grad, W.grad, pb.grad]
+    assert (out.float() - ref.float()).abs().max().item() <= tol * ref.float().abs().max().item()
+    for name, a, b in zip(("fa", "fv", "ln.weight", "ln.bias", "proj.weight", "proj.bias"), got, want):
+        assert a is not None and a.shape == b.shape, name
+        scale = max(b.float().abs().max().item(), 1e-6)
+        assert (a.float() - b.float()).abs().max().item() <= tol * scale, name
+    # inference: same numbers without a graph, folded weights cached until a parameter changes
+    mod.eval()
+    with torch.no_grad():
+        y1 = mod(fa.detach(), fv.detach(), mask)
+        folded = mod._folded
+        y2 = mod(fa.detach(), fv.detach(), mask)
+        assert mod._folded is folded and torch.equal(y1, y2) and y1.grad_fn is None
+        assert (y1.float() - out.float()).abs().max().item() <= 1e-3 * out.float().abs().max().item()
+        mod.post_extract_proj.bias.add_(1.0)
+        y3 = mod(fa.detach(), fv.detach(), mask)
+        assert mod._folded is not folded and (y3.float() - y1.float() - 1.0).abs().max().item() < 5e-2
