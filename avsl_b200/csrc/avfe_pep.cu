@@ -417,6 +417,7 @@ pep_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int ew = wid - 4;
     int acc = 0; uint32_t acc_phase = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the moments kernel in front of this launch has completed
     for (int tile = pair; tile < g.n_tiles; tile += n_pairs) {
       const int nt = tile % g.n_tiles_n, mb = tile / g.n_tiles_n;
       const int b = mb / g.tiles_per_sample, t0 = (mb % g.tiles_per_sample) * (2 * kBM) + (int)rank * kBM;
@@ -481,6 +482,9 @@ __global__ void __launch_bounds__(256, 3)
 pep_stats_kernel(const T* __restrict__ fa, const T* __restrict__ fv, const uint8_t* __restrict__ mask, int C, int Tn,
                  int64_t pitch, float eps, float2* __restrict__ stats) {
   __shared__ float red[8][2][64];
+  // programmatic dependent launch: the GEMM behind this kernel needs the moments only in its epilogue, so
+  // its CTAs may take the SMs this grid's last wave leaves free (they wait with griddepcontrol.wait)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b = blockIdx.y, t0 = blockIdx.x * 64;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tl = (lane & 7) * 8;                       // this lane's 8 time steps inside the 64
@@ -741,7 +745,22 @@ extern "C" int avfe_fuse_ln_proj(const void* fa, const void* fv, const uint8_t* 
       return AVFE_ERR_CUDA;
     }
     const int pairs = g.n_tiles < kNumSMs / 2 ? g.n_tiles : kNumSMs / 2;
-    pep::pep_gemm2_kernel<<<2 * pairs, pep::kThreads, smem, st>>>(map_a, map_v, map_w, g);   // __cluster_dims__(2,1,1)
+    // launched with programmatic stream serialization: producer / issuer warps start while the moments
+    // kernel drains, the epilogue warps wait for it (griddepcontrol.wait)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(pep::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, pep::pep_gemm2_kernel, map_a, map_v, map_w, g) != cudaSuccess) {   // __cluster_dims__(2,1,1)
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
   }
   count_launch();
   return check_launch();
