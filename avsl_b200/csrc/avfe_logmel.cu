@@ -214,6 +214,9 @@ logmel_live_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
                    int64_t L, int64_t Lp, int tiles_per_clip, int* __restrict__ clip_max,
                    uint8_t* __restrict__ silent, int* __restrict__ live_count,
                    int2* __restrict__ live_list, int* __restrict__ tile_min) {
+  // programmatic dependent launch: the tile kernel behind this one loads its tables meanwhile and
+  // waits (griddepcontrol.wait) only in front of its first read of the live list
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -268,6 +271,8 @@ logmel_tile_kernel(const float* __restrict__ audio, const int64_t* __restrict__ 
   // (clip, tile-in-clip) pair is advanced incrementally in 32-bit arithmetic
   const int g = tid / 20, j = tid % 20;
   const bool mel_fast = packed && pack->balanced != 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // logmel_live_kernel (launched in front of this kernel) has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize grid may be set up; it waits for this one to complete
   const int n_live = *live_count;                        // tiles to compute (logmel_live_kernel)
 
   // (clip, tile) records are read from the live list one tile ahead
@@ -468,6 +473,7 @@ logmel_finalize_tiles_kernel(float* __restrict__ out, const int* __restrict__ cl
                              int64_t n_frames, int n_mels, int tiles_per_clip, int vec_ok) {
   const int64_t tile = blockIdx.x, b = tile / tiles_per_clip;
   const int tt = (int)(tile - b * tiles_per_clip);
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the tile kernel has completed (programmatic dependent launch)
   const float floor_v = __fsub_rn(key_float(clip_max[b]), 8.0f);
   const bool sil = silent[tile] != 0;
   if (!sil && !(key_float(tile_min[tile]) < floor_v)) return;      // the common case: nothing to clamp
@@ -614,13 +620,47 @@ static int logmel_run(const float* audio, const int64_t* offsets, int64_t B, int
     return AVFE_ERR_CUDA;
   }
   int64_t ctas = n_tiles < 3 * kNumSMs ? n_tiles : 3 * kNumSMs;   // 3 resident CTAs per SM
-  lm::logmel_tile_kernel<<<(unsigned)ctas, lm::kThreads, sizeof(lm::Smem), s>>>(
-      audio, offsets, B, L, Lp, n_frames, n_mels, mel_filters, pack, out, clip_max, silent,
-      live_count, live_list, tile_min, (int)tiles_per_clip);
+  {
+    // programmatic stream serialization: the tile kernel's prologue (twiddles, window, filter tables into
+    // shared memory) runs under logmel_live_kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(lm::kThreads);
+    cfg.dynamicSmemBytes = sizeof(lm::Smem);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int64_t offsets_B = B;
+    const int tpc = (int)tiles_per_clip;
+    if (cudaLaunchKernelEx(&cfg, lm::logmel_tile_kernel, audio, offsets, offsets_B, L, Lp, n_frames, n_mels, mel_filters,
+                           (const lm::MelPack*)pack, out, clip_max, silent, (const int*)live_count,
+                           (const int2*)live_list, tile_min, tpc) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+  }
   count_launch();
   const int vec_ok = ((n_frames & 3) == 0 && aligned16(out)) ? 1 : 0;
-  lm::logmel_finalize_tiles_kernel<<<(unsigned)n_tiles, 128, 0, s>>>(out, clip_max, silent, tile_min, n_frames, n_mels,
-                                                                      (int)tiles_per_clip, vec_ok);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_tiles);
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int tpc = (int)tiles_per_clip;
+    if (cudaLaunchKernelEx(&cfg, lm::logmel_finalize_tiles_kernel, out, (const int*)clip_max, (const uint8_t*)silent,
+                           (const int*)tile_min, n_frames, n_mels, tpc, vec_ok) != cudaSuccess) {
+      cudaGetLastError();
+      return AVFE_ERR_CUDA;
+    }
+  }
   count_launch();
   return check_launch();
 }
