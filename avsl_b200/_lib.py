@@ -39,6 +39,9 @@ _SIGNATURES = {
     "avfe_logfbank_workspace_bytes": (c_size_t, []),
     "avfe_logfbank_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "avfe_logfbank_prepare": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "avfe_logfbank_prepared_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int,
+                                  c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "avfe_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "avfe_warp_affine_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p]),

@@ -281,14 +281,18 @@ def logfbank_batch(audio: torch.Tensor, offsets=None, stack_order: int = 4, norm
     if int(plan.offsets[-1]) != audio.numel():
         raise ValueError("offsets do not cover the audio tensor")
     key = ("fbank", str(dev), plan.nfilt)
-    fb = _FILTER_CACHE.get(key)
-    if fb is None:
-        fb = torch.from_numpy(_logfbank_filters_np(plan.nfilt)).to(dev)
-        _FILTER_CACHE[key] = fb
+    hit = _FILTER_CACHE.get(key)
     with torch.cuda.device(dev):
-        _lib.call("avfe_logfbank_f32", _lib.ptr(audio), _lib.ptr(plan.d_off), _lib.ptr(plan.d_row), plan.B,
+        if hit is None:
+            # the filterbank and its sparse form (avfe_logfbank_prepare), once per device and nfilt
+            fb = torch.from_numpy(_logfbank_filters_np(plan.nfilt)).to(dev)
+            pack = torch.empty(int(_lib.load().avfe_logfbank_workspace_bytes()), dtype=torch.uint8, device=dev)
+            _lib.call("avfe_logfbank_prepare", _lib.ptr(fb), plan.nfilt, _lib.ptr(pack), pack.numel(), _lib.stream_ptr())
+            hit = _FILTER_CACHE[key] = (fb, pack)
+        fb, pack = hit
+        _lib.call("avfe_logfbank_prepared_f32", _lib.ptr(audio), _lib.ptr(plan.d_off), _lib.ptr(plan.d_row), plan.B,
                   plan.max_len, _lib.ptr(fb), plan.nfilt, plan.stack_order, 1 if normalize else 0,
-                  _lib.ptr(plan.out), _lib.ptr(plan.ws), plan.ws.numel(), _lib.stream_ptr())
+                  _lib.ptr(plan.out), _lib.ptr(pack), pack.numel(), _lib.stream_ptr())
     return plan.out, plan.row_offsets
 
 

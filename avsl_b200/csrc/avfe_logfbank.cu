@@ -294,24 +294,39 @@ extern "C" int64_t avfe_logfbank_num_frames(int64_t n_samples) {
 
 extern "C" size_t avfe_logfbank_workspace_bytes(void) { return sizeof(fbk::FilterPack); }
 
-extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
-                                 int64_t B, int64_t max_samples, const float* fbank, int nfilt,
-                                 int stack, int normalize, float* out, void* workspace,
-                                 size_t workspace_bytes, avfe_stream_t stream) {
+static int logfbank_check(int64_t B, int64_t max_samples, int nfilt, int stack) {
   if (B < 0 || nfilt <= 0 || stack <= 0 || max_samples < 0) return AVFE_ERR_INVALID_ARG;
   if (nfilt > fbk::kMaxFilt || (fbk::kTileFrames % stack) != 0 || (stack & (stack - 1)) != 0) return AVFE_ERR_UNSUPPORTED;
+  return AVFE_OK;
+}
+
+extern "C" int avfe_logfbank_prepare(const float* fbank, int nfilt, void* workspace, size_t workspace_bytes,
+                                     avfe_stream_t stream) {
+  if (nfilt <= 0) return AVFE_ERR_INVALID_ARG;
+  if (nfilt > fbk::kMaxFilt) return AVFE_ERR_UNSUPPORTED;
+  if (!fbank) return AVFE_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < avfe_logfbank_workspace_bytes() || !aligned16(workspace)) return AVFE_ERR_WORKSPACE;
+  fbk::logfbank_prep_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(fbank, nfilt, static_cast<fbk::FilterPack*>(workspace));
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int avfe_logfbank_prepared_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
+                                          int64_t B, int64_t max_samples, const float* fbank, int nfilt,
+                                          int stack, int normalize, float* out, const void* workspace,
+                                          size_t workspace_bytes, avfe_stream_t stream) {
+  const int rc = logfbank_check(B, max_samples, nfilt, stack);
+  if (rc != AVFE_OK) return rc;
   if (B == 0) return AVFE_OK;
   if (!audio || !offsets || !row_offsets || !fbank || !out) return AVFE_ERR_INVALID_ARG;
-  if (!workspace || workspace_bytes < avfe_logfbank_workspace_bytes()) return AVFE_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < avfe_logfbank_workspace_bytes() || !aligned16(workspace)) return AVFE_ERR_WORKSPACE;
   if (B > 65535) return AVFE_ERR_UNSUPPORTED;
   const int64_t nfr = fbk::num_frames(max_samples);
   const int64_t padded = (nfr + stack - 1) / stack * stack;
   const int64_t tiles = (padded + fbk::kTileFrames - 1) / fbk::kTileFrames;
   if (tiles > 0x7fffffffLL) return AVFE_ERR_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!aligned16(workspace)) return AVFE_ERR_WORKSPACE;
-  fbk::FilterPack* pack = static_cast<fbk::FilterPack*>(workspace);
-  fbk::logfbank_prep_kernel<<<1, 256, 0, s>>>(fbank, nfilt, pack);
+  const fbk::FilterPack* pack = static_cast<const fbk::FilterPack*>(workspace);
   if (cudaFuncSetAttribute(fbk::logfbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(fbk::Smem)) != cudaSuccess) {
     cudaGetLastError();
@@ -329,6 +344,20 @@ extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, con
   if (ctas < 1) ctas = 1;
   fbk::logfbank_kernel<<<(unsigned)ctas, fbk::kThreads, sizeof(fbk::Smem), s>>>(audio, offsets, row_offsets, B, fbank, nfilt,
                                                                               pack, stack, normalize, out);
-  count_launch(2);
+  count_launch();
   return check_launch();
+}
+
+extern "C" int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
+                                 int64_t B, int64_t max_samples, const float* fbank, int nfilt,
+                                 int stack, int normalize, float* out, void* workspace,
+                                 size_t workspace_bytes, avfe_stream_t stream) {
+  int rc = logfbank_check(B, max_samples, nfilt, stack);
+  if (rc != AVFE_OK) return rc;
+  if (B == 0) return AVFE_OK;
+  if (!audio || !offsets || !row_offsets || !fbank || !out) return AVFE_ERR_INVALID_ARG;
+  rc = avfe_logfbank_prepare(fbank, nfilt, workspace, workspace_bytes, stream);
+  if (rc != AVFE_OK) return rc;
+  return avfe_logfbank_prepared_f32(audio, offsets, row_offsets, B, max_samples, fbank, nfilt, stack, normalize, out,
+                                    workspace, workspace_bytes, stream);
 }

@@ -153,6 +153,17 @@ AVFE_API int avfe_logfbank_f32(const float* audio, const int64_t* offsets, const
                                int64_t B, int64_t max_samples, const float* fbank, int nfilt,
                                int stack, int normalize, float* out, void* workspace,
                                size_t workspace_bytes, avfe_stream_t stream);
+/* The same in two steps, for callers that keep one filterbank across calls (like avfe_logmel_prepare /
+ * avfe_logmel_prepared_f32): avfe_logfbank_prepare turns `fbank` into its sparse form (supports, packed
+ * weights, the deal of the filters to the kernel's warps) in `workspace` once;
+ * avfe_logfbank_prepared_f32 then runs the feature kernel alone -- `workspace` must hold the result
+ * of a prepare call for the same `fbank` / `nfilt`. */
+AVFE_API int avfe_logfbank_prepare(const float* fbank, int nfilt, void* workspace, size_t workspace_bytes,
+                                   avfe_stream_t stream);
+AVFE_API int avfe_logfbank_prepared_f32(const float* audio, const int64_t* offsets, const int64_t* row_offsets,
+                                        int64_t B, int64_t max_samples, const float* fbank, int nfilt,
+                                        int stack, int normalize, float* out, const void* workspace,
+                                        size_t workspace_bytes, avfe_stream_t stream);
 
 /* SNR noise mixing — add_noise(clean_wav, noise_wav, snr), preprocess/audio_process.py:110-150
  * (the optional augmentation of process_audio_for_av_hubert, :222-224, in front of the logfbank
