@@ -271,6 +271,9 @@ __global__ void __launch_bounds__(256)
 noise_mix_kernel(MixArgs m) {
   const NoiseArgs& a = m.n;
   const int64_t b = blockIdx.y;
+  // behind noise_cluster_kernel the rescale pass is launched programmatically (its grid is set up while
+  // the clusters run); a no-op under a plain launch
+  if (RESCALE) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t c0 = a.clean_offsets[b];
   const int64_t c1 = a.clean_offsets[b + 1];
   const int64_t g0 = c0 & ~(int64_t)3;                    // first group of the clip (may start before it)
@@ -498,6 +501,7 @@ noise_cluster_kernel(MixArgs m, int local_depth) {
   float* hz = sm.heap + slots;
   uint32_t* len_s = reinterpret_cast<uint32_t*>(sm.heap + 2 * slots);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the rescale grid may be set up; it waits for this one
   unsigned rank = 0;
   if (CS > 1) {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -823,7 +827,19 @@ extern "C" int avfe_add_noise(const float* clean, const int64_t* clean_offsets, 
              : cs == 2 ? launch_noise_cluster<2>(m, B, local_depth, s)
                        : launch_noise_cluster<1>(m, B, local_depth, s);
       if (rc != AVFE_OK) return rc;
-      noise_mix_kernel<true><<<dim3(chunks_rs < 16u ? chunks_rs : 16u, (unsigned)B), 256, 0, s>>>(m);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(chunks_rs < 16u ? chunks_rs : 16u, (unsigned)B);
+      cfg.blockDim = dim3(256);
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, noise_mix_kernel<true>, m) != cudaSuccess) {
+        cudaGetLastError();
+        return AVFE_ERR_CUDA;
+      }
       count_launch(2);
       return check_launch();
     }
