@@ -5,13 +5,13 @@
 //   tform warps  (2) window-smoothed similarity fit, cut_patch origin and source footprint of
 //                the CTA's frames, a few frames ahead of everybody else (tform_frame, shared
 //                with tform_kernel), published through a 4-deep descriptor ring
-//   stream warps (8 for an 88-px window, 12 for 96) pull the frame through shared memory in
+//   stream warps (10 for an 88-px window, 9 for 96) pull the frame through shared memory in
 //                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier, L2
-//                evict-first hint) per chunk and a 6- / 4-deep ring per warp, convert BGR->gray
+//                evict-first hint) per chunk and a 4-deep ring per warp, convert BGR->gray
 //                (integer dp2a), store the gray frame with 16-byte stores, and drop the gray
 //                pixels that lie inside the frame's ROI footprint into one of three
 //                shared-memory footprint tiles
-//   blend warps  (22 / 18) float64 bilinear blend of the previous frame's ROI from that tile in
+//   blend warps  (20 / 21) float64 bilinear blend of the previous frame's ROI from that tile in
 //                skimage's operation order: u8 ROI and/or normalised f32 centre crop
 //
 // Hand-over: mbarriers (ring FULL per stage, descriptor FULL/EMPTY, tile EMPTY) and one hardware
@@ -29,20 +29,22 @@ constexpr int kFrameTilePx = 16384;         // staged footprint capacity per slo
 template <int SPAN>
 struct FrameRoles {
   static constexpr int kSide = SPAN;
-  // thread = (column, row phase): 8 phases of 11 rows for the 88-px window (22 blend warps, 8
-  // stream warps); 6 phases of 16 rows for the 96-px one (18 blend warps), which leaves 12 warps
-  // for the stream instead of 6 (-11 % time).  Measured for 88: 6 phases (17 blend / 13 stream
-  // warps, shallower rings) is 1-2 % slower than 8 phases.
-  static constexpr int kPhases = (SPAN == 96) ? 6 : 8;
-  static constexpr int kBlendActive = kPhases * SPAN;                 // 704 or 576 threads with pixels
-  static constexpr int kBlendWarps = (kBlendActive + 31) / 32;        // 22 or 18
-  static constexpr int kRowsMax = (SPAN + kPhases - 1) / kPhases;     // 11 or 16
-  // bulk copies in flight per stream warp (x 3 KB): 144 KB per SM either way
-  static constexpr int kRing = (SPAN == 96) ? 4 : 6;
+  // thread = (column, row phase): 7 phases for both windows -- 88 px: 616 threads = 20 blend warps, 10
+  // stream warps, 13 rows per thread; 96 px: 672 threads = 21 blend warps, 9 stream warps, 14 rows.
+  // Measured (16,441 frames of 224 x 224; 8,000 of 352 x 288): 96 px with 8 / 6 / 7 phases (24+6 / 18+12 /
+  // 21+9 warps): 0.80 / 0.718 / 0.688 ms; 88 px with 8 / 6 / 7 phases: 0.655 / 0.665 / 0.656 ms on 224 x 224
+  // and 0.574 / - / 0.567 ms on 352 x 288.
+  static constexpr int kPhases = 7;
+  static constexpr int kBlendActive = kPhases * SPAN;                 // 616 or 672 threads with pixels
+  static constexpr int kBlendWarps = (kBlendActive + 31) / 32;        // 20 or 21
+  static constexpr int kRowsMax = (SPAN + kPhases - 1) / kPhases;     // 13 or 14
+  // bulk copies in flight per stream warp (x 3 KB): 120 / 108 KB per SM (a fifth stage for the 96-px
+  // window measured 4 % slower)
+  static constexpr int kRing = 4;
   // footprint tiles: the stream may run this many frames ahead of the blend (what fits)
   static constexpr int kSlots = 3;
   static constexpr int kBlendThreads = kBlendWarps * 32;
-  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 12
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 10 or 9
   static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
   static constexpr int kTformFirst = 32 - kTformRoleWarps;            // highest warp ids: scheduled first
   static constexpr int kHandoverThreads = 32 * (kBlendWarps + kStreamWarps);   // tile FULL barriers

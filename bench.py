@@ -614,7 +614,7 @@ def main():
         ms = time_op(run_96, 10)
         n_fr = int(batch_dev.frames.shape[0])
         nbytes = n_fr * (H * W * 3 + 68 * 2 * 8 + H * W + 88 * 88 * 4 + 96 * 96)
-        side["lip_with_u8_roi"] = {"kernel": "lip_frame_kernel<96>: gray + 96x96 u8 ROI + 88x88 f32 crop (6 stream, 24 blend warps)",
+        side["lip_with_u8_roi"] = {"kernel": "lip_frame_kernel<96>: gray + 96x96 u8 ROI + 88x88 f32 crop (9 stream, 21 blend warps)",
                                    "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9}
         del r96
         # the same lip stage on the reference's real frame shape (AMI closeups are 352 x 288): 32 clips x 250 frames
