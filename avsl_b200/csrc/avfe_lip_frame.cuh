@@ -5,13 +5,13 @@
 //   tform warps  (2) window-smoothed similarity fit, cut_patch origin and source footprint of
 //                the CTA's frames, a few frames ahead of everybody else (tform_frame, shared
 //                with tform_kernel), published through a 4-deep descriptor ring
-//   stream warps (10 for an 88-px window, 9 for 96) pull the frame through shared memory in
+//   stream warps (8 for an 88-px window, 9 for 96) pull the frame through shared memory in
 //                1024-px chunks with one bulk async copy (TMA, cp.async.bulk + mbarrier, L2
-//                evict-first hint) per chunk and a 4-deep ring per warp, convert BGR->gray
+//                evict-first hint) per chunk and a 4- / 3-deep ring per warp, convert BGR->gray
 //                (integer dp2a), store the gray frame with 16-byte stores, and drop the gray
-//                pixels that lie inside the frame's ROI footprint into one of three
+//                pixels that lie inside the frame's ROI footprint into one of two
 //                shared-memory footprint tiles
-//   blend warps  (20 / 21) float64 bilinear blend of the previous frame's ROI from that tile in
+//   blend warps  (22 / 21) float64 bilinear blend of the previous frame's ROI from that tile in
 //                skimage's operation order: u8 ROI and/or normalised f32 centre crop
 //
 // Hand-over: mbarriers (ring FULL per stage, descriptor FULL/EMPTY, tile EMPTY) and one hardware
@@ -22,6 +22,25 @@
 
 namespace avfe {
 
+// tuning knobs (profiles/lip_sweep.sh rebuilds the library with other values: -DAVFE_LIP_...)
+#ifndef AVFE_LIP_PHASES_88
+#define AVFE_LIP_PHASES_88 8
+#endif
+#ifndef AVFE_LIP_PHASES_96
+#define AVFE_LIP_PHASES_96 7
+#endif
+#ifndef AVFE_LIP_RING_88
+#define AVFE_LIP_RING_88 4
+#endif
+#ifndef AVFE_LIP_RING_96
+#define AVFE_LIP_RING_96 3
+#endif
+#ifndef AVFE_LIP_SLOTS_88
+#define AVFE_LIP_SLOTS_88 2
+#endif
+#ifndef AVFE_LIP_SLOTS_96
+#define AVFE_LIP_SLOTS_96 2
+#endif
 constexpr int kTformRoleWarps = 2;
 constexpr int kDescRing = 4;
 constexpr int kFrameTilePx = 16384;         // staged footprint capacity per slot (one byte per pixel)
@@ -29,22 +48,25 @@ constexpr int kFrameTilePx = 16384;         // staged footprint capacity per slo
 template <int SPAN>
 struct FrameRoles {
   static constexpr int kSide = SPAN;
-  // thread = (column, row phase): 7 phases for both windows -- 88 px: 616 threads = 20 blend warps, 10
-  // stream warps, 13 rows per thread; 96 px: 672 threads = 21 blend warps, 9 stream warps, 14 rows.
-  // Measured (16,441 frames of 224 x 224; 8,000 of 352 x 288): 96 px with 8 / 6 / 7 phases (24+6 / 18+12 /
-  // 21+9 warps): 0.80 / 0.718 / 0.688 ms; 88 px with 8 / 6 / 7 phases: 0.655 / 0.665 / 0.656 ms on 224 x 224
-  // and 0.574 / - / 0.567 ms on 352 x 288.
-  static constexpr int kPhases = 7;
-  static constexpr int kBlendActive = kPhases * SPAN;                 // 616 or 672 threads with pixels
-  static constexpr int kBlendWarps = (kBlendActive + 31) / 32;        // 20 or 21
-  static constexpr int kRowsMax = (SPAN + kPhases - 1) / kPhases;     // 13 or 14
-  // bulk copies in flight per stream warp (x 3 KB): 120 / 108 KB per SM (a fifth stage for the 96-px
-  // window measured 4 % slower)
-  static constexpr int kRing = 4;
+  // thread = (column, row phase).  88-px window: 8 phases of 11 rows (704 threads = 22 blend warps, 8 stream
+  // warps); 96-px window: 7 phases of 14 rows (672 threads = 21 blend warps, 9 stream warps).  The split,
+  // the ring depth and the number of footprint slots were swept on one box (profiles/lip_sweep.sh,
+  // profiles/r02/lip_sweep.txt; 16,500 frames of 224 x 224 / 8,000 of 352 x 288), phases/ring/slots:
+  //   88 px: 8/6/3 (round 1) 0.661 / 0.581 ms; 7/4/3 0.654 / 0.565; 7/3/3 0.635 / 0.546; 7/3/2 0.626 / 0.540;
+  //          8/4/3 0.634 / 0.555; 8/4/2 0.618 / 0.546 (chosen); 8/3/2 0.648; 8/5/2 0.633; 7/2/3 0.704; 9/6/2 0.733
+  //   96 px: 6/4/3 (round 1) 0.714 ms; 8/4/3 0.764; 7/4/3 0.693; 7/3/3 0.682; 7/3/2 0.680 (chosen); 6/3/2 0.695
+  // About 90-96 KB of bulk copies in flight per SM is the optimum: 144 KB (round 1) is 6 % slower -- deeper
+  // read queues only get in the way of the gray / feature write streams -- and 60-72 KB starves the stream.
+  static constexpr int kPhases = (SPAN == 96) ? AVFE_LIP_PHASES_96 : AVFE_LIP_PHASES_88;
+  static constexpr int kBlendActive = kPhases * SPAN;                 // 704 or 672 threads with pixels
+  static constexpr int kBlendWarps = (kBlendActive + 31) / 32;        // 22 or 21
+  static constexpr int kRowsMax = (SPAN + kPhases - 1) / kPhases;     // 11 or 14
+  // bulk copies in flight per stream warp (x 3 KB): 8 x 4 = 96 KB / 9 x 3 = 81 KB per SM
+  static constexpr int kRing = (SPAN == 96) ? AVFE_LIP_RING_96 : AVFE_LIP_RING_88;
   // footprint tiles: the stream may run this many frames ahead of the blend (what fits)
-  static constexpr int kSlots = 3;
+  static constexpr int kSlots = (SPAN == 96) ? AVFE_LIP_SLOTS_96 : AVFE_LIP_SLOTS_88;
   static constexpr int kBlendThreads = kBlendWarps * 32;
-  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 10 or 9
+  static constexpr int kStreamWarps = 32 - kBlendWarps - kTformRoleWarps;   // 8 or 9
   static constexpr int kStreamFirst = kBlendWarps;                    // warp index of the first stream warp
   static constexpr int kTformFirst = 32 - kTformRoleWarps;            // highest warp ids: scheduled first
   static constexpr int kHandoverThreads = 32 * (kBlendWarps + kStreamWarps);   // tile FULL barriers
