@@ -41,8 +41,14 @@ namespace avfe {
 #ifndef AVFE_LIP_SLOTS_96
 #define AVFE_LIP_SLOTS_96 2
 #endif
+#ifndef AVFE_LIP_EVICT_FIRST
+#define AVFE_LIP_EVICT_FIRST 1
+#endif
+#ifndef AVFE_LIP_DESC_RING
+#define AVFE_LIP_DESC_RING 4
+#endif
 constexpr int kTformRoleWarps = 2;
-constexpr int kDescRing = 4;
+constexpr int kDescRing = AVFE_LIP_DESC_RING;
 constexpr int kFrameTilePx = 16384;         // staged footprint capacity per slot (one byte per pixel)
 
 template <int SPAN>
@@ -150,7 +156,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 // frames are read exactly once: ask L2 to evict them first
 __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
   unsigned long long p;
+#if AVFE_LIP_EVICT_FIRST
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#else
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#endif
   return p;
 }
 
