@@ -22,6 +22,13 @@
 namespace avfe {
 namespace flt {
 
+// tuning knobs (profiles/fuseln_sweep.sh): resident CTAs per SM the two kernels are compiled for
+#ifndef AVFE_FLT_TILE_CTAS
+#define AVFE_FLT_TILE_CTAS 4
+#endif
+#ifndef AVFE_FLT_RING_CTAS
+#define AVFE_FLT_RING_CTAS 3
+#endif
 constexpr int kThreads = 256;
 constexpr int kRowBytes = 16;                  // one channel row of a tile: 4 floats or 8 halves (six CTAs per SM)
 constexpr int kBoxRows = 256;
@@ -84,7 +91,7 @@ __device__ __forceinline__ void fused_row(const uint8_t* tile_a, const uint8_t* 
 // arithmetic: they need the warps more than a second stage -- 59 % of the HBM peak like this, 48 % with the
 // two-stage ring below at three CTAs per SM).  CPL = channels per lane: 2 (a lane stores a pair = 4 bytes).
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, AVFE_FLT_TILE_CTAS)
 fuse_ln_tma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Args a) {
   constexpr int TT = kRowBytes / (int)sizeof(T);
   constexpr int CPL = (sizeof(T) == 4) ? 1 : 2;
@@ -254,7 +261,7 @@ fuse_ln_tma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 // co-resident CTAs), and the barriers, the LayerNorm weights (32 registers) and the launch of 6,000-12,000
 // CTAs are paid once per CTA instead of once per 32 KB tile.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, AVFE_FLT_RING_CTAS)
 fuse_ln_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Args a,
                    const int n_tiles) {
   constexpr int TT = kRowBytes / (int)sizeof(T);
